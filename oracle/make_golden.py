@@ -1,0 +1,134 @@
+"""TEST INFRASTRUCTURE -- generates tests/golden/*.npz from the UNMODIFIED reference modules.
+
+Run in the build container only (needs /root/reference):
+
+    python -m oracle.make_golden
+
+For each case it instantiates REC.model.IDNet.sasrec.SASRec (reference, CPU, dropout 0, fixed
+seed), feeds seeded synthetic (items, masked_index), and stores inputs, every parameter, the
+reference loss, the encoder output, every gradient produced by loss.backward(), the result of
+one torch.optim.AdamW step (trainer.py:100-103,125), predict() scores, and the masked top-k of
+trainer.py:334-336 + collector.py:133.  tests/test_oracle_golden.py pins oracle/sasrec_np.py,
+oracle/torch_port.py and oracle/rowops.c to these files; the GPU parity tests compare the CUDA
+path with the same files.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from oracle.refload import ref_sasrec
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+CASES = {
+    # name: N, D, L, B, heads, layers
+    "sasrec_c1_small": dict(N=401, D=128, L=10, B=8, h=4, layers=2, seed=2020),
+    "sasrec_l20_d64": dict(N=257, D=64, L=20, B=6, h=4, layers=2, seed=7),
+    "sasrec_dh128": dict(N=101, D=256, L=7, B=5, h=2, layers=1, seed=11),
+}
+
+
+def synth_batch(g, N, L, B, full=False):
+    """Left-padded positives with ragged lengths, uniform negatives not in the sequence, neg[:,0]=0
+    -- the layout SEQTrainDataset produces (data/dataset/trainset.py:52-75)."""
+    items = np.zeros((B, 2, L + 1), dtype=np.int64)
+    mask = np.zeros((B, L), dtype=np.int64)
+    for b in range(B):
+        n = L + 1 if (full or b == 0) else int(g.integers(2, L + 2))
+        seq = g.integers(1, N, size=n)
+        if b == 1 and n >= 3:
+            seq[1] = seq[0]  # duplicate ids inside one sequence
+        items[b, 0, L + 1 - n:] = seq
+        s = set(seq.tolist())
+        for t in range(1, n):
+            it = int(g.integers(1, N))
+            while it in s:
+                it = int(g.integers(1, N))
+            items[b, 1, L + 1 - n + t] = it
+        mask[b, L - (n - 1):] = 1
+    return items, mask
+
+
+def make_case(name, c):
+    torch.manual_seed(c["seed"])
+    g = np.random.default_rng(c["seed"])
+    cfg = dict(n_layers=c["layers"], n_heads=c["h"], embedding_size=c["D"], inner_size=2,
+               hidden_dropout_prob=0.0, attn_dropout_prob=0.0, hidden_act="gelu", layer_norm_eps=1e-12,
+               initializer_range=0.02, MAX_ITEM_LIST_LENGTH=c["L"])
+    model = ref_sasrec(cfg, c["N"])
+    # biases / LN params are zeros/ones at init; perturb so that their grads & use are exercised
+    with torch.no_grad():
+        for n_, p in model.named_parameters():
+            if p.ndim == 1:
+                p.add_(0.05 * torch.randn_like(p))
+    model.train()
+    items, mask = synth_batch(g, c["N"], c["L"], c["B"])
+    t_items, t_mask = torch.from_numpy(items), torch.from_numpy(mask)
+
+    cap = {}
+    hk = model.trm_encoder.register_forward_hook(lambda m, i, o: cap.__setitem__("enc_out", o[-1].detach().clone()))
+    out = {"cfg_" + k: np.array(v) for k, v in c.items()}
+    for k, v in model.state_dict().items():
+        out["param/" + k] = v.detach().numpy().copy()
+    out["items"] = items
+    out["masked_index"] = mask
+
+    # ---- eval path first (same initial parameters as the train step below) ----
+    model.eval()
+    Be = c["B"] + 3
+    seqs = np.zeros((Be, c["L"]), dtype=np.int64)
+    hist_u, hist_i = [], []
+    for u in range(Be):
+        n = int(g.integers(1, c["L"] + 6))
+        full = g.integers(1, c["N"], size=n)
+        seq = full[-c["L"]:]
+        seqs[u, c["L"] - len(seq):] = seq
+        hist_u += [u] * n
+        hist_i += full.tolist()
+    hist_u, hist_i = np.array(hist_u, dtype=np.int64), np.array(hist_i, dtype=np.int64)
+    with torch.no_grad():
+        scores = model.predict(torch.from_numpy(seqs), model.compute_item_all())
+        raw = scores.numpy().copy()
+        scores = scores.view(-1, c["N"])
+        scores[:, 0] = -np.inf                                   # trainer.py:334
+        scores[(torch.from_numpy(hist_u), torch.from_numpy(hist_i))] = -np.inf   # trainer.py:335-336
+        tv, ti = torch.topk(scores, 10, dim=-1)                  # collector.py:133
+    model.train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.1)  # overall/ID.yaml:20-23
+    opt.zero_grad()
+    loss = model((t_items, t_mask))
+    loss.backward()
+    hk.remove()
+    out["loss"] = loss.detach().numpy()
+    out["enc_out"] = cap["enc_out"].numpy()
+    for k, p in model.named_parameters():
+        out["grad/" + k] = p.grad.detach().numpy().copy()
+    opt.step()
+    for k in ("item_embedding.weight", "position_embedding.weight", "LayerNorm.weight",
+              "trm_encoder.layer.0.multi_head_attention.query.weight",
+              "trm_encoder.layer.0.feed_forward.dense_2.bias"):
+        out["adamw1/" + k] = dict(model.named_parameters())[k].detach().numpy().copy()
+    # second step with the SAME grads exercises m/v carry-over and bias correction at step 2
+    opt.step()
+    out["adamw2/item_embedding.weight"] = model.item_embedding.weight.detach().numpy().copy()
+
+    out["eval_item_seq"] = seqs
+    out["eval_hist_u"] = hist_u
+    out["eval_hist_i"] = hist_i
+    out["eval_scores_raw"] = raw
+    out["eval_topk_val"] = tv.numpy()
+    out["eval_topk_idx"] = ti.numpy()
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "loss", float(loss.detach()), "size", os.path.getsize(os.path.join(OUT, name + ".npz")) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(1)
+    torch.use_deterministic_algorithms(True)
+    for n, c in CASES.items():
+        if len(sys.argv) > 1 and n not in sys.argv[1:]:
+            continue
+        make_case(n, c)
