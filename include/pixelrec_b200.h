@@ -1,0 +1,187 @@
+/* pixelrec_b200 -- C ABI of the B200-native SASRec hot path (libpixelrec_b200.so).
+ *
+ * The reference (westlake-repl/PixelRec) has NO native / FFI boundary: its hot path is stock
+ * PyTorch ops inside the Python model plugins.  This ABI is therefore defined by this build and
+ * sits one level beneath the Python plugin classes (pixelrec_b200/model/...), each entry point
+ * replacing one group of implicit ATen/cuBLAS kernels of the reference.  The file:line after
+ * "replaces" is relative to /root/reference/code.
+ *
+ * Conventions (all functions):
+ *   - plain C types; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); work is enqueued
+ *     asynchronously on it, nothing synchronises the host;
+ *   - nothing allocates or frees caller memory; scratch comes from the caller, sized by the
+ *     matching *_workspace_bytes() query;
+ *   - return 0 on success, PR_ERR_INVALID_ARGUMENT (<0) for a rejected argument (message in
+ *     pr_last_error_string(), thread-local), or a positive cudaError_t from a failed launch;
+ *   - fp32 tensors are row-major and contiguous unless a stride is part of the signature;
+ *     feature dims must be multiples of 4 floats (16-byte rows) -- true for every reference config;
+ *   - re-entrant across streams and devices (no global mutable state besides cached
+ *     per-device attributes).
+ */
+#ifndef PIXELREC_B200_H_
+#define PIXELREC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PR_ABI_VERSION 1
+#define PR_OK 0
+#define PR_ERR_INVALID_ARGUMENT (-1)
+#define PR_ERR_UNSUPPORTED (-2)
+
+#if defined(__GNUC__)
+#define PR_API __attribute__((visibility("default")))
+#else
+#define PR_API
+#endif
+
+typedef void* pr_stream_t;
+
+/* activation ids for pr_act_* (REC/model/layers.py:640-648 ACT2FN) */
+#define PR_ACT_GELU 0    /* erf form, layers.py:651-660 */
+#define PR_ACT_RELU 1
+#define PR_ACT_SWISH 2
+#define PR_ACT_TANH 3
+#define PR_ACT_SIGMOID 4
+
+PR_API int pr_version(void);
+PR_API const char* pr_last_error_string(void);
+/* number of SMs of the current device (148 on B200); <0 on error */
+PR_API int pr_sm_count(void);
+/* Makes `device` current for this library's CUDA runtime on the calling thread.  The host side calls
+ * it with the device of the tensors it passes (one process per GPU: once, with LOCAL_RANK). */
+PR_API int pr_set_device(int device);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  embedding row gather.     replaces nn.Embedding.forward: REC/model/IDNet/sasrec.py:31,68
+ *                               (same call in gru4rec.py:25,51)
+ *   out[r, :] = W[idx[r], :]   r in [0,R).  Bit-exact copy, pad row 0 included.
+ *   status (optional, may be NULL): *status |= 1 if any idx is outside [0,N) (that row is
+ *   zero-filled) -- the reference raises IndexError / device-asserts there.
+ *   impl: 0 = auto, 1 = LDG.128/STG.128 path, 2 = TMA bulk-copy (smem-staged) path.
+ */
+PR_API int pr_gather_rows_f32(const float* W, int64_t N, int64_t D, const int64_t* idx, int64_t R, float* out,
+                       int32_t* status, int impl, pr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  gradient scatter-add.     replaces autograd's embedding_dense_backward of sasrec.py:68
+ *                               + optimizer.zero_grad's dense fill (trainer/trainer.py:117,122)
+ * Two calls so the index work (depends only on idx) can be done once and overlap the forward:
+ *
+ * pr_scatter_plan: stable LSD radix sort of (idx, position), segment boundaries, compaction.
+ *   perm[R]        positions r sorted by (idx[r], r)
+ *   uniq_ids[U]    ascending distinct ids, padding_idx removed     (capacity min(R,N))
+ *   seg_start[U+1] perm offsets of each id's run                   (capacity min(R,N)+1)
+ *   n_uniq[1]      U
+ *   row2slot       optional [N]: row2slot[uniq_ids[u]] = u; caller pre-fills with -1 once,
+ *                  pr_adamw_rows_f32 restores the -1s it consumes
+ *   status         optional: |= 1 on out-of-range idx (such rows are dropped)
+ *
+ * pr_scatter_add_rows_f32: out_rows[u, :] = scale * sum_{k in run u} dOut[perm[k], :], added
+ *   sequentially in ascending position (deterministic; oracle/sasrec_np.py scatter_add_rows
+ *   defines the same order, so the comparison is bit-exact for scale == 1).
+ *   If dense_G != NULL the same rows are also stored to dense_G[uniq_ids[u], :] (no zero fill).
+ *   R <= 2^24 rows per call.
+ */
+PR_API size_t pr_scatter_plan_workspace_bytes(int64_t R, int64_t N);
+PR_API int pr_scatter_plan(const int64_t* idx, int64_t R, int64_t N, int64_t padding_idx, int32_t* perm, int32_t* uniq_ids,
+                    int32_t* seg_start, int32_t* n_uniq, int32_t* row2slot, void* workspace, size_t workspace_bytes,
+                    int32_t* status, pr_stream_t stream);
+PR_API int pr_scatter_add_rows_f32(const float* dOut, int64_t R, int64_t D, const int32_t* perm, const int32_t* uniq_ids,
+                            const int32_t* seg_start, const int32_t* n_uniq, int64_t max_uniq, float scale,
+                            float* out_rows, float* dense_G, pr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K10 AdamW.                    replaces torch.optim.AdamW.step: trainer/trainer.py:100-103,125
+ * Exact dense semantics (every row decays every step) with a SPARSE gradient:
+ *   g(row) = grad_scale * grad_rows[row2slot[row]] if row2slot[row] >= 0 else 0.
+ * step >= 1 is the 1-based step count used for bias correction; if step_dev != NULL the count is
+ * read from device memory instead (CUDA-graph friendly).  row2slot entries are reset to -1.
+ * pr_adamw_dense_f32: the same update over a flat dense buffer (all non-table parameters).
+ */
+PR_API int pr_adamw_rows_f32(float* W, float* M, float* V, int64_t N, int64_t D, const float* grad_rows, int32_t* row2slot,
+                      float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                      int64_t step, const int64_t* step_dev, pr_stream_t stream);
+PR_API int pr_adamw_dense_f32(float* w, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, float grad_scale, int64_t step, const int64_t* step_dev,
+                       pr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3/K7  (dropout) + residual add + LayerNorm (+ dropout).
+ *   replaces sasrec.py:77-83 (pos-emb add, LayerNorm, dropout)            [post-LN dropout]
+ *        and layers.py:613-615, 669-671 (out_dropout, LayerNorm(h + x))   [pre-add dropout]
+ *   z[r,:] = drop_pre(h[r,:]) + res[res_row(r),:] ;  y = drop_post(LN(z) * gamma + beta)
+ *   h row r = (s,t), s = r / rows_per_seq, t = r % rows_per_seq lives at h + s*h_seq_stride + t*D
+ *   (lets the kernel read input_emb = item_emb[:,0,:-1] straight out of the [B,2,L+1,D] gather
+ *   output without a copy).  res_period > 0: res_row(r) = r % res_period (position embedding
+ *   broadcast over the batch), else res_row(r) = r.
+ *   Dropout masks are Philox4x32-10(seed; counter = r*D/4 + col/4, stream id) keep iff rnd >= p*2^32,
+ *   kept values scaled by 1/(1-p); p == 0 disables.  mean/rstd [rows] are saved for backward.
+ * Backward returns dh (grad of h, dropout applied; row (s,t) at dh + s*dh_seq_stride + t*D, or
+ * contiguous [rows,D] when dh_seq_stride == 0; dh_accumulate != 0 adds into dh instead of storing --
+ * lets the embedding LayerNorm add straight into the [B,2,L+1,D] table-gradient rows), dres (grad
+ * of z, un-reduced: [rows,D]; NULL to skip), and per-CTA partial column sums for dgamma/dbeta: partials [2, n_partials, D] which
+ * pr_colsum_f32 reduces deterministically.
+ */
+PR_API int pr_add_ln_fwd_f32(const float* h, int64_t h_seq_stride, int64_t rows_per_seq, const float* res, int64_t res_period,
+                      const float* gamma, const float* beta, float eps, int64_t rows, int64_t D, float p_pre,
+                      float p_post, uint64_t seed, uint32_t stream_pre, uint32_t stream_post, float* y, float* mean,
+                      float* rstd, pr_stream_t stream);
+PR_API int pr_add_ln_bwd_partials(int64_t rows, int64_t D);
+PR_API int pr_add_ln_bwd_f32(const float* dy, const float* h, int64_t h_seq_stride, int64_t rows_per_seq, const float* res,
+                      int64_t res_period, const float* gamma, const float* mean, const float* rstd, int64_t rows,
+                      int64_t D, float p_pre, float p_post, uint64_t seed, uint32_t stream_pre, uint32_t stream_post,
+                      float* dh, int64_t dh_seq_stride, int dh_accumulate, float* dres, float* partials,
+                      int n_partials, pr_stream_t stream);
+/* out[c] = sum_p partials[p, c]   (p < n_partials), fixed order */
+PR_API int pr_colsum_f32(const float* partials, int n_partials, int64_t D, float* out, pr_stream_t stream);
+
+/* activation of the feed-forward layer: layers.py:640-660,667   y = act(x) ; dx = act'(x) * dy */
+PR_API int pr_act_fwd_f32(const float* x, int64_t n, int act, float* y, pr_stream_t stream);
+PR_API int pr_act_bwd_f32(const float* x, const float* dy, int64_t n, int act, float* dx, pr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4+K6  causal self-attention core.   replaces get_attention_mask sasrec.py:119-126 and
+ *                                      MultiHeadAttention.forward layers.py:590-612
+ *   q,k,v: row (b,t) at ptr + (b*L + t)*ld, head hd occupies floats [hd*dh, (hd+1)*dh)
+ *   key_ids [B,L] int64: key j is valid iff key_ids[b,j] != 0 (masked_index in training,
+ *   item_seq in predict); NULL = all valid.  causal != 0 adds j <= i.
+ *   S = q k^T / sqrt(dh) + (valid ? 0 : -1e9); P = softmax(S); ctx = drop(P) v
+ *   ctx [B,L,h*dh] (heads re-concatenated, layers.py:610-612); probs [B,h,L,L] saved (pre-dropout).
+ *   Fully-masked query rows give the reference's uniform 1/L row (never NaN).
+ *   Limits: L <= 64, dh % 4 == 0, dh <= 128 or dh % 128 == 0.
+ */
+PR_API int pr_sasrec_attn_fwd_f32(const float* q, const float* k, const float* v, int64_t ld, const int64_t* key_ids, int B,
+                           int L, int h, int dh, int causal, float p_drop, uint64_t seed, uint32_t rng_stream,
+                           float* ctx, float* probs, pr_stream_t stream);
+PR_API int pr_sasrec_attn_bwd_f32(const float* q, const float* k, const float* v, int64_t ld, const float* probs,
+                           const float* dctx, int B, int L, int h, int dh, int causal, float p_drop, uint64_t seed,
+                           uint32_t rng_stream, float* dq, float* dk, float* dv, int64_t ld_grad, pr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K8  sampled-negative pairwise loss.   replaces sasrec.py:88-92 (== gru4rec.py:63-67, mosasrec.py:89-93)
+ *   pos[b,t] = <out[b,t], tp[b,t]>, neg[b,t] = <out[b,t], tn[b,t]>,
+ *   loss = mean_b( -sum_t log(sigmoid(pos-neg) + 1e-8) * mask[b,t] )
+ *   tp/tn row (b,t) at ptr + b*t_seq_stride + t*D (reads item_emb[:,0,1:] / [:,1,1:] in place).
+ *   Saves coef[b,t] = dloss/d(pos-neg) (incl. the 1/B of the mean) for backward; loss_terms [B,L]
+ *   scratch (per-position terms, summed in a fixed order -> deterministic); loss [1].
+ *   pos_score / neg_score [B,L] optional (NULL to skip); positions with mask == 0 are not read.
+ * Backward: d_out = g*coef*(tp - tn), d_tp = g*coef*out, d_tn = -g*coef*out, g = *dloss (device scalar).
+ *   d_tp/d_tn rows are written with d_seq_stride (so they can land inside a [B,2,L+1,D] buffer).
+ */
+PR_API int pr_bpr_loss_fwd_f32(const float* out, const float* tp, const float* tn, int64_t t_seq_stride,
+                        const int64_t* mask, int64_t B, int64_t L, int64_t D, float* pos_score, float* neg_score,
+                        float* coef, float* loss_terms, float* loss, pr_stream_t stream);
+PR_API int pr_bpr_loss_bwd_f32(const float* out, const float* tp, const float* tn, int64_t t_seq_stride, const float* coef,
+                        const float* dloss, int64_t B, int64_t L, int64_t D, float* d_out, float* d_tp, float* d_tn,
+                        int64_t d_seq_stride, pr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIXELREC_B200_H_ */

@@ -1,0 +1,49 @@
+// pixelrec_b200 -- ABI housekeeping: version, thread-local error string, cached device attributes.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace pr {
+
+static thread_local char g_err[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+}  // namespace pr
+
+extern "C" int pr_version(void) { return PR_ABI_VERSION; }
+extern "C" const char* pr_last_error_string(void) { return pr::g_err; }
+extern "C" int pr_sm_count(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        pr::set_last_error("pr_sm_count: no CUDA device");
+        return PR_ERR_UNSUPPORTED;
+    }
+    return pr::sm_count();
+}
+extern "C" int pr_set_device(int device) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        pr::set_last_error("pr_set_device(%d): %s", device, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return PR_OK;
+}

@@ -1,0 +1,410 @@
+// pixelrec_b200 -- fused (dropout) + residual + LayerNorm (+ dropout) and the feed-forward activation.
+//   replaces REC/model/IDNet/sasrec.py:77-83 and REC/model/layers.py:613-615, 651-660, 667-671.
+// HBM-bound: one warp owns one row, the row lives in registers (float4 per lane, coalesced 512-B
+// warp transactions), statistics by warp shuffles, dropout masks regenerated from Philox in the
+// backward instead of being stored.
+#include <algorithm>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace pr {
+
+struct LnArgs {
+    const float* h; long long h_seq_stride; long long rows_per_seq;
+    const float* res; long long res_period;
+    const float* gamma; const float* beta; float eps;
+    long long rows; int D4;
+    float p_pre, p_post; unsigned long long seed; unsigned stream_pre, stream_post;
+};
+
+__device__ __forceinline__ float4 drop4(float4 v, const Philox& ph, unsigned long long ctr, unsigned stream,
+                                        unsigned thr, float inv_keep) {
+    const uint4 r = ph(ctr, stream);
+    v.x = (r.x >= thr) ? v.x * inv_keep : 0.f;
+    v.y = (r.y >= thr) ? v.y * inv_keep : 0.f;
+    v.z = (r.z >= thr) ? v.z * inv_keep : 0.f;
+    v.w = (r.w >= thr) ? v.w * inv_keep : 0.f;
+    return v;
+}
+
+template <int VPL>
+__device__ __forceinline__ void load_z(const LnArgs& a, long long row, int lane, const Philox& ph, unsigned thr_pre,
+                                       float inv_keep_pre, float4 (&z)[VPL]) {
+    const long long s = row / a.rows_per_seq, t = row - s * a.rows_per_seq;
+    const float4* h4 = reinterpret_cast<const float4*>(a.h + s * a.h_seq_stride) + t * a.D4;
+    const long long rrow = a.res_period > 0 ? (row % a.res_period) : row;
+    const float4* r4 = a.res ? reinterpret_cast<const float4*>(a.res) + rrow * a.D4 : nullptr;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+        const int c = lane + 32 * j;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < a.D4) {
+            v = h4[c];
+            if (a.p_pre > 0.f) v = drop4(v, ph, (unsigned long long)row * a.D4 + c, a.stream_pre, thr_pre, inv_keep_pre);
+            if (r4) {
+                const float4 r = r4[c];
+                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            }
+        }
+        z[j] = v;
+    }
+}
+
+template <int VPL>
+__device__ __forceinline__ void row_stats(const float4 (&z)[VPL], int lane, int D4, float& mean, float& var) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) s += (z[j].x + z[j].y) + (z[j].z + z[j].w);  // out-of-range chunks hold zeros
+    const float invD = 1.0f / (float)(D4 * 4);
+    mean = warp_sum(s) * invD;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+        if (lane + 32 * j < D4) {
+            const float a = z[j].x - mean, b = z[j].y - mean, c = z[j].z - mean, d = z[j].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    var = warp_sum(q) * invD;
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256) add_ln_fwd_kernel(LnArgs a, float* __restrict__ y, float* __restrict__ mean_out,
+                                                         float* __restrict__ rstd_out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const Philox ph(a.seed);
+    const unsigned thr_pre = drop_threshold(a.p_pre), thr_post = drop_threshold(a.p_post);
+    const float ik_pre = 1.0f / (1.0f - a.p_pre), ik_post = 1.0f / (1.0f - a.p_post);
+    const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(a.beta);
+    for (long long row = warp; row < a.rows; row += nwarps) {
+        float4 z[VPL];
+        load_z<VPL>(a, row, lane, ph, thr_pre, ik_pre, z);
+        float mean, var;
+        row_stats<VPL>(z, lane, a.D4, mean, var);
+        const float rstd = 1.0f / sqrtf(var + a.eps);
+        float4* y4 = reinterpret_cast<float4*>(y) + row * a.D4;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const int c = lane + 32 * j;
+            if (c < a.D4) {
+                const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
+                float4 o;
+                o.x = (z[j].x - mean) * rstd * g.x + b.x;
+                o.y = (z[j].y - mean) * rstd * g.y + b.y;
+                o.z = (z[j].z - mean) * rstd * g.z + b.z;
+                o.w = (z[j].w - mean) * rstd * g.w + b.w;
+                if (a.p_post > 0.f)
+                    o = drop4(o, ph, (unsigned long long)row * a.D4 + c, a.stream_post, thr_post, ik_post);
+                y4[c] = o;
+            }
+        }
+        if (lane == 0) {
+            mean_out[row] = mean;
+            rstd_out[row] = rstd;
+        }
+    }
+}
+
+// backward.  dgamma/dbeta: per-lane register accumulators over the rows of this warp, then a
+// fixed-order sum over the CTA's warps in shared memory -> partials[{0,1}][blockIdx.x][D]
+template <int VPL>
+__global__ void __launch_bounds__(256) add_ln_bwd_kernel(LnArgs a, const float* __restrict__ dy,
+                                                         const float* __restrict__ mean_in,
+                                                         const float* __restrict__ rstd_in, float* __restrict__ dh,
+                                                         long long dh_seq_stride, int dh_accumulate,
+                                                         float* __restrict__ dres, float* __restrict__ partials) {
+    extern __shared__ float4 sm_acc[];  // [2][D4]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const long long warp = (long long)blockIdx.x * nw + wid;
+    const long long nwarps = (long long)gridDim.x * nw;
+    const Philox ph(a.seed);
+    const unsigned thr_pre = drop_threshold(a.p_pre), thr_post = drop_threshold(a.p_post);
+    const float ik_pre = 1.0f / (1.0f - a.p_pre), ik_post = 1.0f / (1.0f - a.p_post);
+    const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
+    const float invD = 1.0f / (float)(a.D4 * 4);
+    float4 accg[VPL], accb[VPL];
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) accg[j] = accb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (long long row = warp; row < a.rows; row += nwarps) {
+        float4 z[VPL];
+        load_z<VPL>(a, row, lane, ph, thr_pre, ik_pre, z);
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        const float4* dy4 = reinterpret_cast<const float4*>(dy) + row * a.D4;
+        float4 dxh[VPL];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const int c = lane + 32 * j;
+            dxh[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < a.D4) {
+                float4 d = ldg_stream(dy4 + c);
+                if (a.p_post > 0.f)
+                    d = drop4(d, ph, (unsigned long long)row * a.D4 + c, a.stream_post, thr_post, ik_post);
+                const float4 g = __ldg(g4 + c);
+                float4 xh;  // z[j] becomes xhat
+                xh.x = (z[j].x - mean) * rstd; xh.y = (z[j].y - mean) * rstd;
+                xh.z = (z[j].z - mean) * rstd; xh.w = (z[j].w - mean) * rstd;
+                z[j] = xh;
+                accg[j].x += d.x * xh.x; accg[j].y += d.y * xh.y; accg[j].z += d.z * xh.z; accg[j].w += d.w * xh.w;
+                accb[j].x += d.x; accb[j].y += d.y; accb[j].z += d.z; accb[j].w += d.w;
+                d.x *= g.x; d.y *= g.y; d.z *= g.z; d.w *= g.w;
+                dxh[j] = d;
+                s1 += (d.x + d.y) + (d.z + d.w);
+                s2 += (d.x * xh.x + d.y * xh.y) + (d.z * xh.z + d.w * xh.w);
+            }
+        }
+        s1 = warp_sum(s1) * invD;
+        s2 = warp_sum(s2) * invD;
+        float4* dh4;
+        if (dh_seq_stride > 0) {
+            const long long sq = row / a.rows_per_seq, tt = row - sq * a.rows_per_seq;
+            dh4 = reinterpret_cast<float4*>(dh + sq * dh_seq_stride) + tt * a.D4;
+        } else {
+            dh4 = reinterpret_cast<float4*>(dh) + row * a.D4;
+        }
+        float4* dr4 = dres ? reinterpret_cast<float4*>(dres) + row * a.D4 : nullptr;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const int c = lane + 32 * j;
+            if (c < a.D4) {
+                float4 dz;
+                dz.x = rstd * (dxh[j].x - s1 - z[j].x * s2);
+                dz.y = rstd * (dxh[j].y - s1 - z[j].y * s2);
+                dz.z = rstd * (dxh[j].z - s1 - z[j].z * s2);
+                dz.w = rstd * (dxh[j].w - s1 - z[j].w * s2);
+                if (dr4) dr4[c] = dz;
+                if (a.p_pre > 0.f)
+                    dz = drop4(dz, ph, (unsigned long long)row * a.D4 + c, a.stream_pre, thr_pre, ik_pre);
+                if (dh_accumulate) {
+                    const float4 o = dh4[c];
+                    dz.x += o.x; dz.y += o.y; dz.z += o.z; dz.w += o.w;
+                }
+                dh4[c] = dz;
+            }
+        }
+    }
+    // CTA reduction in fixed warp order
+    for (int w = 0; w < nw; ++w) {
+        if (wid == w) {
+#pragma unroll
+            for (int j = 0; j < VPL; ++j) {
+                const int c = lane + 32 * j;
+                if (c < a.D4) {
+                    if (w == 0) {
+                        sm_acc[c] = accg[j];
+                        sm_acc[a.D4 + c] = accb[j];
+                    } else {
+                        float4 t = sm_acc[c];
+                        t.x += accg[j].x; t.y += accg[j].y; t.z += accg[j].z; t.w += accg[j].w;
+                        sm_acc[c] = t;
+                        t = sm_acc[a.D4 + c];
+                        t.x += accb[j].x; t.y += accb[j].y; t.z += accb[j].z; t.w += accb[j].w;
+                        sm_acc[a.D4 + c] = t;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    float4* pg = reinterpret_cast<float4*>(partials) + (long long)blockIdx.x * a.D4;
+    float4* pb = reinterpret_cast<float4*>(partials) + ((long long)gridDim.x + blockIdx.x) * a.D4;
+    for (int c = threadIdx.x; c < a.D4; c += blockDim.x) {
+        pg[c] = sm_acc[c];
+        pb[c] = sm_acc[a.D4 + c];
+    }
+}
+
+__global__ void __launch_bounds__(128) colsum_kernel(const float* __restrict__ partials, int n_partials, long long D,
+                                                     float* __restrict__ out) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= D) return;
+    float s = 0.f;
+    for (int p = 0; p < n_partials; ++p) s += partials[(long long)p * D + c];
+    out[c] = s;
+}
+
+// ------------------------------------------------------------------ activations (layers.py:640-660)
+__device__ __forceinline__ float act_f(float x, int act) {
+    switch (act) {
+        case PR_ACT_GELU: return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+        case PR_ACT_RELU: return fmaxf(x, 0.f);
+        case PR_ACT_SWISH: return x / (1.0f + expf(-x));
+        case PR_ACT_TANH: return tanhf(x);
+        default: return 1.0f / (1.0f + expf(-x));
+    }
+}
+__device__ __forceinline__ float act_df(float x, int act) {
+    switch (act) {
+        case PR_ACT_GELU: {
+            const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+            const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+            return cdf + x * pdf;
+        }
+        case PR_ACT_RELU: return x > 0.f ? 1.f : 0.f;
+        case PR_ACT_SWISH: {
+            const float s = 1.0f / (1.0f + expf(-x));
+            return s + x * s * (1.0f - s);
+        }
+        case PR_ACT_TANH: {
+            const float t = tanhf(x);
+            return 1.0f - t * t;
+        }
+        default: {
+            const float s = 1.0f / (1.0f + expf(-x));
+            return s * (1.0f - s);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) act_fwd_kernel(const float* __restrict__ x, long long n, int act,
+                                                      float* __restrict__ y) {
+    const long long n4 = n >> 2, stride = (long long)gridDim.x * blockDim.x;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = i0; i < n4; i += stride) {
+        float4 v = reinterpret_cast<const float4*>(x)[i];
+        v.x = act_f(v.x, act); v.y = act_f(v.y, act); v.z = act_f(v.z, act); v.w = act_f(v.w, act);
+        reinterpret_cast<float4*>(y)[i] = v;
+    }
+    for (long long i = (n4 << 2) + i0; i < n; i += stride) y[i] = act_f(x[i], act);
+}
+
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                      long long n, int act, float* __restrict__ dx) {
+    const long long n4 = n >> 2, stride = (long long)gridDim.x * blockDim.x;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = i0; i < n4; i += stride) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        float4 d = reinterpret_cast<const float4*>(dy)[i];
+        d.x *= act_df(v.x, act); d.y *= act_df(v.y, act); d.z *= act_df(v.z, act); d.w *= act_df(v.w, act);
+        reinterpret_cast<float4*>(dx)[i] = d;
+    }
+    for (long long i = (n4 << 2) + i0; i < n; i += stride) dx[i] = dy[i] * act_df(x[i], act);
+}
+
+static int ln_grid(long long rows) {
+    const long long by_rows = (rows + 7) / 8;
+    return (int)std::max<long long>(1, std::min<long long>(by_rows, (long long)sm_count() * 8));
+}
+static int ln_bwd_grid(long long rows) {
+    const long long by_rows = (rows + 7) / 8;
+    return (int)std::max<long long>(1, std::min<long long>(by_rows, (long long)sm_count() * 4));
+}
+
+static int check_ln_common(const char* who, const void* h, const void* gamma, long long rows, long long D,
+                           long long rows_per_seq, long long h_seq_stride, float p_pre, float p_post) {
+    PR_CHECK_ARG(rows >= 0 && D > 0 && D % 4 == 0, "%s: bad shape rows=%lld D=%lld (D %% 4 must be 0)", who, rows, D);
+    PR_CHECK_ARG(D <= 4096, "%s: D=%lld > 4096 unsupported", who, D);
+    PR_CHECK_ARG(rows_per_seq > 0 && h_seq_stride % 4 == 0, "%s: rows_per_seq must be > 0 and h_seq_stride %% 4 == 0", who);
+    PR_CHECK_ARG(p_pre >= 0.f && p_pre < 1.f && p_post >= 0.f && p_post < 1.f, "%s: dropout p outside [0,1)", who);
+    PR_CHECK_ARG(rows == 0 || (h && gamma), "%s: null pointer", who);
+    return PR_OK;
+}
+
+}  // namespace pr
+
+using namespace pr;
+
+#define PR_DISPATCH_VPL(D4, CALL)         \
+    do {                                  \
+        if ((D4) <= 32) { CALL(1); }      \
+        else if ((D4) <= 64) { CALL(2); } \
+        else if ((D4) <= 128) { CALL(4); }\
+        else if ((D4) <= 256) { CALL(8); }\
+        else if ((D4) <= 512) { CALL(16); }\
+        else { CALL(32); }                \
+    } while (0)
+
+extern "C" int pr_add_ln_fwd_f32(const float* h, int64_t h_seq_stride, int64_t rows_per_seq, const float* res,
+                                 int64_t res_period, const float* gamma, const float* beta, float eps, int64_t rows,
+                                 int64_t D, float p_pre, float p_post, uint64_t seed, uint32_t stream_pre,
+                                 uint32_t stream_post, float* y, float* mean, float* rstd, pr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_ln_common("pr_add_ln_fwd_f32", h, gamma, rows, D, rows_per_seq, h_seq_stride, p_pre, p_post);
+    if (rc) return rc;
+    if (rows == 0) return PR_OK;
+    PR_CHECK_ARG(beta && y && mean && rstd, "pr_add_ln_fwd_f32: null pointer");
+    PR_CHECK_ARG(aligned16(h) && aligned16(res) && aligned16(gamma) && aligned16(beta) && aligned16(y),
+                 "pr_add_ln_fwd_f32: pointers must be 16-byte aligned");
+    LnArgs a{h, h_seq_stride, rows_per_seq, res, res_period, gamma, beta, eps, rows, (int)(D / 4),
+             p_pre, p_post, seed, stream_pre, stream_post};
+    const int grid = ln_grid(rows);
+#define CALL(V) add_ln_fwd_kernel<V><<<grid, 256, 0, stream>>>(a, y, mean, rstd)
+    PR_DISPATCH_VPL(a.D4, CALL);
+#undef CALL
+    PR_CUDA_LAUNCH_CHECK("add_ln_fwd_kernel");
+    return PR_OK;
+}
+
+extern "C" int pr_add_ln_bwd_partials(int64_t rows, int64_t D) {
+    (void)D;
+    if (rows <= 0) return 1;
+    return ln_bwd_grid(rows);
+}
+
+extern "C" int pr_add_ln_bwd_f32(const float* dy, const float* h, int64_t h_seq_stride, int64_t rows_per_seq,
+                                 const float* res, int64_t res_period, const float* gamma, const float* mean,
+                                 const float* rstd, int64_t rows, int64_t D, float p_pre, float p_post, uint64_t seed,
+                                 uint32_t stream_pre, uint32_t stream_post, float* dh, int64_t dh_seq_stride,
+                                 int dh_accumulate, float* dres, float* partials, int n_partials,
+                                 pr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_ln_common("pr_add_ln_bwd_f32", h, gamma, rows, D, rows_per_seq, h_seq_stride, p_pre, p_post);
+    if (rc) return rc;
+    PR_CHECK_ARG(partials, "pr_add_ln_bwd_f32: partials is null");
+    const int grid = ln_bwd_grid(rows);
+    PR_CHECK_ARG(n_partials == (rows > 0 ? grid : 1), "pr_add_ln_bwd_f32: n_partials=%d, expected %d (pr_add_ln_bwd_partials)",
+                 n_partials, rows > 0 ? grid : 1);
+    if (rows == 0) {
+        PR_CUDA_CALL(cudaMemsetAsync(partials, 0, sizeof(float) * 2 * (size_t)D, stream));
+        return PR_OK;
+    }
+    PR_CHECK_ARG(dy && mean && rstd && dh, "pr_add_ln_bwd_f32: null pointer");
+    PR_CHECK_ARG(dh_seq_stride >= 0 && dh_seq_stride % 4 == 0, "pr_add_ln_bwd_f32: dh_seq_stride must be >= 0 and %% 4 == 0");
+    PR_CHECK_ARG(aligned16(dy) && aligned16(h) && aligned16(res) && aligned16(gamma) && aligned16(dh) && aligned16(dres) &&
+                     aligned16(partials),
+                 "pr_add_ln_bwd_f32: pointers must be 16-byte aligned");
+    LnArgs a{h, h_seq_stride, rows_per_seq, res, res_period, gamma, nullptr, 0.f, rows, (int)(D / 4),
+             p_pre, p_post, seed, stream_pre, stream_post};
+    const size_t smem = (size_t)2 * D * sizeof(float);
+#define CALL(V) add_ln_bwd_kernel<V><<<grid, 256, smem, stream>>>(a, dy, mean, rstd, dh, dh_seq_stride, dh_accumulate, dres, partials)
+    PR_DISPATCH_VPL(a.D4, CALL);
+#undef CALL
+    PR_CUDA_LAUNCH_CHECK("add_ln_bwd_kernel");
+    return PR_OK;
+}
+
+extern "C" int pr_colsum_f32(const float* partials, int n_partials, int64_t D, float* out, pr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PR_CHECK_ARG(n_partials >= 1 && D > 0, "pr_colsum_f32: bad shape");
+    PR_CHECK_ARG(partials && out, "pr_colsum_f32: null pointer");
+    colsum_kernel<<<(int)((D + 127) / 128), 128, 0, stream>>>(partials, n_partials, D, out);
+    PR_CUDA_LAUNCH_CHECK("colsum_kernel");
+    return PR_OK;
+}
+
+extern "C" int pr_act_fwd_f32(const float* x, int64_t n, int act, float* y, pr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PR_CHECK_ARG(n >= 0 && act >= 0 && act <= PR_ACT_SIGMOID, "pr_act_fwd_f32: bad n/act");
+    if (n == 0) return PR_OK;
+    PR_CHECK_ARG(x && y && aligned16(x) && aligned16(y), "pr_act_fwd_f32: null/unaligned pointer");
+    const int grid = (int)std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, (long long)sm_count() * 16));
+    act_fwd_kernel<<<grid, 256, 0, stream>>>(x, n, act, y);
+    PR_CUDA_LAUNCH_CHECK("act_fwd_kernel");
+    return PR_OK;
+}
+
+extern "C" int pr_act_bwd_f32(const float* x, const float* dy, int64_t n, int act, float* dx, pr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PR_CHECK_ARG(n >= 0 && act >= 0 && act <= PR_ACT_SIGMOID, "pr_act_bwd_f32: bad n/act");
+    if (n == 0) return PR_OK;
+    PR_CHECK_ARG(x && dy && dx && aligned16(x) && aligned16(dy) && aligned16(dx), "pr_act_bwd_f32: null/unaligned pointer");
+    const int grid = (int)std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, (long long)sm_count() * 16));
+    act_bwd_kernel<<<grid, 256, 0, stream>>>(x, dy, n, act, dx);
+    PR_CUDA_LAUNCH_CHECK("act_bwd_kernel");
+    return PR_OK;
+}

@@ -1,0 +1,696 @@
+// pixelrec_b200 -- table row kernels for sm_100a:
+//   K1  pr_gather_rows_f32       (REC/model/IDNet/sasrec.py:31,68  nn.Embedding forward)
+//   K2  pr_scatter_plan / pr_scatter_add_rows_f32  (autograd embedding_dense_backward of sasrec.py:68)
+//   K10 pr_adamw_rows_f32 / pr_adamw_dense_f32     (trainer/trainer.py:100-103,125 torch.optim.AdamW)
+// All of this is HBM-bound byte/row movement: 128-bit accesses, rows staged through shared memory
+// by the TMA engine (cp.async.bulk) for the gather, grids sized in multiples of the SM count.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace pr {
+
+// =====================================================================================
+// K1 gather, path 1: LDG.128 / STG.128, one warp per 4 rows, all loads issued before the stores
+// =====================================================================================
+constexpr int G_ROWS = 4;  // rows in flight per warp iteration
+
+__global__ void __launch_bounds__(256) gather_rows_ldg_kernel(const float4* __restrict__ W, long long N, int D4,
+                                                              const long long* __restrict__ idx, long long R,
+                                                              float4* __restrict__ out, int* __restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long ngroups = (R + G_ROWS - 1) / G_ROWS;
+    for (long long g = warp; g < ngroups; g += nwarps) {
+        const long long r0 = g * G_ROWS;
+        const float4* src[G_ROWS];
+        bool live[G_ROWS];
+#pragma unroll
+        for (int j = 0; j < G_ROWS; ++j) {
+            live[j] = (r0 + j) < R;
+            long long id = live[j] ? __ldg(idx + r0 + j) : 0;
+            const bool ok = (id >= 0) && (id < N);
+            if (live[j] && !ok) {
+                if (status && lane == 0) atomicOr(status, 1);
+            }
+            src[j] = ok ? (W + id * (long long)D4) : nullptr;
+        }
+        for (int c = lane; c < D4; c += 32) {
+            float4 v[G_ROWS];
+#pragma unroll
+            for (int j = 0; j < G_ROWS; ++j) v[j] = src[j] ? __ldg(src[j] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < G_ROWS; ++j)
+                if (live[j]) stg_stream(out + (r0 + j) * (long long)D4 + c, v[j]);
+        }
+    }
+}
+
+// =====================================================================================
+// K1 gather, path 2: TMA engine.  One warp per CTA drives a ring of shared-memory stages:
+//   lane l issues cp.async.bulk global->shared for row l of the stage (2 KB at D=512), the
+//   stage's mbarrier counts the bytes, then ONE cp.async.bulk shared->global writes the whole
+//   stage (its rows are contiguous in `out`).  No data ever touches registers.
+// =====================================================================================
+constexpr int GB_STAGES = 6;
+constexpr int GB_STAGE_BYTES = 16 * 1024;  // target bytes per stage (8 rows at D=512)
+
+__global__ void __launch_bounds__(32) gather_rows_bulk_kernel(const float* __restrict__ W, long long N, int D,
+                                                              const long long* __restrict__ idx, long long R,
+                                                              float* __restrict__ out, int rows_per_stage,
+                                                              int* __restrict__ status) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[GB_STAGES];
+    const int lane = threadIdx.x;
+    const uint32_t row_bytes = (uint32_t)D * 4u;
+    const uint32_t stage_bytes = row_bytes * (uint32_t)rows_per_stage;
+    if (lane == 0) {
+        for (int s = 0; s < GB_STAGES; ++s) mbar_init(&full_bar[s], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const long long nchunks = (R + rows_per_stage - 1) / rows_per_stage;
+    long long n_my = 0;
+    if ((long long)blockIdx.x < nchunks) n_my = (nchunks - 1 - blockIdx.x) / gridDim.x + 1;
+    // ids of the next chunk are prefetched one iteration ahead so the bulk issue never waits on them
+    long long id_next = -1;
+    if (n_my > 0) {
+        const long long r = (long long)blockIdx.x * rows_per_stage + lane;
+        if (lane < rows_per_stage && r < R) id_next = __ldg(idx + r);
+    }
+
+    for (long long it = 0; it < n_my + (GB_STAGES - 1); ++it) {
+        // ---- drain: chunk jt landed -> one bulk store of the whole stage
+        const long long jt = it - (GB_STAGES - 1);
+        if (jt >= 0) {
+            const int s = (int)(jt % GB_STAGES);
+            const uint32_t parity = (uint32_t)((jt / GB_STAGES) & 1);
+            mbar_wait(&full_bar[s], parity);
+            const long long chunk = (long long)blockIdx.x + jt * gridDim.x;
+            const long long r0 = chunk * rows_per_stage;
+            const int nrows = (int)min((long long)rows_per_stage, R - r0);
+            if (lane == 0) {
+                bulk_s2g(out + r0 * (long long)D, smem_raw + (size_t)s * stage_bytes, (uint32_t)nrows * row_bytes);
+                bulk_commit();
+            }
+        }
+        // ---- fill: issue the row loads of chunk `it`
+        if (it < n_my) {
+            const int s = (int)(it % GB_STAGES);
+            // the stage was last read by the store committed one loop iteration ago (2 groups back now)
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+            const long long chunk = (long long)blockIdx.x + it * gridDim.x;
+            const long long r0 = chunk * rows_per_stage;
+            const int nrows = (int)min((long long)rows_per_stage, R - r0);
+            const long long id = id_next;
+            {
+                const long long rn = (chunk + gridDim.x) * rows_per_stage + lane;
+                id_next = (it + 1 < n_my && lane < rows_per_stage && rn < R) ? __ldg(idx + rn) : -1;
+            }
+            const bool ok = (lane < nrows) && id >= 0 && id < N;
+            const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+            unsigned char* slot = smem_raw + (size_t)s * stage_bytes + (size_t)lane * row_bytes;
+            if (lane < nrows && !ok) {  // out-of-range id: zero row + flag (reference raises IndexError)
+                if (status) atomicOr(status, 1);
+                float4* z = reinterpret_cast<float4*>(slot);
+                for (int c = 0; c < D / 4; ++c) z[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                fence_proxy_async();
+            }
+            if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], (uint32_t)__popc(okmask) * row_bytes);
+            __syncwarp();
+            if (ok) bulk_g2s(slot, W + id * (long long)D, row_bytes, &full_bar[s]);
+        }
+    }
+    if (lane == 0) bulk_wait_all<0>();
+}
+
+// =====================================================================================
+// K2 plan: stable LSD radix sort (8-bit digits) of (key, position), run boundaries, compaction
+// =====================================================================================
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 keys per CTA
+constexpr int SCAN_THREADS = 1024;
+
+__global__ void __launch_bounds__(256) plan_convert_kernel(const long long* __restrict__ idx, int R, long long N,
+                                                           long long pad, uint32_t* __restrict__ keys,
+                                                           int* __restrict__ vals, int* __restrict__ status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const long long id = idx[i];
+    const bool oor = (id < 0) || (id >= N);
+    if (oor && status) atomicOr(status, 1);
+    keys[i] = (oor || id == pad) ? (uint32_t)N : (uint32_t)id;  // sentinel N sorts last and is dropped
+    vals[i] = i;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32_t* __restrict__ keys, int R, int shift,
+                                                             uint32_t* __restrict__ tile_hist, int T) {
+    __shared__ uint32_t hist[256];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        const int i = base + j * RS_THREADS + threadIdx.x;
+        if (i < R) atomicAdd(&hist[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    tile_hist[(size_t)threadIdx.x * T + blockIdx.x] = hist[threadIdx.x];  // digit-major
+}
+
+// single-CTA in-place exclusive scan of a[0..n); optionally writes the grand total
+__global__ void __launch_bounds__(SCAN_THREADS) scan_single_kernel(uint32_t* __restrict__ a, int n,
+                                                                   uint32_t* __restrict__ total_out) {
+    __shared__ uint32_t warp_tot[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int chunk = (n + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int lo = min(n, tid * chunk), hi = min(n, lo + chunk);
+    uint32_t s = 0;
+    for (int i = lo; i < hi; ++i) s += a[i];
+    uint32_t inc = s;  // inclusive warp scan
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t w = warp_tot[lane];
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        warp_tot[lane] = winc - w;  // exclusive offsets of the warps
+        if (lane == 31 && total_out) *total_out = winc;
+    }
+    __syncthreads();
+    uint32_t run = warp_tot[wid] + (inc - s);
+    for (int i = lo; i < hi; ++i) {
+        const uint32_t t = a[i];
+        a[i] = run;
+        run += t;
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* __restrict__ keys_in,
+                                                                const int* __restrict__ vals_in,
+                                                                uint32_t* __restrict__ keys_out,
+                                                                int* __restrict__ vals_out, int R, int shift,
+                                                                const uint32_t* __restrict__ tile_base, int T) {
+    __shared__ uint32_t whist[RS_THREADS / 32][256];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int i = tid; i < (RS_THREADS / 32) * 256; i += RS_THREADS) (&whist[0][0])[i] = 0;
+    __syncthreads();
+    // warp w owns the contiguous sub-tile [base, base + 256): order inside = (round j, lane) -> stable
+    const int base = blockIdx.x * RS_TILE + w * (32 * RS_ITEMS);
+    uint32_t key[RS_ITEMS];
+    uint32_t local[RS_ITEMS];
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        const int i = base + j * 32 + lane;
+        const bool valid = i < R;
+        key[j] = valid ? keys_in[i] : 0xffffffffu;
+        const uint32_t d = (key[j] >> shift) & 255u;
+        const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 0x100u);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const int leader = __ffs(peers) - 1;
+        uint32_t b = 0;
+        if (valid) b = whist[w][d];
+        __syncwarp();
+        if (valid && lane == leader) whist[w][d] = b + (uint32_t)__popc(peers);
+        __syncwarp();
+        local[j] = b + (uint32_t)rank;
+    }
+    __syncthreads();
+    {  // exclusive prefix over the 8 warps, per digit (thread == digit)
+        uint32_t run = 0;
+#pragma unroll
+        for (int ww = 0; ww < RS_THREADS / 32; ++ww) {
+            const uint32_t t = whist[ww][tid];
+            whist[ww][tid] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        const int i = base + j * 32 + lane;
+        if (i < R) {
+            const uint32_t d = (key[j] >> shift) & 255u;
+            const uint32_t pos = tile_base[(size_t)d * T + blockIdx.x] + whist[w][d] + local[j];
+            keys_out[pos] = key[j];
+            vals_out[pos] = vals_in[i];
+        }
+    }
+}
+
+// flags[i] = 1 at the first position of every run of a real key (< N)
+__global__ void __launch_bounds__(256) seg_flag_kernel(const uint32_t* __restrict__ skeys, int R, uint32_t N,
+                                                       uint32_t* __restrict__ flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const uint32_t k = skeys[i];
+    flags[i] = (k < N && (i == 0 || skeys[i - 1] != k)) ? 1u : 0u;
+}
+
+// multi-CTA exclusive scan, phase 1: per-tile totals
+__global__ void __launch_bounds__(RS_THREADS) scan_tile_reduce_kernel(const uint32_t* __restrict__ a, int n,
+                                                                      uint32_t* __restrict__ tile_sum) {
+    __shared__ uint32_t ws[RS_THREADS / 32];
+    const int base = blockIdx.x * RS_TILE;
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        const int i = base + j * RS_THREADS + threadIdx.x;
+        if (i < n) s += a[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < RS_THREADS / 32; ++w) t += ws[w];
+        tile_sum[blockIdx.x] = t;
+    }
+}
+
+// phase 3: out[i] = tile_off[tile] + exclusive prefix inside the tile (blocked: thread owns 8 consecutive)
+__global__ void __launch_bounds__(RS_THREADS) scan_tile_apply_kernel(const uint32_t* __restrict__ a, int n,
+                                                                     const uint32_t* __restrict__ tile_off,
+                                                                     uint32_t* __restrict__ out) {
+    __shared__ uint32_t ws[RS_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int base = blockIdx.x * RS_TILE + tid * RS_ITEMS;
+    uint32_t v[RS_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        v[j] = (base + j < n) ? a[base + j] : 0u;
+        s += v[j];
+    }
+    uint32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) ws[wid] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < wid; ++w) woff += ws[w];
+    uint32_t run = tile_off[blockIdx.x] + woff + (inc - s);
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        if (base + j < n) out[base + j] = run;
+        run += v[j];
+    }
+}
+
+__global__ void __launch_bounds__(256) seg_emit_kernel(const uint32_t* __restrict__ skeys,
+                                                       const uint32_t* __restrict__ flags,
+                                                       const uint32_t* __restrict__ pos, int R, uint32_t N,
+                                                       int* __restrict__ uniq_ids, int* __restrict__ seg_start,
+                                                       int* __restrict__ n_uniq, int* __restrict__ row2slot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const uint32_t k = skeys[i];
+    const uint32_t u = pos[i];
+    if (flags[i]) {
+        uniq_ids[u] = (int)k;
+        seg_start[u] = i;
+        if (row2slot) row2slot[k] = (int)u;
+    }
+    if (k >= N && (i == 0 || skeys[i - 1] < N)) {  // first dropped row closes the last real run
+        seg_start[u] = i;
+        *n_uniq = (int)u;
+    }
+    if (i == R - 1 && k < N) {
+        seg_start[u + flags[i]] = R;
+        *n_uniq = (int)(u + flags[i]);
+    }
+}
+
+__global__ void plan_empty_kernel(int* seg_start, int* n_uniq) {
+    seg_start[0] = 0;
+    *n_uniq = 0;
+}
+
+// =====================================================================================
+// K2 segment reduce: one warp per (unique id, 32*VPL-float4 column block); rows of a run are
+// added sequentially in ascending position -> deterministic, matches the oracle bit for bit
+// =====================================================================================
+template <int VPL>
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float4* __restrict__ dOut, int D4, int ncb,
+                                                               const int* __restrict__ perm,
+                                                               const int* __restrict__ uniq_ids,
+                                                               const int* __restrict__ seg_start,
+                                                               const int* __restrict__ n_uniq, long long max_uniq,
+                                                               float scale, float4* __restrict__ out_rows,
+                                                               float4* __restrict__ dense_G) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    long long U = *n_uniq;
+    if (U > max_uniq) U = max_uniq;
+    const long long nwork = U * ncb;
+    for (long long wk = warp; wk < nwork; wk += nwarps) {
+        const int u = (int)(wk / ncb);
+        const int c0 = (int)(wk % ncb) * (32 * VPL) + lane;
+        const int s = seg_start[u], e = seg_start[u + 1];
+        float4 acc[VPL];
+        {
+            const float4* row = dOut + (long long)perm[s] * D4;
+#pragma unroll
+            for (int j = 0; j < VPL; ++j) {
+                const int c = c0 + 32 * j;
+                acc[j] = (c < D4) ? ldg_stream(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        for (int k0 = s + 1; k0 < e; k0 += 32) {
+            const int nk = min(32, e - k0);
+            const int myp = (lane < nk) ? perm[k0 + lane] : 0;
+#pragma unroll 2
+            for (int kk = 0; kk < nk; ++kk) {
+                const float4* row = dOut + (long long)__shfl_sync(0xffffffffu, myp, kk) * D4;
+                float4 v[VPL];
+#pragma unroll
+                for (int j = 0; j < VPL; ++j) {
+                    const int c = c0 + 32 * j;
+                    v[j] = (c < D4) ? ldg_stream(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < VPL; ++j) {
+                    acc[j].x += v[j].x; acc[j].y += v[j].y; acc[j].z += v[j].z; acc[j].w += v[j].w;
+                }
+            }
+        }
+        const long long id = uniq_ids[u];
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const int c = c0 + 32 * j;
+            if (c < D4) {
+                float4 r = acc[j];
+                if (scale != 1.0f) { r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale; }
+                if (out_rows) out_rows[(long long)u * D4 + c] = r;
+                if (dense_G) dense_G[id * D4 + c] = r;
+            }
+        }
+    }
+}
+
+// =====================================================================================
+// K10 AdamW (torch.optim.AdamW semantics), dense over every row, gradient looked up through row2slot
+// =====================================================================================
+struct AdamConsts {
+    float decay, beta1, one_m_beta1, beta2, one_m_beta2, step_size, inv_sqrt_bc2, eps, gscale;
+};
+
+__device__ __forceinline__ AdamConsts adam_consts(float lr, float b1, float b2, float eps, float wd, float gscale,
+                                                  long long step, const long long* step_dev) {
+    if (step_dev) step = *step_dev;
+    const double bc1 = 1.0 - pow((double)b1, (double)step);
+    const double bc2 = 1.0 - pow((double)b2, (double)step);
+    AdamConsts c;
+    c.decay = 1.0f - lr * wd;
+    c.beta1 = b1; c.one_m_beta1 = 1.0f - b1;
+    c.beta2 = b2; c.one_m_beta2 = 1.0f - b2;
+    c.step_size = (float)((double)lr / bc1);
+    c.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    c.eps = eps;
+    c.gscale = gscale;
+    return c;
+}
+
+__device__ __forceinline__ void adam_elem(float& w, float& m, float& v, float g, const AdamConsts& c) {
+    g *= c.gscale;
+    w *= c.decay;
+    m = m * c.beta1 + g * c.one_m_beta1;
+    v = v * c.beta2 + (g * g) * c.one_m_beta2;
+    const float denom = sqrtf(v) * c.inv_sqrt_bc2 + c.eps;
+    w -= c.step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) adamw_rows_kernel(float4* __restrict__ W, float4* __restrict__ M,
+                                                         float4* __restrict__ V, long long N, int D4,
+                                                         const float4* __restrict__ grad_rows,
+                                                         int* __restrict__ row2slot, float lr, float b1, float b2,
+                                                         float eps, float wd, float gscale, long long step,
+                                                         const long long* __restrict__ step_dev) {
+    const AdamConsts c = adam_consts(lr, b1, b2, eps, wd, gscale, step, step_dev);
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long row = warp; row < N; row += nwarps) {
+        int slot = -1;
+        if (row2slot) {
+            if (lane == 0) {
+                slot = row2slot[row];
+                if (slot >= 0) row2slot[row] = -1;
+            }
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+        }
+        const float4* g4 = (slot >= 0) ? grad_rows + (long long)slot * D4 : nullptr;
+        float4* w4 = W + row * D4;
+        float4* m4 = M + row * D4;
+        float4* v4 = V + row * D4;
+        for (int cidx = lane; cidx < D4; cidx += 32) {
+            float4 w = w4[cidx], m = m4[cidx], v = v4[cidx];
+            const float4 g = g4 ? ldg_stream(g4 + cidx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            adam_elem(w.x, m.x, v.x, g.x, c);
+            adam_elem(w.y, m.y, v.y, g.y, c);
+            adam_elem(w.z, m.z, v.z, g.z, c);
+            adam_elem(w.w, m.w, v.w, g.w, c);
+            w4[cidx] = w; m4[cidx] = m; v4[cidx] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) adamw_dense_kernel(float* __restrict__ w, const float* __restrict__ g,
+                                                          float* __restrict__ m, float* __restrict__ v, long long n,
+                                                          float lr, float b1, float b2, float eps, float wd,
+                                                          float gscale, long long step,
+                                                          const long long* __restrict__ step_dev) {
+    const AdamConsts c = adam_consts(lr, b1, b2, eps, wd, gscale, step, step_dev);
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    float4* w4 = reinterpret_cast<float4*>(w);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 ww = w4[i], mm = m4[i], vv = v4[i];
+        const float4 gg = g4[i];
+        adam_elem(ww.x, mm.x, vv.x, gg.x, c);
+        adam_elem(ww.y, mm.y, vv.y, gg.y, c);
+        adam_elem(ww.z, mm.z, vv.z, gg.z, c);
+        adam_elem(ww.w, mm.w, vv.w, gg.w, c);
+        w4[i] = ww; m4[i] = mm; v4[i] = vv;
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float ww = w[i], mm = m[i], vv = v[i];
+        adam_elem(ww, mm, vv, g[i], c);
+        w[i] = ww; m[i] = mm; v[i] = vv;
+    }
+}
+
+static inline int ceil_div_ll(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace pr
+
+using namespace pr;
+
+// ------------------------------------------------------------------------------------------ C ABI
+extern "C" int pr_gather_rows_f32(const float* W, int64_t N, int64_t D, const int64_t* idx, int64_t R, float* out,
+                                  int32_t* status, int impl, pr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PR_CHECK_ARG(N > 0 && D > 0 && R >= 0, "pr_gather_rows_f32: bad shape N=%lld D=%lld R=%lld", (long long)N,
+                 (long long)D, (long long)R);
+    PR_CHECK_ARG(D % 4 == 0, "pr_gather_rows_f32: D=%lld must be a multiple of 4", (long long)D);
+    PR_CHECK_ARG(impl >= 0 && impl <= 2, "pr_gather_rows_f32: impl must be 0,1,2");
+    if (R == 0) return PR_OK;
+    PR_CHECK_ARG(W && idx && out, "pr_gather_rows_f32: null pointer");
+    PR_CHECK_ARG(aligned16(W) && aligned16(out), "pr_gather_rows_f32: W/out must be 16-byte aligned");
+    const int sms = sm_count();
+    const long long row_bytes = D * 4;
+    if (impl == 0) impl = (row_bytes >= 512 && row_bytes <= 32 * 1024) ? 2 : 1;
+    if (impl == 2) {
+        PR_CHECK_ARG(row_bytes <= 32 * 1024, "pr_gather_rows_f32: bulk path needs rows <= 32 KiB");
+        int rps = (int)(GB_STAGE_BYTES / row_bytes);
+        if (rps < 1) rps = 1;
+        if (rps > 32) rps = 32;
+        const size_t smem = (size_t)GB_STAGES * rps * row_bytes;
+        if (smem > 48 * 1024)
+            PR_CUDA_CALL(cudaFuncSetAttribute(gather_rows_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem));
+        const long long nchunks = (R + rps - 1) / rps;
+        int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        if (ctas_per_sm > 16) ctas_per_sm = 16;
+        const int grid = (int)std::min<long long>(nchunks, (long long)sms * ctas_per_sm);
+        gather_rows_bulk_kernel<<<grid, 32, smem, stream>>>(W, N, (int)D, (const long long*)idx, R, out, rps, status);
+        PR_CUDA_LAUNCH_CHECK("gather_rows_bulk_kernel");
+    } else {
+        const long long ngroups = (R + G_ROWS - 1) / G_ROWS;
+        const int grid = (int)std::min<long long>((ngroups + 7) / 8, (long long)sms * 8);
+        gather_rows_ldg_kernel<<<grid, 256, 0, stream>>>((const float4*)W, N, (int)(D / 4), (const long long*)idx, R,
+                                                         (float4*)out, status);
+        PR_CUDA_LAUNCH_CHECK("gather_rows_ldg_kernel");
+    }
+    return PR_OK;
+}
+
+namespace {
+struct PlanLayout {
+    size_t keys0, keys1, tmpv, tile_hist, flags, pos, tile_sum, total;
+    int T;
+};
+PlanLayout plan_layout(int64_t R) {
+    PlanLayout L;
+    const size_t r = (size_t)((R + 63) / 64 * 64);
+    L.T = (int)((R + RS_TILE - 1) / RS_TILE);
+    if (L.T < 1) L.T = 1;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t at = o; o += (n * 4 + 255) / 256 * 256; return at; };
+    L.keys0 = take(r);
+    L.keys1 = take(r);
+    L.tmpv = take(r);
+    L.tile_hist = take((size_t)256 * L.T);
+    L.flags = take(r);
+    L.pos = take(r);
+    L.tile_sum = take((size_t)L.T + 1);
+    L.total = o;
+    return L;
+}
+}  // namespace
+
+extern "C" size_t pr_scatter_plan_workspace_bytes(int64_t R, int64_t N) {
+    (void)N;
+    if (R < 0) return 0;
+    return plan_layout(R).total;
+}
+
+extern "C" int pr_scatter_plan(const int64_t* idx, int64_t R, int64_t N, int64_t padding_idx, int32_t* perm,
+                               int32_t* uniq_ids, int32_t* seg_start, int32_t* n_uniq, int32_t* row2slot,
+                               void* workspace, size_t workspace_bytes, int32_t* status, pr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PR_CHECK_ARG(R >= 0 && R <= (1 << 24), "pr_scatter_plan: R=%lld outside [0, 2^24]", (long long)R);
+    PR_CHECK_ARG(N > 0 && N < 0x7fffffffLL, "pr_scatter_plan: N=%lld outside (0, 2^31)", (long long)N);
+    PR_CHECK_ARG(seg_start && n_uniq, "pr_scatter_plan: null output");
+    if (R == 0) {
+        plan_empty_kernel<<<1, 1, 0, stream>>>(seg_start, n_uniq);
+        PR_CUDA_LAUNCH_CHECK("plan_empty_kernel");
+        return PR_OK;
+    }
+    PR_CHECK_ARG(idx && perm && uniq_ids && workspace, "pr_scatter_plan: null pointer");
+    const PlanLayout L = plan_layout(R);
+    PR_CHECK_ARG(workspace_bytes >= L.total, "pr_scatter_plan: workspace %zu < required %zu", workspace_bytes, L.total);
+    char* ws = (char*)workspace;
+    uint32_t* kbuf[2] = {(uint32_t*)(ws + L.keys0), (uint32_t*)(ws + L.keys1)};
+    int* tmpv = (int*)(ws + L.tmpv);
+    uint32_t* tile_hist = (uint32_t*)(ws + L.tile_hist);
+    uint32_t* flags = (uint32_t*)(ws + L.flags);
+    uint32_t* pos = (uint32_t*)(ws + L.pos);
+    uint32_t* tile_sum = (uint32_t*)(ws + L.tile_sum);
+    const int T = L.T;
+    int bits = 1;
+    while ((1LL << bits) <= N) ++bits;  // keys take values 0..N (N = sentinel)
+    const int passes = (bits + 7) / 8;
+    // ping-pong so that the final pass lands the positions in `perm`
+    int* vbuf[2];
+    if (passes % 2 == 0) { vbuf[0] = perm; vbuf[1] = tmpv; } else { vbuf[0] = tmpv; vbuf[1] = perm; }
+    const int iR = (int)R;
+    plan_convert_kernel<<<ceil_div_ll(R, 256), 256, 0, stream>>>((const long long*)idx, iR, N, padding_idx, kbuf[0],
+                                                                 vbuf[0], status);
+    PR_CUDA_LAUNCH_CHECK("plan_convert_kernel");
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+        const int shift = 8 * p;
+        rs_hist_kernel<<<T, RS_THREADS, 0, stream>>>(kbuf[cur], iR, shift, tile_hist, T);
+        scan_single_kernel<<<1, SCAN_THREADS, 0, stream>>>(tile_hist, 256 * T, nullptr);
+        rs_scatter_kernel<<<T, RS_THREADS, 0, stream>>>(kbuf[cur], vbuf[cur], kbuf[cur ^ 1], vbuf[cur ^ 1], iR, shift,
+                                                        tile_hist, T);
+        cur ^= 1;
+    }
+    PR_CUDA_LAUNCH_CHECK("radix sort passes");
+    const uint32_t* skeys = kbuf[cur];
+    seg_flag_kernel<<<ceil_div_ll(R, 256), 256, 0, stream>>>(skeys, iR, (uint32_t)N, flags);
+    scan_tile_reduce_kernel<<<T, RS_THREADS, 0, stream>>>(flags, iR, tile_sum);
+    scan_single_kernel<<<1, SCAN_THREADS, 0, stream>>>(tile_sum, T, nullptr);
+    scan_tile_apply_kernel<<<T, RS_THREADS, 0, stream>>>(flags, iR, tile_sum, pos);
+    seg_emit_kernel<<<ceil_div_ll(R, 256), 256, 0, stream>>>(skeys, flags, pos, iR, (uint32_t)N, uniq_ids, seg_start,
+                                                             n_uniq, row2slot);
+    PR_CUDA_LAUNCH_CHECK("segment kernels");
+    return PR_OK;
+}
+
+extern "C" int pr_scatter_add_rows_f32(const float* dOut, int64_t R, int64_t D, const int32_t* perm,
+                                       const int32_t* uniq_ids, const int32_t* seg_start, const int32_t* n_uniq,
+                                       int64_t max_uniq, float scale, float* out_rows, float* dense_G,
+                                       pr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PR_CHECK_ARG(D > 0 && D % 4 == 0, "pr_scatter_add_rows_f32: D=%lld must be a positive multiple of 4", (long long)D);
+    PR_CHECK_ARG(R >= 0 && max_uniq >= 0, "pr_scatter_add_rows_f32: negative size");
+    if (R == 0 || max_uniq == 0) return PR_OK;
+    PR_CHECK_ARG(dOut && perm && uniq_ids && seg_start && n_uniq, "pr_scatter_add_rows_f32: null pointer");
+    PR_CHECK_ARG(out_rows || dense_G, "pr_scatter_add_rows_f32: no output given");
+    PR_CHECK_ARG(aligned16(dOut) && aligned16(out_rows) && aligned16(dense_G),
+                 "pr_scatter_add_rows_f32: pointers must be 16-byte aligned");
+    const int D4 = (int)(D / 4);
+    const int sms = sm_count();
+    const long long work_hint = std::min<long long>(max_uniq, R);
+#define PR_LAUNCH_SCATTER(VPL)                                                                                      \
+    do {                                                                                                            \
+        const int ncb = (D4 + 32 * VPL - 1) / (32 * VPL);                                                           \
+        const int grid = (int)std::max<long long>(1, std::min<long long>((work_hint * ncb + 7) / 8, (long long)sms * 8)); \
+        scatter_add_rows_kernel<VPL><<<grid, 256, 0, stream>>>((const float4*)dOut, D4, ncb, perm, uniq_ids,        \
+                                                               seg_start, n_uniq, max_uniq, scale, (float4*)out_rows, \
+                                                               (float4*)dense_G);                                   \
+    } while (0)
+    if (D4 <= 32) PR_LAUNCH_SCATTER(1);
+    else if (D4 <= 64) PR_LAUNCH_SCATTER(2);
+    else if (D4 <= 128) PR_LAUNCH_SCATTER(4);
+    else PR_LAUNCH_SCATTER(8);
+#undef PR_LAUNCH_SCATTER
+    PR_CUDA_LAUNCH_CHECK("scatter_add_rows_kernel");
+    return PR_OK;
+}
+
+extern "C" int pr_adamw_rows_f32(float* W, float* M, float* V, int64_t N, int64_t D, const float* grad_rows,
+                                 int32_t* row2slot, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                 float grad_scale, int64_t step, const int64_t* step_dev, pr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PR_CHECK_ARG(N > 0 && D > 0 && D % 4 == 0, "pr_adamw_rows_f32: bad shape N=%lld D=%lld", (long long)N, (long long)D);
+    PR_CHECK_ARG(W && M && V, "pr_adamw_rows_f32: null state pointer");
+    PR_CHECK_ARG((row2slot == nullptr) || grad_rows, "pr_adamw_rows_f32: row2slot given without grad_rows");
+    PR_CHECK_ARG(step >= 1 || step_dev, "pr_adamw_rows_f32: step must be >= 1");
+    PR_CHECK_ARG(aligned16(W) && aligned16(M) && aligned16(V) && aligned16(grad_rows), "pr_adamw_rows_f32: alignment");
+    const int grid = (int)std::min<long long>((N + 7) / 8, (long long)sm_count() * 8);
+    adamw_rows_kernel<<<grid, 256, 0, stream>>>((float4*)W, (float4*)M, (float4*)V, N, (int)(D / 4),
+                                                (const float4*)grad_rows, row2slot, lr, beta1, beta2, eps,
+                                                weight_decay, grad_scale, step, (const long long*)step_dev);
+    PR_CUDA_LAUNCH_CHECK("adamw_rows_kernel");
+    return PR_OK;
+}
+
+extern "C" int pr_adamw_dense_f32(float* w, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                                  float beta2, float eps, float weight_decay, float grad_scale, int64_t step,
+                                  const int64_t* step_dev, pr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PR_CHECK_ARG(n >= 0, "pr_adamw_dense_f32: negative n");
+    if (n == 0) return PR_OK;
+    PR_CHECK_ARG(w && g && m && v, "pr_adamw_dense_f32: null pointer");
+    PR_CHECK_ARG(step >= 1 || step_dev, "pr_adamw_dense_f32: step must be >= 1");
+    PR_CHECK_ARG(aligned16(w) && aligned16(g) && aligned16(m) && aligned16(v), "pr_adamw_dense_f32: alignment");
+    const int grid = (int)std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, (long long)sm_count() * 8));
+    adamw_dense_kernel<<<grid, 256, 0, stream>>>(w, g, m, v, n, lr, beta1, beta2, eps, weight_decay, grad_scale, step,
+                                                 (const long long*)step_dev);
+    PR_CUDA_LAUNCH_CHECK("adamw_dense_kernel");
+    return PR_OK;
+}

@@ -1,0 +1,379 @@
+"""Tensor-level wrappers and autograd Functions over the C ABI (pixelrec_b200/lib.py).
+
+PyTorch is plumbing here: device memory, the current stream, autograd bookkeeping and the cuBLAS
+linear layers.  Every function below launches hand-written sm_100a kernels through
+libpixelrec_b200.so and raises if given anything but CUDA tensors -- there is no CPU / eager fallback.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import lib as _lib
+
+ACT_IDS = {"gelu": 0, "relu": 1, "swish": 2, "tanh": 3, "sigmoid": 4}
+LAUNCHES = {"count": 0}   # kernels of OURS launched (bench.py reports it as gpu_launches)
+
+_cur_dev = [None]
+
+
+def _L():
+    return _lib.load()
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t):
+    dev = t.device.index
+    if _cur_dev[0] != dev:
+        _lib.check(_L().pr_set_device(dev), "pr_set_device")
+        _cur_dev[0] = dev
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _req(t, dtype, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.PixelRecB200Error(f"{name}: expected a CUDA tensor (pixelrec_b200 has no CPU fallback), got "
+                                     f"{type(t).__name__} on {getattr(t, 'device', None)}")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return t
+
+
+def _count(n=1):
+    LAUNCHES["count"] += n
+
+
+# ------------------------------------------------------------------------------------------- K1 gather
+def gather_rows(W, idx, impl=0, status=None):
+    """out[..., :] = W[idx[...], :]  (REC/model/IDNet/sasrec.py:68).  impl: 0 auto, 1 LDG, 2 TMA bulk."""
+    _req(W, torch.float32, "W")
+    _req(idx, torch.int64, "idx")
+    N, D = W.shape
+    R = idx.numel()
+    out = torch.empty(*idx.shape, D, device=W.device, dtype=torch.float32)
+    _lib.check(_L().pr_gather_rows_f32(_p(W), N, D, _p(idx), R, _p(out), _p(status), impl, _stream(W)), "pr_gather_rows_f32")
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------- K2 scatter
+class ScatterPlan:
+    """Device-side sort/segment plan of one index tensor (pr_scatter_plan)."""
+
+    def __init__(self, idx, N, padding_idx=0, row2slot=None, status=None):
+        _req(idx, torch.int64, "idx")
+        dev = idx.device
+        self.R = idx.numel()
+        self.N = int(N)
+        self.max_uniq = max(1, min(self.R, self.N))
+        i32 = dict(device=dev, dtype=torch.int32)
+        self.perm = torch.empty(max(self.R, 1), **i32)
+        self.uniq_ids = torch.empty(self.max_uniq, **i32)
+        self.seg_start = torch.empty(self.max_uniq + 1, **i32)
+        self.n_uniq = torch.empty(1, **i32)
+        self.row2slot = row2slot
+        ws_bytes = _L().pr_scatter_plan_workspace_bytes(self.R, self.N)
+        self._ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
+        pad = -1 if padding_idx is None else int(padding_idx)
+        _lib.check(_L().pr_scatter_plan(_p(idx), self.R, self.N, pad, _p(self.perm), _p(self.uniq_ids),
+                                        _p(self.seg_start), _p(self.n_uniq), _p(row2slot), _p(self._ws), ws_bytes,
+                                        _p(status), _stream(idx)), "pr_scatter_plan")
+        bits = max(1, int(self.N).bit_length())
+        _count(1 + 3 * ((bits + 7) // 8) + 5 if self.R else 1)
+
+
+def scatter_add_rows(dOut, plan: ScatterPlan, scale=1.0, dense_G=None, out_rows=True):
+    """Sparse gradient rows [max_uniq, D] (rows >= n_uniq are undefined) and/or dense_G[uniq] = rows."""
+    _req(dOut, torch.float32, "dOut")
+    D = dOut.shape[-1]
+    if dOut.numel() != plan.R * D:
+        raise ValueError("scatter_add_rows: dOut does not match the plan")
+    rows = torch.empty(plan.max_uniq, D, device=dOut.device, dtype=torch.float32) if out_rows else None
+    if dense_G is not None:
+        _req(dense_G, torch.float32, "dense_G")
+    _lib.check(_L().pr_scatter_add_rows_f32(_p(dOut), plan.R, D, _p(plan.perm), _p(plan.uniq_ids), _p(plan.seg_start),
+                                            _p(plan.n_uniq), plan.max_uniq, float(scale), _p(rows), _p(dense_G),
+                                            _stream(dOut)), "pr_scatter_add_rows_f32")
+    _count()
+    return rows
+
+
+# ------------------------------------------------------------------------------------------- K10 AdamW
+def adamw_rows(W, M, V, grad_rows, row2slot, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, step_dev=None):
+    _req(W, torch.float32, "W"); _req(M, torch.float32, "M"); _req(V, torch.float32, "V")
+    N, D = W.shape
+    _lib.check(_L().pr_adamw_rows_f32(_p(W), _p(M), _p(V), N, D, _p(grad_rows), _p(row2slot), lr, beta1, beta2, eps,
+                                      weight_decay, grad_scale, int(step), _p(step_dev), _stream(W)), "pr_adamw_rows_f32")
+    _count()
+
+
+def adamw_dense(w, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, step_dev=None):
+    for t, n in ((w, "w"), (g, "g"), (m, "m"), (v, "v")):
+        _req(t, torch.float32, n)
+    _lib.check(_L().pr_adamw_dense_f32(_p(w), _p(g), _p(m), _p(v), w.numel(), lr, beta1, beta2, eps, weight_decay,
+                                       grad_scale, int(step), _p(step_dev), _stream(w)), "pr_adamw_dense_f32")
+    _count()
+
+
+# ------------------------------------------------------------------------------------------- dropout rng
+class DropoutRng:
+    """Philox seed/stream bookkeeping.  One seed per forward call, one stream id per dropout site."""
+
+    def __init__(self, seed=0):
+        self.base = int(seed) & 0xFFFFFFFFFFFF
+        self.calls = 0
+
+    def next_seed(self):
+        self.calls += 1
+        return (self.base * 1000003 + self.calls) & 0xFFFFFFFFFFFFFFFF
+
+
+# ------------------------------------------------------------------------------------------- K3/K7 add+LN
+class GradSlab:
+    """Shared [B,2,L+1,D] table-gradient buffer: the loss backward creates it, the embedding LayerNorm
+    backward accumulates its rows in place, the gather backward consumes it (see SASRec.forward)."""
+
+    def __init__(self):
+        self.dE = None
+
+
+class AddLnFn(torch.autograd.Function):
+    """y = drop_post(LN(drop_pre(h) + res)).  `layout` = None for contiguous h [rows, D], or
+    (rows_per_seq, seq_stride_floats, n_seq) to read rows (s,t) out of a larger tensor in place."""
+
+    @staticmethod
+    def forward(ctx, h, res, gamma, beta, eps, p_pre, p_post, seed, stream_pre, stream_post, layout, res_period, slab):
+        _req(h, torch.float32, "h"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
+        if res is not None:
+            _req(res, torch.float32, "res")
+        D = gamma.numel()
+        if layout is None:
+            rows = h.numel() // D
+            rps, sstride = rows if rows > 0 else 1, 0
+            out_shape = h.shape
+        else:
+            rps, sstride, nseq = layout
+            rows = rps * nseq
+            out_shape = (nseq, rps, D)
+        y = torch.empty(out_shape, device=h.device, dtype=torch.float32)
+        mean = torch.empty(max(rows, 1), device=h.device, dtype=torch.float32)
+        rstd = torch.empty(max(rows, 1), device=h.device, dtype=torch.float32)
+        _lib.check(_L().pr_add_ln_fwd_f32(_p(h), sstride, rps, _p(res), res_period, _p(gamma), _p(beta), eps, rows, D,
+                                          p_pre, p_post, seed, stream_pre, stream_post, _p(y), _p(mean), _p(rstd),
+                                          _stream(h)), "pr_add_ln_fwd_f32")
+        _count()
+        ctx.save_for_backward(h, res, gamma, mean, rstd)
+        ctx.cfg = (eps, p_pre, p_post, seed, stream_pre, stream_post, layout, res_period, rows, D, rps, sstride)
+        ctx.slab = slab
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, res, gamma, mean, rstd = ctx.saved_tensors
+        eps, p_pre, p_post, seed, s_pre, s_post, layout, res_period, rows, D, rps, sstride = ctx.cfg
+        dy = dy.contiguous()
+        n_part = _L().pr_add_ln_bwd_partials(rows, D)
+        partials = torch.empty(2, n_part, D, device=dy.device, dtype=torch.float32)
+        need_res = res is not None and ctx.needs_input_grad[1]
+        # without pre-add dropout dh == dz == dres: one buffer serves both grads
+        share = need_res and res_period <= 0 and p_pre == 0.0 and layout is None
+        dres_rows = torch.empty(rows, D, device=dy.device, dtype=torch.float32) if (need_res and res_period <= 0 and not share) else None
+        slab = ctx.slab
+        ret_dh = None
+        if layout is None:
+            dh = torch.empty_like(h)
+            dh_stride, acc = 0, 0
+            ret_dh = dh
+        elif slab is not None and slab.dE is not None:
+            dh, dh_stride, acc = slab.dE, sstride, 1           # accumulate into the shared table-grad slab
+        else:
+            dh = torch.zeros_like(h)
+            dh_stride, acc = sstride, 0
+            ret_dh = dh
+        # position-embedding style residual (broadcast over sequences): its grad is the per-t sum of dz
+        dz_tmp = None
+        if need_res and res_period > 0:
+            dz_tmp = torch.empty(rows, D, device=dy.device, dtype=torch.float32)
+        _lib.check(_L().pr_add_ln_bwd_f32(_p(dy), _p(h), sstride, rps, _p(res), res_period, _p(gamma), _p(mean), _p(rstd),
+                                          rows, D, p_pre, p_post, seed, s_pre, s_post, _p(dh), dh_stride, acc,
+                                          _p(dres_rows if dres_rows is not None else dz_tmp), _p(partials), n_part,
+                                          _stream(dy)), "pr_add_ln_bwd_f32")
+        dgb = torch.empty(2, D, device=dy.device, dtype=torch.float32)
+        _lib.check(_L().pr_colsum_f32(_p(partials), n_part, D, _p(dgb[0]), _stream(dy)), "pr_colsum_f32")
+        _lib.check(_L().pr_colsum_f32(_p(partials[1]), n_part, D, _p(dgb[1]), _stream(dy)), "pr_colsum_f32")
+        _count(3)
+        dres = None
+        if need_res:
+            if res_period > 0:
+                dres = torch.zeros_like(res)
+                dres[:res_period] = dz_tmp.view(-1, res_period, D).sum(0)
+            elif share:
+                dres = ret_dh.view(res.shape)
+            else:
+                dres = dres_rows.view(res.shape)
+        return ret_dh, dres, dgb[0], dgb[1], None, None, None, None, None, None, None, None, None
+
+
+def add_ln(h, res, gamma, beta, eps, p_pre=0.0, p_post=0.0, seed=0, stream_pre=0, stream_post=0, layout=None,
+           res_period=0, slab=None):
+    return AddLnFn.apply(h, res, gamma, beta, float(eps), float(p_pre), float(p_post), int(seed), int(stream_pre),
+                         int(stream_post), layout, int(res_period), slab)
+
+
+# ------------------------------------------------------------------------------------------- activation
+class ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        _req(x, torch.float32, "x")
+        y = torch.empty_like(x)
+        _lib.check(_L().pr_act_fwd_f32(_p(x), x.numel(), act, _p(y), _stream(x)), "pr_act_fwd_f32")
+        _count()
+        ctx.save_for_backward(x)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        _lib.check(_L().pr_act_bwd_f32(_p(x), _p(dy), x.numel(), ctx.act, _p(dx), _stream(x)), "pr_act_bwd_f32")
+        _count()
+        return dx, None
+
+
+def activation(x, name):
+    if name not in ACT_IDS:
+        raise KeyError(f"hidden_act {name!r} not in {sorted(ACT_IDS)} (REC/model/layers.py:640-648)")
+    return ActFn.apply(x, ACT_IDS[name])
+
+
+# ------------------------------------------------------------------------------------------- K4+K6 attention
+class AttnFn(torch.autograd.Function):
+    """ctx = softmax(q k^T / sqrt(dh) + mask(key_ids, causal)) v on a fused [B, L, 3*D] q|k|v tensor."""
+
+    @staticmethod
+    def forward(ctx, qkv, key_ids, n_heads, causal, p_drop, seed, rng_stream):
+        _req(qkv, torch.float32, "qkv")
+        B, Lq, D3 = qkv.shape
+        D = D3 // 3
+        dh = D // n_heads
+        if key_ids is not None:
+            _req(key_ids, torch.int64, "key_ids")
+        out = torch.empty(B, Lq, D, device=qkv.device, dtype=torch.float32)
+        probs = torch.empty(B, n_heads, Lq, Lq, device=qkv.device, dtype=torch.float32)
+        base = qkv.data_ptr()
+        _lib.check(_L().pr_sasrec_attn_fwd_f32(base, base + 4 * D, base + 8 * D, D3, _p(key_ids), B, Lq, n_heads, dh,
+                                               int(causal), p_drop, seed, rng_stream, _p(out), _p(probs),
+                                               _stream(qkv)), "pr_sasrec_attn_fwd_f32")
+        _count()
+        ctx.save_for_backward(qkv, probs)
+        ctx.cfg = (B, Lq, n_heads, dh, int(causal), p_drop, seed, rng_stream)
+        return out
+
+    @staticmethod
+    def backward(ctx, dctx):
+        qkv, probs = ctx.saved_tensors
+        B, Lq, h, dh, causal, p_drop, seed, rng_stream = ctx.cfg
+        D = h * dh
+        dctx = dctx.contiguous()
+        dqkv = torch.empty_like(qkv)
+        base, gbase = qkv.data_ptr(), dqkv.data_ptr()
+        _lib.check(_L().pr_sasrec_attn_bwd_f32(base, base + 4 * D, base + 8 * D, 3 * D, _p(probs), _p(dctx), B, Lq, h,
+                                               dh, causal, p_drop, seed, rng_stream, gbase, gbase + 4 * D,
+                                               gbase + 8 * D, 3 * D, _stream(qkv)), "pr_sasrec_attn_bwd_f32")
+        _count()
+        return dqkv, None, None, None, None, None, None
+
+
+def attention(qkv, key_ids, n_heads, causal=True, p_drop=0.0, seed=0, rng_stream=0):
+    return AttnFn.apply(qkv, key_ids, int(n_heads), bool(causal), float(p_drop), int(seed), int(rng_stream))
+
+
+# ------------------------------------------------------------------------------------------- K8 loss
+class BprLossFn(torch.autograd.Function):
+    """loss(out [B,L,D], E [B,2,L+1,D], mask [B,L]) of sasrec.py:88-92; targets are read in place from E."""
+
+    @staticmethod
+    def forward(ctx, out, E, mask, slab):
+        _req(out, torch.float32, "out"); _req(E, torch.float32, "E"); _req(mask, torch.int64, "masked_index")
+        B, L, D = out.shape
+        if tuple(E.shape) != (B, 2, L + 1, D):
+            raise ValueError(f"E must be [B,2,L+1,D]={B, 2, L + 1, D}, got {tuple(E.shape)}")
+        coef = torch.empty(B, L, device=out.device, dtype=torch.float32)
+        terms = torch.empty(B, L, device=out.device, dtype=torch.float32)
+        scores = torch.empty(2, B, L, device=out.device, dtype=torch.float32)
+        loss = torch.empty((), device=out.device, dtype=torch.float32)
+        eb = E.data_ptr()
+        plane = (L + 1) * D
+        _lib.check(_L().pr_bpr_loss_fwd_f32(_p(out), eb + 4 * D, eb + 4 * (plane + D), 2 * plane, _p(mask), B, L, D,
+                                            _p(scores[0]), _p(scores[1]), _p(coef), _p(terms), _p(loss), _stream(out)),
+                   "pr_bpr_loss_fwd_f32")
+        _count(2)
+        ctx.save_for_backward(out, E, coef)
+        ctx.slab = slab
+        ctx.scores = scores
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        out, E, coef = ctx.saved_tensors
+        B, L, D = out.shape
+        dloss = dloss.contiguous().to(torch.float32)
+        d_out = torch.empty_like(out)
+        dE = torch.empty_like(E)
+        dE[:, :, 0].zero_()   # rows (b,0,0) receive only the embedding-LN grad; (b,1,0) is dead (sasrec.py:74)
+        gb = dE.data_ptr()
+        eb = E.data_ptr()
+        plane = (L + 1) * D
+        _lib.check(_L().pr_bpr_loss_bwd_f32(_p(out), eb + 4 * D, eb + 4 * (plane + D), 2 * plane, _p(coef), _p(dloss),
+                                            B, L, D, _p(d_out), gb + 4 * D, gb + 4 * (plane + D), 2 * plane,
+                                            _stream(out)), "pr_bpr_loss_bwd_f32")
+        _count()
+        if ctx.slab is not None:
+            ctx.slab.dE = dE
+        return d_out, dE, None, None
+
+
+def bpr_loss(out, E, masked_index, slab=None):
+    return BprLossFn.apply(out, E, masked_index, slab)
+
+
+# ------------------------------------------------------------------------------------------- table gather w/ sparse grad
+class GatherFn(torch.autograd.Function):
+    """E = W[idx].  backward: dense mode returns a zero-filled [N,D] grad (reference semantics);
+    sparse mode deposits (plan, reduced rows) on `sink` and leaves W.grad untouched."""
+
+    @staticmethod
+    def forward(ctx, W, idx, padding_idx, sink, impl):
+        out = gather_rows(W, idx, impl)
+        ctx.save_for_backward(idx)
+        ctx.N = W.shape[0]
+        ctx.padding_idx = padding_idx
+        ctx.sink = sink
+        return out
+
+    @staticmethod
+    def backward(ctx, dE):
+        (idx,) = ctx.saved_tensors
+        dE = dE.contiguous()
+        sink = ctx.sink
+        if sink is not None and sink.sparse:
+            plan = ScatterPlan(idx, ctx.N, ctx.padding_idx, row2slot=sink.row2slot)
+            rows = scatter_add_rows(dE, plan)
+            sink.deposit(plan, rows)
+            return None, None, None, None, None
+        plan = ScatterPlan(idx, ctx.N, ctx.padding_idx)
+        G = torch.zeros(ctx.N, dE.shape[-1], device=dE.device, dtype=torch.float32)
+        scatter_add_rows(dE, plan, dense_G=G, out_rows=False)
+        return G, None, None, None, None
+
+
+def inv_sqrt(x):
+    return 1.0 / math.sqrt(x)

@@ -1,0 +1,89 @@
+"""GPU parity: warp-specialised TMA-fed attention core (K4+K6) vs the oracle (layers.py:590-612 +
+sasrec.py:119-126), forward and backward, with key padding, causal mask and Philox dropout."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import philox_np as PH
+from oracle import sasrec_np as O
+from tests.gpu_util import dev, rel, t
+
+pytestmark = pytest.mark.gpu
+TOL = 3e-5
+
+
+def _case(B, L, h, dh, p, seed, pad=True, causal=True):
+    g = np.random.default_rng(B * 1000 + L * 10 + dh)
+    D = h * dh
+    qkv = g.standard_normal((B, L, 3 * D)).astype(np.float32)
+    ids = np.ones((B, L), dtype=np.int64)
+    if pad:
+        for b in range(B):
+            n = int(g.integers(1, L + 1))
+            ids[b, :L - n] = 0                                 # left padding, >= 1 valid key
+        ids[0] = 1
+    dctx = g.standard_normal((B, L, D)).astype(np.float32)
+    mask = O.attention_mask(ids, np.float64) if causal else np.where((ids != 0)[:, None, None, :], 0.0, -1e9) * np.ones((1, 1, L, 1))
+    drop = PH.attn_keep_scale(B, h, L, p, seed, 5).astype(np.float64)
+    q, k, v = (qkv[..., i * D:(i + 1) * D].astype(np.float64) for i in range(3))
+    ctx_ref, cache = O.attn_core_fwd(q, k, v, mask, h, drop if p > 0 else None)
+    dq, dk, dv = O.attn_core_bwd(dctx.astype(np.float64), cache)
+    return qkv, ids, dctx, ctx_ref, cache[3], np.concatenate([dq, dk, dv], -1)
+
+
+@pytest.mark.parametrize("B,L,h,dh", [(3, 10, 4, 32), (5, 20, 4, 128), (2, 7, 2, 128), (4, 20, 4, 16), (2, 12, 4, 64),
+                                      (3, 20, 4, 512), (2, 10, 2, 256), (3, 32, 2, 64), (70, 20, 4, 128), (2, 1, 4, 32),
+                                      (2, 50, 12, 64)])
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_attention_fwd_bwd(B, L, h, dh, p):
+    from pixelrec_b200 import ops
+    seed = 99
+    qkv, ids, dctx, ctx_ref, p_ref, dqkv_ref = _case(B, L, h, dh, p, seed)
+    tq = t(qkv).requires_grad_()
+    ctx = ops.attention(tq, t(ids), h, True, p, seed, 5)
+    ctx.backward(t(dctx))
+    torch.cuda.synchronize()
+    valid = ids.astype(bool)                                   # fully-masked query rows are don't-care
+    got = ctx.detach().cpu().numpy()
+    assert np.isfinite(got).all()
+    assert rel(got[valid], ctx_ref[valid]) < TOL
+    assert rel(tq.grad.cpu().numpy(), dqkv_ref) < TOL * 3
+
+
+def test_attention_fully_masked_rows_uniform_never_nan():
+    """Left-padded query rows: every key gets -1e9 -> the reference's softmax is uniform over all L keys."""
+    from pixelrec_b200 import ops
+    B, L, h, dh = 2, 10, 4, 32
+    g = np.random.default_rng(0)
+    qkv = t(g.standard_normal((B, L, 3 * h * dh)).astype(np.float32))
+    ids = np.ones((B, L), dtype=np.int64)
+    ids[0, :6] = 0
+    ids[1, :] = 0                                              # a completely empty sequence
+    out = ops.AttnFn.apply(qkv, t(ids), h, True, 0.0, 0, 0)
+    probs_ref = O.softmax_lastdim(np.zeros((L,)) - 1e9)
+    assert torch.isfinite(out).all()
+    v = qkv[..., 2 * h * dh:]
+    assert torch.allclose(out[1, 0], v[1].mean(0), atol=1e-5)   # uniform average of all L values
+    assert abs(probs_ref.sum() - 1) < 1e-12
+
+
+def test_attention_bidirectional_no_padding():
+    """causal=False, key_ids=None: the ViT item-encoder configuration (PixelNet) of the same kernel."""
+    from pixelrec_b200 import ops
+    B, L, h, dh = 3, 50, 12, 64
+    g = np.random.default_rng(1)
+    D = h * dh
+    qkv = g.standard_normal((B, L, 3 * D)).astype(np.float32)
+    q, k, v = (qkv[..., i * D:(i + 1) * D].astype(np.float64) for i in range(3))
+    ref, _ = O.attn_core_fwd(q, k, v, np.zeros((B, 1, L, L)), h)
+    out = ops.attention(t(qkv), None, h, False, 0.0, 0, 0)
+    assert rel(out.cpu().numpy(), ref) < TOL
+
+
+def test_attention_rejects_bad_shapes():
+    from pixelrec_b200 import ops
+    from pixelrec_b200.lib import PixelRecB200Error
+    with pytest.raises(PixelRecB200Error):
+        ops.attention(torch.zeros(1, 65, 3 * 64, device=dev()), None, 2, True)      # L > 64
+    with pytest.raises(PixelRecB200Error):
+        ops.attention(torch.zeros(1, 8, 3 * 96, device=dev()), None, 2, True)       # dh = 48

@@ -1,0 +1,152 @@
+"""GPU parity: fused (dropout)+add+LayerNorm(+dropout), activations, and the pairwise loss vs the oracle.
+fp32 tolerance 1e-5 relative-to-max (well inside north_star's 1e-3)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import philox_np as PH
+from oracle import sasrec_np as O
+from tests.gpu_util import dev, rel, t
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-5
+
+
+def _ln_ref(h, res, gamma, beta, eps, mpre, mpost):
+    z = h * mpre + res
+    y, cache = O.layernorm_fwd(z.astype(np.float64), gamma.astype(np.float64), beta.astype(np.float64), eps)
+    return y * mpost, cache
+
+
+@pytest.mark.parametrize("rows,D", [(1, 4), (37, 64), (100, 128), (333, 512), (17, 768), (65, 1024), (40, 2048), (9, 4096), (50, 36)])
+@pytest.mark.parametrize("p_pre,p_post", [(0.0, 0.0), (0.1, 0.0), (0.0, 0.5)])
+def test_add_ln_fwd_bwd(rows, D, p_pre, p_post):
+    from pixelrec_b200 import ops
+    g = np.random.default_rng(rows * D)
+    h = g.standard_normal((rows, D)).astype(np.float32)
+    res = g.standard_normal((rows, D)).astype(np.float32)
+    gamma = (1 + 0.1 * g.standard_normal(D)).astype(np.float32)
+    beta = (0.1 * g.standard_normal(D)).astype(np.float32)
+    dy = g.standard_normal((rows, D)).astype(np.float32)
+    seed, s_pre, s_post = 1234567, 3, 9
+    mpre = PH.rowwise_keep_scale(rows, D, p_pre, seed, s_pre)
+    mpost = PH.rowwise_keep_scale(rows, D, p_post, seed, s_post)
+    y_ref, cache = _ln_ref(h, res, gamma, beta, 1e-12, mpre, mpost)
+    dz, dg, db = O.layernorm_bwd((dy * mpost).astype(np.float64), gamma.astype(np.float64), cache)
+
+    th, tr = t(h).requires_grad_(), t(res).requires_grad_()
+    tg, tb = t(gamma).requires_grad_(), t(beta).requires_grad_()
+    y = ops.add_ln(th, tr, tg, tb, 1e-12, p_pre=p_pre, p_post=p_post, seed=seed, stream_pre=s_pre, stream_post=s_post)
+    y.backward(t(dy))
+    torch.cuda.synchronize()
+    assert rel(y.detach().cpu().numpy(), y_ref) < TOL
+    if p_pre > 0 or p_post > 0:   # the mask really is the Philox one (exact zeros in the same places)
+        zero_ref = (mpost == 0) if p_post > 0 else None
+        if zero_ref is not None:
+            assert np.array_equal(y.detach().cpu().numpy() == 0, zero_ref)
+    assert rel(tr.grad.cpu().numpy(), dz) < TOL
+    assert rel(th.grad.cpu().numpy(), dz * mpre) < TOL
+    assert rel(tg.grad.cpu().numpy(), dg) < TOL and rel(tb.grad.cpu().numpy(), db) < TOL
+
+
+@pytest.mark.parametrize("B,L,D", [(3, 10, 128), (5, 20, 512), (2, 7, 64)])
+@pytest.mark.parametrize("p", [0.0, 0.25])
+def test_embed_ln_strided_layout_and_posemb(B, L, D, p):
+    """sasrec.py:72,77-83: LN(E[:,0,:-1] + P[0:L]) read in place from the [B,2,L+1,D] gather output;
+    grad wrt E lands only on rows (b,0,t<L); grad wrt P is the sum over the batch."""
+    from pixelrec_b200 import ops
+    g = np.random.default_rng(B + L + D)
+    E = g.standard_normal((B, 2, L + 1, D)).astype(np.float32)
+    P = g.standard_normal((L + 3, D)).astype(np.float32)          # max_seq_length > L: extra rows get zero grad
+    gamma = (1 + 0.1 * g.standard_normal(D)).astype(np.float32)
+    beta = (0.1 * g.standard_normal(D)).astype(np.float32)
+    dy = g.standard_normal((B, L, D)).astype(np.float32)
+    mpost = PH.rowwise_keep_scale(B * L, D, p, 77, 0).reshape(B, L, D)
+    z = E[:, 0, :-1] + P[:L][None]
+    y_ref, cache = O.layernorm_fwd(z.astype(np.float64), gamma.astype(np.float64), beta.astype(np.float64), 1e-12)
+    y_ref = y_ref * mpost
+    dz, dg, db = O.layernorm_bwd((dy * mpost).astype(np.float64), gamma.astype(np.float64), cache)
+    tE, tP = t(E).requires_grad_(), t(P).requires_grad_()
+    tg, tb = t(gamma).requires_grad_(), t(beta).requires_grad_()
+    y = ops.add_ln(tE, tP, tg, tb, 1e-12, p_post=p, seed=77, stream_post=0, layout=(L, 2 * (L + 1) * D, B), res_period=L)
+    assert y.shape == (B, L, D)
+    y.backward(t(dy))
+    torch.cuda.synchronize()
+    assert rel(y.detach().cpu().numpy(), y_ref) < TOL
+    gE = tE.grad.cpu().numpy()
+    assert rel(gE[:, 0, :-1], dz) < TOL
+    assert (gE[:, 1] == 0).all() and (gE[:, 0, -1] == 0).all()
+    gP = tP.grad.cpu().numpy()
+    assert rel(gP[:L], dz.sum(0)) < TOL and (gP[L:] == 0).all()
+    assert rel(tg.grad.cpu().numpy(), dg) < TOL and rel(tb.grad.cpu().numpy(), db) < TOL
+
+
+@pytest.mark.parametrize("act", ["gelu", "relu", "swish", "tanh", "sigmoid"])
+@pytest.mark.parametrize("n", [5, 4096, 100001])
+def test_activation(act, n):
+    from pixelrec_b200 import ops
+    g = np.random.default_rng(n)
+    x = (3 * g.standard_normal(n)).astype(np.float32)
+    dy = g.standard_normal(n).astype(np.float32)
+    x64 = x.astype(np.float64)
+    sig = 1 / (1 + np.exp(-x64))
+    ref = {"gelu": (O.gelu_fwd(x64), O.gelu_bwd(x64, dy.astype(np.float64))),
+           "relu": (np.maximum(x64, 0), dy * (x64 > 0)),
+           "swish": (x64 * sig, dy * (sig + x64 * sig * (1 - sig))),
+           "tanh": (np.tanh(x64), dy * (1 - np.tanh(x64) ** 2)),
+           "sigmoid": (sig, dy * sig * (1 - sig))}[act]
+    tx = t(x).requires_grad_()
+    y = ops.activation(tx, act)
+    y.backward(t(dy))
+    assert rel(y.detach().cpu().numpy(), ref[0]) < 1e-6 and rel(tx.grad.cpu().numpy(), ref[1]) < 1e-6
+    with pytest.raises(KeyError):
+        ops.activation(tx, "mish")
+
+
+@pytest.mark.parametrize("B,L,D", [(4, 10, 128), (64, 20, 512), (3, 7, 64), (2, 20, 2048), (5, 3, 36)])
+def test_bpr_loss_fwd_bwd(B, L, D):
+    from pixelrec_b200 import ops
+    g = np.random.default_rng(B * L + D)
+    out = g.standard_normal((B, L, D)).astype(np.float32)
+    E = (0.3 * g.standard_normal((B, 2, L + 1, D))).astype(np.float32)
+    mask = (g.random((B, L)) < 0.7).astype(np.int64)
+    mask[0] = 1
+    mask[-1] = 0                                              # a fully padded sequence contributes exactly 0
+    o64, e64 = out.astype(np.float64), E.astype(np.float64)
+    loss_ref, cache = O.bpr_loss_fwd(o64, e64[:, 0, 1:], e64[:, 1, 1:], mask)
+    d_out, d_tp, d_tn = O.bpr_loss_bwd(o64, e64[:, 0, 1:], e64[:, 1, 1:], cache, dloss=1.7)
+    to, tE = t(out).requires_grad_(), t(E).requires_grad_()
+    loss = ops.bpr_loss(to, tE, t(mask))
+    (loss * 1.7).backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref) / abs(loss_ref) < TOL
+    assert rel(to.grad.cpu().numpy(), d_out) < TOL
+    gE = tE.grad.cpu().numpy()
+    assert rel(gE[:, 0, 1:], d_tp) < TOL and rel(gE[:, 1, 1:], d_tn) < TOL
+    assert (gE[:, :, 0] == 0).all()
+    assert (gE[-1] == 0).all() and (to.grad[-1] == 0).all()
+
+
+def test_bpr_loss_known_answer_at_zero_scores():
+    """out == 0 -> sigmoid(0) = 0.5 -> loss = (#valid positions / B) * -log(0.5 + 1e-8)  (SURVEY 8c sanity)."""
+    from pixelrec_b200 import ops
+    B, L, D = 8, 10, 128
+    out = torch.zeros(B, L, D, device=dev())
+    E = torch.randn(B, 2, L + 1, D, device=dev())
+    mask = torch.ones(B, L, dtype=torch.int64, device=dev())
+    mask[:, :3] = 0
+    loss = ops.bpr_loss(out, E, mask)
+    assert abs(loss.item() - 7 * -np.log(0.5 + 1e-8)) < 1e-5
+
+
+def test_bpr_loss_saturation_no_nan():
+    from pixelrec_b200 import ops
+    B, L, D = 2, 4, 64
+    out = torch.full((B, L, D), 10.0, device=dev())
+    E = torch.zeros(B, 2, L + 1, D, device=dev())
+    E[:, 1] = 10.0                                            # pos - neg = -6400 -> sigmoid underflows to 0
+    out.requires_grad_()
+    loss = ops.bpr_loss(out, E, torch.ones(B, L, dtype=torch.int64, device=dev()))
+    loss.backward()
+    assert torch.isfinite(loss) and abs(loss.item() - L * -np.log(1e-8)) < 1e-3    # the reference's +1e-8 floor
+    assert torch.isfinite(out.grad).all()

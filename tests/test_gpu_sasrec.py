@@ -1,0 +1,119 @@
+"""GPU parity of the whole plugin against goldens produced by the UNMODIFIED reference SASRec
+(oracle/make_golden.py): loss, every parameter gradient, an AdamW step, predict() scores and the masked
+top-k.  Tolerances: 1e-3 relative (north_star) for TF32 linear layers, 1e-4 with matmul_precision fp32."""
+import numpy as np
+import pytest
+import torch
+
+from tests.gpu_util import dev, rel, t
+
+pytestmark = pytest.mark.gpu
+
+
+class _Data:
+    def __init__(self, n):
+        self.item_num = n
+
+
+def build(golden, dropout=0.0, seed=2020):
+    from pixelrec_b200.model.IDNet.sasrec import SASRec
+    c = golden["cfg"]
+    cfg = dict(n_layers=c["layers"], n_heads=c["h"], embedding_size=c["D"], inner_size=2, hidden_dropout_prob=dropout,
+               attn_dropout_prob=dropout, hidden_act="gelu", layer_norm_eps=1e-12, initializer_range=0.02,
+               MAX_ITEM_LIST_LENGTH=c["L"], seed=seed)
+    m = SASRec(cfg, _Data(c["N"]))
+    missing = m.load_state_dict({k: torch.from_numpy(v) for k, v in golden["params"].items()}, strict=True)
+    return m.to(dev())
+
+
+@pytest.mark.parametrize("tf32,tol", [(False, 1e-4), (True, 1e-3)])
+def test_forward_backward_matches_reference(golden, tf32, tol):
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    torch.backends.cudnn.allow_tf32 = tf32
+    m = build(golden)
+    m.train()
+    loss = m((t(golden["items"]), t(golden["masked_index"])))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - float(golden["loss"])) / float(golden["loss"]) < tol
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    for k, ref in golden["grads"].items():
+        assert grads[k] is not None, k
+        got = grads[k].cpu().numpy()
+        if k.endswith("key.bias"):        # mathematically zero; reference holds 1e-12 noise
+            assert np.abs(got).max() < 1e-6
+            continue
+        assert rel(got, ref) < tol * 3, (k, rel(got, ref))
+    assert (grads["item_embedding.weight"][0] == 0).all()        # padding_idx row
+    torch.backends.cuda.matmul.allow_tf32 = True
+
+
+def test_sparse_table_grad_and_fused_adamw_step(golden):
+    """The product path: sparse table gradient + FusedAdamW == reference torch.optim.AdamW(lr 1e-4, wd 0.1) step."""
+    from pixelrec_b200.trainer.optim import FusedAdamW
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = build(golden)
+    m.train()
+    opt = FusedAdamW(m.parameters(), lr=1e-4, weight_decay=0.1, tables=[m.item_embedding])
+    for step in (1, 2):
+        opt.zero_grad()
+        loss = m((t(golden["items"]), t(golden["masked_index"])))
+        if step == 1:
+            loss.backward()
+            assert m.item_embedding.weight.grad is None and len(m.item_embedding.sink.pending) == 1
+            saved = [(p, r.clone()) for p, r in m.item_embedding.sink.pending]
+            dense_g = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+        else:   # goldens apply the SAME gradient twice: replay step-1 grads
+            m.item_embedding.sink.pending[:] = saved
+            m.item_embedding.sink.row2slot[saved[0][0].uniq_ids[:saved[0][0].n_uniq.item()].long()] = \
+                torch.arange(saved[0][0].n_uniq.item(), dtype=torch.int32, device=dev())
+            for k, p in m.named_parameters():
+                if k in dense_g:
+                    p.grad.copy_(dense_g[k])
+        opt.step()
+        torch.cuda.synchronize()
+        if step == 1:
+            for k in ("item_embedding.weight", "position_embedding.weight", "LayerNorm.weight",
+                      "trm_encoder.layer.0.multi_head_attention.query.weight", "trm_encoder.layer.0.feed_forward.dense_2.bias"):
+                got = dict(m.named_parameters())[k].detach().cpu().numpy()
+                assert np.abs(got - golden["adamw1/" + k]).max() < 2e-6, k
+        else:
+            got = m.item_embedding.weight.detach().cpu().numpy()
+            assert np.abs(got - golden["adamw2/item_embedding.weight"]).max() < 4e-6
+    torch.backends.cuda.matmul.allow_tf32 = True
+
+
+def test_predict_and_masked_topk(golden):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = build(golden).eval()
+    seqs = t(golden["eval_item_seq"])
+    scores = m.predict(seqs, m.compute_item_all())
+    assert scores.shape == golden["eval_scores_raw"].shape
+    assert rel(scores.cpu().numpy(), golden["eval_scores_raw"]) < 1e-4
+    scores[:, 0] = -np.inf                                        # trainer.py:334-336
+    scores[t(golden["eval_hist_u"]), t(golden["eval_hist_i"])] = -np.inf
+    _, idx = torch.topk(scores, 10, dim=-1)
+    assert np.array_equal(idx.cpu().numpy(), golden["eval_topk_idx"])
+    torch.backends.cuda.matmul.allow_tf32 = True
+
+
+def test_training_with_dropout_is_finite_and_seeded():
+    from pixelrec_b200.model.IDNet.sasrec import SASRec
+    cfg = dict(n_layers=2, n_heads=4, embedding_size=128, inner_size=2, hidden_dropout_prob=0.1, attn_dropout_prob=0.1,
+               hidden_act="gelu", layer_norm_eps=1e-12, initializer_range=0.02, MAX_ITEM_LIST_LENGTH=10, seed=2020)
+    g = np.random.default_rng(0)
+    items = g.integers(1, 500, size=(32, 2, 11)).astype(np.int64)
+    mask = np.ones((32, 10), dtype=np.int64)
+    losses = []
+    for rep in range(2):
+        torch.manual_seed(0)
+        m = SASRec(cfg, _Data(500)).to(dev()).train()
+        l1 = m((t(items), t(mask)))
+        l2 = m((t(items), t(mask)))
+        l1.backward()
+        losses.append((l1.item(), l2.item()))
+        assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+        assert abs(l1.item() - 10 * np.log(2)) < 0.2              # init loss ~ L * ln 2
+    assert losses[0] == losses[1] and losses[0][0] != losses[0][1]   # same seed -> same masks; new mask each call
+    m.eval()
+    assert m((t(items), t(mask))).item() == m((t(items), t(mask))).item()
