@@ -105,10 +105,19 @@ __device__ __forceinline__ void tile_outer_store(const float* __restrict__ M, co
     }
 }
 
+// NOTE on the `produced` counter: an mbarrier parity wait can only tell the current phase from the previous
+// one.  Several consumer warps wait on the SAME stage barrier for different phases (tile t and tile t+S belong
+// to different warps), so a warp may start waiting for tile t+S before tile t has even landed -- its parity
+// wait would then succeed spuriously.  Consumers therefore first spin on `produced` (tiles armed so far,
+// bumped in order by the producer AFTER it saw tile t-S released), which guarantees the barrier is already in
+// tile t's phase when the parity wait starts.
 struct TileRing {
-    unsigned char* tiles; uint64_t* full; uint64_t* empty; int S; uint32_t tile_bytes;
+    unsigned char* tiles; uint64_t* full; uint64_t* empty; volatile unsigned long long* produced; int S;
+    uint32_t tile_bytes;
     __device__ __forceinline__ const float4* wait_full(long long t) const {
         const int s = (int)(t % S);
+        while (*produced <= (unsigned long long)t) {
+        }
         mbar_wait(&full[s], (uint32_t)((t / S) & 1));
         return reinterpret_cast<const float4*>(tiles + (size_t)s * tile_bytes);
     }
@@ -128,11 +137,12 @@ __device__ __forceinline__ void produce_tile(const TileRing& ring, long long t, 
     __syncwarp();
     unsigned char* dst = ring.tiles + (size_t)s * ring.tile_bytes;
     for (int r = lane; r < L; r += 32) bulk_g2s(dst + (size_t)r * row_bytes, src + (long long)r * ld, row_bytes, &ring.full[s]);
+    if (lane == 0) *ring.produced = (unsigned long long)t + 1ull;
 }
 
 __device__ __forceinline__ TileRing ring_setup(unsigned char* smem, int S, uint32_t tile_bytes, size_t private_bytes,
                                                unsigned char** private_base) {
-    // layout: [tiles S*tile_bytes][private][full S][empty S]
+    // layout: [tiles S*tile_bytes][private][full 32][empty 32][produced]
     TileRing r;
     r.tiles = smem;
     r.S = S;
@@ -141,7 +151,9 @@ __device__ __forceinline__ TileRing ring_setup(unsigned char* smem, int S, uint3
     uint64_t* bars = reinterpret_cast<uint64_t*>(*private_base + private_bytes);
     r.full = bars;
     r.empty = bars + ATT_MAX_STAGES;
+    r.produced = reinterpret_cast<volatile unsigned long long*>(bars + 2 * ATT_MAX_STAGES);
     if (threadIdx.x == 0) {
+        *r.produced = 0ull;
         for (int s = 0; s < S; ++s) {
             mbar_init(&r.full[s], 1);
             mbar_init(&r.empty[s], 1);
@@ -395,7 +407,7 @@ static int launch_attn(AttnArgs& A, cudaStream_t stream) {
     constexpr int NCW = BWD ? C::NCW_BWD : C::NCW;
     const size_t tile = (size_t)LMAX * CW4 * 16;
     const size_t priv = (size_t)NCW * (BWD ? 3 : 1) * LMAX * C::LP * 4;
-    const size_t bars = (size_t)2 * ATT_MAX_STAGES * 8;
+    const size_t bars = (size_t)2 * ATT_MAX_STAGES * 8 + 16;
     const size_t budget = 220 * 1024;
     PR_CHECK_ARG(priv + bars + 4 * tile <= budget, "attention: L=%d dh=%d does not fit shared memory", A.L, A.dh);
     int S = (int)((budget - priv - bars) / tile);

@@ -1,0 +1,72 @@
+"""load_data / bulid_dataloader with the reference's plugin registration table for the SEQ family
+(REC/data/utils.py:15-114; the misspelt name is the reference's public name and is kept)."""
+import math
+import random
+from functools import partial
+from logging import getLogger
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader
+
+from ..utils.utils import get_rank, get_world_size
+from .dataload import Data, SyntheticData
+from .dataset import SEQTrainDataset, SeqEvalDataset, seq_eval_collate
+
+DATASET_TABLE = {   # model -> (train set, eval set, eval collate)   (data/utils.py:24-53, hot-path rows)
+    "SASRec": (SEQTrainDataset, SeqEvalDataset, seq_eval_collate),
+    "GRU4Rec": (SEQTrainDataset, SeqEvalDataset, seq_eval_collate),
+}
+
+
+def load_data(config):
+    if config["dataset"] == "synthetic" or config["synthetic_users"]:
+        return SyntheticData(config)
+    return Data(config)
+
+
+class NonConsecutiveSequentialDistributedSampler(torch.utils.data.Sampler):
+    """rank r evaluates users r, r+W, r+2W, ... (data/utils.py:134-159)."""
+
+    def __init__(self, dataset, rank=None, num_replicas=None):
+        self.dataset = dataset
+        self.num_replicas = get_world_size() if num_replicas is None else num_replicas
+        self.rank = get_rank() if rank is None else rank
+        self.total_size = len(dataset)
+        self.num_samples = math.ceil((self.total_size - self.rank) / self.num_replicas)
+
+    def __iter__(self):
+        return iter(range(self.rank, self.total_size, self.num_replicas))
+
+    def __len__(self):
+        return self.num_samples
+
+
+def _worker_init(worker_id, num_workers, rank, seed):
+    s = (num_workers * rank + worker_id + seed) % (2 ** 32)
+    np.random.seed(s)
+    random.seed(s)
+
+
+def bulid_dataloader(config, dataload):
+    model_name = config["model"]
+    if model_name not in DATASET_TABLE:
+        raise KeyError(f"model {model_name!r} has no dataset binding (hot-path models: {sorted(DATASET_TABLE)})")
+    dataload.build()
+    train_cls, eval_cls, collate = DATASET_TABLE[model_name]
+    train_data = train_cls(config, dataload)
+    valid_data = eval_cls(config, dataload, phase="valid")
+    test_data = eval_cls(config, dataload, phase="test")
+    log = getLogger()
+    log.info(f"[Training]: train_batch_size = [{config['train_batch_size']}]")
+    log.info(f"[Evaluation]: eval_batch_size = [{config['eval_batch_size']}]")
+    world, rank = get_world_size(), get_rank()
+    train_sampler = torch.utils.data.distributed.DistributedSampler(train_data, num_replicas=world, rank=rank)
+    workers = config["num_workers"] if config["num_workers"] is not None else 10
+    init_fn = partial(_worker_init, num_workers=workers, rank=rank, seed=torch.initial_seed())
+    pin = torch.cuda.is_available()
+    train_loader = DataLoader(train_data, batch_size=config["train_batch_size"], num_workers=workers, pin_memory=pin,
+                              sampler=train_sampler, worker_init_fn=init_fn)
+    mk = lambda ds: DataLoader(ds, batch_size=config["eval_batch_size"], num_workers=workers, pin_memory=pin,
+                               sampler=NonConsecutiveSequentialDistributedSampler(ds), collate_fn=collate)
+    return train_loader, mk(valid_data), mk(test_data)

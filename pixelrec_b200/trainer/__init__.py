@@ -1,0 +1,4 @@
+from .optim import FusedAdamW
+from .trainer import Trainer
+
+__all__ = ["Trainer", "FusedAdamW"]

@@ -1,0 +1,222 @@
+"""Trainer -- the caller of the hot path.  Same public surface and epoch/eval/checkpoint behaviour as the
+reference's REC/trainer/trainer.py:19-409 (`Trainer(config, model)`, `.fit`, `.evaluate`,
+`.resume_checkpoint`), with the B200 changes:
+  * optimizer = FusedAdamW (one launch for all dense params, sparse-gradient dense-semantics update of the
+    embedding table) instead of torch.optim.AdamW (trainer.py:66-103);
+  * no per-step `.item()` sync: the running loss stays on the device, NaN is checked once per epoch
+    (the reference syncs every step, trainer.py:120-121);
+  * works with or without an initialised process group (the reference requires one, trainer.py:39).
+"""
+import os
+from logging import getLogger
+from time import time
+
+import numpy as np
+import torch
+from torch.nn.utils.clip_grad import clip_grad_norm_
+
+from ..evaluator import Collector, Evaluator
+from ..model.layers import TableEmbedding
+from ..utils.utils import (barrier, calculate_valid_score, dict2str, dist_ready, early_stopping, ensure_dir,
+                           get_local_time, get_rank, get_world_size)
+from .optim import FusedAdamW
+
+
+def unwrap(model):
+    return model.module if hasattr(model, "module") else model
+
+
+class Trainer:
+    def __init__(self, config, model):
+        self.config = config
+        self.model = model
+        self.logger = getLogger()
+        self.optim_args = config["optim_args"]
+        self.epochs = config["epochs"]
+        self.eval_step = min(config["eval_step"], self.epochs)
+        self.stopping_step = config["stopping_step"]
+        self.clip_grad_norm = config["clip_grad_norm"]
+        self.valid_metric = config["valid_metric"].lower()
+        self.valid_metric_bigger = config["valid_metric_bigger"]
+        self.test_batch_size = config["eval_batch_size"]
+        self.device = config["device"]
+        self.rank = get_rank()
+        self.checkpoint_dir = config["checkpoint_dir"] or "saved"
+        if self.rank == 0:
+            ensure_dir(self.checkpoint_dir)
+        self.saved_model_file = os.path.join(self.checkpoint_dir, "{}-{}.pth".format(config["model"], get_local_time()))
+        self.use_modality = config["use_modality"]
+        self.start_epoch = 0
+        self.cur_step = 0
+        self.best_valid_score = -np.inf if self.valid_metric_bigger else np.inf
+        self.best_valid_result = None
+        self.train_loss_dict = {}
+        self.optimizer = self._build_optimizer()
+        self.eval_collector = Collector(config)
+        self.evaluator = Evaluator(config)
+        self.item_feature = None
+        self.tot_item_num = None
+
+    # ------------------------------------------------------------------ optimizer (trainer.py:66-103)
+    def _build_optimizer(self):
+        m = unwrap(self.model)
+        tables = [mod for mod in m.modules() if isinstance(mod, TableEmbedding)]
+        a = self.optim_args
+        if len(a) == 4:   # PixelNet: two groups keyed on 'visual_encoder' in the parameter name
+            modal, rec = [], []
+            for name, p in m.named_parameters():
+                if p.requires_grad:
+                    (modal if "visual_encoder" in name else rec).append(p)
+            groups = [dict(params=modal, lr=a["modal_lr"], weight_decay=a["modal_decay"]),
+                      dict(params=rec, lr=a["rec_lr"], weight_decay=a["rec_decay"])]
+            groups = [g for g in groups if g["params"]]
+            return FusedAdamW(groups, tables=tables)
+        params = [p for p in m.parameters() if p.requires_grad]
+        return FusedAdamW(params, lr=a["learning_rate"], weight_decay=a["weight_decay"], tables=tables)
+
+    # ------------------------------------------------------------------ train loop (trainer.py:105-128)
+    def to_device(self, data):
+        if isinstance(data, (tuple, list)):
+            return tuple(d.to(self.device, non_blocking=True) for d in data)
+        if isinstance(data, dict):
+            return {k: v.to(self.device, non_blocking=True) for k, v in data.items()}
+        return data.to(self.device, non_blocking=True)
+
+    def _train_epoch(self, train_data, epoch_idx, loss_func=None, show_progress=False):
+        self.model.train()
+        total = torch.zeros((), device=self.device)
+        for data in train_data:
+            self.optimizer.zero_grad()
+            losses = self.model(self.to_device(data))
+            total += losses.detach()
+            losses.backward()
+            if self.clip_grad_norm:
+                clip_grad_norm_(self.model.parameters(), **self.clip_grad_norm)
+            self.optimizer.step()
+        total_loss = float(total.item())        # ONE device->host sync per epoch
+        self._check_nan(total_loss)
+        return total_loss
+
+    @staticmethod
+    def _check_nan(loss):
+        if np.isnan(loss):
+            raise ValueError("Training loss is nan")
+
+    def _valid_epoch(self, valid_data, show_progress=False):
+        barrier()
+        result = self.evaluate(valid_data, load_best_model=False, show_progress=show_progress)
+        score = calculate_valid_score(result, self.valid_metric)
+        barrier()
+        return score, result
+
+    # ------------------------------------------------------------------ checkpoint (trainer.py:138-190)
+    def _save_checkpoint(self, epoch, verbose=True):
+        if self.rank == 0:
+            state = {
+                "config": self.config, "epoch": epoch, "cur_step": self.cur_step,
+                "best_valid_score": self.best_valid_score, "state_dict": unwrap(self.model).state_dict(),
+                "optimizer": self.optimizer.state_dict(), "rng_state": torch.get_rng_state(),
+                "cuda_rng_state": torch.cuda.get_rng_state() if torch.cuda.is_available() else None,
+            }
+            torch.save(state, self.saved_model_file)
+            if verbose:
+                self.logger.info(f"Saving current: {self.saved_model_file}")
+        barrier()
+
+    def resume_checkpoint(self, resume_file):
+        ck = torch.load(str(resume_file), map_location="cpu", weights_only=False)
+        self.start_epoch = ck["epoch"] + 1
+        self.cur_step = ck["cur_step"]
+        self.best_valid_score = ck["best_valid_score"]
+        if ck["config"]["model"].lower() != self.config["model"].lower():
+            self.logger.warning("Architecture configuration given in config file is different from that of checkpoint.")
+        unwrap(self.model).load_state_dict(ck["state_dict"])     # the reference forgets this
+        self.optimizer.load_state_dict(ck["optimizer"])
+        torch.set_rng_state(ck["rng_state"])
+        if ck.get("cuda_rng_state") is not None and torch.cuda.is_available():
+            torch.cuda.set_rng_state(ck["cuda_rng_state"])
+        self.logger.info("Checkpoint loaded. Resume training from epoch {}".format(self.start_epoch))
+
+    # ------------------------------------------------------------------ fit (trainer.py:256-326)
+    def fit(self, train_data, valid_data=None, verbose=True, saved=True, show_progress=False, callback_fn=None):
+        if saved and self.start_epoch >= self.epochs:
+            self._save_checkpoint(-1, verbose=verbose)
+        for epoch_idx in range(self.start_epoch, self.epochs):
+            if self.config["need_training"] is None or self.config["need_training"]:
+                if hasattr(train_data, "sampler") and hasattr(train_data.sampler, "set_epoch"):
+                    train_data.sampler.set_epoch(epoch_idx)
+                t0 = time()
+                train_loss = self._train_epoch(train_data, epoch_idx, show_progress=show_progress)
+                self.train_loss_dict[epoch_idx] = train_loss
+                if verbose:
+                    self.logger.info("epoch %d training [time: %.2fs, train loss: %.4f]" % (epoch_idx, time() - t0, train_loss))
+            if self.eval_step <= 0 or not valid_data:
+                if saved:
+                    self._save_checkpoint(epoch_idx, verbose=verbose)
+                continue
+            if (epoch_idx + 1) % self.eval_step == 0:
+                t0 = time()
+                valid_score, valid_result = self._valid_epoch(valid_data, show_progress=show_progress)
+                self.best_valid_score, self.cur_step, stop_flag, update_flag = early_stopping(
+                    valid_score, self.best_valid_score, self.cur_step, max_step=self.stopping_step,
+                    bigger=self.valid_metric_bigger)
+                if verbose:
+                    self.logger.info("epoch %d evaluating [time: %.2fs, valid_score: %f]" % (epoch_idx, time() - t0, valid_score))
+                    self.logger.info("valid result: \n" + dict2str(valid_result))
+                if update_flag:
+                    if saved:
+                        self._save_checkpoint(epoch_idx, verbose=verbose)
+                    self.best_valid_result = valid_result
+                if callback_fn:
+                    callback_fn(epoch_idx, valid_score)
+                if stop_flag:
+                    if verbose:
+                        self.logger.info("Finished training, best eval result in epoch %d" %
+                                         (epoch_idx - self.cur_step * self.eval_step))
+                    break
+        return self.best_valid_score, self.best_valid_result
+
+    # ------------------------------------------------------------------ evaluation (trainer.py:327-409)
+    @torch.no_grad()
+    def _full_sort_batch_eval(self, batched_data):
+        user, history_index, positive_u, positive_i = batched_data
+        scores = unwrap(self.model).predict(self.to_device(user), self.item_feature)
+        scores = scores.view(-1, self.tot_item_num)
+        scores[:, 0] = -np.inf
+        if history_index is not None:
+            hu, hi = history_index
+            scores[hu.to(self.device), hi.to(self.device)] = -np.inf
+        return scores, positive_u, positive_i
+
+    @torch.no_grad()
+    def compute_item_feature(self, config, data):
+        self.item_feature = unwrap(self.model).compute_item_all()
+
+    def distributed_concat(self, tensor, num_total_examples):
+        if dist_ready():
+            outs = [tensor.clone() for _ in range(get_world_size())]
+            torch.distributed.all_gather(outs, tensor)
+            tensor = torch.cat(outs, dim=0)
+        return tensor.sum() / num_total_examples
+
+    @torch.no_grad()
+    def evaluate(self, eval_data, load_best_model=True, model_file=None, show_progress=False):
+        if not eval_data:
+            return
+        if load_best_model:
+            ck = torch.load(model_file or self.saved_model_file, map_location="cpu", weights_only=False)
+            unwrap(self.model).load_state_dict(ck["state_dict"])
+            self.logger.info("Loading model structure and parameters from {}".format(model_file or self.saved_model_file))
+        self.model.eval()
+        self.tot_item_num = eval_data.dataset.dataload.item_num
+        self.compute_item_feature(self.config, eval_data.dataset.dataload)
+        for batched_data in eval_data:
+            scores, positive_u, positive_i = self._full_sort_batch_eval(batched_data)
+            self.eval_collector.eval_batch_collect(scores, positive_u, positive_i)
+        num_total_examples = len(eval_data.sampler.dataset)
+        result = self.evaluator.evaluate(self.eval_collector.get_data_struct())
+        places = 5 if self.config["metric_decimal_place"] is None else self.config["metric_decimal_place"]
+        for k, v in result.items():
+            r = self.distributed_concat(torch.tensor([v], dtype=torch.float64).to(self.device), num_total_examples).cpu()
+            result[k] = round(r.item(), places)
+        return result

@@ -149,7 +149,7 @@ def test_adamw_rows_vs_oracle(N, D):
         torch.cuda.synchronize()
         assert (row2slot == -1).all()                              # consumed entries are restored
         assert np.abs(dW.cpu().numpy() - W).max() < 3e-7
-        assert rel(dM.cpu().numpy(), M) < 1e-5 and rel(dV.cpu().numpy(), V, 1e-12) < 1e-5
+        assert rel(dM.cpu().numpy(), M) < 1e-5 and rel(dV.cpu().numpy(), V, 1e-12) < 1e-4
     # rows without gradient still decay (dense AdamW semantics of trainer.py:102)
     assert np.abs(dW.cpu().numpy()[0] - W[0]).max() < 3e-7 and not np.array_equal(W[0], (0.02 * np.ones(1)))
 

@@ -132,3 +132,21 @@ def test_train_sample_layout():
     # longer than L+1: keeps the most recent L+1 (trainset.py:46-50)
     items, mask = O.seq_train_sample(list(range(1, 10)), 50, 5, rng)
     assert items[0].tolist() == [4, 5, 6, 7, 8, 9] and mask.tolist() == [1] * 5
+
+
+def test_torch_port_matches_reference_golden(golden):
+    """oracle/torch_port.py (the CPU baseline bench.py times) reproduces the reference's loss and gradients."""
+    import torch
+    from oracle import torch_port as TP
+    c = golden["cfg"]
+    P = {k: torch.from_numpy(v.copy()).requires_grad_() for k, v in golden["params"].items()}
+    loss, out = TP.forward_loss(P, torch.from_numpy(golden["items"]), torch.from_numpy(golden["masked_index"]), c["layers"], c["h"])
+    loss.backward()
+    assert abs(loss.item() - float(golden["loss"])) < 1e-5
+    for k, ref in golden["grads"].items():
+        if k.endswith("key.bias"):
+            continue
+        assert rel(P[k].grad.numpy(), ref) < 1e-4, k
+    tv, ti = TP.predict_topk({k: v.detach() for k, v in P.items()}, torch.from_numpy(golden["eval_item_seq"]),
+                             torch.from_numpy(golden["eval_hist_u"]), torch.from_numpy(golden["eval_hist_i"]), 10, c["layers"], c["h"])
+    assert np.array_equal(ti.numpy(), golden["eval_topk_idx"])

@@ -6,9 +6,9 @@ rc=0
 for f in tests/test_gpu_rows.py tests/test_gpu_ln_loss.py tests/test_gpu_attn.py tests/test_gpu_sasrec.py "$@"; do
   [ -f "$f" ] || continue
   n=$(basename $f .py)
-  timeout 900 python -m pytest $f -q -m gpu -x --timeout=300 > gpurun_out/$n.log 2>&1
+  timeout 900 python -u -m pytest $f -v -m gpu ${PYTEST_X:-} --timeout=120 --timeout-method=thread -p no:cacheprovider > gpurun_out/$n.log 2>&1
   r=$?
-  echo "$n rc=$r $(tail -1 gpurun_out/$n.log)"
+  echo "$n rc=$r $(tail -1 gpurun_out/$n.log)"; grep -E "FAILED|Timeout|rror" gpurun_out/$n.log | head -8
   [ $r -ne 0 ] && rc=1
 done
 exit $rc

@@ -62,7 +62,9 @@ def main():
     for impl in (1, 2):
         rec(f"gather_impl{impl}", timeit(lambda: ops.gather_rows(W, idx, impl=impl), flush=flush), bytes_=R * (8 * D + 8))
     rec("torch_index_select", timeit(lambda: W[idx.view(-1)], flush=flush), bytes_=R * (8 * D + 8))
-    rec("torch_copy_same_bytes", timeit(lambda: torch.empty(R, D, device=dev).copy_(flush[:R * D].view(R, D)), flush=None), bytes_=R * 8 * D)
+    src_copy = torch.randn(R, D, device=dev)
+    dst_copy = torch.empty(R, D, device=dev)
+    rec("torch_copy_same_bytes", timeit(lambda: dst_copy.copy_(src_copy), flush=flush), bytes_=R * 8 * D)
 
     dE = torch.randn(R, D, device=dev)
     rec("scatter_plan", timeit(lambda: ops.ScatterPlan(idx, N, 0), flush=flush))
