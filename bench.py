@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- sequences/sec of the SASRec training hot path on Pixel200K-shaped synthetic interactions.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--batch B]
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...)
+
+One "step" = one pass of the hot path over one batch: zero_grad -> forward (gather, pos-emb+LN, 2 post-LN
+transformer layers, sampled-negative pairwise loss) -> backward (incl. the scatter-add of the table gradient)
+-> AdamW over every parameter (dense semantics on the table), dropout 0.1 as shipped -- the loop body of
+the reference's REC/trainer/trainer.py:116-125 on BASELINE.json configs[1] (IDNet/sasrec, N=97001 items, D=512,
+L=20, 4 heads, 2 layers).  Batch per GPU is fixed (weak scaling); the table is row-sharded for N > 1.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job sequences/s with inputs resident in HBM; `e2e` = the same
+through the public plugin API with pinned-HOST batches copied in every step and the loss read back every step;
+`roofline` = the embedding-gather kernel (BASELINE.json's named kernel) timed live with CUDA events inside the
+timed region; `roofline_kernels` = every kernel of ours, timed the same way in an extra pass; `cpu_baseline` =
+the oracle torch port of the reference step on the host cores (bounded sample).
+
+--impl reference: times the reference's CPU implementation of the same step (oracle/torch_port.py, the pinned
+restatement of the reference's PyTorch path -- the reference tree itself cannot travel to the GPU box) on all
+host threads; rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sequences/sec SASRec Pixel200K-shape"
+C2 = dict(N=97001, D=512, L=20, heads=4, layers=2, inner=2, dropout=0.1, lr=1e-4, wd=0.1, users=200000)
+
+
+def synth_batch(g, B, N, L, perm, p):
+    """SEQTrainDataset-format batch (REC/data/dataset/trainset.py:52-75): left-padded long-tail positives,
+    uniform negatives, lengths uniform in [3, L+1].  Returns items int64 [B,2,L+1], masked_index int64 [B,L]."""
+    W = L + 1
+    lens = g.integers(3, W + 1, size=B)
+    pos = perm[g.choice(N - 1, size=(B, W), p=p)]
+    col = np.arange(W)[None, :]
+    valid = col >= (W - lens)[:, None]
+    pos = np.where(valid, pos, 0)
+    neg = g.integers(1, N, size=(B, W))
+    neg_valid = col > (W - lens)[:, None]
+    neg = np.where(neg_valid, neg, 0)
+    items = np.stack([pos, neg], 1).astype(np.int64)
+    mask = neg_valid[:, 1:].astype(np.int64)
+    return items, mask
+
+
+def popularity(N, seed=2020):
+    g = np.random.default_rng(seed)
+    r = np.arange(1, N, dtype=np.float64)
+    p = 1.0 / (r + 10.0) ** 0.8
+    p /= p.sum()
+    return g.permutation(N - 1) + 1, p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_step_rate(B_cpu, steps, warmup, threads=None, seed=0):
+    """Times oracle/torch_port.TrainStep (== trainer.py:116-125 around the reference's ops) on the host cores."""
+    import torch
+    from oracle import torch_port as TP
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    c = C2
+    P = TP.init_params(c["N"], c["D"], c["L"], c["layers"], c["inner"], seed=2020)
+    step = TP.TrainStep(P, c["layers"], c["heads"], lr=c["lr"], weight_decay=c["wd"], p_drop=c["dropout"])
+    g = np.random.default_rng(seed)
+    perm, p = popularity(c["N"])
+    batches = [tuple(torch.from_numpy(x) for x in synth_batch(g, B_cpu, c["N"], c["L"], perm, p)) for _ in range(2)]
+    for i in range(warmup):
+        step(*batches[i % 2])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        loss = step(*batches[i % 2])
+    dt = time.perf_counter() - t0
+    return B_cpu * steps / dt, dt / steps * 1e3, cores, float(loss)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    # bounded sample: calibrate the per-step batch so (steps + warmup) finishes in ~2 minutes
+    rate, ms, cores, _ = cpu_step_rate(128, 1, 1)
+    budget_s = 120.0
+    per_step = budget_s / max(args.steps + args.warmup, 1)
+    B_cpu = int(min(1024, max(64, (per_step * rate) // 64 * 64)))
+    rate, ms, cores, loss = cpu_step_rate(B_cpu, args.steps, args.warmup)
+    sample = f"{args.steps} steps x {B_cpu} sequences per step on {cores} host threads (torch {torch.__version__} CPU fp32)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "sequences/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(B_cpu, 1, note="CPU reference arm; per-step batch is a bounded sample"),
+        "cpu_baseline": {"value": rate, "unit": "sequences/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(B, world, note=None):
+    c = C2
+    cfg = {"workload": f"C2 IDNet/sasrec Pixel200K-shape: N={c['N']} items, emb_dim={c['D']}, seq_len={c['L']}, "
+                       f"{c['heads']} heads, {c['layers']} layers, inner {c['inner']}x, dropout {c['dropout']}, "
+                       f"AdamW(lr {c['lr']}, wd {c['wd']}) dense semantics, batch {B}/GPU",
+           "batch_per_gpu": B, "global_batch": B * world, "seq_len": c["L"],
+           "parallelism": f"dp{world} + item table row-sharded {world}-way" if world > 1 else "single GPU",
+           "l2": "working set (table+Adam state 597 MB, activations > 2 GB per step) >> 126 MB L2; a pool of distinct batches rotates"}
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch N>1 with torch.distributed.run (see the docstring)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: pixelrec_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from pixelrec_b200 import ops
+    from pixelrec_b200.dist import broadcast_dense_params
+    from pixelrec_b200.model.IDNet.sasrec import SASRec
+    from pixelrec_b200.trainer.optim import FusedAdamW
+
+    torch.backends.cuda.matmul.allow_tf32 = True       # linear layers: cuBLAS TF32 (torch 1.10's default on Ampere)
+    c = C2
+    B = args.batch
+    torch.manual_seed(2020)
+
+    class Dl:
+        item_num = c["N"]
+    cfg = dict(n_layers=c["layers"], n_heads=c["heads"], embedding_size=c["D"], inner_size=c["inner"],
+               hidden_dropout_prob=c["dropout"], attn_dropout_prob=c["dropout"], hidden_act="gelu", layer_norm_eps=1e-12,
+               initializer_range=0.02, MAX_ITEM_LIST_LENGTH=c["L"], seed=2020 + rank)
+    model = SASRec(cfg, Dl()).to(dev).train()
+    broadcast_dense_params(model)
+    opt = FusedAdamW(model.parameters(), lr=c["lr"], weight_decay=c["wd"],
+                     tables=[model.item_embedding])
+
+    g = np.random.default_rng(1000 + rank)
+    perm, p = popularity(c["N"])
+    POOL = 6
+    host = []
+    for _ in range(POOL):
+        items, mask = synth_batch(g, B, c["N"], c["L"], perm, p)
+        host.append((torch.from_numpy(items).pin_memory(), torch.from_numpy(mask).pin_memory()))
+    resident = [(a.to(dev), b.to(dev)) for a, b in host]
+    h2d = host[0][0].numel() * 8 + host[0][1].numel() * 8
+
+    def step(batch):
+        opt.zero_grad()
+        loss = model(batch)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, K):
+        sync_all()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(K):
+            fn(i)
+        e.record()
+        sync_all()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for i in range(max(args.warmup, 3)):
+        step(resident[i % POOL])
+    # ---- timed region 1: inputs resident in HBM; the gather kernel is event-timed live inside it
+    clocks = ClockSampler(local)
+    ops.PROFILE.update(on=True, names={"gather_rows"}, events={})
+    launches0 = ops.LAUNCHES["count"]
+    clocks.start()
+    ms = timed(lambda i: step(resident[i % POOL]), args.steps)
+    clk = clocks.stop()
+    launches = ops.LAUNCHES["count"] - launches0
+    gather_n, gather_ms = ops.profile_summary().get("gather_rows", (0, float("nan")))
+    ops.PROFILE.update(on=False, events={})
+    value = B * world * args.steps / (ms / 1e3)
+
+    # ---- timed region 2 (e2e): pinned-host batches copied in each step, loss read back each step
+    def e2e_step(i):
+        a, b = host[i % POOL]
+        loss = step((a.to(dev, non_blocking=True), b.to(dev, non_blocking=True)))
+        return loss.item()
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e = B * world * args.steps / (ms_e2e / 1e3)
+
+    # ---- extra pass: every kernel of ours, event-timed (roofline_kernels)
+    ops.PROFILE.update(on=True, names=None, events={})
+    for i in range(min(args.steps, 5)):
+        step(resident[i % POOL])
+    torch.cuda.synchronize()
+    prof = ops.profile_summary()
+    ops.PROFILE.update(on=False, events={})
+
+    hbm, _, peak_src = peaks()
+    L, D, N = c["L"], c["D"], c["N"]
+    R_u = B * (2 * L + 1)                                   # rows actually consumed
+    n_local = (N + world - 1) // world
+    alg = {                                                 # algorithmic bytes per launch (SURVEY.md section 8d / DESIGN.md)
+        "gather_rows": R_u * (8 * D + 8),
+        "scatter_add_rows": None,                           # depends on U (unique ids); filled below
+        "adamw_rows": 6 * n_local * D * 4,
+        "add_ln_fwd": 3 * B * L * D * 4, "add_ln_bwd": 5 * B * L * D * 4,
+        "attn_fwd": 16 * B * L * D, "attn_bwd": 32 * B * L * D,
+        "bpr_fwd": 3 * B * L * D * 4, "bpr_bwd": 6 * B * L * D * 4,
+        "act_fwd": 2 * B * L * 2 * D * 4, "act_bwd": 3 * B * L * 2 * D * 4,
+    }
+    kernels = {}
+    for name, (n, mean_ms) in sorted(prof.items()):
+        entry = {"launches_per_step": n / max(min(args.steps, 5), 1), "ms": mean_ms}
+        if alg.get(name):
+            entry["GBps"] = alg[name] / mean_ms / 1e6
+            entry["frac_of_hbm_peak"] = entry["GBps"] / hbm
+        kernels[name] = entry
+    gather_gbps = alg["gather_rows"] / gather_ms / 1e6 if gather_n else None
+    if world > 1:
+        gather_gbps = None   # sharded path: several gathers of different sizes per step; see roofline_kernels
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (tf32 tensor-core linear layers, fp32 everywhere else)", "data": "synthetic",
+        "config": workload_config(B, world),
+        "e2e": {"value": e2e, "unit": "sequences/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {"kernel": "gather_rows_bulk_kernel (pr_gather_rows_f32, K1)", "bound": "hbm",
+                     "achieved": gather_gbps, "peak": hbm, "unit": "GB/s",
+                     "frac": (gather_gbps / hbm) if gather_gbps else None, "traffic": None,
+                     "algorithmic_bytes_per_launch": alg["gather_rows"], "launch_ms": gather_ms if gather_n else None,
+                     "launches_timed": gather_n, "peak_source": peak_src,
+                     "note": "long-tail ids repeat inside a step, so part of the table reads hit L2: achieved can exceed the DRAM copy peak"},
+        "roofline_kernels": kernels,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            rate, cms, cores, _ = cpu_step_rate(1024, 3, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": "sequences/s", "cores": cores, "kind": "port", "ms_per_step": cms,
+                                    "sample": f"3 timed steps x 1024 sequences (1 warm-up) of the same C2 step (fwd+bwd+dense AdamW, dropout 0.1), oracle/torch_port.py on {cores} host threads"}
+        except Exception as ex:  # pragma: no cover
+            line["cpu_baseline"] = {"value": None, "unit": "sequences/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="sequences per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

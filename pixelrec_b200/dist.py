@@ -1,0 +1,178 @@
+"""Multi-GPU plumbing of the hot path: one process per GPU, `torch.distributed` (NCCL over
+NVLink/NVSwitch) ONLY at the shard boundary.
+
+  * batch: data parallel -- every rank runs the full model on its own sequences (the reference's DDP, run.py:40);
+    dense (non-table) gradients are summed with ONE all_reduce of the optimizer's flat gradient buffer and scaled
+    by 1/world inside the fused AdamW kernel (== DDP's mean);
+  * item table: ROW-SHARDED, owner(i) = i % world, local row = i // world (interleaving spreads the popular head
+    of the long-tail).  Forward: bucket the step's indices by owner -> all_to_all_single(indices) -> the owner
+    gathers its rows with pr_gather_rows_f32 straight into the send buffer -> all_to_all_single(rows) ->
+    un-permute with pr_gather_rows_f32.  Backward is the mirror image and ends in pr_scatter_plan +
+    pr_scatter_add_rows_f32 on the owner (duplicates across ranks are reduced there) feeding the sharded
+    dense-semantics AdamW.  There is no dense [N,D] gradient and no dense all-reduce of the table anywhere
+    (the reference all-reduces N*D*4 bytes every step).
+
+The row kernels are reached through `ROWS` so that the exchange logic can be unit-tested on CPU/gloo with an
+oracle-backed stand-in (tests/test_dist_gloo.py); the product default is the CUDA library and nothing else.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import ops
+
+
+class CudaRows:
+    """Default row backend: our sm_100a kernels."""
+
+    @staticmethod
+    def gather(W, idx):
+        return ops.gather_rows(W, idx)
+
+    @staticmethod
+    def plan(idx, N, padding_idx, row2slot=None):
+        return ops.ScatterPlan(idx, N, padding_idx, row2slot=row2slot)
+
+    @staticmethod
+    def scatter(dOut, plan):
+        return ops.scatter_add_rows(dOut, plan)
+
+
+ROWS = CudaRows
+
+
+def world_info(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def shard_rows(N, world, rank):
+    """Number of table rows owned by `rank` under owner(i) = i % world."""
+    return (N - rank + world - 1) // world
+
+
+class ExchangePlan:
+    """Index bucketing for one lookup: who owns each requested row, in which order rows travel."""
+
+    def __init__(self, idx, world, group=None):
+        flat = idx.reshape(-1)
+        self.R = flat.numel()
+        owner = flat % world
+        self.perm = torch.argsort(owner, stable=True)                 # positions sorted by owner
+        self.inv_perm = torch.empty_like(self.perm)
+        self.inv_perm[self.perm] = torch.arange(self.R, device=flat.device)
+        send_counts = torch.bincount(owner, minlength=world)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=group)
+        both = torch.stack([send_counts, recv_counts]).cpu()          # the one host sync of the exchange
+        self.send_splits = both[0].tolist()
+        self.recv_splits = both[1].tolist()
+        local_rows = torch.div(flat, world, rounding_mode="floor")[self.perm].contiguous()
+        self.recv_rows = torch.empty(sum(self.recv_splits), dtype=torch.int64, device=flat.device)
+        dist.all_to_all_single(self.recv_rows, local_rows, self.recv_splits, self.send_splits, group=group)
+
+
+class ShardedGatherFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, W_local, idx, table):
+        world, rank = table.world, table.rank
+        plan = ExchangePlan(idx, world, table.group)
+        D = W_local.shape[1]
+        rows_send = ROWS.gather(W_local, plan.recv_rows)                              # owner-side gather
+        rows_recv = torch.empty(plan.R, D, dtype=W_local.dtype, device=W_local.device)
+        dist.all_to_all_single(rows_recv, rows_send, plan.send_splits, plan.recv_splits, group=table.group)
+        out = ROWS.gather(rows_recv, plan.inv_perm)                                   # back to request order
+        ctx.plan = plan
+        ctx.table = table
+        ctx.D = D
+        return out.view(*idx.shape, D)
+
+    @staticmethod
+    def backward(ctx, dE):
+        plan, table, D = ctx.plan, ctx.table, ctx.D
+        dE = dE.contiguous().view(plan.R, D)
+        d_send = ROWS.gather(dE, plan.perm)                                           # owner order
+        d_recv = torch.empty(len(plan.recv_rows), D, dtype=dE.dtype, device=dE.device)
+        dist.all_to_all_single(d_recv, d_send, plan.recv_splits, plan.send_splits, group=table.group)
+        splan = ROWS.plan(plan.recv_rows, table.n_local, table.local_padding_idx, row2slot=table.sink.row2slot)
+        rows = ROWS.scatter(d_recv, splan)
+        table.sink.deposit(splan, rows)
+        return None, None, None
+
+
+class ShardedTableEmbedding(nn.Module):
+    """Row-sharded drop-in for model.layers.TableEmbedding.  `weight` holds only the local shard
+    [ceil((N-rank)/world), D]; state_dict()/load_state_dict() speak the reference's full `weight` [N, D]."""
+
+    def __init__(self, num_embeddings, embedding_dim, padding_idx=None, group=None):
+        super().__init__()
+        from .model.layers import TableGradSink
+        self.group = group
+        self.world, self.rank = world_info(group)
+        self.num_embeddings = num_embeddings
+        self.embedding_dim = embedding_dim
+        self.padding_idx = padding_idx
+        self.n_local = shard_rows(num_embeddings, self.world, self.rank)
+        # the global padding id lives on rank (padding_idx % world) at local row padding_idx // world
+        self.local_padding_idx = None
+        if padding_idx is not None and padding_idx % self.world == self.rank:
+            self.local_padding_idx = padding_idx // self.world
+        self.weight = nn.Parameter(torch.empty(self.n_local, embedding_dim))
+        nn.init.normal_(self.weight)
+        self.sink = TableGradSink(self)
+        self.sink.sparse = True          # a sharded table has no dense-gradient mode
+        self._register_state_dict_hook(self._full_on_save)
+        self._register_load_state_dict_pre_hook(self._shard_on_load)
+
+    def forward(self, idx):
+        if self.sink.row2slot is None:
+            self.sink.enable_sparse()
+        return ShardedGatherFn.apply(self.weight, idx.contiguous(), self)
+
+    @torch.no_grad()
+    def full_weight(self):
+        """All-gather the shards into the reference layout [N, D] (compute_item_all / checkpoints)."""
+        if self.world == 1:
+            return self.weight.detach()
+        n_max = shard_rows(self.num_embeddings, self.world, 0)
+        pad = torch.zeros(n_max, self.embedding_dim, dtype=self.weight.dtype, device=self.weight.device)
+        pad[:self.n_local] = self.weight
+        chunks = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(chunks, pad, group=self.group)
+        allw = torch.stack(chunks)                                   # [world, n_max, D]; row i = shard i%world, i//world
+        return allw.permute(1, 0, 2).reshape(-1, self.embedding_dim)[:self.num_embeddings].contiguous()
+
+    @staticmethod
+    def _full_on_save(module, state_dict, prefix, local_metadata):
+        state_dict[prefix + "weight"] = module.full_weight()
+
+    def _shard_on_load(self, state_dict, prefix, *args):
+        key = prefix + "weight"
+        if key in state_dict and state_dict[key].shape[0] == self.num_embeddings:
+            state_dict[key] = state_dict[key][self.rank::self.world].contiguous()
+
+    def extra_repr(self):
+        return f"{self.num_embeddings} rows sharded {self.world}-way (local {self.n_local}), dim {self.embedding_dim}"
+
+
+def make_table(num_embeddings, embedding_dim, padding_idx=None, sharding="auto"):
+    """TableEmbedding on one GPU, ShardedTableEmbedding when a process group with world > 1 is up."""
+    from .model.layers import TableEmbedding
+    world, _ = world_info()
+    if world > 1 and sharding != "replicated":
+        return ShardedTableEmbedding(num_embeddings, embedding_dim, padding_idx)
+    return TableEmbedding(num_embeddings, embedding_dim, padding_idx)
+
+
+@torch.no_grad()
+def broadcast_dense_params(model, src=0):
+    """Replicated (non-table) parameters start identical on every rank (DDP does the same at wrap time)."""
+    if world_info()[0] == 1:
+        return
+    sharded = {id(m.weight) for m in model.modules() if isinstance(m, ShardedTableEmbedding)}
+    for p in model.parameters():
+        if id(p) not in sharded:
+            dist.broadcast(p.data, src)

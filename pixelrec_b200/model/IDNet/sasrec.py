@@ -7,6 +7,7 @@ from torch import nn
 from ... import ops
 from ...utils.enum_type import InputType
 from ..basemodel import BaseModel
+from ...dist import ShardedTableEmbedding, make_table
 from ..layers import TableEmbedding, TransformerEncoder
 
 
@@ -27,7 +28,8 @@ class SASRec(BaseModel):
         self.max_seq_length = config["MAX_ITEM_LIST_LENGTH"]
         self.item_num = dataload.item_num
 
-        self.item_embedding = TableEmbedding(self.item_num, self.hidden_size, padding_idx=0)
+        self.item_embedding = make_table(self.item_num, self.hidden_size, padding_idx=0,
+                                         sharding=config["table_sharding"] or "auto")
         self.position_embedding = nn.Embedding(self.max_seq_length, self.hidden_size)
         self.trm_encoder = TransformerEncoder(
             n_layers=self.n_layers, n_heads=self.n_heads, hidden_size=self.hidden_size, inner_size=self.inner_size,
@@ -39,7 +41,7 @@ class SASRec(BaseModel):
 
     def _init_weights(self, module):
         """sasrec.py:51-61.  NB: like the reference this re-initialises the pad row (id 0) to N(0, std)."""
-        if isinstance(module, (nn.Linear, nn.Embedding, TableEmbedding)):
+        if isinstance(module, (nn.Linear, nn.Embedding, TableEmbedding, ShardedTableEmbedding)):
             module.weight.data.normal_(mean=0.0, std=self.initializer_range)
         elif isinstance(module, nn.LayerNorm):
             module.bias.data.zero_()
@@ -85,4 +87,7 @@ class SASRec(BaseModel):
 
     @torch.no_grad()
     def compute_item_all(self):
+        """sasrec.py:115-117; a row-sharded table is all-gathered into the reference's [N, D] layout."""
+        if isinstance(self.item_embedding, ShardedTableEmbedding):
+            return self.item_embedding.full_weight()
         return self.item_embedding.weight

@@ -49,6 +49,42 @@ def _count(n=1):
     LAUNCHES["count"] += n
 
 
+# Optional live kernel timing (bench.py roofline): PROFILE["names"] = set of kernel names (or None = all);
+# every wrapped launch then records a CUDA event pair on the launching stream into PROFILE["events"][name].
+PROFILE = {"on": False, "names": None, "events": {}}
+
+
+class _prof:
+    __slots__ = ("name", "dev", "s")
+
+    def __init__(self, name, t):
+        self.name = name
+        self.dev = t.device
+        self.s = None
+
+    def __enter__(self):
+        if PROFILE["on"] and (PROFILE["names"] is None or self.name in PROFILE["names"]):
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.s.record(torch.cuda.current_stream(self.dev))
+        return self
+
+    def __exit__(self, *exc):
+        if self.s is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(torch.cuda.current_stream(self.dev))
+            PROFILE["events"].setdefault(self.name, []).append((self.s, e))
+        return False
+
+
+def profile_summary():
+    """name -> (n_launches, mean_ms); call after torch.cuda.synchronize()."""
+    out = {}
+    for name, evs in PROFILE["events"].items():
+        ms = [s.elapsed_time(e) for s, e in evs]
+        out[name] = (len(ms), sum(ms) / max(len(ms), 1))
+    return out
+
+
 # ------------------------------------------------------------------------------------------- K1 gather
 def gather_rows(W, idx, impl=0, status=None):
     """out[..., :] = W[idx[...], :]  (REC/model/IDNet/sasrec.py:68).  impl: 0 auto, 1 LDG, 2 TMA bulk."""
@@ -57,7 +93,8 @@ def gather_rows(W, idx, impl=0, status=None):
     N, D = W.shape
     R = idx.numel()
     out = torch.empty(*idx.shape, D, device=W.device, dtype=torch.float32)
-    _lib.check(_L().pr_gather_rows_f32(_p(W), N, D, _p(idx), R, _p(out), _p(status), impl, _stream(W)), "pr_gather_rows_f32")
+    with _prof("gather_rows", W):
+        _lib.check(_L().pr_gather_rows_f32(_p(W), N, D, _p(idx), R, _p(out), _p(status), impl, _stream(W)), "pr_gather_rows_f32")
     _count()
     return out
 
@@ -81,9 +118,10 @@ class ScatterPlan:
         ws_bytes = _L().pr_scatter_plan_workspace_bytes(self.R, self.N)
         self._ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
         pad = -1 if padding_idx is None else int(padding_idx)
-        _lib.check(_L().pr_scatter_plan(_p(idx), self.R, self.N, pad, _p(self.perm), _p(self.uniq_ids),
-                                        _p(self.seg_start), _p(self.n_uniq), _p(row2slot), _p(self._ws), ws_bytes,
-                                        _p(status), _stream(idx)), "pr_scatter_plan")
+        with _prof("scatter_plan", idx):
+            _lib.check(_L().pr_scatter_plan(_p(idx), self.R, self.N, pad, _p(self.perm), _p(self.uniq_ids),
+                                            _p(self.seg_start), _p(self.n_uniq), _p(row2slot), _p(self._ws), ws_bytes,
+                                            _p(status), _stream(idx)), "pr_scatter_plan")
         bits = max(1, int(self.N).bit_length())
         _count(1 + 3 * ((bits + 7) // 8) + 5 if self.R else 1)
 
@@ -97,9 +135,10 @@ def scatter_add_rows(dOut, plan: ScatterPlan, scale=1.0, dense_G=None, out_rows=
     rows = torch.empty(plan.max_uniq, D, device=dOut.device, dtype=torch.float32) if out_rows else None
     if dense_G is not None:
         _req(dense_G, torch.float32, "dense_G")
-    _lib.check(_L().pr_scatter_add_rows_f32(_p(dOut), plan.R, D, _p(plan.perm), _p(plan.uniq_ids), _p(plan.seg_start),
-                                            _p(plan.n_uniq), plan.max_uniq, float(scale), _p(rows), _p(dense_G),
-                                            _stream(dOut)), "pr_scatter_add_rows_f32")
+    with _prof("scatter_add_rows", dOut):
+        _lib.check(_L().pr_scatter_add_rows_f32(_p(dOut), plan.R, D, _p(plan.perm), _p(plan.uniq_ids), _p(plan.seg_start),
+                                                _p(plan.n_uniq), plan.max_uniq, float(scale), _p(rows), _p(dense_G),
+                                                _stream(dOut)), "pr_scatter_add_rows_f32")
     _count()
     return rows
 
@@ -108,16 +147,18 @@ def scatter_add_rows(dOut, plan: ScatterPlan, scale=1.0, dense_G=None, out_rows=
 def adamw_rows(W, M, V, grad_rows, row2slot, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, step_dev=None):
     _req(W, torch.float32, "W"); _req(M, torch.float32, "M"); _req(V, torch.float32, "V")
     N, D = W.shape
-    _lib.check(_L().pr_adamw_rows_f32(_p(W), _p(M), _p(V), N, D, _p(grad_rows), _p(row2slot), lr, beta1, beta2, eps,
-                                      weight_decay, grad_scale, int(step), _p(step_dev), _stream(W)), "pr_adamw_rows_f32")
+    with _prof("adamw_rows", W):
+        _lib.check(_L().pr_adamw_rows_f32(_p(W), _p(M), _p(V), N, D, _p(grad_rows), _p(row2slot), lr, beta1, beta2, eps,
+                                          weight_decay, grad_scale, int(step), _p(step_dev), _stream(W)), "pr_adamw_rows_f32")
     _count()
 
 
 def adamw_dense(w, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, step_dev=None):
     for t, n in ((w, "w"), (g, "g"), (m, "m"), (v, "v")):
         _req(t, torch.float32, n)
-    _lib.check(_L().pr_adamw_dense_f32(_p(w), _p(g), _p(m), _p(v), w.numel(), lr, beta1, beta2, eps, weight_decay,
-                                       grad_scale, int(step), _p(step_dev), _stream(w)), "pr_adamw_dense_f32")
+    with _prof("adamw_dense", w):
+        _lib.check(_L().pr_adamw_dense_f32(_p(w), _p(g), _p(m), _p(v), w.numel(), lr, beta1, beta2, eps, weight_decay,
+                                           grad_scale, int(step), _p(step_dev), _stream(w)), "pr_adamw_dense_f32")
     _count()
 
 
@@ -164,9 +205,10 @@ class AddLnFn(torch.autograd.Function):
         y = torch.empty(out_shape, device=h.device, dtype=torch.float32)
         mean = torch.empty(max(rows, 1), device=h.device, dtype=torch.float32)
         rstd = torch.empty(max(rows, 1), device=h.device, dtype=torch.float32)
-        _lib.check(_L().pr_add_ln_fwd_f32(_p(h), sstride, rps, _p(res), res_period, _p(gamma), _p(beta), eps, rows, D,
-                                          p_pre, p_post, seed, stream_pre, stream_post, _p(y), _p(mean), _p(rstd),
-                                          _stream(h)), "pr_add_ln_fwd_f32")
+        with _prof("add_ln_fwd", h):
+            _lib.check(_L().pr_add_ln_fwd_f32(_p(h), sstride, rps, _p(res), res_period, _p(gamma), _p(beta), eps, rows, D,
+                                              p_pre, p_post, seed, stream_pre, stream_post, _p(y), _p(mean), _p(rstd),
+                                              _stream(h)), "pr_add_ln_fwd_f32")
         _count()
         ctx.save_for_backward(h, res, gamma, mean, rstd)
         ctx.cfg = (eps, p_pre, p_post, seed, stream_pre, stream_post, layout, res_period, rows, D, rps, sstride)
@@ -200,10 +242,11 @@ class AddLnFn(torch.autograd.Function):
         dz_tmp = None
         if need_res and res_period > 0:
             dz_tmp = torch.empty(rows, D, device=dy.device, dtype=torch.float32)
-        _lib.check(_L().pr_add_ln_bwd_f32(_p(dy), _p(h), sstride, rps, _p(res), res_period, _p(gamma), _p(mean), _p(rstd),
-                                          rows, D, p_pre, p_post, seed, s_pre, s_post, _p(dh), dh_stride, acc,
-                                          _p(dres_rows if dres_rows is not None else dz_tmp), _p(partials), n_part,
-                                          _stream(dy)), "pr_add_ln_bwd_f32")
+        with _prof("add_ln_bwd", dy):
+            _lib.check(_L().pr_add_ln_bwd_f32(_p(dy), _p(h), sstride, rps, _p(res), res_period, _p(gamma), _p(mean), _p(rstd),
+                                              rows, D, p_pre, p_post, seed, s_pre, s_post, _p(dh), dh_stride, acc,
+                                              _p(dres_rows if dres_rows is not None else dz_tmp), _p(partials), n_part,
+                                              _stream(dy)), "pr_add_ln_bwd_f32")
         dgb = torch.empty(2, D, device=dy.device, dtype=torch.float32)
         _lib.check(_L().pr_colsum_f32(_p(partials), n_part, D, _p(dgb[0]), _stream(dy)), "pr_colsum_f32")
         _lib.check(_L().pr_colsum_f32(_p(partials[1]), n_part, D, _p(dgb[1]), _stream(dy)), "pr_colsum_f32")
@@ -232,7 +275,8 @@ class ActFn(torch.autograd.Function):
     def forward(ctx, x, act):
         _req(x, torch.float32, "x")
         y = torch.empty_like(x)
-        _lib.check(_L().pr_act_fwd_f32(_p(x), x.numel(), act, _p(y), _stream(x)), "pr_act_fwd_f32")
+        with _prof("act_fwd", x):
+            _lib.check(_L().pr_act_fwd_f32(_p(x), x.numel(), act, _p(y), _stream(x)), "pr_act_fwd_f32")
         _count()
         ctx.save_for_backward(x)
         ctx.act = act
@@ -243,7 +287,8 @@ class ActFn(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         dy = dy.contiguous()
         dx = torch.empty_like(x)
-        _lib.check(_L().pr_act_bwd_f32(_p(x), _p(dy), x.numel(), ctx.act, _p(dx), _stream(x)), "pr_act_bwd_f32")
+        with _prof("act_bwd", x):
+            _lib.check(_L().pr_act_bwd_f32(_p(x), _p(dy), x.numel(), ctx.act, _p(dx), _stream(x)), "pr_act_bwd_f32")
         _count()
         return dx, None
 
@@ -269,9 +314,10 @@ class AttnFn(torch.autograd.Function):
         out = torch.empty(B, Lq, D, device=qkv.device, dtype=torch.float32)
         probs = torch.empty(B, n_heads, Lq, Lq, device=qkv.device, dtype=torch.float32)
         base = qkv.data_ptr()
-        _lib.check(_L().pr_sasrec_attn_fwd_f32(base, base + 4 * D, base + 8 * D, D3, _p(key_ids), B, Lq, n_heads, dh,
-                                               int(causal), p_drop, seed, rng_stream, _p(out), _p(probs),
-                                               _stream(qkv)), "pr_sasrec_attn_fwd_f32")
+        with _prof("attn_fwd", qkv):
+            _lib.check(_L().pr_sasrec_attn_fwd_f32(base, base + 4 * D, base + 8 * D, D3, _p(key_ids), B, Lq, n_heads, dh,
+                                                   int(causal), p_drop, seed, rng_stream, _p(out), _p(probs),
+                                                   _stream(qkv)), "pr_sasrec_attn_fwd_f32")
         _count()
         ctx.save_for_backward(qkv, probs)
         ctx.cfg = (B, Lq, n_heads, dh, int(causal), p_drop, seed, rng_stream)
@@ -285,9 +331,10 @@ class AttnFn(torch.autograd.Function):
         dctx = dctx.contiguous()
         dqkv = torch.empty_like(qkv)
         base, gbase = qkv.data_ptr(), dqkv.data_ptr()
-        _lib.check(_L().pr_sasrec_attn_bwd_f32(base, base + 4 * D, base + 8 * D, 3 * D, _p(probs), _p(dctx), B, Lq, h,
-                                               dh, causal, p_drop, seed, rng_stream, gbase, gbase + 4 * D,
-                                               gbase + 8 * D, 3 * D, _stream(qkv)), "pr_sasrec_attn_bwd_f32")
+        with _prof("attn_bwd", qkv):
+            _lib.check(_L().pr_sasrec_attn_bwd_f32(base, base + 4 * D, base + 8 * D, 3 * D, _p(probs), _p(dctx), B, Lq, h,
+                                                   dh, causal, p_drop, seed, rng_stream, gbase, gbase + 4 * D,
+                                                   gbase + 8 * D, 3 * D, _stream(qkv)), "pr_sasrec_attn_bwd_f32")
         _count()
         return dqkv, None, None, None, None, None, None
 
@@ -312,9 +359,10 @@ class BprLossFn(torch.autograd.Function):
         loss = torch.empty((), device=out.device, dtype=torch.float32)
         eb = E.data_ptr()
         plane = (L + 1) * D
-        _lib.check(_L().pr_bpr_loss_fwd_f32(_p(out), eb + 4 * D, eb + 4 * (plane + D), 2 * plane, _p(mask), B, L, D,
-                                            _p(scores[0]), _p(scores[1]), _p(coef), _p(terms), _p(loss), _stream(out)),
-                   "pr_bpr_loss_fwd_f32")
+        with _prof("bpr_fwd", out):
+            _lib.check(_L().pr_bpr_loss_fwd_f32(_p(out), eb + 4 * D, eb + 4 * (plane + D), 2 * plane, _p(mask), B, L, D,
+                                                _p(scores[0]), _p(scores[1]), _p(coef), _p(terms), _p(loss), _stream(out)),
+                       "pr_bpr_loss_fwd_f32")
         _count(2)
         ctx.save_for_backward(out, E, coef)
         ctx.slab = slab
@@ -332,9 +380,10 @@ class BprLossFn(torch.autograd.Function):
         gb = dE.data_ptr()
         eb = E.data_ptr()
         plane = (L + 1) * D
-        _lib.check(_L().pr_bpr_loss_bwd_f32(_p(out), eb + 4 * D, eb + 4 * (plane + D), 2 * plane, _p(coef), _p(dloss),
-                                            B, L, D, _p(d_out), gb + 4 * D, gb + 4 * (plane + D), 2 * plane,
-                                            _stream(out)), "pr_bpr_loss_bwd_f32")
+        with _prof("bpr_bwd", out):
+            _lib.check(_L().pr_bpr_loss_bwd_f32(_p(out), eb + 4 * D, eb + 4 * (plane + D), 2 * plane, _p(coef), _p(dloss),
+                                                B, L, D, _p(d_out), gb + 4 * D, gb + 4 * (plane + D), 2 * plane,
+                                                _stream(out)), "pr_bpr_loss_bwd_f32")
         _count()
         if ctx.slab is not None:
             ctx.slab.dE = dE

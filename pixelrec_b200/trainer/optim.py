@@ -13,6 +13,7 @@ eps 1e-8) and the same param-group semantics, but:
 import torch
 
 from .. import ops
+from ..dist import ShardedTableEmbedding, world_info
 from ..model.layers import TableEmbedding
 
 
@@ -20,11 +21,14 @@ class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, tables=(), grad_scale=1.0):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
-        self.grad_scale = float(grad_scale)
+        self.world, _ = world_info()
+        # data parallel: gradients are SUMMED over ranks (all_reduce of the flat buffers / row exchange of the
+        # sharded table) and scaled by 1/world inside the kernels == DDP's gradient mean (run.py:40)
+        self.grad_scale = float(grad_scale) / self.world
         self._step = 0
         self._tables = {}
         for tb in tables:
-            if not isinstance(tb, TableEmbedding):
+            if not isinstance(tb, (TableEmbedding, ShardedTableEmbedding)):
                 raise TypeError("tables must be TableEmbedding modules")
             self._tables[id(tb.weight)] = tb
         self._flat = []          # per group: dict(w, g, m, v, params)
@@ -95,6 +99,10 @@ class FusedAdamW(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         self._step += 1
+        if self.world > 1:
+            for f in self._flat:
+                if f is not None:
+                    torch.distributed.all_reduce(f["g"])
         for gi, group in enumerate(self.param_groups):
             b1, b2 = group["betas"]
             f = self._flat[gi]

@@ -16,6 +16,7 @@ import torch
 from torch.nn.utils.clip_grad import clip_grad_norm_
 
 from ..evaluator import Collector, Evaluator
+from ..dist import ShardedTableEmbedding
 from ..model.layers import TableEmbedding
 from ..utils.utils import (barrier, calculate_valid_score, dict2str, dist_ready, early_stopping, ensure_dir,
                            get_local_time, get_rank, get_world_size)
@@ -60,7 +61,7 @@ class Trainer:
     # ------------------------------------------------------------------ optimizer (trainer.py:66-103)
     def _build_optimizer(self):
         m = unwrap(self.model)
-        tables = [mod for mod in m.modules() if isinstance(mod, TableEmbedding)]
+        tables = [mod for mod in m.modules() if isinstance(mod, (TableEmbedding, ShardedTableEmbedding))]
         a = self.optim_args
         if len(a) == 4:   # PixelNet: two groups keyed on 'visual_encoder' in the parameter name
             modal, rec = [], []
@@ -111,10 +112,11 @@ class Trainer:
 
     # ------------------------------------------------------------------ checkpoint (trainer.py:138-190)
     def _save_checkpoint(self, epoch, verbose=True):
+        model_state = unwrap(self.model).state_dict()      # collective when the table is sharded: every rank calls it
         if self.rank == 0:
             state = {
                 "config": self.config, "epoch": epoch, "cur_step": self.cur_step,
-                "best_valid_score": self.best_valid_score, "state_dict": unwrap(self.model).state_dict(),
+                "best_valid_score": self.best_valid_score, "state_dict": model_state,
                 "optimizer": self.optimizer.state_dict(), "rng_state": torch.get_rng_state(),
                 "cuda_rng_state": torch.cuda.get_rng_state() if torch.cuda.is_available() else None,
             }
