@@ -11,6 +11,15 @@ from ...dist import ShardedTableEmbedding, make_table
 from ..layers import TableEmbedding, TransformerEncoder
 
 
+def _opt(config, key, default=None):
+    """config[key] with the reference Config's missing-key-is-None behaviour, for plain dicts too."""
+    try:
+        v = config[key]
+    except KeyError:
+        v = None
+    return default if v is None else v
+
+
 class SASRec(BaseModel):
     input_type = InputType.SEQ
 
@@ -29,14 +38,14 @@ class SASRec(BaseModel):
         self.item_num = dataload.item_num
 
         self.item_embedding = make_table(self.item_num, self.hidden_size, padding_idx=0,
-                                         sharding=config["table_sharding"] or "auto")
+                                         sharding=_opt(config, "table_sharding", "auto"))
         self.position_embedding = nn.Embedding(self.max_seq_length, self.hidden_size)
         self.trm_encoder = TransformerEncoder(
             n_layers=self.n_layers, n_heads=self.n_heads, hidden_size=self.hidden_size, inner_size=self.inner_size,
             hidden_dropout_prob=self.hidden_dropout_prob, attn_dropout_prob=self.attn_dropout_prob,
             hidden_act=self.hidden_act, layer_norm_eps=self.layer_norm_eps)
         self.LayerNorm = nn.LayerNorm(self.hidden_size, eps=self.layer_norm_eps)
-        self.rng = ops.DropoutRng(config["seed"] or 0)
+        self.rng = ops.DropoutRng(_opt(config, "seed", 0))
         self.apply(self._init_weights)
 
     def _init_weights(self, module):

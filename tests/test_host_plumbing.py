@@ -1,0 +1,148 @@
+"""CPU tests of the host side: C-ABI library loads and exports what include/pixelrec_b200.h declares, the
+reference's yaml files load unchanged, plugin lookup / dataset binding / data pipeline / evaluator / early
+stopping behave like the reference, and the product path refuses to run without CUDA (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+YAML_DIR = os.path.join(ROOT, "configs")
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from pixelrec_b200 import lib
+    L = lib.load()
+    declared = lib.header_symbols()
+    assert len(declared) >= 20 and set(declared) == set(lib.SIGNATURES)
+    for s in declared:
+        assert hasattr(L, s), s
+    assert L.pr_version() == 1
+    # argument counts of the ctypes table match the header prototypes
+    hdr = open(lib.HEADER_PATH).read()
+    for name, (_, args) in lib.SIGNATURES.items():
+        m = re.search(r"PR_API[^;]*?\b" + name + r"\s*\(([^;]*?)\)\s*;", hdr, re.S)
+        assert m, name
+        params = [p for p in m.group(1).split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(args), (name, len(params), len(args))
+    # invalid arguments are rejected on the host before any launch (no GPU needed)
+    assert L.pr_gather_rows_f32(None, 0, 4, None, 0, None, None, 0, None) == -1
+    assert b"bad shape" in L.pr_last_error_string()
+    assert L.pr_scatter_plan_workspace_bytes(1000, 50) > 0
+
+
+def test_no_cpu_fallback():
+    from pixelrec_b200 import ops
+    from pixelrec_b200.lib import PixelRecB200Error
+    with pytest.raises(PixelRecB200Error):
+        ops.gather_rows(torch.zeros(4, 8), torch.zeros(2, dtype=torch.long))
+    with pytest.raises(PixelRecB200Error):
+        ops.bpr_loss(torch.zeros(1, 2, 8), torch.zeros(1, 2, 3, 8), torch.ones(1, 2, dtype=torch.long))
+
+
+def _yaml(*names):
+    return [os.path.join(YAML_DIR, n) for n in names]
+
+
+def test_reference_yaml_files_load_unchanged():
+    from pixelrec_b200.config import Config
+    from pixelrec_b200.utils import InputType
+    c = Config(_yaml("IDNet/sasrec.yaml", "overall/ID.yaml"))
+    assert c["model"] == "SASRec" and c["embedding_size"] == 512 and c["n_heads"] == 4
+    assert isinstance(c["layer_norm_eps"], float) and c["layer_norm_eps"] == 1e-12     # custom float resolver
+    assert c["does_not_exist"] is None and "does_not_exist" not in c                    # configurator.py:148-152
+    assert c["MODEL_INPUT_TYPE"] == InputType.SEQ and c["valid_metric_bigger"] is True
+    assert c["optim_args"] == {"learning_rate": 0.0001, "weight_decay": 0.1} and c["topk"] == [5, 10]
+    assert c.model_class.__name__ == "SASRec" and c["MAX_ITEM_LIST_LENGTH"] == 10
+    c["device"] = "cuda:0"
+    assert c.device == "cuda:0"
+    with pytest.raises(ValueError):
+        Config(config_dict=dict(model="SASRec", metrics=["Recall"], valid_metric="Recall@10", topk=[0]))
+    with pytest.raises(NotImplementedError):
+        Config(config_dict=dict(model="SASRec", metrics=["Nope"], valid_metric="Recall@10", topk=[5]))
+    with pytest.raises(ValueError):
+        Config(config_dict=dict(model="NotAModel", metrics=["Recall"], valid_metric="Recall@10", topk=[5]))
+
+
+def test_plugin_constructs_with_config_and_dict():
+    from pixelrec_b200.config import Config
+    from pixelrec_b200.model.IDNet.sasrec import SASRec
+
+    class Dl:
+        item_num = 50
+    c = Config(_yaml("IDNet/sasrec.yaml", "overall/ID.yaml"), config_dict=dict(embedding_size=64))
+    m = SASRec(c, Dl())
+    keys = set(m.state_dict().keys())
+    assert {"item_embedding.weight", "position_embedding.weight", "LayerNorm.weight",
+            "trm_encoder.layer.1.multi_head_attention.query.weight", "trm_encoder.layer.0.feed_forward.dense_2.bias"} <= keys
+    assert m.item_embedding.weight.shape == (50, 64) and m.item_embedding.weight[0].abs().sum() > 0   # pad row re-initialised
+    d = dict(n_layers=1, n_heads=2, embedding_size=32, inner_size=2, hidden_dropout_prob=0.1, attn_dropout_prob=0.1,
+             hidden_act="gelu", layer_norm_eps=1e-12, initializer_range=0.02, MAX_ITEM_LIST_LENGTH=5)
+    m2 = SASRec(d, Dl())
+    assert "Trainable parameters" in str(m2)
+    with pytest.raises(ValueError):
+        SASRec(dict(d, n_heads=3), Dl())                   # layers.py:558-562
+
+
+def test_data_pipeline_matches_reference_semantics(tmp_path):
+    from pixelrec_b200.config import Config
+    from pixelrec_b200.data import bulid_dataloader, load_data
+    from pixelrec_b200.data.dataload import split_windows
+    rows = ["item_id,user_id,timestamp"]
+    g = np.random.default_rng(0)
+    t = 0
+    for u in range(12):
+        for _ in range(int(g.integers(4, 30))):
+            t += 1
+            rows.append(f"i{int(g.integers(0, 40))},u{u},{t}")
+    (tmp_path / "toy.csv").write_text("\n".join(rows))
+    c = Config(_yaml("IDNet/sasrec.yaml", "overall/ID.yaml"),
+               config_dict=dict(data_path=str(tmp_path), dataset="toy", MAX_ITEM_LIST_LENGTH=5, train_batch_size=4,
+                                eval_batch_size=8, num_workers=0))
+    data = load_data(c)
+    assert data.item_num == len(set(r.split(",")[0] for r in rows[1:])) + 1          # [PAD] = 0
+    tr, va, te = bulid_dataloader(c, data)
+    for uid, seq in data.user_seq.items():
+        assert (seq > 0).all()
+    # windows: a history longer than L+1 drops its oldest n % (L+1) items and is cut into L+1 chunks
+    assert [len(w) for w in split_windows(list(range(14)), 6)] == [6, 6] and split_windows(list(range(14)), 6)[0][0] == 2
+    assert [len(w) for w in split_windows(list(range(5)), 6)] == [5]
+    items, mask = next(iter(tr))
+    assert items.shape == (4, 2, 6) and mask.shape == (4, 5) and items.dtype == torch.int64
+    for b in range(4):
+        pos, neg, m = items[b, 0], items[b, 1], mask[b]
+        n = int((pos != 0).sum())
+        assert (pos[:6 - n] == 0).all() and m.sum() == n - 1 and (neg[:6 - n + 1] == 0).all()
+        assert all(int(x) not in set(pos.tolist()) for x in neg[6 - n + 1:])
+    item_seq, (hu, hi), pu, pi = next(iter(va))
+    assert item_seq.shape[1] == 5 and len(hu) == len(hi) and pu.tolist() == list(range(item_seq.shape[0]))
+    first = list(data.user_seq.values())[0]
+    assert pi[0].item() == first[-2] and item_seq[0].tolist()[-1] == first[-3]
+    # vectorised batch builder has the same layout
+    ds = tr.dataset
+    it2, m2 = ds.sample_batch(np.arange(len(ds)), np.random.default_rng(1))
+    assert it2.shape[1:] == (2, 6) and ((it2[:, 1] != 0).sum(1) == m2.sum(1)).all()
+    assert ((it2[:, 0] != 0).sum(1) - 1 == m2.sum(1)).all()
+
+
+def test_evaluator_and_early_stopping():
+    from pixelrec_b200.evaluator import Collector, Evaluator
+    from pixelrec_b200.utils import early_stopping
+    from oracle import sasrec_np as O
+    cfg = {"topk": [2, 5], "metrics": ["Recall", "NDCG"], "device": "cpu"}
+    col, ev = Collector(cfg), Evaluator(cfg)
+    g = np.random.default_rng(3)
+    scores = torch.from_numpy(g.standard_normal((6, 30)).astype(np.float32))
+    pu, pi = torch.arange(6), torch.from_numpy(g.integers(1, 30, size=6))
+    col.eval_batch_collect(scores, pu, pi)
+    res = ev.evaluate(col.get_data_struct())
+    idx = np.argsort(-scores.numpy(), axis=1, kind="stable")[:, :5]
+    pos, plen = O.topk_hits(idx, pu.numpy(), pi.numpy(), 6)
+    ref = O.recall_ndcg(pos, plen, [2, 5])
+    for k in ref:
+        assert abs(res[k] - ref[k]) < 1e-12, k
+    assert early_stopping(0.5, 0.4, 3, 5) == (0.5, 0, False, True)
+    assert early_stopping(0.3, 0.4, 5, 5) == (0.4, 6, True, False)
+    assert early_stopping(0.3, 0.4, 0, 5, bigger=False) == (0.3, 0, False, True)
