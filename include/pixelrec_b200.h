@@ -120,7 +120,7 @@ PR_API int pr_adamw_dense_f32(float* w, const float* g, float* m, float* v, int6
  *   (lets the kernel read input_emb = item_emb[:,0,:-1] straight out of the [B,2,L+1,D] gather
  *   output without a copy).  res_period > 0: res_row(r) = r % res_period (position embedding
  *   broadcast over the batch), else res_row(r) = r.
- *   Dropout masks are Philox4x32-10(seed; counter = r*D/4 + col/4, stream id) keep iff rnd >= p*2^32,
+ *   Dropout masks: Philox4x32-10(seed; counter, stream id), 16-bit fields, keep iff field >= round(p*2^16) (layout in ln.cu),
  *   kept values scaled by 1/(1-p); p == 0 disables.  mean/rstd [rows] are saved for backward.
  * Backward returns dh (grad of h, dropout applied; row (s,t) at dh + s*dh_seq_stride + t*D, or
  * contiguous [rows,D] when dh_seq_stride == 0; dh_accumulate != 0 adds into dh instead of storing --
@@ -138,8 +138,8 @@ PR_API int pr_add_ln_bwd_f32(const float* dy, const float* h, int64_t h_seq_stri
                       int64_t D, float p_pre, float p_post, uint64_t seed, uint32_t stream_pre, uint32_t stream_post,
                       float* dh, int64_t dh_seq_stride, int dh_accumulate, float* dres, float* partials,
                       int n_partials, pr_stream_t stream);
-/* out[c] = sum_p partials[p, c]   (p < n_partials), fixed order */
-PR_API int pr_colsum_f32(const float* partials, int n_partials, int64_t D, float* out, pr_stream_t stream);
+/* out[m, c] = sum_p partials[m, p, c]   (m < n_mats, p < n_partials), fixed order */
+PR_API int pr_colsum_f32(const float* partials, int n_mats, int n_partials, int64_t D, float* out, pr_stream_t stream);
 
 /* activation of the feed-forward layer: layers.py:640-660,667   y = act(x) ; dx = act'(x) * dy */
 PR_API int pr_act_fwd_f32(const float* x, int64_t n, int act, float* y, pr_stream_t stream);

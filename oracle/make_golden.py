@@ -132,3 +132,34 @@ if __name__ == "__main__":
         if len(sys.argv) > 1 and n not in sys.argv[1:]:
             continue
         make_case(n, c)
+
+
+def make_gru_case():
+    """GRU4Rec golden (REC/model/IDNet/gru4rec.py): loss + table gradient from the unmodified reference module."""
+    from oracle.refload import ref_gru4rec
+    torch.manual_seed(5)
+    g = np.random.default_rng(5)
+    N, D, L, B = 151, 64, 6, 7
+    model = ref_gru4rec(dict(embedding_size=D, hidden_size=1, num_layers=1, dropout_prob=0), N)
+    model.train()
+    items, mask = synth_batch(g, N, L, B)
+    out = {"items": items, "masked_index": mask, "cfg_N": np.array(N), "cfg_D": np.array(D), "cfg_L": np.array(L)}
+    for k, v in model.state_dict().items():
+        out["param/" + k] = v.detach().numpy().copy()
+    loss = model((torch.from_numpy(items), torch.from_numpy(mask)))
+    loss.backward()
+    out["loss"] = loss.detach().numpy()
+    for k, p in model.named_parameters():
+        out["grad/" + k] = p.grad.detach().numpy().copy()
+    seqs = g.integers(1, N, size=(5, L)).astype(np.int64)
+    seqs[0, :3] = 0
+    with torch.no_grad():
+        model.eval()
+        out["eval_item_seq"] = seqs
+        out["eval_scores_raw"] = model.predict(torch.from_numpy(seqs), model.compute_item_all()).numpy()
+    np.savez_compressed(os.path.join(OUT, "gru4rec_small.npz"), **out)
+    print("gru4rec_small loss", float(loss.detach()))
+
+
+if __name__ == "__main__" and (len(sys.argv) == 1 or "gru4rec_small" in sys.argv[1:]):
+    make_gru_case()

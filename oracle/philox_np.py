@@ -36,34 +36,45 @@ def philox4x32_10(ctr, stream, seed):
 
 
 def drop_threshold(p):
-    t = float(np.float32(p)) * 4294967296.0
-    return np.uint32(min(max(t, 0.0), 4294967295.0))
+    """16-bit threshold: keep iff field >= round(p * 2^16)  (common.cuh drop_threshold)."""
+    t = float(np.float32(p)) * 65536.0 + 0.5
+    return np.uint32(min(max(t, 0.0), 65535.0))
+
+
+def _fields8(r):
+    """[..., 4] uint32 words -> [..., 8] 16-bit fields in keep_bits8 order: low halves of w0..w3, then high halves."""
+    return np.concatenate([r & np.uint32(0xFFFF), r >> np.uint32(16)], -1)
 
 
 def rowwise_keep_scale(rows, D, p, seed, stream, dtype=np.float32):
-    """Multiplicative mask [rows, D] of pr_add_ln_*: element (r, 4c+e) <- Philox(ctr=r*D/4+c)[e]."""
+    """Multiplicative mask [rows, D] of pr_add_ln_*: float4 column c = lane + 32*j (lane = c % 32, j = c // 32),
+    element e: field (4*(j&1) + e) of Philox(ctr = row*D/4 + lane + 64*(j>>1))   (ln.cu row_keep_bits)."""
     if p <= 0:
         return np.ones((rows, D), dtype=dtype)
     D4 = D // 4
-    ctr = (np.arange(rows, dtype=np.uint64)[:, None] * np.uint64(D4) + np.arange(D4, dtype=np.uint64)[None, :])
-    r = philox4x32_10(ctr, stream, seed).reshape(rows, D)
-    keep = r >= drop_threshold(p)
+    c = np.arange(D4, dtype=np.uint64)
+    lane, j = c % np.uint64(32), c // np.uint64(32)
+    ctr = np.arange(rows, dtype=np.uint64)[:, None] * np.uint64(D4) + (lane + np.uint64(64) * (j >> np.uint64(1)))[None, :]
+    f = _fields8(philox4x32_10(ctr, stream, seed))                     # [rows, D4, 8]
+    half = (j & np.uint64(1)).astype(np.int64)                          # [D4]
+    sel = (4 * half[:, None] + np.arange(4)[None, :])                   # [D4, 4]
+    fld = np.take_along_axis(f, np.broadcast_to(sel[None], (rows, D4, 4)), -1).reshape(rows, D)
+    keep = fld >= drop_threshold(p)
     inv = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
     return np.where(keep, inv, np.float32(0)).astype(dtype)
 
 
 def attn_keep_scale(B, h, L, p, seed, stream, dtype=np.float32):
-    """Mask [B,h,L,L] of pr_sasrec_attn_*: entry (item, i, j) <- Philox(ctr=((item*L+i)*8 + j%8)*2 + (j//8)//4)[(j//8)%4]."""
+    """Mask [B,h,L,L] of pr_sasrec_attn_*: entry (item, i, j) <- field (j // 8) of Philox(ctr = (item*L + i)*8 + j % 8)."""
     if p <= 0:
         return np.ones((B, h, L, L), dtype=dtype)
     item = np.arange(B * h, dtype=np.uint64)[:, None, None]
     i = np.arange(L, dtype=np.uint64)[None, :, None]
     j = np.arange(L, dtype=np.uint64)[None, None, :]
-    jj = j // np.uint64(8)
-    ctr = ((item * np.uint64(L) + i) * np.uint64(8) + (j % np.uint64(8))) * np.uint64(2) + jj // np.uint64(4)
-    r = philox4x32_10(ctr, stream, seed)                       # [B*h, L, L, 4]
-    comp = np.broadcast_to((jj % np.uint64(4)).astype(np.int64), ctr.shape)
-    rr = np.take_along_axis(r, comp[..., None], -1)[..., 0]
-    keep = rr >= drop_threshold(p)
+    ctr = (item * np.uint64(L) + i) * np.uint64(8) + (j % np.uint64(8))
+    f = _fields8(philox4x32_10(ctr, stream, seed))                     # [B*h, L, L, 8]
+    jj = np.broadcast_to((j // np.uint64(8)).astype(np.int64), ctr.shape)
+    fld = np.take_along_axis(f, jj[..., None], -1)[..., 0]
+    keep = fld >= drop_threshold(p)
     inv = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
     return np.where(keep, inv, np.float32(0)).astype(dtype).reshape(B, h, L, L)

@@ -164,19 +164,15 @@ __device__ __forceinline__ TileRing ring_setup(unsigned char* smem, int S, uint3
     return r;
 }
 
-// dropout keep-mask for score entry (row i, col j = b + 8*jj) of `item`: Philox counter
-// ((item*L + i)*8 + b)*2 + jj/4, component jj%4   (oracle/philox_np.py attn_keep_mask restates it)
+// dropout keep-mask for score entry (row i, col j = b + 8*jj) of `item`: bit jj of keep_bits8(Philox(counter
+// (item*L + i)*8 + b, stream))   (oracle/philox_np.py attn_keep_scale restates it; CJ <= 8)
 template <int CJ>
 __device__ __forceinline__ void attn_keep(const Philox& ph, unsigned stream, long long item, int L, int i, int b,
                                           unsigned thr, bool (&keep)[CJ]) {
+    static_assert(CJ <= 8, "one Philox draw covers 8 score columns per lane");
+    const unsigned m = keep_bits8(ph((unsigned long long)((item * L + i) * 8 + b), stream), thr);
 #pragma unroll
-    for (int q = 0; q < (CJ + 3) / 4; ++q) {
-        const uint4 r = ph((unsigned long long)(((item * L + i) * 8 + b) * 2 + q), stream);
-        const unsigned rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (q * 4 + e < CJ) keep[q * 4 + e] = rr[e] >= thr;
-    }
+    for (int jj = 0; jj < CJ; ++jj) keep[jj] = (m >> jj) & 1u;
 }
 
 // =============================================================================================== forward

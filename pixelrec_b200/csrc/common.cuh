@@ -137,12 +137,26 @@ struct Philox {
         return make_uint4(c0, c1, c2, c3);
     }
 };
-// keep-probability threshold: element kept iff rnd >= thr, thr = round(p * 2^32) (p in [0,1))
+// dropout: an element is kept iff its 16-bit random field >= thr, thr = round(p * 2^16) (p in [0,1)).
+// One Philox call (128 bits) serves 8 elements.
 __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
-    double t = (double)p * 4294967296.0;
+    double t = (double)p * 65536.0 + 0.5;
     if (t < 0) t = 0;
-    if (t > 4294967295.0) t = 4294967295.0;
+    if (t > 65535.0) t = 65535.0;
     return (uint32_t)t;
+}
+// 8 keep bits from one Philox draw: bit e (e<4) <- low half of word e, bit 4+e <- high half of word e
+__device__ __forceinline__ uint32_t keep_bits8(const uint4& r, uint32_t thr) {
+    uint32_t m = 0;
+    m |= ((r.x & 0xffffu) >= thr) ? 1u : 0u;
+    m |= ((r.y & 0xffffu) >= thr) ? 2u : 0u;
+    m |= ((r.z & 0xffffu) >= thr) ? 4u : 0u;
+    m |= ((r.w & 0xffffu) >= thr) ? 8u : 0u;
+    m |= ((r.x >> 16) >= thr) ? 16u : 0u;
+    m |= ((r.y >> 16) >= thr) ? 32u : 0u;
+    m |= ((r.z >> 16) >= thr) ? 64u : 0u;
+    m |= ((r.w >> 16) >= thr) ? 128u : 0u;
+    return m;
 }
 
 }  // namespace pr

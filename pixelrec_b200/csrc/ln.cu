@@ -18,35 +18,43 @@ struct LnArgs {
     float p_pre, p_post; unsigned long long seed; unsigned stream_pre, stream_post;
 };
 
-__device__ __forceinline__ float4 drop4(float4 v, const Philox& ph, unsigned long long ctr, unsigned stream,
-                                        unsigned thr, float inv_keep) {
-    const uint4 r = ph(ctr, stream);
-    v.x = (r.x >= thr) ? v.x * inv_keep : 0.f;
-    v.y = (r.y >= thr) ? v.y * inv_keep : 0.f;
-    v.z = (r.z >= thr) ? v.z * inv_keep : 0.f;
-    v.w = (r.w >= thr) ? v.w * inv_keep : 0.f;
+// keep bits of one row for this lane: chunk j (= float4 column lane + 32*j) uses bits [4*(j&1), +4) of
+// mk[j>>1], drawn from Philox(counter = row*D4 + lane + 64*(j>>1), stream)   (oracle/philox_np.py restates it)
+template <int VPL>
+__device__ __forceinline__ void row_keep_bits(const Philox& ph, unsigned stream, unsigned thr, long long row, int D4,
+                                              int lane, unsigned (&mk)[(VPL + 1) / 2]) {
+#pragma unroll
+    for (int q = 0; q < (VPL + 1) / 2; ++q)
+        mk[q] = keep_bits8(ph((unsigned long long)row * D4 + lane + 64 * q, stream), thr);
+}
+
+__device__ __forceinline__ float4 apply_keep(float4 v, unsigned bits4, float inv_keep) {
+    v.x = (bits4 & 1u) ? v.x * inv_keep : 0.f;
+    v.y = (bits4 & 2u) ? v.y * inv_keep : 0.f;
+    v.z = (bits4 & 4u) ? v.z * inv_keep : 0.f;
+    v.w = (bits4 & 8u) ? v.w * inv_keep : 0.f;
     return v;
 }
 
 template <int VPL>
-__device__ __forceinline__ void load_z(const LnArgs& a, long long row, int lane, const Philox& ph, unsigned thr_pre,
+__device__ __forceinline__ void load_z(const LnArgs& a, long long row, int lane, const unsigned (&mk_pre)[(VPL + 1) / 2],
                                        float inv_keep_pre, float4 (&z)[VPL]) {
     const long long s = row / a.rows_per_seq, t = row - s * a.rows_per_seq;
     const float4* h4 = reinterpret_cast<const float4*>(a.h + s * a.h_seq_stride) + t * a.D4;
     const long long rrow = a.res_period > 0 ? (row % a.res_period) : row;
     const float4* r4 = a.res ? reinterpret_cast<const float4*>(a.res) + rrow * a.D4 : nullptr;
+    float4 hv[VPL], rv[VPL];
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {     // issue every load of the row before touching the data
+        const int c = lane + 32 * j;
+        hv[j] = (c < a.D4) ? h4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        rv[j] = (r4 && c < a.D4) ? r4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
-        const int c = lane + 32 * j;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < a.D4) {
-            v = h4[c];
-            if (a.p_pre > 0.f) v = drop4(v, ph, (unsigned long long)row * a.D4 + c, a.stream_pre, thr_pre, inv_keep_pre);
-            if (r4) {
-                const float4 r = r4[c];
-                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-            }
-        }
+        float4 v = hv[j];
+        if (a.p_pre > 0.f) v = apply_keep(v, mk_pre[j >> 1] >> (4 * (j & 1)), inv_keep_pre);
+        v.x += rv[j].x; v.y += rv[j].y; v.z += rv[j].z; v.w += rv[j].w;
         z[j] = v;
     }
 }
@@ -70,7 +78,7 @@ __device__ __forceinline__ void row_stats(const float4 (&z)[VPL], int lane, int 
 }
 
 template <int VPL>
-__global__ void __launch_bounds__(256) add_ln_fwd_kernel(LnArgs a, float* __restrict__ y, float* __restrict__ mean_out,
+__global__ void __launch_bounds__(256, (VPL <= 4) ? 4 : 1) add_ln_fwd_kernel(LnArgs a, float* __restrict__ y, float* __restrict__ mean_out,
                                                          float* __restrict__ rstd_out) {
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -82,7 +90,10 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(LnArgs a, float* __rest
     const float4* b4 = reinterpret_cast<const float4*>(a.beta);
     for (long long row = warp; row < a.rows; row += nwarps) {
         float4 z[VPL];
-        load_z<VPL>(a, row, lane, ph, thr_pre, ik_pre, z);
+        unsigned mk_pre[(VPL + 1) / 2], mk_post[(VPL + 1) / 2];
+        if (a.p_pre > 0.f) row_keep_bits<VPL>(ph, a.stream_pre, thr_pre, row, a.D4, lane, mk_pre);
+        if (a.p_post > 0.f) row_keep_bits<VPL>(ph, a.stream_post, thr_post, row, a.D4, lane, mk_post);
+        load_z<VPL>(a, row, lane, mk_pre, ik_pre, z);
         float mean, var;
         row_stats<VPL>(z, lane, a.D4, mean, var);
         const float rstd = 1.0f / sqrtf(var + a.eps);
@@ -97,8 +108,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(LnArgs a, float* __rest
                 o.y = (z[j].y - mean) * rstd * g.y + b.y;
                 o.z = (z[j].z - mean) * rstd * g.z + b.z;
                 o.w = (z[j].w - mean) * rstd * g.w + b.w;
-                if (a.p_post > 0.f)
-                    o = drop4(o, ph, (unsigned long long)row * a.D4 + c, a.stream_post, thr_post, ik_post);
+                if (a.p_post > 0.f) o = apply_keep(o, mk_post[j >> 1] >> (4 * (j & 1)), ik_post);
                 y4[c] = o;
             }
         }
@@ -112,7 +122,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(LnArgs a, float* __rest
 // backward.  dgamma/dbeta: per-lane register accumulators over the rows of this warp, then a
 // fixed-order sum over the CTA's warps in shared memory -> partials[{0,1}][blockIdx.x][D]
 template <int VPL>
-__global__ void __launch_bounds__(256) add_ln_bwd_kernel(LnArgs a, const float* __restrict__ dy,
+__global__ void __launch_bounds__(256, (VPL <= 4) ? 3 : 1) add_ln_bwd_kernel(LnArgs a, const float* __restrict__ dy,
                                                          const float* __restrict__ mean_in,
                                                          const float* __restrict__ rstd_in, float* __restrict__ dh,
                                                          long long dh_seq_stride, int dh_accumulate,
@@ -132,7 +142,10 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(LnArgs a, const float* 
 
     for (long long row = warp; row < a.rows; row += nwarps) {
         float4 z[VPL];
-        load_z<VPL>(a, row, lane, ph, thr_pre, ik_pre, z);
+        unsigned mk_pre[(VPL + 1) / 2], mk_post[(VPL + 1) / 2];
+        if (a.p_pre > 0.f) row_keep_bits<VPL>(ph, a.stream_pre, thr_pre, row, a.D4, lane, mk_pre);
+        if (a.p_post > 0.f) row_keep_bits<VPL>(ph, a.stream_post, thr_post, row, a.D4, lane, mk_post);
+        load_z<VPL>(a, row, lane, mk_pre, ik_pre, z);
         const float mean = mean_in[row], rstd = rstd_in[row];
         const float4* dy4 = reinterpret_cast<const float4*>(dy) + row * a.D4;
         float4 dxh[VPL];
@@ -143,8 +156,7 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(LnArgs a, const float* 
             dxh[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c < a.D4) {
                 float4 d = ldg_stream(dy4 + c);
-                if (a.p_post > 0.f)
-                    d = drop4(d, ph, (unsigned long long)row * a.D4 + c, a.stream_post, thr_post, ik_post);
+                if (a.p_post > 0.f) d = apply_keep(d, mk_post[j >> 1] >> (4 * (j & 1)), ik_post);
                 const float4 g = __ldg(g4 + c);
                 float4 xh;  // z[j] becomes xhat
                 xh.x = (z[j].x - mean) * rstd; xh.y = (z[j].y - mean) * rstd;
@@ -178,8 +190,7 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(LnArgs a, const float* 
                 dz.z = rstd * (dxh[j].z - s1 - z[j].z * s2);
                 dz.w = rstd * (dxh[j].w - s1 - z[j].w * s2);
                 if (dr4) dr4[c] = dz;
-                if (a.p_pre > 0.f)
-                    dz = drop4(dz, ph, (unsigned long long)row * a.D4 + c, a.stream_pre, thr_pre, ik_pre);
+                if (a.p_pre > 0.f) dz = apply_keep(dz, mk_pre[j >> 1] >> (4 * (j & 1)), ik_pre);
                 if (dh_accumulate) {
                     const float4 o = dh4[c];
                     dz.x += o.x; dz.y += o.y; dz.z += o.z; dz.w += o.w;
@@ -219,13 +230,24 @@ __global__ void __launch_bounds__(256) add_ln_bwd_kernel(LnArgs a, const float* 
     }
 }
 
-__global__ void __launch_bounds__(128) colsum_kernel(const float* __restrict__ partials, int n_partials, long long D,
-                                                     float* __restrict__ out) {
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= D) return;
+// out[m][c] = sum_p partials[m][p][c].  32 columns x 32 row-groups per CTA; group y adds rows p = y, y+32, ...
+// in order, then the 32 group sums are added in order -> deterministic.
+__global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ partials, int n_partials, long long D,
+                                                      float* __restrict__ out) {
+    __shared__ float sm[32][33];
+    const long long c = (long long)blockIdx.x * 32 + threadIdx.x;
+    const float* P = partials + (long long)blockIdx.y * n_partials * D;
     float s = 0.f;
-    for (int p = 0; p < n_partials; ++p) s += partials[(long long)p * D + c];
-    out[c] = s;
+    if (c < D)
+        for (int p = threadIdx.y; p < n_partials; p += 32) s += P[(long long)p * D + c];
+    sm[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < D) {
+        float t = 0.f;
+#pragma unroll
+        for (int y = 0; y < 32; ++y) t += sm[y][threadIdx.x];
+        out[(long long)blockIdx.y * D + c] = t;
+    }
 }
 
 // ------------------------------------------------------------------ activations (layers.py:640-660)
@@ -378,11 +400,12 @@ extern "C" int pr_add_ln_bwd_f32(const float* dy, const float* h, int64_t h_seq_
     return PR_OK;
 }
 
-extern "C" int pr_colsum_f32(const float* partials, int n_partials, int64_t D, float* out, pr_stream_t stream_) {
+extern "C" int pr_colsum_f32(const float* partials, int n_mats, int n_partials, int64_t D, float* out,
+                             pr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    PR_CHECK_ARG(n_partials >= 1 && D > 0, "pr_colsum_f32: bad shape");
+    PR_CHECK_ARG(n_partials >= 1 && D > 0 && n_mats >= 1 && n_mats <= 65535, "pr_colsum_f32: bad shape");
     PR_CHECK_ARG(partials && out, "pr_colsum_f32: null pointer");
-    colsum_kernel<<<(int)((D + 127) / 128), 128, 0, stream>>>(partials, n_partials, D, out);
+    colsum_kernel<<<dim3((unsigned)((D + 31) / 32), (unsigned)n_mats), dim3(32, 32), 0, stream>>>(partials, n_partials, D, out);
     PR_CUDA_LAUNCH_CHECK("colsum_kernel");
     return PR_OK;
 }

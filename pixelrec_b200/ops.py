@@ -248,9 +248,9 @@ class AddLnFn(torch.autograd.Function):
                                               _p(dres_rows if dres_rows is not None else dz_tmp), _p(partials), n_part,
                                               _stream(dy)), "pr_add_ln_bwd_f32")
         dgb = torch.empty(2, D, device=dy.device, dtype=torch.float32)
-        _lib.check(_L().pr_colsum_f32(_p(partials), n_part, D, _p(dgb[0]), _stream(dy)), "pr_colsum_f32")
-        _lib.check(_L().pr_colsum_f32(_p(partials[1]), n_part, D, _p(dgb[1]), _stream(dy)), "pr_colsum_f32")
-        _count(3)
+        with _prof("colsum", dy):
+            _lib.check(_L().pr_colsum_f32(_p(partials), 2, n_part, D, _p(dgb), _stream(dy)), "pr_colsum_f32")
+        _count(2)
         dres = None
         if need_res:
             if res_period > 0:

@@ -117,3 +117,30 @@ def test_training_with_dropout_is_finite_and_seeded():
     assert losses[0] == losses[1] and losses[0][0] != losses[0][1]   # same seed -> same masks; new mask each call
     m.eval()
     assert m((t(items), t(mask))).item() == m((t(items), t(mask))).item()
+
+
+def test_gru4rec_plugin_matches_reference_golden():
+    """config 5 backbone: our table gather / scatter-add / loss around cuDNN's GRU vs the reference module."""
+    import os
+    from pixelrec_b200.model.IDNet.gru4rec import GRU4Rec
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "gru4rec_small.npz"))
+    N, D, L = int(z["cfg_N"]), int(z["cfg_D"]), int(z["cfg_L"])
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+    class Dl:
+        item_num, user_num = N, 0
+    m = GRU4Rec(dict(embedding_size=D, hidden_size=1, num_layers=1, dropout_prob=0), Dl())
+    m.load_state_dict({k[len("param/"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param/")})
+    m = m.to(dev()).train()
+    loss = m((t(z["items"]), t(z["masked_index"])))
+    loss.backward()
+    assert abs(loss.item() - float(z["loss"])) / float(z["loss"]) < 1e-4
+    for k, p in m.named_parameters():
+        assert rel(p.grad.cpu().numpy(), z["grad/" + k]) < 1e-3, k
+    assert (m.item_embedding.weight.grad[0] == 0).all()
+    m.eval()
+    sc = m.predict(t(z["eval_item_seq"]), m.compute_item_all())
+    assert rel(sc.cpu().numpy(), z["eval_scores_raw"]) < 1e-4
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
