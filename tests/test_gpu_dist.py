@@ -1,0 +1,118 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices, skipped otherwise): one training step with the row-sharded table +
+data parallelism over NCCL equals the single-GPU step on the concatenated batch (DDP-mean semantics, run.py:40)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(n_layers=2, n_heads=4, embedding_size=128, inner_size=2, hidden_dropout_prob=0.0, attn_dropout_prob=0.0,
+           hidden_act="gelu", layer_norm_eps=1e-12, initializer_range=0.02, MAX_ITEM_LIST_LENGTH=10, seed=3)
+N, B, L = 1003, 24, 10
+
+
+class _Dl:
+    item_num = N
+
+
+def _batch(world):
+    g = np.random.default_rng(9)
+    items = g.integers(1, N, size=(world * B, 2, L + 1)).astype(np.int64)
+    items[:, 1, 0] = 0
+    items[::5, 0, :4] = 0
+    items[::5, 1, :5] = 0
+    mask = (items[:, 1, 1:] != 0).astype(np.int64)
+    items[3, 0, 5] = items[B + 2, 0, 7]            # the same id requested from two ranks
+    return items, mask
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _single(world, state):
+    from pixelrec_b200.model.IDNet.sasrec import SASRec
+    from pixelrec_b200.trainer.optim import FusedAdamW
+    dev = torch.device("cuda", 0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = SASRec(CFG, _Dl())
+    m.load_state_dict(state)
+    m = m.to(dev).train()
+    opt = FusedAdamW(m.parameters(), lr=1e-3, weight_decay=0.1, tables=[m.item_embedding])
+    items, mask = _batch(world)
+    opt.zero_grad()
+    loss = m((torch.from_numpy(items).to(dev), torch.from_numpy(mask).to(dev)))
+    loss.backward()
+    opt.step()
+    return loss.item(), {k: v.detach().cpu() for k, v in m.state_dict().items()}
+
+
+def _worker(rank, world, port, state, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from pixelrec_b200.dist import ShardedTableEmbedding
+        from pixelrec_b200.model.IDNet.sasrec import SASRec
+        from pixelrec_b200.trainer.optim import FusedAdamW
+        torch.backends.cuda.matmul.allow_tf32 = False
+        m = SASRec(CFG, _Dl())
+        assert isinstance(m.item_embedding, ShardedTableEmbedding)
+        m.load_state_dict(state)
+        m = m.to(dev).train()
+        opt = FusedAdamW(m.parameters(), lr=1e-3, weight_decay=0.1, tables=[m.item_embedding])
+        items, mask = _batch(world)
+        sl = slice(rank * B, (rank + 1) * B)
+        opt.zero_grad()
+        loss = m((torch.from_numpy(items[sl]).to(dev), torch.from_numpy(mask[sl]).to(dev)))
+        loss.backward()
+        opt.step()
+        lt = loss.detach().clone()
+        dist.all_reduce(lt)
+        sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}        # collective (gathers the table)
+        # eval path: full-catalog scores from the all-gathered table
+        m.eval()
+        sc = m.predict(torch.from_numpy(items[sl][:, 0, 1:]).to(dev), m.compute_item_all())
+        assert sc.shape == (B, N)
+        if rank == 0:
+            q.put(("ok", lt.item() / world, sd))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put(("err", traceback.format_exc(), None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sharded_dp_step_equals_single_gpu(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from pixelrec_b200.model.IDNet.sasrec import SASRec
+    torch.manual_seed(1)
+    state = {k: v.clone() for k, v in SASRec(CFG, _Dl()).state_dict().items()}
+    ref_loss, ref_sd = _single(world, state)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, state, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    status, loss, sd = q.get(timeout=300)
+    for p in procs:
+        p.join(60)
+    assert status == "ok", loss
+    assert abs(loss - ref_loss) / abs(ref_loss) < 1e-5
+    for k in ref_sd:
+        assert sd[k].shape == ref_sd[k].shape, k
+        err = (sd[k] - ref_sd[k]).abs().max().item()
+        assert err < 2e-5, (k, err)            # lr 1e-3: one AdamW step moves weights by <= 1e-3
