@@ -129,7 +129,7 @@ def cpu_step_rate(B_cpu, steps, warmup, threads=None, seed=0):
     return B_cpu * steps / dt, dt / steps * 1e3, cores, float(loss)
 
 
-def run_reference(args):
+def run_reference(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -150,7 +150,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    out.emit(json.dumps(line))
 
 
 def workload_config(B, world, note=None):
@@ -167,7 +167,7 @@ def workload_config(B, world, note=None):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
-def run_ours(args):
+def run_ours(args, out):
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -320,9 +320,29 @@ def run_ours(args):
         except Exception as ex:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "unit": "sequences/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        out.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+class StdoutGuard:
+    """Only the JSON line may reach stdout: libraries (NCCL prints its version banner with printf) get stderr."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 def main():
@@ -334,10 +354,11 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="sequences per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    with StdoutGuard() as out:
+        if args.impl == "reference":
+            run_reference(args, out)
+        else:
+            run_ours(args, out)
 
 
 if __name__ == "__main__":
