@@ -181,6 +181,22 @@ PR_API int pr_bpr_loss_bwd_f32(const float* out, const float* tp, const float* t
                         const float* dloss, int64_t B, int64_t L, int64_t D, float* d_out, float* d_tp, float* d_tn,
                         int64_t d_seq_stride, pr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K9  full-catalog scoring + mask + top-k, tcgen05 tensor cores (TF32 in, fp32 accumulate in TMEM).
+ *   replaces  scores = seq_output @ item_feature.T           REC/model/IDNet/sasrec.py:112 (gru4rec.py:79)
+ *             scores[:,0] = -inf; scores[hist_u,hist_i]=-inf REC/trainer/trainer.py:334-336
+ *             torch.topk(scores, max(topk))                  REC/evaluator/collector.py:133
+ *   seq_out [B_e, D], W [N, D] (item_feature), D % 32 == 0; hist_u/hist_i [n_hist] int64 (may be NULL when
+ *   n_hist == 0); mask_col0 != 0 masks the [PAD] column.  Outputs topk_val [B_e, k] (descending; -inf when
+ *   fewer than k unmasked items) and topk_idx [B_e, k] int64 (ties: lower item id first; -1 for -inf slots).
+ *   The [B_e, N] score matrix is never written.  k <= 32.  workspace: 256-byte aligned device buffer.
+ */
+PR_API size_t pr_score_topk_workspace_bytes(int64_t B_e, int64_t N, int k);
+PR_API int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float* W, int64_t N, int64_t D,
+                             const int64_t* hist_u, const int64_t* hist_i, int64_t n_hist, int mask_col0, int k,
+                             float* topk_val, int64_t* topk_idx, void* workspace, size_t workspace_bytes,
+                             pr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,432 @@
+// pixelrec_b200 -- K9: full-catalog scoring GEMM fused with masking and per-row top-k, on tcgen05 tensor cores.
+//   replaces  scores = seq_output @ item_feature.T            REC/model/IDNet/sasrec.py:112
+//             scores[:,0] = -inf ; scores[history] = -inf     REC/trainer/trainer.py:334-336
+//             torch.topk(scores, max(topk))                   REC/evaluator/collector.py:133
+//   (reference: cuBLAS SGEMM -> 397 MB [1024, 97K] logits written, re-read by index_put and by topk).
+//
+// This is the one genuine dense contraction of the path: 2*B_e*D*N FLOP (101.7 GFLOP at C2) -> tensor cores.
+//   * operands stay fp32 in HBM/L2; TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) stages [128 x 32] / [256 x 32]
+//     K-major tiles into a 4-stage shared-memory ring; tcgen05.mma.kind::tf32 (UMMA 128x256x8, single issuing
+//     thread) accumulates a [128 users x 256 items] fp32 tile in TMEM; two TMEM buffers (2 x 256 columns) let the
+//     epilogue of tile t overlap the MMAs of tile t+1.
+//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue (one TMEM lane
+//     quadrant each; thread == user row).  Epilogue: tcgen05.ld 32 columns at a time, apply the mask bitmap word
+//     (pad column 0, history, columns >= N), keep a sorted top-K list per thread in registers.  Logits are never
+//     written to memory.
+//   * grid = m_tiles x n_splits (<= #SMs); every CTA walks its share of the N tiles; a small second kernel merges
+//     the n_splits candidate lists per row (ties -> lower item id, like a stable sort).
+#include <cuda.h>
+
+#include <algorithm>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace pr {
+
+constexpr int SC_BM = 128;       // users per tile (UMMA M)
+constexpr int SC_BN = 256;       // items per tile (UMMA N)
+constexpr int SC_BK = 32;        // floats per k-block = one 128-byte swizzle row
+constexpr int SC_STAGES = 4;
+constexpr int SC_A_BYTES = SC_BM * SC_BK * 4;            // 16 KiB
+constexpr int SC_B_BYTES = SC_BN * SC_BK * 4;            // 32 KiB
+constexpr int SC_STAGE_BYTES = SC_A_BYTES + SC_B_BYTES;  // 48 KiB
+constexpr int SC_THREADS = 192;
+constexpr int SC_TMEM_COLS = 512;
+
+struct ScoreArgs {
+    int kblocks;          // D / 32
+    int m_tiles, n_tiles, tiles_per_split, n_splits;
+    int n_words;          // mask words per row = n_tiles * 8
+    const uint32_t* mask; // [m_tiles*128][n_words]
+    float* cand_val;      // [m_tiles*128][n_splits][K]
+    int* cand_idx;
+};
+
+// ---- PTX wrappers (tcgen05 / TMA) --------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs read from fp32 words, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows 128 B apart, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64))
+__device__ __forceinline__ uint64_t sw128_kmajor_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2,
+// A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t tf32_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// sorted (descending) insert; strict '>' keeps the earlier (lower) column on ties
+template <int K>
+__device__ __forceinline__ void topk_insert(float (&val)[K], int (&idx)[K], float v, int c) {
+#pragma unroll
+    for (int i = K - 1; i > 0; --i) {
+        const bool shift = v > val[i - 1];
+        const bool here = v > val[i];
+        idx[i] = shift ? idx[i - 1] : (here ? c : idx[i]);
+        val[i] = shift ? val[i - 1] : (here ? v : val[i]);
+    }
+    if (v > val[0]) { val[0] = v; idx[0] = c; }
+}
+
+template <int K>
+__global__ void __launch_bounds__(SC_THREADS, 1) score_topk_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmB,
+                                                                   const ScoreArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // SWIZZLE_128B tiles (TMA destination == UMMA operand) must sit on 1024-byte boundaries
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ __align__(8) uint64_t full_bar[SC_STAGES], empty_bar[SC_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x % a.m_tiles, split = blockIdx.x / a.m_tiles;
+    const int t_begin = split * a.tiles_per_split;
+    const int t_end = min(a.n_tiles, t_begin + a.tiles_per_split);
+    const int n_my = t_end - t_begin;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, SC_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            long long it = 0;
+            for (int t = 0; t < n_my; ++t) {
+                const int n0 = (t_begin + t) * SC_BN;
+                for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
+                    const int s = (int)(it % SC_STAGES);
+                    mbar_wait(&empty_bar[s], (uint32_t)(((it / SC_STAGES) & 1) ^ 1));
+                    mbar_arrive_expect_tx(&full_bar[s], SC_STAGE_BYTES);
+                    unsigned char* st = smem + (size_t)s * SC_STAGE_BYTES;
+                    tma_load_2d(st, &tmA, kb * SC_BK, m_tile * SC_BM, &full_bar[s]);
+                    tma_load_2d(st + SC_A_BYTES, &tmB, kb * SC_BK, n0, &full_bar[s]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = tf32_idesc(SC_BM, SC_BN);
+            long long it = 0;
+            for (int t = 0; t < n_my; ++t) {
+                const int buf = t & 1;
+                mbar_wait(&tempty_bar[buf], (uint32_t)(((t >> 1) & 1) ^ 1));   // epilogue drained this TMEM buffer
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * SC_BN;
+                for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
+                    const int s = (int)(it % SC_STAGES);
+                    mbar_wait(&full_bar[s], (uint32_t)((it / SC_STAGES) & 1));
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)s * SC_STAGE_BYTES);
+                    const uint64_t adesc = sw128_kmajor_desc(sa), bdesc = sw128_kmajor_desc(sa + SC_A_BYTES);
+#pragma unroll
+                    for (int k4 = 0; k4 < SC_BK / 8; ++k4)   // UMMA K = 8 tf32 = 32 bytes -> +2 in the 16-byte address field
+                        umma_tf32(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) ? 1u : 0u);
+                    umma_commit(&empty_bar[s]);                // stage reusable once these MMAs have read it
+                }
+                umma_commit(&tfull_bar[buf]);                   // accumulator tile complete
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue warps 2..5 (thread == user row)
+        const int q = warp & 3;                                 // TMEM lane quadrant this warp may access
+        const int row = m_tile * SC_BM + q * 32 + lane;
+        float val[K];
+        int idx[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) { val[i] = -INFINITY; idx[i] = -1; }
+        const uint32_t* mrow = a.mask + (size_t)row * a.n_words;
+        for (int t = 0; t < n_my; ++t) {
+            const int buf = t & 1;
+            const int tile = t_begin + t;
+            const uint4 mw0 = *reinterpret_cast<const uint4*>(mrow + tile * 8);
+            const uint4 mw1 = *reinterpret_cast<const uint4*>(mrow + tile * 8 + 4);
+            const uint32_t mw[8] = {mw0.x, mw0.y, mw0.z, mw0.w, mw1.x, mw1.y, mw1.z, mw1.w};
+            mbar_wait(&tfull_bar[buf], (uint32_t)((t >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * SC_BN;
+#pragma unroll 1
+            for (int c = 0; c < SC_BN / 32; ++c) {
+                float v[32];
+                __syncwarp();                                   // tcgen05.ld is warp-collective (.sync.aligned)
+                tmem_ld32(taddr + c * 32, v);
+                const uint32_t w = mw[c];
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = ((w >> j) & 1u) ? -INFINITY : v[j];
+                    mx = fmaxf(mx, v[j]);
+                }
+                if (mx > val[K - 1]) {
+                    const int c0 = tile * SC_BN + c * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (v[j] > val[K - 1]) topk_insert<K>(val, idx, v[j], c0 + j);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        }
+        float* cv = a.cand_val + ((size_t)row * a.n_splits + split) * K;
+        int* ci = a.cand_idx + ((size_t)row * a.n_splits + split) * K;
+#pragma unroll
+        for (int i = 0; i < K; ++i) { cv[i] = val[i]; ci[i] = idx[i]; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, SC_TMEM_COLS);
+}
+
+// merge the n_splits sorted candidate lists of a row: k rounds of warp arg-max (value desc, then item id asc)
+__global__ void __launch_bounds__(128) score_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
+                                                          int n_cand, long long B_e, int k, float* __restrict__ out_val,
+                                                          long long* __restrict__ out_idx) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= B_e) return;
+    constexpr int MAXC = 32;                      // up to 1024 candidates per row
+    float v[MAXC];
+    int id[MAXC];
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int c = lane + 32 * i;
+        const bool ok = c < n_cand;
+        v[i] = ok ? cand_val[row * n_cand + c] : -INFINITY;
+        id[i] = ok ? cand_idx[row * n_cand + c] : -1;
+        if (id[i] < 0) v[i] = -INFINITY;
+    }
+    for (int r = 0; r < k; ++r) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff, bslot = -1;
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const bool better = (id[i] >= 0) && (v[i] > bv || (v[i] == bv && id[i] < bi));
+            if (better) { bv = v[i]; bi = id[i]; bslot = i; }
+        }
+        float wv = bv;
+        int wi = bi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+            if (ov > wv || (ov == wv && oi < wi)) { wv = ov; wi = oi; }
+        }
+        if (bslot >= 0 && wi == bi && wv == bv) {
+#pragma unroll
+            for (int i = 0; i < MAXC; ++i)
+                if (i == bslot) id[i] = -1;          // consumed (item ids are unique per row)
+        }
+        if (lane == 0) {
+            const bool none = (wi == 0x7fffffff);
+            out_val[row * k + r] = none ? -INFINITY : wv;
+            out_idx[row * k + r] = none ? -1 : (long long)wi;
+        }
+    }
+}
+
+// mask bitmap: bit (row, col) set -> score forced to -inf.  base: pad column 0 (optional) and columns >= N
+__global__ void __launch_bounds__(256) score_mask_base_kernel(uint32_t* __restrict__ mask, long long rows, int n_words,
+                                                              long long N, int mask_col0) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * n_words) return;
+    const int w = (int)(i % n_words);
+    const long long c0 = (long long)w * 32;
+    uint32_t bits = 0;
+    if (c0 + 32 > N) bits = (c0 >= N) ? 0xffffffffu : (0xffffffffu << (int)(N - c0));
+    if (w == 0 && mask_col0) bits |= 1u;
+    mask[i] = bits;
+}
+__global__ void __launch_bounds__(256) score_mask_hist_kernel(uint32_t* __restrict__ mask, int n_words, long long B_e,
+                                                              long long N, const long long* __restrict__ hu,
+                                                              const long long* __restrict__ hi, long long n_hist) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_hist) return;
+    const long long u = hu[p], i = hi[p];
+    if (u < 0 || u >= B_e || i < 0 || i >= N) return;
+    atomicOr(mask + u * n_words + (i >> 5), 1u << (i & 31));
+}
+
+// ---- host --------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// [rows, D] fp32 row-major -> boxes of [box_rows x 32 floats], 128-byte swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* tm, const float* base, long long rows, long long D, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_last_error("cuTensorMapEncodeTiled entry point not available");
+        return PR_ERR_UNSUPPORTED;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)D * 4};
+    cuuint32_t box[2] = {(cuuint32_t)SC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld D=%lld)", (int)r, rows, D);
+        return PR_ERR_INVALID_ARGUMENT;
+    }
+    return PR_OK;
+}
+
+struct ScorePlan {
+    int m_tiles, n_tiles, n_splits, tiles_per_split, n_words, K;
+    size_t mask_bytes, cand_bytes, total;
+};
+static ScorePlan score_plan(long long B_e, long long N, int k) {
+    ScorePlan p;
+    p.K = (k <= 16) ? 16 : 32;
+    p.m_tiles = (int)((B_e + SC_BM - 1) / SC_BM);
+    p.n_tiles = (int)((N + SC_BN - 1) / SC_BN);
+    int sms = sm_count();
+    int splits = std::max(1, sms / std::max(1, p.m_tiles));
+    splits = std::min(splits, p.n_tiles);
+    splits = std::min(splits, 1024 / p.K);               // merge kernel handles <= 1024 candidates per row
+    p.tiles_per_split = (p.n_tiles + splits - 1) / splits;
+    p.n_splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+    p.n_words = p.n_tiles * 8;
+    const size_t rows = (size_t)p.m_tiles * SC_BM;
+    p.mask_bytes = (rows * p.n_words * 4 + 255) / 256 * 256;
+    p.cand_bytes = (rows * p.n_splits * p.K * 4 + 255) / 256 * 256;
+    p.total = p.mask_bytes + 2 * p.cand_bytes;
+    return p;
+}
+
+}  // namespace pr
+
+using namespace pr;
+
+extern "C" size_t pr_score_topk_workspace_bytes(int64_t B_e, int64_t N, int k) {
+    if (B_e <= 0 || N <= 0 || k <= 0 || k > 32) return 0;
+    return score_plan(B_e, N, k).total;
+}
+
+extern "C" int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float* W, int64_t N, int64_t D,
+                                 const int64_t* hist_u, const int64_t* hist_i, int64_t n_hist, int mask_col0, int k,
+                                 float* topk_val, int64_t* topk_idx, void* workspace, size_t workspace_bytes,
+                                 pr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PR_CHECK_ARG(B_e > 0 && N > 0 && D > 0, "pr_score_topk_f32: bad shape B_e=%lld N=%lld D=%lld", (long long)B_e,
+                 (long long)N, (long long)D);
+    PR_CHECK_ARG(D % SC_BK == 0, "pr_score_topk_f32: D=%lld must be a multiple of %d", (long long)D, SC_BK);
+    PR_CHECK_ARG(k >= 1 && k <= 32 && k <= N, "pr_score_topk_f32: k=%d outside [1, min(32, N)]", k);
+    PR_CHECK_ARG(N < (1LL << 31) - 512, "pr_score_topk_f32: N too large");
+    PR_CHECK_ARG(seq_out && W && topk_val && topk_idx && workspace, "pr_score_topk_f32: null pointer");
+    PR_CHECK_ARG(aligned16(seq_out) && aligned16(W), "pr_score_topk_f32: seq_out / W must be 16-byte aligned");
+    PR_CHECK_ARG(n_hist >= 0 && (n_hist == 0 || (hist_u && hist_i)), "pr_score_topk_f32: bad history arguments");
+    const ScorePlan p = score_plan(B_e, N, k);
+    PR_CHECK_ARG(workspace_bytes >= p.total, "pr_score_topk_f32: workspace %zu < required %zu", workspace_bytes, p.total);
+    PR_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "pr_score_topk_f32: workspace must be 256-byte aligned");
+
+    char* ws = (char*)workspace;
+    uint32_t* mask = (uint32_t*)ws;
+    float* cand_val = (float*)(ws + p.mask_bytes);
+    int* cand_idx = (int*)(ws + p.mask_bytes + p.cand_bytes);
+    const long long rows = (long long)p.m_tiles * SC_BM;
+    const long long nmask = rows * p.n_words;
+    score_mask_base_kernel<<<(int)((nmask + 255) / 256), 256, 0, stream>>>(mask, rows, p.n_words, N, mask_col0);
+    if (n_hist > 0)
+        score_mask_hist_kernel<<<(int)((n_hist + 255) / 256), 256, 0, stream>>>(mask, p.n_words, B_e, N, (const long long*)hist_u,
+                                                                                (const long long*)hist_i, n_hist);
+    PR_CUDA_LAUNCH_CHECK("score_mask kernels");
+
+    CUtensorMap tmA, tmB;
+    int rc = make_map(&tmA, seq_out, B_e, D, SC_BM);
+    if (rc) return rc;
+    rc = make_map(&tmB, W, N, D, SC_BN);
+    if (rc) return rc;
+
+    ScoreArgs a;
+    a.kblocks = (int)(D / SC_BK);
+    a.m_tiles = p.m_tiles; a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.n_splits = p.n_splits;
+    a.n_words = p.n_words; a.mask = mask; a.cand_val = cand_val; a.cand_idx = cand_idx;
+    const size_t smem = (size_t)SC_STAGES * SC_STAGE_BYTES + 1024;     // +1 KiB slack for the 1024-byte alignment
+    const int grid = p.m_tiles * p.n_splits;
+    if (p.K == 16) {
+        PR_CUDA_CALL(cudaFuncSetAttribute(score_topk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        score_topk_kernel<16><<<grid, SC_THREADS, smem, stream>>>(tmA, tmB, a);
+    } else {
+        PR_CUDA_CALL(cudaFuncSetAttribute(score_topk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        score_topk_kernel<32><<<grid, SC_THREADS, smem, stream>>>(tmA, tmB, a);
+    }
+    PR_CUDA_LAUNCH_CHECK("score_topk_kernel");
+    score_merge_kernel<<<(int)((B_e + 3) / 4), 128, 0, stream>>>(cand_val, cand_idx, p.n_splits * p.K, B_e, k, topk_val,
+                                                                 (long long*)topk_idx);
+    PR_CUDA_LAUNCH_CHECK("score_merge_kernel");
+    return PR_OK;
+}

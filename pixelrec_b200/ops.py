@@ -424,5 +424,31 @@ class GatherFn(torch.autograd.Function):
         return G, None, None, None, None
 
 
+# ------------------------------------------------------------------------------------------- K9 score + top-k
+def score_topk(seq_out, item_feature, k, hist_u=None, hist_i=None, mask_col0=True):
+    """Fused  (seq_out @ item_feature.T) -> mask(col 0, history) -> top-k  on tcgen05 tensor cores.
+    Returns (values [B_e,k] fp32 descending, indices [B_e,k] int64); the [B_e,N] scores are never materialised."""
+    _req(seq_out, torch.float32, "seq_out")
+    _req(item_feature, torch.float32, "item_feature")
+    B_e, D = seq_out.shape
+    N = item_feature.shape[0]
+    n_hist = 0
+    if hist_u is not None and hist_u.numel():
+        _req(hist_u, torch.int64, "hist_u"); _req(hist_i, torch.int64, "hist_i")
+        n_hist = hist_u.numel()
+    ws_bytes = _L().pr_score_topk_workspace_bytes(B_e, N, k)
+    if ws_bytes == 0:
+        raise _lib.PixelRecB200Error(f"score_topk: unsupported shape B_e={B_e} N={N} k={k}")
+    ws = torch.empty(ws_bytes, device=seq_out.device, dtype=torch.uint8)
+    val = torch.empty(B_e, k, device=seq_out.device, dtype=torch.float32)
+    idx = torch.empty(B_e, k, device=seq_out.device, dtype=torch.int64)
+    with _prof("score_topk", seq_out):
+        _lib.check(_L().pr_score_topk_f32(_p(seq_out), B_e, _p(item_feature), N, D, _p(hist_u) if n_hist else None,
+                                          _p(hist_i) if n_hist else None, n_hist, int(bool(mask_col0)), int(k), _p(val),
+                                          _p(idx), _p(ws), ws_bytes, _stream(seq_out)), "pr_score_topk_f32")
+    _count(4 if n_hist else 3)
+    return val, idx
+
+
 def inv_sqrt(x):
     return 1.0 / math.sqrt(x)

@@ -1,0 +1,55 @@
+"""Eval scoring: fused tcgen05 score+mask+top-k vs the reference's path (cuBLAS matmul -> index_put(-inf) -> torch.topk)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pixelrec_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda", 0)
+B_e, N, D, k = 1024, 97001, 512, 10
+g = np.random.default_rng(0)
+seq = torch.randn(B_e, D, device=dev)
+W = torch.randn(N, D, device=dev) * 0.02
+hu = torch.arange(B_e, device=dev).repeat_interleave(20)
+hi = torch.randint(1, N, (B_e * 20,), device=dev)
+flush = torch.empty(64 * 1024 * 1024, device=dev)
+
+
+def timeit(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.add_(1.0)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    return float(np.median(ts))
+
+
+def ref_path():
+    sc = seq @ W.t()
+    sc[:, 0] = -float("inf")
+    sc[hu, hi] = -float("inf")
+    return torch.topk(sc, k, dim=-1)
+
+
+out = {}
+for tf32 in (True, False):
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    out[f"reference_path_tf32={tf32}_ms"] = timeit(ref_path)
+out["fused_tcgen05_ms"] = timeit(lambda: ops.score_topk(seq, W, k, hu, hi))
+out["fused_TFLOPs"] = 2 * B_e * N * D / out["fused_tcgen05_ms"] / 1e9
+torch.backends.cuda.matmul.allow_tf32 = False
+v1, i1 = ref_path()
+v2, i2 = ops.score_topk(seq, W, k, hu, hi)
+out["idx_agreement_vs_fp32"] = float((i1 == i2).float().mean())
+out["max_abs_val_diff"] = float((v1 - v2).abs().max())
+print(json.dumps(out))
+json.dump(out, open("gpurun_out/bench_score.json", "w"), indent=1)

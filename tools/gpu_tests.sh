@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 rc=0
-for f in tests/test_gpu_rows.py tests/test_gpu_ln_loss.py tests/test_gpu_attn.py tests/test_gpu_sasrec.py tests/test_gpu_e2e.py tests/test_gpu_dist.py "$@"; do
+for f in tests/test_gpu_rows.py tests/test_gpu_ln_loss.py tests/test_gpu_attn.py tests/test_gpu_sasrec.py tests/test_gpu_e2e.py tests/test_gpu_dist.py tests/test_gpu_score.py "$@"; do
   [ -f "$f" ] || continue
   n=$(basename $f .py)
   timeout 900 python -u -m pytest $f -v -m gpu ${PYTEST_X:-} --timeout=120 --timeout-method=thread -p no:cacheprovider > gpurun_out/$n.log 2>&1
