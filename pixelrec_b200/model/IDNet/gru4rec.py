@@ -53,10 +53,14 @@ class GRU4Rec(BaseModel):
     @torch.no_grad()
     def predict(self, item_seq, item_feature):
         """gru4rec.py:70-80: the history is embedded from `item_feature` itself."""
-        x = self.emb_dropout(ops.gather_rows(item_feature.contiguous(), item_seq.contiguous()))
+        return torch.matmul(self.encode_last(item_seq, item_feature), item_feature.t())
+
+    @torch.no_grad()
+    def encode_last(self, item_seq, item_feature=None):
+        feat = self.compute_item_all() if item_feature is None else item_feature
+        x = self.emb_dropout(ops.gather_rows(feat.contiguous(), item_seq.contiguous()))
         out, _ = self.gru_layers(x)
-        hidden = self.dense(out)[:, -1]
-        return torch.matmul(hidden, item_feature.t())
+        return self.dense(out)[:, -1].contiguous()
 
     @torch.no_grad()
     def compute_item_all(self):

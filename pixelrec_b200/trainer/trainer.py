@@ -15,6 +15,7 @@ import numpy as np
 import torch
 from torch.nn.utils.clip_grad import clip_grad_norm_
 
+from .. import ops
 from ..evaluator import Collector, Evaluator
 from ..dist import ShardedTableEmbedding
 from ..model.layers import TableEmbedding
@@ -191,6 +192,27 @@ class Trainer:
         return scores, positive_u, positive_i
 
     @torch.no_grad()
+    def _fused_topk_batch_eval(self, batched_data):
+        """Same contract as _full_sort_batch_eval + Collector's torch.topk, but through pr_score_topk_f32:
+        encoder -> tcgen05 scoring GEMM with the pad-column / history mask and the top-k fused in its epilogue.
+        The [B_e, N] score matrix (397 MB at C2) is never written."""
+        user, history_index, positive_u, positive_i = batched_data
+        model = unwrap(self.model)
+        seq_out = model.encode_last(self.to_device(user))
+        hu = hi = None
+        if history_index is not None:
+            hu, hi = (x.to(self.device).contiguous() for x in history_index)
+        _, topk_idx = ops.score_topk(seq_out, self.item_feature.contiguous(), max(self.config["topk"]), hu, hi, mask_col0=True)
+        return topk_idx, positive_u, positive_i
+
+    def _use_fused_topk(self):
+        mode = (self.config["eval_scoring"] or "tcgen05").lower()
+        model = unwrap(self.model)
+        D = self.item_feature.shape[1]
+        return (mode == "tcgen05" and hasattr(model, "encode_last") and D % 32 == 0 and max(self.config["topk"]) <= 32
+                and self.item_feature.is_cuda)
+
+    @torch.no_grad()
     def compute_item_feature(self, config, data):
         self.item_feature = unwrap(self.model).compute_item_all()
 
@@ -212,9 +234,14 @@ class Trainer:
         self.model.eval()
         self.tot_item_num = eval_data.dataset.dataload.item_num
         self.compute_item_feature(self.config, eval_data.dataset.dataload)
+        fused = self._use_fused_topk()
         for batched_data in eval_data:
-            scores, positive_u, positive_i = self._full_sort_batch_eval(batched_data)
-            self.eval_collector.eval_batch_collect(scores, positive_u, positive_i)
+            if fused:
+                topk_idx, positive_u, positive_i = self._fused_topk_batch_eval(batched_data)
+                self.eval_collector.eval_batch_collect_topk(topk_idx, positive_u, positive_i)
+            else:
+                scores, positive_u, positive_i = self._full_sort_batch_eval(batched_data)
+                self.eval_collector.eval_batch_collect(scores, positive_u, positive_i)
         num_total_examples = len(eval_data.sampler.dataset)
         result = self.evaluator.evaluate(self.eval_collector.get_data_struct())
         places = 5 if self.config["metric_decimal_place"] is None else self.config["metric_decimal_place"]

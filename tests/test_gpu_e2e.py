@@ -59,3 +59,31 @@ def test_training_loss_decreases():
         opt.step()
         losses.append(loss.item())
     assert losses[-1] < 0.5 * losses[0], (losses[0], losses[-1])
+
+
+def test_fused_eval_equals_reference_eval_path(tmp_path, monkeypatch):
+    """Trainer.evaluate through the tcgen05 score+top-k kernel gives the same Recall/NDCG as the reference path
+    (predict -> mask -> torch.topk) on the same model."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA")
+    monkeypatch.chdir(tmp_path)
+    from pixelrec_b200.config import Config
+    from pixelrec_b200.data import bulid_dataloader, load_data
+    from pixelrec_b200.trainer import Trainer
+    from pixelrec_b200.utils import get_model, init_seed
+    cfg = dict(dataset="synthetic", synthetic_users=700, synthetic_items=500, MAX_ITEM_LIST_LENGTH=10, embedding_size=64,
+               train_batch_size=64, eval_batch_size=256, epochs=1, num_workers=0, checkpoint_dir=str(tmp_path / "saved"))
+    files = [os.path.join(ROOT, "configs/IDNet/sasrec.yaml"), os.path.join(ROOT, "configs/overall/ID.yaml")]
+    res = {}
+    for mode in ("tcgen05", "cublas"):
+        c = Config(files, config_dict=dict(cfg, eval_scoring=mode))
+        c["device"] = torch.device("cuda", 0)
+        init_seed(7, True)
+        data = load_data(c)
+        _, valid, _ = bulid_dataloader(c, data)
+        model = get_model(c["model"])(c, data).to(c["device"])
+        tr = Trainer(c, model)
+        res[mode] = tr.evaluate(valid, load_best_model=False)
+    assert res["tcgen05"].keys() == res["cublas"].keys()
+    for k in res["cublas"]:
+        assert abs(res["tcgen05"][k] - res["cublas"][k]) < 5e-3, (k, res)
