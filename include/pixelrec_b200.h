@@ -48,6 +48,7 @@ typedef void* pr_stream_t;
 #define PR_ACT_SWISH 2
 #define PR_ACT_TANH 3
 #define PR_ACT_SIGMOID 4
+#define PR_ACT_QUICK_GELU 5   /* x * sigmoid(1.702 x): CLIP ViT item encoder (REC/model/load.py:91-99, HF CLIPVisionModel) */
 
 PR_API int pr_version(void);
 PR_API const char* pr_last_error_string(void);
@@ -162,6 +163,16 @@ PR_API int pr_sasrec_attn_fwd_f32(const float* q, const float* k, const float* v
 PR_API int pr_sasrec_attn_bwd_f32(const float* q, const float* k, const float* v, int64_t ld, const float* probs,
                            const float* dctx, int B, int L, int h, int dh, int causal, float p_drop, uint64_t seed,
                            uint32_t rng_stream, float* dq, float* dk, float* dv, int64_t ld_grad, pr_stream_t stream);
+
+/* Tensor-core variant of the attention core (same arguments, same saved tensors, same dropout masks): the two
+ * per-head products run as mma.sync TF32 with fp32 accumulation.  Limits: L <= 32, dh % 8 == 0.  Used when TF32
+ * matrix products are allowed (as for the linear layers); the _f32 entry points above are the strict-fp32 path. */
+PR_API int pr_sasrec_attn_fwd_tf32(const float* q, const float* k, const float* v, int64_t ld, const int64_t* key_ids, int B,
+                            int L, int h, int dh, int causal, float p_drop, uint64_t seed, uint32_t rng_stream,
+                            float* ctx, float* probs, pr_stream_t stream);
+PR_API int pr_sasrec_attn_bwd_tf32(const float* q, const float* k, const float* v, int64_t ld, const float* probs,
+                            const float* dctx, int B, int L, int h, int dh, int causal, float p_drop, uint64_t seed,
+                            uint32_t rng_stream, float* dq, float* dk, float* dv, int64_t ld_grad, pr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K8  sampled-negative pairwise loss.   replaces sasrec.py:88-92 (== gru4rec.py:63-67, mosasrec.py:89-93)

@@ -163,3 +163,42 @@ def make_gru_case():
 
 if __name__ == "__main__" and (len(sys.argv) == 1 or "gru4rec_small" in sys.argv[1:]):
     make_gru_case()
+
+
+def make_vit_case():
+    """CLIP ViT item encoder golden: HF transformers CLIPVisionModel (the class the reference instantiates,
+    REC/model/load.py:94; random init -- no hub access) + the reference's own MeanItemEncoder wrapper
+    (REC/model/layers.py:121-128) on a small config: output vectors and parameter gradients."""
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    from oracle.refload import load_reference
+    load_reference()
+    from REC.model.layers import Identity, MeanItemEncoder
+    torch.manual_seed(3)
+    cfg = CLIPVisionConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, image_size=96,
+                           patch_size=32)
+    m = CLIPVisionModel(cfg)
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.ndim == 1:
+                p.add_(0.05 * torch.randn_like(p))
+    for index, (name, p) in enumerate(m.named_parameters()):
+        if index < 5 + 16:                      # freeze embeddings, pre-LN and the first layer (the reference's tune_scale rule)
+            p.requires_grad = False
+    m.vision_model.post_layernorm = Identity()
+    enc = MeanItemEncoder(item_encoder=m, input_dim=64, output_dim=48, act_name="relu", dnn_layers=[])
+    x = torch.randn(5, 3, 96, 96)
+    out = enc(x)
+    g = torch.randn_like(out)
+    out.backward(g)
+    d = {"x": x.numpy(), "out": out.detach().numpy(), "gout": g.numpy()}
+    for k, v in enc.state_dict().items():
+        d["param/" + k] = v.numpy().copy()
+    for k, p in enc.named_parameters():
+        if p.grad is not None:
+            d["grad/" + k] = p.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "vit_small.npz"), **d)
+    print("vit_small", out.shape, len([k for k in d if k.startswith("grad/")]), "grads")
+
+
+if __name__ == "__main__" and (len(sys.argv) == 1 or "vit_small" in sys.argv[1:]):
+    make_vit_case()

@@ -1,0 +1,522 @@
+// pixelrec_b200 -- K4+K6, tensor-core variant: the same warp-specialised, TMA-fed attention pipeline as attn.cu
+// (REC/model/IDNet/sasrec.py:119-126 + REC/model/layers.py:590-612), but the two tiny per-head matrix products
+// run on the tensor cores (mma.sync m16n8k8 TF32, fp32 accumulate) instead of FFMA.  attn.cu is issue-bound on
+// FFMA (ncu: 34 % issue active, 9 warps/SM, 0.28 of the HBM roofline); here a (batch, head) item costs ~200
+// tensor instructions instead of ~3400 FFMA, which moves the kernel onto the HBM roofline it belongs to.
+//
+// Used when TF32 is allowed for matrix products (the linear layers of the model already run TF32 -- what
+// torch 1.10 did on Ampere); attn.cu remains the strict-fp32 path.  Dropout masks, masking semantics, probs
+// layout and the saved tensors are identical to attn.cu, so forward/backward of the two paths interoperate.
+//
+// Fragment trick: the contraction index of a product is arbitrary as long as A and B agree.  For O = P V (and
+// dQ = dS K) the key index is permuted (mma k = t <-> key 2t, k = t+4 <-> key 2t+1) so that the accumulator
+// fragments of S = Q K^T are bit-for-bit the A fragments of the next product: P never leaves registers.
+//
+// Shared-memory tiles have a padded row stride of CW+4 floats (rows are separate bulk copies, so padding is
+// free): both access patterns (row = g, col = t  and  row = 2t, col = g) are then bank-conflict-free.
+#include <algorithm>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace pr {
+
+constexpr int TC_MAX_STAGES = 32;
+
+struct TcArgs {
+    const float* q; const float* k; const float* v; long long ld;
+    const long long* key_ids;
+    int B, L, h, dh, nc, causal;
+    float p_drop; unsigned long long seed; unsigned rng_stream;
+    float inv_sqrt;
+    float* ctx; float* probs;
+    const float* dctx; float* dq; float* dk; float* dv; long long ld_grad;
+    int stages;
+};
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int MT, int NT>
+struct TcCfg {
+    static constexpr int ROWS = (16 * MT > 8 * NT) ? 16 * MT : 8 * NT;   // smem rows of a tile (padded, zero beyond L)
+    static constexpr int LS = 16 * MT + 4;                               // row stride of the private L x L tiles (== 4 mod 16)
+    static constexpr int PR = 8 * NT;                                     // rows of the private tiles
+    static constexpr int NCW = 8;
+};
+
+// ring of [ROWS x (CW+4)] fp32 tiles; same protocol as attn.cu (see the note on `produced` there)
+struct TcRing {
+    unsigned char* tiles; uint64_t* full; uint64_t* empty; volatile unsigned long long* produced; int S;
+    uint32_t tile_bytes, row_stride_bytes;
+    __device__ __forceinline__ const float* wait_full(long long t) const {
+        const int s = (int)(t % S);
+        while (*produced <= (unsigned long long)t) {
+        }
+        mbar_wait(&full[s], (uint32_t)((t / S) & 1));
+        return reinterpret_cast<const float*>(tiles + (size_t)s * tile_bytes);
+    }
+    __device__ __forceinline__ void release(long long t, int lane) const {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[(int)(t % S)]);
+    }
+};
+
+__device__ __forceinline__ void tc_produce(const TcRing& ring, long long t, const float* src, long long ld, int L, int CW,
+                                           int lane) {
+    const int s = (int)(t % ring.S);
+    mbar_wait(&ring.empty[s], (uint32_t)(((t / ring.S) & 1) ^ 1));
+    const uint32_t row_bytes = (uint32_t)CW * 4u;
+    if (lane == 0) mbar_arrive_expect_tx(&ring.full[s], row_bytes * (uint32_t)L);
+    __syncwarp();
+    unsigned char* dst = ring.tiles + (size_t)s * ring.tile_bytes;
+    for (int r = lane; r < L; r += 32)
+        bulk_g2s(dst + (size_t)r * ring.row_stride_bytes, src + (long long)r * ld, row_bytes, &ring.full[s]);
+    if (lane == 0) *ring.produced = (unsigned long long)t + 1ull;
+}
+
+// zero the ring once (rows >= L are never written by the bulk copies and must read as 0), then init the barriers
+__device__ __forceinline__ TcRing tc_ring_setup(unsigned char* smem, int S, uint32_t tile_bytes, uint32_t row_stride_bytes,
+                                                size_t private_bytes, unsigned char** private_base) {
+    TcRing r;
+    r.tiles = smem;
+    r.S = S;
+    r.tile_bytes = tile_bytes;
+    r.row_stride_bytes = row_stride_bytes;
+    *private_base = smem + (size_t)S * tile_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(*private_base + private_bytes);
+    r.full = bars;
+    r.empty = bars + TC_MAX_STAGES;
+    r.produced = reinterpret_cast<volatile unsigned long long*>(bars + 2 * TC_MAX_STAGES);
+    float4* z = reinterpret_cast<float4*>(smem);
+    const size_t n16 = ((size_t)S * tile_bytes + private_bytes) / 16;
+    for (size_t i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0) {
+        *r.produced = 0ull;
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&r.full[s], 1);
+            mbar_init(&r.empty[s], 1);
+        }
+        fence_mbar_init();
+    }
+    fence_proxy_async();      // generic-proxy zero fill is ordered before the async-proxy bulk copies
+    __syncthreads();
+    return r;
+}
+
+// acc[mi][nj] += X[16mi + {g, g+8}][d] * Y[8nj + g][d]  over one CW-wide tile pair  ("row x row" product)
+template <int MT, int NT>
+__device__ __forceinline__ void tc_rowrow(const float* __restrict__ Xs, const float* __restrict__ Ys, int stride, int CW,
+                                          int g, int t, float (&acc)[MT][NT][4]) {
+    const float* xr[MT][2];
+    const float* yr[NT];
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi) {
+        xr[mi][0] = Xs + (16 * mi + g) * stride + t;
+        xr[mi][1] = Xs + (16 * mi + g + 8) * stride + t;
+    }
+#pragma unroll
+    for (int nj = 0; nj < NT; ++nj) yr[nj] = Ys + (8 * nj + g) * stride + t;
+#pragma unroll 4
+    for (int ks = 0; ks < CW; ks += 8) {
+        uint32_t a[MT][4], b[NT][2];
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi) {
+            a[mi][0] = to_tf32(xr[mi][0][ks]);
+            a[mi][1] = to_tf32(xr[mi][1][ks]);
+            a[mi][2] = to_tf32(xr[mi][0][ks + 4]);
+            a[mi][3] = to_tf32(xr[mi][1][ks + 4]);
+        }
+#pragma unroll
+        for (int nj = 0; nj < NT; ++nj) {
+            b[nj][0] = to_tf32(yr[nj][ks]);
+            b[nj][1] = to_tf32(yr[nj][ks + 4]);
+        }
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+            for (int nj = 0; nj < NT; ++nj) mma_tf32(acc[mi][nj], a[mi][0], a[mi][1], a[mi][2], a[mi][3], b[nj][0], b[nj][1]);
+    }
+}
+
+// out[16mi + {g,g+8}][d] = sum_j Afrag[mi][ks] (x) X[8ks + {2t, 2t+1}][d]   for every 8-wide column tile of X; rows < L
+// are stored.  Afrag holds A fragments with the permuted contraction index (k = t <-> row 2t, k = t+4 <-> row 2t+1).
+template <int MT, int KT>
+__device__ __forceinline__ void tc_frag_times_tile(const uint32_t (&af)[MT][KT][4], const float* __restrict__ Xs, int stride,
+                                                   int CW, int L, int g, int t, float* __restrict__ out, long long out_ld) {
+    for (int nd = 0; nd < CW; nd += 8) {
+        float acc[MT][4];
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi) acc[mi][0] = acc[mi][1] = acc[mi][2] = acc[mi][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KT; ++ks) {
+            const uint32_t b0 = to_tf32(Xs[(8 * ks + 2 * t) * stride + nd + g]);
+            const uint32_t b1 = to_tf32(Xs[(8 * ks + 2 * t + 1) * stride + nd + g]);
+#pragma unroll
+            for (int mi = 0; mi < MT; ++mi) mma_tf32(acc[mi], af[mi][ks][0], af[mi][ks][1], af[mi][ks][2], af[mi][ks][3], b0, b1);
+        }
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi) {
+            const int r0 = 16 * mi + g, r1 = r0 + 8;
+            if (r0 < L) *reinterpret_cast<float2*>(out + (long long)r0 * out_ld + nd + 2 * t) = make_float2(acc[mi][0], acc[mi][1]);
+            if (r1 < L) *reinterpret_cast<float2*>(out + (long long)r1 * out_ld + nd + 2 * t) = make_float2(acc[mi][2], acc[mi][3]);
+        }
+    }
+}
+
+// A fragments of M^T from a private smem matrix M[r][c] (row stride LS): out rows = c, contraction over r (permuted)
+template <int MT, int KT>
+__device__ __forceinline__ void tc_load_transposed(const float* __restrict__ M, int LS, int g, int t, uint32_t (&af)[MT][KT][4]) {
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ks = 0; ks < KT; ++ks) {
+            const float* r0 = M + (8 * ks + 2 * t) * LS + 16 * mi + g;
+            const float* r1 = r0 + LS;
+            af[mi][ks][0] = to_tf32(r0[0]);      // (row c = 16mi+g,   k = t   <-> r = 8ks+2t)
+            af[mi][ks][1] = to_tf32(r0[8]);      // (row c = 16mi+g+8, k = t)
+            af[mi][ks][2] = to_tf32(r1[0]);      // (row c = 16mi+g,   k = t+4 <-> r = 8ks+2t+1)
+            af[mi][ks][3] = to_tf32(r1[8]);
+        }
+}
+
+// keep bits for score row i, columns j = 8*nj + 2t + e (e = 0,1): same Philox layout as attn.cu attn_keep
+template <int NT>
+__device__ __forceinline__ void tc_keep(const Philox& ph, unsigned stream, long long item, int L, int i, int t, unsigned thr,
+                                        unsigned (&bits)[2]) {
+    static_assert(NT <= 8, "one Philox draw covers 8 column tiles");
+    bits[0] = keep_bits8(ph((unsigned long long)((item * L + i) * 8 + 2 * t), stream), thr);
+    bits[1] = keep_bits8(ph((unsigned long long)((item * L + i) * 8 + 2 * t + 1), stream), thr);
+}
+
+// =============================================================================================== forward
+template <int MT, int NT>
+__global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_fwd_kernel(TcArgs A) {
+    using C = TcCfg<MT, NT>;
+    constexpr int NCW = C::NCW;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int CW = min(A.dh, 128), stride = CW + 4;
+    unsigned char* priv;
+    const TcRing ring = tc_ring_setup(smem, A.stages, (uint32_t)(C::ROWS * stride * 4), (uint32_t)(stride * 4), 0, &priv);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int L = A.L, nc = A.nc, T = 3 * nc;
+    const long long n_items = (long long)A.B * A.h;
+    if (warp == NCW) {
+        long long tt = 0;
+        for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const long long b = item / A.h;
+            const int hd = (int)(item - b * A.h);
+            const long long off = b * L * A.ld + (long long)hd * A.dh;
+            for (int c = 0; c < nc; ++c) {
+                tc_produce(ring, tt++, A.q + off + c * CW, A.ld, L, CW, lane);
+                tc_produce(ring, tt++, A.k + off + c * CW, A.ld, L, CW, lane);
+            }
+            for (int c = 0; c < nc; ++c) tc_produce(ring, tt++, A.v + off + c * CW, A.ld, L, CW, lane);
+        }
+        return;
+    }
+    const int g = lane >> 2, t = lane & 3;
+    const Philox ph(A.seed);
+    const unsigned thr = drop_threshold(A.p_drop);
+    const float inv_keep = 1.0f / (1.0f - A.p_drop);
+    long long n = 0;
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        if ((int)(n % NCW) != warp) continue;
+        const long long bb = item / A.h;
+        const int hd = (int)(item - bb * A.h);
+        const long long t0 = n * T;
+        float acc[MT][NT][4];
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+            for (int nj = 0; nj < NT; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = acc[mi][nj][2] = acc[mi][nj][3] = 0.f;
+        for (int c = 0; c < nc; ++c) {
+            const float* Qs = ring.wait_full(t0 + 2 * c);
+            const float* Ks = ring.wait_full(t0 + 2 * c + 1);
+            tc_rowrow<MT, NT>(Qs, Ks, stride, CW, g, t, acc);
+            ring.release(t0 + 2 * c, lane);
+            ring.release(t0 + 2 * c + 1, lane);
+        }
+        // ---- mask + softmax on the accumulator fragments: thread holds rows {16mi+g, +8}, cols 8nj + 2t + {0,1}
+        bool kvalid[NT][2];
+#pragma unroll
+        for (int nj = 0; nj < NT; ++nj)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = 8 * nj + 2 * t + e;
+                kvalid[nj][e] = (j < L) && (A.key_ids == nullptr || A.key_ids[bb * L + j] != 0);
+            }
+        uint32_t pf[MT][NT][4];          // dropped P as A fragments of the next product
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int i = 16 * mi + g + 8 * hrow;
+                float s[NT][2];
+                float mx = -INFINITY;
+#pragma unroll
+                for (int nj = 0; nj < NT; ++nj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = 8 * nj + 2 * t + e;
+                        const bool ok = kvalid[nj][e] && (!A.causal || j <= i);
+                        float x = acc[mi][nj][2 * hrow + e] * A.inv_sqrt + (ok ? 0.0f : -1e9f);
+                        if (j >= L) x = -INFINITY;
+                        s[nj][e] = x;
+                        mx = fmaxf(mx, x);
+                    }
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                float sum = 0.f;
+#pragma unroll
+                for (int nj = 0; nj < NT; ++nj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float ex = (8 * nj + 2 * t + e < L) ? expf(s[nj][e] - mx) : 0.f;
+                        s[nj][e] = ex;
+                        sum += ex;
+                    }
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                const float inv = 1.0f / sum;
+                unsigned kb[2] = {0xffu, 0xffu};
+                if (A.p_drop > 0.f) tc_keep<NT>(ph, A.rng_stream, item, L, i, t, thr, kb);
+#pragma unroll
+                for (int nj = 0; nj < NT; ++nj) {
+                    const int j = 8 * nj + 2 * t;
+                    const float p0 = s[nj][0] * inv, p1 = s[nj][1] * inv;
+                    if (i < L) {
+                        float* pr = A.probs + (item * L + i) * L + j;
+                        if (j < L) pr[0] = p0;
+                        if (j + 1 < L) pr[1] = p1;
+                    }
+                    float d0 = p0, d1 = p1;
+                    if (A.p_drop > 0.f) {
+                        d0 = ((kb[0] >> nj) & 1u) ? p0 * inv_keep : 0.f;
+                        d1 = ((kb[1] >> nj) & 1u) ? p1 * inv_keep : 0.f;
+                    }
+                    // accumulator (c0,c1 | c2,c3) -> A fragment (a0,a2 | a1,a3) of the key-permuted product
+                    pf[mi][nj][hrow] = to_tf32(d0);
+                    pf[mi][nj][2 + hrow] = to_tf32(d1);
+                }
+            }
+        // ---- O = drop(P) V, chunk by chunk
+        for (int c = 0; c < nc; ++c) {
+            const long long tv = t0 + 2 * nc + c;
+            const float* Vs = ring.wait_full(tv);
+            float* out = A.ctx + bb * L * (long long)(A.h * A.dh) + (long long)hd * A.dh + c * CW;
+            tc_frag_times_tile<MT, NT>(pf, Vs, stride, CW, L, g, t, out, (long long)A.h * A.dh);
+            ring.release(tv, lane);
+        }
+    }
+}
+
+// =============================================================================================== backward
+template <int MT, int NT>
+__global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_bwd_kernel(TcArgs A) {
+    using C = TcCfg<MT, NT>;
+    constexpr int NCW = C::NCW, LS = C::LS, PR = C::PR;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int CW = min(A.dh, 128), stride = CW + 4;
+    unsigned char* priv;
+    const TcRing ring = tc_ring_setup(smem, A.stages, (uint32_t)(C::ROWS * stride * 4), (uint32_t)(stride * 4),
+                                      (size_t)NCW * 2 * PR * LS * 4, &priv);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int L = A.L, nc = A.nc, T = 5 * nc;
+    const long long n_items = (long long)A.B * A.h;
+    const long long Dm = (long long)A.h * A.dh;
+    if (warp == NCW) {
+        long long tt = 0;
+        for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const long long b = item / A.h;
+            const int hd = (int)(item - b * A.h);
+            const long long off = b * L * A.ld + (long long)hd * A.dh;
+            const long long offo = b * L * Dm + (long long)hd * A.dh;
+            for (int c = 0; c < nc; ++c) {
+                tc_produce(ring, tt++, A.dctx + offo + c * CW, Dm, L, CW, lane);
+                tc_produce(ring, tt++, A.v + off + c * CW, A.ld, L, CW, lane);
+            }
+            for (int c = 0; c < nc; ++c) {
+                tc_produce(ring, tt++, A.dctx + offo + c * CW, Dm, L, CW, lane);
+                tc_produce(ring, tt++, A.k + off + c * CW, A.ld, L, CW, lane);
+                tc_produce(ring, tt++, A.q + off + c * CW, A.ld, L, CW, lane);
+            }
+        }
+        return;
+    }
+    float* Pd_s = reinterpret_cast<float*>(priv) + (size_t)warp * 2 * PR * LS;   // Pd_s[i][j]   (i < 8NT rows, j < 16MT cols)
+    float* dS_s = Pd_s + PR * LS;
+    const int g = lane >> 2, t = lane & 3;
+    const Philox ph(A.seed);
+    const unsigned thr = drop_threshold(A.p_drop);
+    const float inv_keep = 1.0f / (1.0f - A.p_drop);
+    long long n = 0;
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        if ((int)(n % NCW) != warp) continue;
+        const long long bb = item / A.h;
+        const int hd = (int)(item - bb * A.h);
+        const long long t0 = n * T;
+        float acc[MT][NT][4];
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+            for (int nj = 0; nj < NT; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = acc[mi][nj][2] = acc[mi][nj][3] = 0.f;
+        for (int c = 0; c < nc; ++c) {              // dPd = dO V^T
+            const float* dOs = ring.wait_full(t0 + 2 * c);
+            const float* Vs = ring.wait_full(t0 + 2 * c + 1);
+            tc_rowrow<MT, NT>(dOs, Vs, stride, CW, g, t, acc);
+            ring.release(t0 + 2 * c, lane);
+            ring.release(t0 + 2 * c + 1, lane);
+        }
+        uint32_t dsf[MT][NT][4];                    // dS as A fragments (key-permuted) for dQ = dS K
+        __syncwarp();                               // previous item's transposed reads are done
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int i = 16 * mi + g + 8 * hrow;
+                unsigned kb[2] = {0xffu, 0xffu};
+                if (A.p_drop > 0.f) tc_keep<NT>(ph, A.rng_stream, item, L, i, t, thr, kb);
+                float p[NT][2], dp[NT][2];
+                float rd = 0.f;
+#pragma unroll
+                for (int nj = 0; nj < NT; ++nj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int j = 8 * nj + 2 * t + e;
+                        const bool in = (i < L) && (j < L);
+                        p[nj][e] = in ? A.probs[(item * L + i) * L + j] : 0.f;
+                        float d = in ? acc[mi][nj][2 * hrow + e] : 0.f;
+                        if (A.p_drop > 0.f) d = ((kb[e] >> nj) & 1u) ? d * inv_keep : 0.f;
+                        dp[nj][e] = d;
+                        rd = fmaf(d, p[nj][e], rd);
+                    }
+                rd += __shfl_xor_sync(0xffffffffu, rd, 1);
+                rd += __shfl_xor_sync(0xffffffffu, rd, 2);
+#pragma unroll
+                for (int nj = 0; nj < NT; ++nj) {
+                    float ds[2], pd[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        ds[e] = p[nj][e] * (dp[nj][e] - rd) * A.inv_sqrt;
+                        pd[e] = p[nj][e];
+                        if (A.p_drop > 0.f) pd[e] = ((kb[e] >> nj) & 1u) ? pd[e] * inv_keep : 0.f;
+                    }
+                    dsf[mi][nj][hrow] = to_tf32(ds[0]);
+                    dsf[mi][nj][2 + hrow] = to_tf32(ds[1]);
+                    if (i < PR) {                   // rows beyond 8NT are never read back (they are >= L anyway)
+                        const int j = 8 * nj + 2 * t;
+                        *reinterpret_cast<float2*>(Pd_s + i * LS + j) = make_float2(pd[0], pd[1]);
+                        *reinterpret_cast<float2*>(dS_s + i * LS + j) = make_float2(ds[0], ds[1]);
+                    }
+                }
+            }
+        __syncwarp();
+        uint32_t pT[MT][NT][4], dsT[MT][NT][4];
+        tc_load_transposed<MT, NT>(Pd_s, LS, g, t, pT);       // A = Pd^T  (rows = keys j, contraction over queries i)
+        tc_load_transposed<MT, NT>(dS_s, LS, g, t, dsT);      // A = dS^T
+        for (int c = 0; c < nc; ++c) {
+            const long long tb = t0 + 2 * nc + 3 * c;
+            const long long go = bb * L * A.ld_grad + (long long)hd * A.dh + c * CW;
+            const float* dOs = ring.wait_full(tb);
+            tc_frag_times_tile<MT, NT>(pT, dOs, stride, CW, L, g, t, A.dv + go, A.ld_grad);     // dV = Pd^T dO
+            ring.release(tb, lane);
+            const float* Ks = ring.wait_full(tb + 1);
+            tc_frag_times_tile<MT, NT>(dsf, Ks, stride, CW, L, g, t, A.dq + go, A.ld_grad);     // dQ = dS K
+            ring.release(tb + 1, lane);
+            const float* Qs = ring.wait_full(tb + 2);
+            tc_frag_times_tile<MT, NT>(dsT, Qs, stride, CW, L, g, t, A.dk + go, A.ld_grad);     // dK = dS^T Q
+            ring.release(tb + 2, lane);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- host
+template <int MT, int NT, bool BWD>
+static int launch_tc(TcArgs& A, cudaStream_t stream) {
+    using C = TcCfg<MT, NT>;
+    const int CW = std::min(A.dh, 128), stride = CW + 4;
+    const size_t tile = (size_t)C::ROWS * stride * 4;
+    const size_t priv = BWD ? (size_t)C::NCW * 2 * C::PR * C::LS * 4 : 0;
+    const size_t bars = (size_t)2 * TC_MAX_STAGES * 8 + 16;
+    const size_t budget = 220 * 1024;
+    PR_CHECK_ARG(priv + bars + 4 * tile <= budget, "attention(tf32): L=%d dh=%d does not fit shared memory", A.L, A.dh);
+    int S = (int)((budget - priv - bars) / tile);
+    S = std::min(S, TC_MAX_STAGES);
+    S = std::min(S, std::max(4, (BWD ? 5 : 3) * A.nc * C::NCW * 2));
+    A.stages = S;
+    const size_t smem = (size_t)S * tile + priv + bars;
+    auto kern = BWD ? attn_tc_bwd_kernel<MT, NT> : attn_tc_fwd_kernel<MT, NT>;
+    PR_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long n_items = (long long)A.B * A.h;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((n_items + C::NCW - 1) / C::NCW, sm_count()));
+    kern<<<grid, (C::NCW + 1) * 32, smem, stream>>>(A);
+    PR_CUDA_LAUNCH_CHECK(BWD ? "attn_tc_bwd_kernel" : "attn_tc_fwd_kernel");
+    return PR_OK;
+}
+
+template <bool BWD>
+static int dispatch_tc(TcArgs& A, cudaStream_t stream) {
+    if (A.L <= 16) return launch_tc<1, 2, BWD>(A, stream);
+    if (A.L <= 24) return launch_tc<2, 3, BWD>(A, stream);
+    if (A.L <= 32) return launch_tc<2, 4, BWD>(A, stream);
+    set_last_error("attention(tf32): L=%d > 32 unsupported (use the fp32 kernel)", A.L);
+    return PR_ERR_UNSUPPORTED;
+}
+
+static int check_tc(const char* who, const float* q, const float* k, const float* v, long long ld, int B, int L, int h, int dh,
+                    float p) {
+    PR_CHECK_ARG(B > 0 && L > 0 && h > 0 && dh > 0, "%s: bad shape B=%d L=%d h=%d dh=%d", who, B, L, h, dh);
+    PR_CHECK_ARG(L <= 32, "%s: L=%d > 32 unsupported by the tensor-core path", who, L);
+    PR_CHECK_ARG(dh % 8 == 0 && (dh <= 128 || dh % 128 == 0), "%s: dh=%d must be a multiple of 8, <= 128 or a multiple of 128", who, dh);
+    PR_CHECK_ARG(ld % 4 == 0 && ld >= (long long)h * dh, "%s: ld=%lld must be a multiple of 4 and >= h*dh", who, ld);
+    PR_CHECK_ARG(q && k && v && aligned16(q) && aligned16(k) && aligned16(v), "%s: q/k/v null or not 16-byte aligned", who);
+    PR_CHECK_ARG(p >= 0.f && p < 1.f, "%s: dropout p outside [0,1)", who);
+    return PR_OK;
+}
+
+}  // namespace pr
+
+using namespace pr;
+
+extern "C" int pr_sasrec_attn_fwd_tf32(const float* q, const float* k, const float* v, int64_t ld, const int64_t* key_ids,
+                                       int B, int L, int h, int dh, int causal, float p_drop, uint64_t seed,
+                                       uint32_t rng_stream, float* ctx, float* probs, pr_stream_t stream_) {
+    int rc = check_tc("pr_sasrec_attn_fwd_tf32", q, k, v, ld, B, L, h, dh, p_drop);
+    if (rc) return rc;
+    PR_CHECK_ARG(ctx && probs && aligned16(ctx), "pr_sasrec_attn_fwd_tf32: ctx/probs null or unaligned");
+    TcArgs A{};
+    A.q = q; A.k = k; A.v = v; A.ld = ld; A.key_ids = (const long long*)key_ids;
+    A.B = B; A.L = L; A.h = h; A.dh = dh; A.nc = (dh + 127) / 128; A.causal = causal;
+    A.p_drop = p_drop; A.seed = seed; A.rng_stream = rng_stream;
+    A.inv_sqrt = (float)(1.0 / sqrt((double)dh));
+    A.ctx = ctx; A.probs = probs;
+    return dispatch_tc<false>(A, (cudaStream_t)stream_);
+}
+
+extern "C" int pr_sasrec_attn_bwd_tf32(const float* q, const float* k, const float* v, int64_t ld, const float* probs,
+                                       const float* dctx, int B, int L, int h, int dh, int causal, float p_drop,
+                                       uint64_t seed, uint32_t rng_stream, float* dq, float* dk, float* dv, int64_t ld_grad,
+                                       pr_stream_t stream_) {
+    int rc = check_tc("pr_sasrec_attn_bwd_tf32", q, k, v, ld, B, L, h, dh, p_drop);
+    if (rc) return rc;
+    PR_CHECK_ARG(probs && dctx && dq && dk && dv, "pr_sasrec_attn_bwd_tf32: null pointer");
+    PR_CHECK_ARG(aligned16(dctx) && aligned16(dq) && aligned16(dk) && aligned16(dv), "pr_sasrec_attn_bwd_tf32: unaligned pointer");
+    PR_CHECK_ARG(ld_grad % 4 == 0 && ld_grad >= (int64_t)h * dh, "pr_sasrec_attn_bwd_tf32: bad ld_grad");
+    TcArgs A{};
+    A.q = q; A.k = k; A.v = v; A.ld = ld;
+    A.B = B; A.L = L; A.h = h; A.dh = dh; A.nc = (dh + 127) / 128; A.causal = causal;
+    A.p_drop = p_drop; A.seed = seed; A.rng_stream = rng_stream;
+    A.inv_sqrt = (float)(1.0 / sqrt((double)dh));
+    A.probs = const_cast<float*>(probs); A.dctx = dctx; A.dq = dq; A.dk = dk; A.dv = dv; A.ld_grad = ld_grad;
+    return dispatch_tc<true>(A, (cudaStream_t)stream_);
+}

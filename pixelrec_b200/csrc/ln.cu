@@ -257,6 +257,7 @@ __device__ __forceinline__ float act_f(float x, int act) {
         case PR_ACT_RELU: return fmaxf(x, 0.f);
         case PR_ACT_SWISH: return x / (1.0f + expf(-x));
         case PR_ACT_TANH: return tanhf(x);
+        case PR_ACT_QUICK_GELU: return x / (1.0f + expf(-1.702f * x));
         default: return 1.0f / (1.0f + expf(-x));
     }
 }
@@ -275,6 +276,10 @@ __device__ __forceinline__ float act_df(float x, int act) {
         case PR_ACT_TANH: {
             const float t = tanhf(x);
             return 1.0f - t * t;
+        }
+        case PR_ACT_QUICK_GELU: {
+            const float s = 1.0f / (1.0f + expf(-1.702f * x));
+            return s + 1.702f * x * s * (1.0f - s);
         }
         default: {
             const float s = 1.0f / (1.0f + expf(-x));
@@ -412,7 +417,7 @@ extern "C" int pr_colsum_f32(const float* partials, int n_mats, int n_partials, 
 
 extern "C" int pr_act_fwd_f32(const float* x, int64_t n, int act, float* y, pr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    PR_CHECK_ARG(n >= 0 && act >= 0 && act <= PR_ACT_SIGMOID, "pr_act_fwd_f32: bad n/act");
+    PR_CHECK_ARG(n >= 0 && act >= 0 && act <= PR_ACT_QUICK_GELU, "pr_act_fwd_f32: bad n/act");
     if (n == 0) return PR_OK;
     PR_CHECK_ARG(x && y && aligned16(x) && aligned16(y), "pr_act_fwd_f32: null/unaligned pointer");
     const int grid = (int)std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, (long long)sm_count() * 16));
@@ -423,7 +428,7 @@ extern "C" int pr_act_fwd_f32(const float* x, int64_t n, int act, float* y, pr_s
 
 extern "C" int pr_act_bwd_f32(const float* x, const float* dy, int64_t n, int act, float* dx, pr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    PR_CHECK_ARG(n >= 0 && act >= 0 && act <= PR_ACT_SIGMOID, "pr_act_bwd_f32: bad n/act");
+    PR_CHECK_ARG(n >= 0 && act >= 0 && act <= PR_ACT_QUICK_GELU, "pr_act_bwd_f32: bad n/act");
     if (n == 0) return PR_OK;
     PR_CHECK_ARG(x && dy && dx && aligned16(x) && aligned16(dy) && aligned16(dx), "pr_act_bwd_f32: null/unaligned pointer");
     const int grid = (int)std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, (long long)sm_count() * 16));

@@ -12,7 +12,7 @@ import torch
 
 from . import lib as _lib
 
-ACT_IDS = {"gelu": 0, "relu": 1, "swish": 2, "tanh": 3, "sigmoid": 4}
+ACT_IDS = {"gelu": 0, "relu": 1, "swish": 2, "tanh": 3, "sigmoid": 4, "quick_gelu": 5}
 LAUNCHES = {"count": 0}   # kernels of OURS launched (bench.py reports it as gpu_launches)
 
 _cur_dev = [None]
@@ -304,43 +304,47 @@ class AttnFn(torch.autograd.Function):
     """ctx = softmax(q k^T / sqrt(dh) + mask(key_ids, causal)) v on a fused [B, L, 3*D] q|k|v tensor."""
 
     @staticmethod
-    def forward(ctx, qkv, key_ids, n_heads, causal, p_drop, seed, rng_stream):
+    def forward(ctx, qkv, key_ids, n_heads, causal, p_drop, seed, rng_stream, tf32=None):
         _req(qkv, torch.float32, "qkv")
         B, Lq, D3 = qkv.shape
         D = D3 // 3
         dh = D // n_heads
+        if tf32 is None:   # follow the policy of the linear layers (model.layers / matmul_precision)
+            tf32 = torch.backends.cuda.matmul.allow_tf32
+        tf32 = bool(tf32) and Lq <= 32 and dh % 8 == 0
+        fwd = _L().pr_sasrec_attn_fwd_tf32 if tf32 else _L().pr_sasrec_attn_fwd_f32
         if key_ids is not None:
             _req(key_ids, torch.int64, "key_ids")
         out = torch.empty(B, Lq, D, device=qkv.device, dtype=torch.float32)
         probs = torch.empty(B, n_heads, Lq, Lq, device=qkv.device, dtype=torch.float32)
         base = qkv.data_ptr()
         with _prof("attn_fwd", qkv):
-            _lib.check(_L().pr_sasrec_attn_fwd_f32(base, base + 4 * D, base + 8 * D, D3, _p(key_ids), B, Lq, n_heads, dh,
-                                                   int(causal), p_drop, seed, rng_stream, _p(out), _p(probs),
-                                                   _stream(qkv)), "pr_sasrec_attn_fwd_f32")
+            _lib.check(fwd(base, base + 4 * D, base + 8 * D, D3, _p(key_ids), B, Lq, n_heads, dh,
+                           int(causal), p_drop, seed, rng_stream, _p(out), _p(probs), _stream(qkv)), "pr_sasrec_attn_fwd")
         _count()
         ctx.save_for_backward(qkv, probs)
-        ctx.cfg = (B, Lq, n_heads, dh, int(causal), p_drop, seed, rng_stream)
+        ctx.cfg = (B, Lq, n_heads, dh, int(causal), p_drop, seed, rng_stream, tf32)
         return out
 
     @staticmethod
     def backward(ctx, dctx):
         qkv, probs = ctx.saved_tensors
-        B, Lq, h, dh, causal, p_drop, seed, rng_stream = ctx.cfg
+        B, Lq, h, dh, causal, p_drop, seed, rng_stream, tf32 = ctx.cfg
         D = h * dh
         dctx = dctx.contiguous()
         dqkv = torch.empty_like(qkv)
         base, gbase = qkv.data_ptr(), dqkv.data_ptr()
+        bwd = _L().pr_sasrec_attn_bwd_tf32 if tf32 else _L().pr_sasrec_attn_bwd_f32
         with _prof("attn_bwd", qkv):
-            _lib.check(_L().pr_sasrec_attn_bwd_f32(base, base + 4 * D, base + 8 * D, 3 * D, _p(probs), _p(dctx), B, Lq, h,
-                                                   dh, causal, p_drop, seed, rng_stream, gbase, gbase + 4 * D,
-                                                   gbase + 8 * D, 3 * D, _stream(qkv)), "pr_sasrec_attn_bwd_f32")
+            _lib.check(bwd(base, base + 4 * D, base + 8 * D, 3 * D, _p(probs), _p(dctx), B, Lq, h, dh, causal, p_drop, seed,
+                           rng_stream, gbase, gbase + 4 * D, gbase + 8 * D, 3 * D, _stream(qkv)), "pr_sasrec_attn_bwd")
         _count()
-        return dqkv, None, None, None, None, None, None
+        return dqkv, None, None, None, None, None, None, None
 
 
-def attention(qkv, key_ids, n_heads, causal=True, p_drop=0.0, seed=0, rng_stream=0):
-    return AttnFn.apply(qkv, key_ids, int(n_heads), bool(causal), float(p_drop), int(seed), int(rng_stream))
+def attention(qkv, key_ids, n_heads, causal=True, p_drop=0.0, seed=0, rng_stream=0, tf32=None):
+    """tf32: None = follow torch.backends.cuda.matmul.allow_tf32 (the linear layers' policy), True/False to force."""
+    return AttnFn.apply(qkv, key_ids, int(n_heads), bool(causal), float(p_drop), int(seed), int(rng_stream), tf32)
 
 
 # ------------------------------------------------------------------------------------------- K8 loss

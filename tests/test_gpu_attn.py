@@ -44,7 +44,7 @@ def test_attention_fwd_bwd(B, L, h, dh, p):
     seed = 99
     qkv, ids, dctx, ctx_ref, p_ref, dqkv_ref = _case(B, L, h, dh, p, seed)
     tq = t(qkv).requires_grad_()
-    ctx = ops.attention(tq, t(ids), h, True, p, seed, 5)
+    ctx = ops.attention(tq, t(ids), h, True, p, seed, 5, tf32=False)
     ctx.backward(t(dctx))
     torch.cuda.synchronize()
     valid = ids.astype(bool)                                   # fully-masked query rows are don't-care
@@ -70,7 +70,7 @@ def test_attention_masked_rows_match_fp32_reference_arithmetic(B, L, h, dh):
     ctx_ref, cache = O.attn_core_fwd(q, k, v, O.attention_mask(ids, np.float32), h)
     dq, dk, dv = O.attn_core_bwd(dctx, cache)
     tq = t(qkv).requires_grad_()
-    ctx = ops.attention(tq, t(ids), h, True, 0.0, 0, 0)
+    ctx = ops.attention(tq, t(ids), h, True, 0.0, 0, 0, tf32=False)
     ctx.backward(t(dctx))
     assert rel(ctx.detach().cpu().numpy(), ctx_ref) < 1e-5
     assert rel(tq.grad.cpu().numpy(), np.concatenate([dq, dk, dv], -1)) < 1e-4
@@ -85,7 +85,7 @@ def test_attention_fully_masked_rows_uniform_never_nan():
     ids = np.ones((B, L), dtype=np.int64)
     ids[0, :6] = 0
     ids[1, :] = 0                                              # a completely empty sequence
-    out = ops.AttnFn.apply(qkv, t(ids), h, True, 0.0, 0, 0)
+    out = ops.AttnFn.apply(qkv, t(ids), h, True, 0.0, 0, 0, False)
     probs_ref = O.softmax_lastdim(np.zeros((L,)) - 1e9)
     assert torch.isfinite(out).all()
     v = qkv[..., 2 * h * dh:]
@@ -102,7 +102,7 @@ def test_attention_bidirectional_no_padding():
     qkv = g.standard_normal((B, L, 3 * D)).astype(np.float32)
     q, k, v = (qkv[..., i * D:(i + 1) * D].astype(np.float64) for i in range(3))
     ref, _ = O.attn_core_fwd(q, k, v, np.zeros((B, 1, L, L)), h)
-    out = ops.attention(t(qkv), None, h, False, 0.0, 0, 0)
+    out = ops.attention(t(qkv), None, h, False, 0.0, 0, 0, tf32=False)
     assert rel(out.cpu().numpy(), ref) < TOL
 
 
@@ -113,3 +113,43 @@ def test_attention_rejects_bad_shapes():
         ops.attention(torch.zeros(1, 65, 3 * 64, device=dev()), None, 2, True)      # L > 64
     with pytest.raises(PixelRecB200Error):
         ops.attention(torch.zeros(1, 8, 3 * 96, device=dev()), None, 2, True)       # dh = 48
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core path
+TOL_TF32 = 2e-3      # TF32 operands (10-bit mantissa), fp32 accumulate; north_star tolerance is 1e-3 on loss/logits
+
+
+@pytest.mark.parametrize("B,L,h,dh", [(3, 10, 4, 32), (5, 20, 4, 128), (2, 7, 2, 128), (4, 20, 4, 16), (2, 12, 4, 64),
+                                      (3, 20, 4, 512), (2, 10, 2, 256), (3, 32, 2, 64), (70, 20, 4, 128), (2, 1, 4, 32),
+                                      (300, 20, 4, 128), (4, 16, 4, 8), (3, 24, 2, 128)])
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_attention_tensor_core_path(B, L, h, dh, p):
+    """mma.sync TF32 attention core vs the fp64 oracle (same masks, same Philox dropout bits as the fp32 kernel)."""
+    from pixelrec_b200 import ops
+    seed = 99
+    qkv, ids, dctx, ctx_ref, p_ref, dqkv_ref = _case(B, L, h, dh, p, seed)
+    tq = t(qkv).requires_grad_()
+    ctx = ops.attention(tq, t(ids), h, True, p, seed, 5, tf32=True)
+    ctx.backward(t(dctx))
+    torch.cuda.synchronize()
+    valid = ids.astype(bool)
+    got = ctx.detach().cpu().numpy()
+    assert np.isfinite(got).all() and torch.isfinite(tq.grad).all()
+    assert rel(got[valid], ctx_ref[valid]) < TOL_TF32
+    assert rel(tq.grad.cpu().numpy(), dqkv_ref) < TOL_TF32 * 2
+
+
+def test_attention_tensor_core_exact_on_tf32_representable_inputs():
+    """With operands exactly representable in TF32 the tensor-core path must agree with the fp32 FFMA kernel to fp32
+    rounding (1e-6), which pins the fragment layouts independently of TF32 rounding noise."""
+    from pixelrec_b200 import ops
+    g = np.random.default_rng(4)
+    B, L, h, dh = 6, 20, 4, 128
+    qkv = (g.integers(-8, 9, size=(B, L, 3 * h * dh)) / 8.0).astype(np.float32)
+    ids = np.ones((B, L), dtype=np.int64)
+    ids[1, :7] = 0
+    a = ops.attention(t(qkv), t(ids), h, True, 0.0, 0, 0, tf32=False)
+    b = ops.attention(t(qkv), t(ids), h, True, 0.0, 0, 0, tf32=True)
+    valid = torch.from_numpy(ids.astype(bool)).to(a.device)
+    # S = QK^T is exact; P is fp32 -> rounded to TF32 before P V, so O carries ~2^-11 relative error
+    assert (a - b)[valid].abs().max().item() < 2e-3 * a.abs().max().item()

@@ -146,3 +146,43 @@ def test_evaluator_and_early_stopping():
     assert early_stopping(0.5, 0.4, 3, 5) == (0.5, 0, False, True)
     assert early_stopping(0.3, 0.4, 5, 5) == (0.4, 6, True, False)
     assert early_stopping(0.3, 0.4, 0, 5, bigger=False) == (0.3, 0, False, True)
+
+
+def test_vit_encoder_state_dict_matches_hf_reference_layout():
+    """Our CLIP ViT item encoder has exactly the parameter names, shapes and ORDER of HF CLIPVisionModel wrapped in
+    the reference's MeanItemEncoder (golden generated from those classes), so checkpoints interchange and the
+    reference's index-based freezing (tune_scale) hits the same tensors."""
+    from pixelrec_b200.model.vit import CLIPVisionConfig, CLIPVisionModel, Identity, MeanItemEncoder
+    z = np.load(os.path.join(ROOT, "tests", "golden", "vit_small.npz"))
+    m = CLIPVisionModel(CLIPVisionConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4,
+                                         image_size=96, patch_size=32))
+    m.vision_model.post_layernorm = Identity()
+    enc = MeanItemEncoder(m, 64, 48, "relu")
+    ref_keys = [k[len("param/"):] for k in z.files if k.startswith("param/")]
+    ours = list(enc.state_dict().keys())
+    assert ours == ref_keys
+    for k, v in enc.state_dict().items():
+        assert tuple(v.shape) == z["param/" + k].shape, k
+    enc.load_state_dict({k: torch.from_numpy(z["param/" + k]) for k in ref_keys}, strict=True)
+    names = [n for n, _ in m.named_parameters()]
+    assert names[:5] == ["vision_model.embeddings.class_embedding", "vision_model.embeddings.patch_embedding.weight",
+                         "vision_model.embeddings.position_embedding.weight", "vision_model.pre_layrnorm.weight",
+                         "vision_model.pre_layrnorm.bias"]
+    assert names[5].endswith("layers.0.self_attn.k_proj.weight") and names[5 + 16].endswith("layers.1.self_attn.k_proj.weight")
+
+
+def test_mosasrec_plugin_constructs_from_reference_yaml_keys():
+    from pixelrec_b200.config import Config
+    c = Config(_yaml("PixelNet/sasrec.yaml", "overall/ViT.yaml"),
+               config_dict=dict(embedding_size=64, vit_config=dict(hidden_size=64, intermediate_size=128, num_hidden_layers=12,
+                                                                   num_attention_heads=4, image_size=64)))
+
+    class Dl:
+        item_num = 30
+    m = c.model_class(c, Dl())
+    assert c.model_class.__name__ == "MOSASRec" and len(c["optim_args"]) == 4
+    frozen = [n for n, p in m.named_parameters() if not p.requires_grad]
+    assert len(frozen) == 165 and all("visual_encoder" in n for n in frozen)            # ViT.yaml tune_scale: 165
+    trainable_vit = [n for n, p in m.named_parameters() if p.requires_grad and "visual_encoder" in n]
+    assert any("layers.10." in n for n in trainable_vit) and not any("layers.9." in n for n in trainable_vit)
+    assert "visual_encoder.rec_fc.0.weight" in dict(m.named_parameters())
