@@ -165,7 +165,7 @@ PR_API int pr_sasrec_attn_bwd_f32(const float* q, const float* k, const float* v
                            uint32_t rng_stream, float* dq, float* dk, float* dv, int64_t ld_grad, pr_stream_t stream);
 
 /* Tensor-core variant of the attention core (same arguments, same saved tensors, same dropout masks): the two
- * per-head products run as mma.sync TF32 with fp32 accumulation.  Limits: L <= 32, dh % 8 == 0.  Used when TF32
+ * per-head products run as mma.sync TF32 with fp32 accumulation, tiles arrive by 2-D swizzled TMA.  Limits: L <= 32, dh % 32 == 0.  Used when TF32
  * matrix products are allowed (as for the linear layers); the _f32 entry points above are the strict-fp32 path. */
 PR_API int pr_sasrec_attn_fwd_tf32(const float* q, const float* k, const float* v, int64_t ld, const int64_t* key_ids, int B,
                             int L, int h, int dh, int causal, float p_drop, uint64_t seed, uint32_t rng_stream,

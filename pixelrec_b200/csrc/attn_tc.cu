@@ -12,8 +12,13 @@
 // dQ = dS K) the key index is permuted (mma k = t <-> key 2t, k = t+4 <-> key 2t+1) so that the accumulator
 // fragments of S = Q K^T are bit-for-bit the A fragments of the next product: P never leaves registers.
 //
-// Shared-memory tiles have a padded row stride of CW+4 floats (rows are separate bulk copies, so padding is
-// free): both access patterns (row = g, col = t  and  row = 2t, col = g) are then bank-conflict-free.
+// Tiles are fed by 2-D TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B): one TMA operation moves an [L x 32-float] box
+// (the first version issued one 512-byte cp.async.bulk per row and was bound by the TMA engine's per-operation
+// rate: 1.8 TB/s at dh = 128 no matter how cheap the math was).  A [L x CW] tile is CW/32 such boxes; inside a box
+// element (r, c) sits at r*128 B + (((c/4) ^ (r%8)) * 16 B) + (c%4)*4 B, which makes both fragment access patterns
+// (row = g, col = k0 + t  and  row = 2t, col = n0 + g) bank-conflict-free without padding.
+#include <cuda.h>
+
 #include <algorithm>
 #include <math.h>
 
@@ -46,18 +51,28 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// word offset of element (r, c) inside a swizzled tile made of [ROWS x 32-float] boxes
+__device__ __forceinline__ int sw_off(int r, int c, int box_words) {
+    return (c >> 5) * box_words + r * 32 + (((((c >> 2) & 7) ^ (r & 7))) << 2) + (c & 3);
+}
+__device__ __forceinline__ void tma_box_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
 template <int MT, int NT>
 struct TcCfg {
-    static constexpr int ROWS = (16 * MT > 8 * NT) ? 16 * MT : 8 * NT;   // smem rows of a tile (padded, zero beyond L)
+    static constexpr int ROWS = (16 * MT > 8 * NT) ? 16 * MT : 8 * NT;   // smem rows of a box (padded, zero beyond L)
     static constexpr int LS = 16 * MT + 4;                               // row stride of the private L x L tiles (== 4 mod 16)
     static constexpr int PR = 8 * NT;                                     // rows of the private tiles
     static constexpr int NCW = 8;
 };
 
-// ring of [ROWS x (CW+4)] fp32 tiles; same protocol as attn.cu (see the note on `produced` there)
+// ring of swizzled [ROWS x CW] fp32 tiles (CW/32 boxes each); same protocol as attn.cu (see the note on `produced` there)
 struct TcRing {
     unsigned char* tiles; uint64_t* full; uint64_t* empty; volatile unsigned long long* produced; int S;
-    uint32_t tile_bytes, row_stride_bytes;
+    uint32_t tile_bytes, box_bytes;
     __device__ __forceinline__ const float* wait_full(long long t) const {
         const int s = (int)(t % S);
         while (*produced <= (unsigned long long)t) {
@@ -71,27 +86,28 @@ struct TcRing {
     }
 };
 
-__device__ __forceinline__ void tc_produce(const TcRing& ring, long long t, const float* src, long long ld, int L, int CW,
-                                           int lane) {
+// producer: one elected lane issues CW/32 box loads ([L rows x 32 floats] each) for tile t
+__device__ __forceinline__ void tc_produce(const TcRing& ring, long long t, const CUtensorMap* tm, int col0, int row0, int L,
+                                           int CW, int lane) {
     const int s = (int)(t % ring.S);
     mbar_wait(&ring.empty[s], (uint32_t)(((t / ring.S) & 1) ^ 1));
-    const uint32_t row_bytes = (uint32_t)CW * 4u;
-    if (lane == 0) mbar_arrive_expect_tx(&ring.full[s], row_bytes * (uint32_t)L);
+    if (lane == 0) {
+        mbar_arrive_expect_tx(&ring.full[s], (uint32_t)(CW * 4) * (uint32_t)L);
+        unsigned char* dst = ring.tiles + (size_t)s * ring.tile_bytes;
+        for (int bx = 0; bx < CW / 32; ++bx) tma_box_2d(dst + (size_t)bx * ring.box_bytes, tm, col0 + 32 * bx, row0, &ring.full[s]);
+        *ring.produced = (unsigned long long)t + 1ull;
+    }
     __syncwarp();
-    unsigned char* dst = ring.tiles + (size_t)s * ring.tile_bytes;
-    for (int r = lane; r < L; r += 32)
-        bulk_g2s(dst + (size_t)r * ring.row_stride_bytes, src + (long long)r * ld, row_bytes, &ring.full[s]);
-    if (lane == 0) *ring.produced = (unsigned long long)t + 1ull;
 }
 
 // zero the ring once (rows >= L are never written by the bulk copies and must read as 0), then init the barriers
-__device__ __forceinline__ TcRing tc_ring_setup(unsigned char* smem, int S, uint32_t tile_bytes, uint32_t row_stride_bytes,
+__device__ __forceinline__ TcRing tc_ring_setup(unsigned char* smem, int S, uint32_t tile_bytes, uint32_t box_bytes,
                                                 size_t private_bytes, unsigned char** private_base) {
     TcRing r;
     r.tiles = smem;
     r.S = S;
     r.tile_bytes = tile_bytes;
-    r.row_stride_bytes = row_stride_bytes;
+    r.box_bytes = box_bytes;
     *private_base = smem + (size_t)S * tile_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(*private_base + private_bytes);
     r.full = bars;
@@ -115,31 +131,28 @@ __device__ __forceinline__ TcRing tc_ring_setup(unsigned char* smem, int S, uint
 
 // acc[mi][nj] += X[16mi + {g, g+8}][d] * Y[8nj + g][d]  over one CW-wide tile pair  ("row x row" product)
 template <int MT, int NT>
-__device__ __forceinline__ void tc_rowrow(const float* __restrict__ Xs, const float* __restrict__ Ys, int stride, int CW,
+__device__ __forceinline__ void tc_rowrow(const float* __restrict__ Xs, const float* __restrict__ Ys, int box_words, int CW,
                                           int g, int t, float (&acc)[MT][NT][4]) {
-    const float* xr[MT][2];
-    const float* yr[NT];
-#pragma unroll
-    for (int mi = 0; mi < MT; ++mi) {
-        xr[mi][0] = Xs + (16 * mi + g) * stride + t;
-        xr[mi][1] = Xs + (16 * mi + g + 8) * stride + t;
-    }
-#pragma unroll
-    for (int nj = 0; nj < NT; ++nj) yr[nj] = Ys + (8 * nj + g) * stride + t;
+    // every row used here has (row & 7) == g, so the swizzle term is shared by all of them
 #pragma unroll 4
     for (int ks = 0; ks < CW; ks += 8) {
+        const int base = (ks >> 5) * box_words + t;
+        const int ch0 = ((((ks >> 2) & 7) ^ g) << 2), ch1 = (((((ks >> 2) + 1) & 7) ^ g) << 2);
         uint32_t a[MT][4], b[NT][2];
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi) {
-            a[mi][0] = to_tf32(xr[mi][0][ks]);
-            a[mi][1] = to_tf32(xr[mi][1][ks]);
-            a[mi][2] = to_tf32(xr[mi][0][ks + 4]);
-            a[mi][3] = to_tf32(xr[mi][1][ks + 4]);
+            const float* r0 = Xs + base + (16 * mi + g) * 32;
+            const float* r1 = r0 + 8 * 32;
+            a[mi][0] = to_tf32(r0[ch0]);
+            a[mi][1] = to_tf32(r1[ch0]);
+            a[mi][2] = to_tf32(r0[ch1]);
+            a[mi][3] = to_tf32(r1[ch1]);
         }
 #pragma unroll
         for (int nj = 0; nj < NT; ++nj) {
-            b[nj][0] = to_tf32(yr[nj][ks]);
-            b[nj][1] = to_tf32(yr[nj][ks + 4]);
+            const float* r0 = Ys + base + (8 * nj + g) * 32;
+            b[nj][0] = to_tf32(r0[ch0]);
+            b[nj][1] = to_tf32(r0[ch1]);
         }
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi)
@@ -151,16 +164,21 @@ __device__ __forceinline__ void tc_rowrow(const float* __restrict__ Xs, const fl
 // out[16mi + {g,g+8}][d] = sum_j Afrag[mi][ks] (x) X[8ks + {2t, 2t+1}][d]   for every 8-wide column tile of X; rows < L
 // are stored.  Afrag holds A fragments with the permuted contraction index (k = t <-> row 2t, k = t+4 <-> row 2t+1).
 template <int MT, int KT>
-__device__ __forceinline__ void tc_frag_times_tile(const uint32_t (&af)[MT][KT][4], const float* __restrict__ Xs, int stride,
+__device__ __forceinline__ void tc_frag_times_tile(const uint32_t (&af)[MT][KT][4], const float* __restrict__ Xs, int box_words,
                                                    int CW, int L, int g, int t, float* __restrict__ out, long long out_ld) {
     for (int nd = 0; nd < CW; nd += 8) {
+        // column nd + g: 16-byte chunk ((nd>>2) + (g>>2)) & 7, word g & 3; rows 2t / 2t+1 (+8ks): (row & 7) = 2t / 2t+1
+        const int cbase = (nd >> 5) * box_words + (g & 3);
+        const int chunk = ((nd >> 2) + (g >> 2)) & 7;
+        const int o0 = cbase + (2 * t) * 32 + ((chunk ^ (2 * t)) << 2);
+        const int o1 = cbase + (2 * t + 1) * 32 + ((chunk ^ (2 * t + 1)) << 2);
         float acc[MT][4];
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi) acc[mi][0] = acc[mi][1] = acc[mi][2] = acc[mi][3] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < KT; ++ks) {
-            const uint32_t b0 = to_tf32(Xs[(8 * ks + 2 * t) * stride + nd + g]);
-            const uint32_t b1 = to_tf32(Xs[(8 * ks + 2 * t + 1) * stride + nd + g]);
+            const uint32_t b0 = to_tf32(Xs[o0 + ks * 256]);       // 8 rows further: same (row & 7), +8*32 words
+            const uint32_t b1 = to_tf32(Xs[o1 + ks * 256]);
 #pragma unroll
             for (int mi = 0; mi < MT; ++mi) mma_tf32(acc[mi], af[mi][ks][0], af[mi][ks][1], af[mi][ks][2], af[mi][ks][3], b0, b1);
         }
@@ -200,13 +218,18 @@ __device__ __forceinline__ void tc_keep(const Philox& ph, unsigned stream, long 
 
 // =============================================================================================== forward
 template <int MT, int NT>
-__global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_fwd_kernel(TcArgs A) {
+__global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                                       const __grid_constant__ CUtensorMap tmK,
+                                                                                       const __grid_constant__ CUtensorMap tmV,
+                                                                                       const TcArgs A) {
     using C = TcCfg<MT, NT>;
     constexpr int NCW = C::NCW;
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int CW = min(A.dh, 128), stride = CW + 4;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzled boxes need 1 KiB alignment
+    const int CW = min(A.dh, 128);
+    constexpr int box_words = C::ROWS * 32;
     unsigned char* priv;
-    const TcRing ring = tc_ring_setup(smem, A.stages, (uint32_t)(C::ROWS * stride * 4), (uint32_t)(stride * 4), 0, &priv);
+    const TcRing ring = tc_ring_setup(smem, A.stages, (uint32_t)((CW / 32) * box_words * 4), (uint32_t)(box_words * 4), 0, &priv);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int L = A.L, nc = A.nc, T = 3 * nc;
     const long long n_items = (long long)A.B * A.h;
@@ -215,12 +238,12 @@ __global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_fwd_
         for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
             const long long b = item / A.h;
             const int hd = (int)(item - b * A.h);
-            const long long off = b * L * A.ld + (long long)hd * A.dh;
+            const int row0 = (int)(b * L), col0 = hd * A.dh;
             for (int c = 0; c < nc; ++c) {
-                tc_produce(ring, tt++, A.q + off + c * CW, A.ld, L, CW, lane);
-                tc_produce(ring, tt++, A.k + off + c * CW, A.ld, L, CW, lane);
+                tc_produce(ring, tt++, &tmQ, col0 + c * CW, row0, L, CW, lane);
+                tc_produce(ring, tt++, &tmK, col0 + c * CW, row0, L, CW, lane);
             }
-            for (int c = 0; c < nc; ++c) tc_produce(ring, tt++, A.v + off + c * CW, A.ld, L, CW, lane);
+            for (int c = 0; c < nc; ++c) tc_produce(ring, tt++, &tmV, col0 + c * CW, row0, L, CW, lane);
         }
         return;
     }
@@ -242,7 +265,7 @@ __global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_fwd_
         for (int c = 0; c < nc; ++c) {
             const float* Qs = ring.wait_full(t0 + 2 * c);
             const float* Ks = ring.wait_full(t0 + 2 * c + 1);
-            tc_rowrow<MT, NT>(Qs, Ks, stride, CW, g, t, acc);
+            tc_rowrow<MT, NT>(Qs, Ks, box_words, CW, g, t, acc);
             ring.release(t0 + 2 * c, lane);
             ring.release(t0 + 2 * c + 1, lane);
         }
@@ -314,7 +337,7 @@ __global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_fwd_
             const long long tv = t0 + 2 * nc + c;
             const float* Vs = ring.wait_full(tv);
             float* out = A.ctx + bb * L * (long long)(A.h * A.dh) + (long long)hd * A.dh + c * CW;
-            tc_frag_times_tile<MT, NT>(pf, Vs, stride, CW, L, g, t, out, (long long)A.h * A.dh);
+            tc_frag_times_tile<MT, NT>(pf, Vs, box_words, CW, L, g, t, out, (long long)A.h * A.dh);
             ring.release(tv, lane);
         }
     }
@@ -322,33 +345,37 @@ __global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_fwd_
 
 // =============================================================================================== backward
 template <int MT, int NT>
-__global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_bwd_kernel(TcArgs A) {
+__global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                                       const __grid_constant__ CUtensorMap tmK,
+                                                                                       const __grid_constant__ CUtensorMap tmV,
+                                                                                       const __grid_constant__ CUtensorMap tmDO,
+                                                                                       const TcArgs A) {
     using C = TcCfg<MT, NT>;
     constexpr int NCW = C::NCW, LS = C::LS, PR = C::PR;
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int CW = min(A.dh, 128), stride = CW + 4;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int CW = min(A.dh, 128);
+    constexpr int box_words = C::ROWS * 32;
     unsigned char* priv;
-    const TcRing ring = tc_ring_setup(smem, A.stages, (uint32_t)(C::ROWS * stride * 4), (uint32_t)(stride * 4),
+    const TcRing ring = tc_ring_setup(smem, A.stages, (uint32_t)((CW / 32) * box_words * 4), (uint32_t)(box_words * 4),
                                       (size_t)NCW * 2 * PR * LS * 4, &priv);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int L = A.L, nc = A.nc, T = 5 * nc;
     const long long n_items = (long long)A.B * A.h;
-    const long long Dm = (long long)A.h * A.dh;
     if (warp == NCW) {
         long long tt = 0;
         for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
             const long long b = item / A.h;
             const int hd = (int)(item - b * A.h);
-            const long long off = b * L * A.ld + (long long)hd * A.dh;
-            const long long offo = b * L * Dm + (long long)hd * A.dh;
+            const int row0 = (int)(b * L), col0 = hd * A.dh;
             for (int c = 0; c < nc; ++c) {
-                tc_produce(ring, tt++, A.dctx + offo + c * CW, Dm, L, CW, lane);
-                tc_produce(ring, tt++, A.v + off + c * CW, A.ld, L, CW, lane);
+                tc_produce(ring, tt++, &tmDO, col0 + c * CW, row0, L, CW, lane);
+                tc_produce(ring, tt++, &tmV, col0 + c * CW, row0, L, CW, lane);
             }
             for (int c = 0; c < nc; ++c) {
-                tc_produce(ring, tt++, A.dctx + offo + c * CW, Dm, L, CW, lane);
-                tc_produce(ring, tt++, A.k + off + c * CW, A.ld, L, CW, lane);
-                tc_produce(ring, tt++, A.q + off + c * CW, A.ld, L, CW, lane);
+                tc_produce(ring, tt++, &tmDO, col0 + c * CW, row0, L, CW, lane);
+                tc_produce(ring, tt++, &tmK, col0 + c * CW, row0, L, CW, lane);
+                tc_produce(ring, tt++, &tmQ, col0 + c * CW, row0, L, CW, lane);
             }
         }
         return;
@@ -373,7 +400,7 @@ __global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_bwd_
         for (int c = 0; c < nc; ++c) {              // dPd = dO V^T
             const float* dOs = ring.wait_full(t0 + 2 * c);
             const float* Vs = ring.wait_full(t0 + 2 * c + 1);
-            tc_rowrow<MT, NT>(dOs, Vs, stride, CW, g, t, acc);
+            tc_rowrow<MT, NT>(dOs, Vs, box_words, CW, g, t, acc);
             ring.release(t0 + 2 * c, lane);
             ring.release(t0 + 2 * c + 1, lane);
         }
@@ -428,38 +455,83 @@ __global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_bwd_
             const long long tb = t0 + 2 * nc + 3 * c;
             const long long go = bb * L * A.ld_grad + (long long)hd * A.dh + c * CW;
             const float* dOs = ring.wait_full(tb);
-            tc_frag_times_tile<MT, NT>(pT, dOs, stride, CW, L, g, t, A.dv + go, A.ld_grad);     // dV = Pd^T dO
+            tc_frag_times_tile<MT, NT>(pT, dOs, box_words, CW, L, g, t, A.dv + go, A.ld_grad);     // dV = Pd^T dO
             ring.release(tb, lane);
             const float* Ks = ring.wait_full(tb + 1);
-            tc_frag_times_tile<MT, NT>(dsf, Ks, stride, CW, L, g, t, A.dq + go, A.ld_grad);     // dQ = dS K
+            tc_frag_times_tile<MT, NT>(dsf, Ks, box_words, CW, L, g, t, A.dq + go, A.ld_grad);     // dQ = dS K
             ring.release(tb + 1, lane);
             const float* Qs = ring.wait_full(tb + 2);
-            tc_frag_times_tile<MT, NT>(dsT, Qs, stride, CW, L, g, t, A.dk + go, A.ld_grad);     // dK = dS^T Q
+            tc_frag_times_tile<MT, NT>(dsT, Qs, box_words, CW, L, g, t, A.dk + go, A.ld_grad);     // dK = dS^T Q
             ring.release(tb + 2, lane);
         }
     }
 }
 
 // ----------------------------------------------------------------------------------------------- host
+typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TcEncodeFn tc_encode_fn() {
+    static TcEncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (TcEncodeFn)p;
+    }
+    return fn;
+}
+// [rows, cols] fp32 view with row pitch ld floats -> boxes of [L rows x 32 floats], 128-byte swizzle
+static int tc_make_map(CUtensorMap* tm, const float* base, long long rows, long long cols, long long ld, int L) {
+    TcEncodeFn fn = tc_encode_fn();
+    if (!fn) {
+        set_last_error("cuTensorMapEncodeTiled entry point not available");
+        return PR_ERR_UNSUPPORTED;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32u, (cuuint32_t)L};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return PR_ERR_INVALID_ARGUMENT;
+    }
+    return PR_OK;
+}
+
 template <int MT, int NT, bool BWD>
 static int launch_tc(TcArgs& A, cudaStream_t stream) {
     using C = TcCfg<MT, NT>;
-    const int CW = std::min(A.dh, 128), stride = CW + 4;
-    const size_t tile = (size_t)C::ROWS * stride * 4;
+    const int CW = std::min(A.dh, 128);
+    const size_t tile = (size_t)(CW / 32) * C::ROWS * 128;
     const size_t priv = BWD ? (size_t)C::NCW * 2 * C::PR * C::LS * 4 : 0;
     const size_t bars = (size_t)2 * TC_MAX_STAGES * 8 + 16;
     const size_t budget = 220 * 1024;
-    PR_CHECK_ARG(priv + bars + 4 * tile <= budget, "attention(tf32): L=%d dh=%d does not fit shared memory", A.L, A.dh);
-    int S = (int)((budget - priv - bars) / tile);
+    PR_CHECK_ARG(priv + bars + 4 * tile + 1024 <= budget, "attention(tf32): L=%d dh=%d does not fit shared memory", A.L, A.dh);
+    int S = (int)((budget - priv - bars - 1024) / tile);
     S = std::min(S, TC_MAX_STAGES);
     S = std::min(S, std::max(4, (BWD ? 5 : 3) * A.nc * C::NCW * 2));
     A.stages = S;
-    const size_t smem = (size_t)S * tile + priv + bars;
-    auto kern = BWD ? attn_tc_bwd_kernel<MT, NT> : attn_tc_fwd_kernel<MT, NT>;
-    PR_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)S * tile + priv + bars + 1024;
+    const long long rows = (long long)A.B * A.L, cols = (long long)A.h * A.dh;
+    CUtensorMap tmQ, tmK, tmV, tmDO;
+    int rc;
+    if ((rc = tc_make_map(&tmQ, A.q, rows, cols, A.ld, A.L))) return rc;
+    if ((rc = tc_make_map(&tmK, A.k, rows, cols, A.ld, A.L))) return rc;
+    if ((rc = tc_make_map(&tmV, A.v, rows, cols, A.ld, A.L))) return rc;
     const long long n_items = (long long)A.B * A.h;
     const int grid = (int)std::max<long long>(1, std::min<long long>((n_items + C::NCW - 1) / C::NCW, sm_count()));
-    kern<<<grid, (C::NCW + 1) * 32, smem, stream>>>(A);
+    if (BWD) {
+        if ((rc = tc_make_map(&tmDO, A.dctx, rows, cols, cols, A.L))) return rc;
+        PR_CUDA_CALL(cudaFuncSetAttribute(attn_tc_bwd_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attn_tc_bwd_kernel<MT, NT><<<grid, (C::NCW + 1) * 32, smem, stream>>>(tmQ, tmK, tmV, tmDO, A);
+    } else {
+        PR_CUDA_CALL(cudaFuncSetAttribute(attn_tc_fwd_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attn_tc_fwd_kernel<MT, NT><<<grid, (C::NCW + 1) * 32, smem, stream>>>(tmQ, tmK, tmV, A);
+    }
     PR_CUDA_LAUNCH_CHECK(BWD ? "attn_tc_bwd_kernel" : "attn_tc_fwd_kernel");
     return PR_OK;
 }
@@ -477,7 +549,7 @@ static int check_tc(const char* who, const float* q, const float* k, const float
                     float p) {
     PR_CHECK_ARG(B > 0 && L > 0 && h > 0 && dh > 0, "%s: bad shape B=%d L=%d h=%d dh=%d", who, B, L, h, dh);
     PR_CHECK_ARG(L <= 32, "%s: L=%d > 32 unsupported by the tensor-core path", who, L);
-    PR_CHECK_ARG(dh % 8 == 0 && (dh <= 128 || dh % 128 == 0), "%s: dh=%d must be a multiple of 8, <= 128 or a multiple of 128", who, dh);
+    PR_CHECK_ARG(dh % 32 == 0 && (dh <= 128 || dh % 128 == 0), "%s: dh=%d must be 32, 64, 96, 128 or a multiple of 128", who, dh);
     PR_CHECK_ARG(ld % 4 == 0 && ld >= (long long)h * dh, "%s: ld=%lld must be a multiple of 4 and >= h*dh", who, ld);
     PR_CHECK_ARG(q && k && v && aligned16(q) && aligned16(k) && aligned16(v), "%s: q/k/v null or not 16-byte aligned", who);
     PR_CHECK_ARG(p >= 0.f && p < 1.f, "%s: dropout p outside [0,1)", who);

@@ -311,7 +311,7 @@ class AttnFn(torch.autograd.Function):
         dh = D // n_heads
         if tf32 is None:   # follow the policy of the linear layers (model.layers / matmul_precision)
             tf32 = torch.backends.cuda.matmul.allow_tf32
-        tf32 = bool(tf32) and Lq <= 32 and dh % 8 == 0
+        tf32 = bool(tf32) and Lq <= 32 and dh % 32 == 0 and (dh <= 128 or dh % 128 == 0)
         fwd = _L().pr_sasrec_attn_fwd_tf32 if tf32 else _L().pr_sasrec_attn_fwd_f32
         if key_ids is not None:
             _req(key_ids, torch.int64, "key_ids")

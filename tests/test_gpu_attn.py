@@ -121,11 +121,13 @@ TOL_TF32 = 2e-3      # TF32 operands (10-bit mantissa), fp32 accumulate; north_s
 
 @pytest.mark.parametrize("B,L,h,dh", [(3, 10, 4, 32), (5, 20, 4, 128), (2, 7, 2, 128), (4, 20, 4, 16), (2, 12, 4, 64),
                                       (3, 20, 4, 512), (2, 10, 2, 256), (3, 32, 2, 64), (70, 20, 4, 128), (2, 1, 4, 32),
-                                      (300, 20, 4, 128), (4, 16, 4, 8), (3, 24, 2, 128)])
+                                      (300, 20, 4, 128), (4, 16, 4, 96), (3, 24, 2, 128)])
 @pytest.mark.parametrize("p", [0.0, 0.1])
 def test_attention_tensor_core_path(B, L, h, dh, p):
     """mma.sync TF32 attention core vs the fp64 oracle (same masks, same Philox dropout bits as the fp32 kernel)."""
     from pixelrec_b200 import ops
+    if dh % 32:
+        pytest.skip("tensor-core path needs dh % 32 == 0 (the fp32 kernel covers the rest)")
     seed = 99
     qkv, ids, dctx, ctx_ref, p_ref, dqkv_ref = _case(B, L, h, dh, p, seed)
     tq = t(qkv).requires_grad_()

@@ -33,6 +33,11 @@ def test_vit_item_encoder_matches_hf_golden():
     for k, p in enc.named_parameters():
         if "grad/" + k in z.files:
             assert p.grad is not None, k
+            n += 1
+            if k.endswith("k_proj.bias"):            # mathematically zero (softmax shift invariance): fp noise only
+                assert p.grad.abs().max().item() < 1e-5
+                continue
+            n -= 1
             assert rel(p.grad.cpu().numpy(), z["grad/" + k], 1e-6) < 1e-3, (k, rel(p.grad.cpu().numpy(), z["grad/" + k], 1e-6))
             n += 1
         else:
