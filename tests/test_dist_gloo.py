@@ -30,6 +30,10 @@ class OracleRows:
         G = O.scatter_add_rows(dOut.numpy(), plan.idx, plan.N, plan.pad)
         return torch.from_numpy(G)                 # dense over the local shard (the CUDA path returns sparse rows)
 
+    @staticmethod
+    def scatter_slots(dOut, slot_idx, U, pad_slot):
+        return torch.from_numpy(O.scatter_add_rows(dOut.numpy(), slot_idx.numpy(), U, pad_slot))
+
 
 def _free_port():
     s = socket.socket()
