@@ -26,8 +26,6 @@
 
 namespace pr {
 
-constexpr int TC_MAX_STAGES = 32;
-
 struct TcArgs {
     const float* q; const float* k; const float* v; long long ld;
     const long long* key_ids;
@@ -36,7 +34,6 @@ struct TcArgs {
     float inv_sqrt;
     float* ctx; float* probs;
     const float* dctx; float* dq; float* dk; float* dv; long long ld_grad;
-    int stages;
 };
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
@@ -63,70 +60,56 @@ __device__ __forceinline__ void tma_box_2d(void* smem_dst, const CUtensorMap* tm
 
 template <int MT, int NT>
 struct TcCfg {
-    static constexpr int ROWS = (16 * MT > 8 * NT) ? 16 * MT : 8 * NT;   // smem rows of a box (padded, zero beyond L)
+    static constexpr int ROWS = 8 * NT;                                  // smem rows of a box (keys; zero beyond L)
     static constexpr int LS = 16 * MT + 4;                               // row stride of the private L x L tiles (== 4 mod 16)
     static constexpr int PR = 8 * NT;                                     // rows of the private tiles
-    static constexpr int NCW = 8;
 };
 
-// ring of swizzled [ROWS x CW] fp32 tiles (CW/32 boxes each); same protocol as attn.cu (see the note on `produced` there)
-struct TcRing {
-    unsigned char* tiles; uint64_t* full; uint64_t* empty; volatile unsigned long long* produced; int S;
-    uint32_t tile_bytes, box_bytes;
-    __device__ __forceinline__ const float* wait_full(long long t) const {
-        const int s = (int)(t % S);
-        while (*produced <= (unsigned long long)t) {
+// One warp = one self-contained pipeline: it issues the 2-D TMA loads of its own (batch, head) items into private
+// buffers, waits on its own mbarriers and computes.  (The first design fed 8 consumer warps from one producer warp
+// through a shared in-order ring: ncu showed the consumers spinning on the ring ~60 % of the time and the producer
+// blocked on full stages -- 0.28 of the HBM roofline no matter how cheap the math was.)
+struct WarpBuf {
+    float* buf[3];            // three [ROWS x CW] swizzled tiles
+    uint64_t* bar[3];         // one mbarrier per tile
+    unsigned phase[3];        // parity to wait for next
+    __device__ __forceinline__ void issue(int i, const CUtensorMap* tm, int col0, int row0, int L, int CW, int box_bytes,
+                                          int lane) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar[i], (uint32_t)(CW * 4) * (uint32_t)L);
+            for (int bx = 0; bx < CW / 32; ++bx)
+                tma_box_2d(reinterpret_cast<unsigned char*>(buf[i]) + (size_t)bx * box_bytes, tm, col0 + 32 * bx, row0, bar[i]);
         }
-        mbar_wait(&full[s], (uint32_t)((t / S) & 1));
-        return reinterpret_cast<const float*>(tiles + (size_t)s * tile_bytes);
     }
-    __device__ __forceinline__ void release(long long t, int lane) const {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[(int)(t % S)]);
+    __device__ __forceinline__ void wait(int i) {
+        mbar_wait(bar[i], phase[i] & 1u);
+        phase[i] ^= 1u;
     }
 };
 
-// producer: one elected lane issues CW/32 box loads ([L rows x 32 floats] each) for tile t
-__device__ __forceinline__ void tc_produce(const TcRing& ring, long long t, const CUtensorMap* tm, int col0, int row0, int L,
-                                           int CW, int lane) {
-    const int s = (int)(t % ring.S);
-    mbar_wait(&ring.empty[s], (uint32_t)(((t / ring.S) & 1) ^ 1));
-    if (lane == 0) {
-        mbar_arrive_expect_tx(&ring.full[s], (uint32_t)(CW * 4) * (uint32_t)L);
-        unsigned char* dst = ring.tiles + (size_t)s * ring.tile_bytes;
-        for (int bx = 0; bx < CW / 32; ++bx) tma_box_2d(dst + (size_t)bx * ring.box_bytes, tm, col0 + 32 * bx, row0, &ring.full[s]);
-        *ring.produced = (unsigned long long)t + 1ull;
-    }
-    __syncwarp();
-}
-
-// zero the ring once (rows >= L are never written by the bulk copies and must read as 0), then init the barriers
-__device__ __forceinline__ TcRing tc_ring_setup(unsigned char* smem, int S, uint32_t tile_bytes, uint32_t box_bytes,
-                                                size_t private_bytes, unsigned char** private_base) {
-    TcRing r;
-    r.tiles = smem;
-    r.S = S;
-    r.tile_bytes = tile_bytes;
-    r.box_bytes = box_bytes;
-    *private_base = smem + (size_t)S * tile_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(*private_base + private_bytes);
-    r.full = bars;
-    r.empty = bars + TC_MAX_STAGES;
-    r.produced = reinterpret_cast<volatile unsigned long long*>(bars + 2 * TC_MAX_STAGES);
+// carve per-warp buffers out of dynamic smem, zero them (rows >= L must read as 0), init the barriers
+template <int NW>
+__device__ __forceinline__ WarpBuf warp_setup(unsigned char* smem, int tile_bytes, size_t private_bytes_per_warp,
+                                              unsigned char** priv, int warp) {
+    const size_t per_warp = (size_t)3 * tile_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NW * per_warp + NW * private_bytes_per_warp);
     float4* z = reinterpret_cast<float4*>(smem);
-    const size_t n16 = ((size_t)S * tile_bytes + private_bytes) / 16;
+    const size_t n16 = (NW * per_warp + NW * private_bytes_per_warp) / 16;
     for (size_t i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (threadIdx.x == 0) {
-        *r.produced = 0ull;
-        for (int s = 0; s < S; ++s) {
-            mbar_init(&r.full[s], 1);
-            mbar_init(&r.empty[s], 1);
-        }
+        for (int i = 0; i < 3 * NW; ++i) mbar_init(&bars[i], 1);
         fence_mbar_init();
     }
-    fence_proxy_async();      // generic-proxy zero fill is ordered before the async-proxy bulk copies
+    fence_proxy_async();
     __syncthreads();
-    return r;
+    WarpBuf w;
+    for (int i = 0; i < 3; ++i) {
+        w.buf[i] = reinterpret_cast<float*>(smem + warp * per_warp + (size_t)i * tile_bytes);
+        w.bar[i] = &bars[3 * warp + i];
+        w.phase[i] = 0;
+    }
+    *priv = smem + NW * per_warp + (size_t)warp * private_bytes_per_warp;
+    return w;
 }
 
 // acc[mi][nj] += X[16mi + {g, g+8}][d] * Y[8nj + g][d]  over one CW-wide tile pair  ("row x row" product)
@@ -142,7 +125,8 @@ __device__ __forceinline__ void tc_rowrow(const float* __restrict__ Xs, const fl
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi) {
             const float* r0 = Xs + base + (16 * mi + g) * 32;
-            const float* r1 = r0 + 8 * 32;
+            // query rows >= 8*NT do not exist in the tile (and are >= L): alias them, their results are discarded
+            const float* r1 = (16 * mi + 8 < 8 * NT) ? r0 + 8 * 32 : r0;
             a[mi][0] = to_tf32(r0[ch0]);
             a[mi][1] = to_tf32(r1[ch0]);
             a[mi][2] = to_tf32(r0[ch1]);
@@ -217,63 +201,66 @@ __device__ __forceinline__ void tc_keep(const Philox& ph, unsigned stream, long 
 }
 
 // =============================================================================================== forward
-template <int MT, int NT>
-__global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                                                       const __grid_constant__ CUtensorMap tmK,
-                                                                                       const __grid_constant__ CUtensorMap tmV,
-                                                                                       const TcArgs A) {
+template <int MT, int NT, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                 const __grid_constant__ CUtensorMap tmK,
+                                                                 const __grid_constant__ CUtensorMap tmV, const TcArgs A) {
     using C = TcCfg<MT, NT>;
-    constexpr int NCW = C::NCW;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzled boxes need 1 KiB alignment
     const int CW = min(A.dh, 128);
-    constexpr int box_words = C::ROWS * 32;
-    unsigned char* priv;
-    const TcRing ring = tc_ring_setup(smem, A.stages, (uint32_t)((CW / 32) * box_words * 4), (uint32_t)(box_words * 4), 0, &priv);
+    constexpr int box_words = C::ROWS * 32, box_bytes = box_words * 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int L = A.L, nc = A.nc, T = 3 * nc;
+    unsigned char* priv;
+    WarpBuf wb = warp_setup<NW>(smem, (CW / 32) * box_bytes, 0, &priv, warp);
+    const int L = A.L, nc = A.nc;
     const long long n_items = (long long)A.B * A.h;
-    // contiguous block of items per CTA: the h heads of a sequence (adjacent 512-byte pieces of the same rows) and
-    // consecutive sequences are read by the same SM back to back -> DRAM pages / L2 lines are reused while hot
-    // (a round-robin assignment scattered every row over 12 SMs and ran at 0.28 of the HBM roofline)
-    const long long items_per_cta = (n_items + gridDim.x - 1) / gridDim.x;
-    const long long item_lo = (long long)blockIdx.x * items_per_cta;
-    const long long item_hi = min(n_items, item_lo + items_per_cta);
-    if (warp == NCW) {
-        long long tt = 0;
-        for (long long item = item_lo; item < item_hi; ++item) {
-            const long long b = item / A.h;
-            const int hd = (int)(item - b * A.h);
-            const int row0 = (int)(b * L), col0 = hd * A.dh;
-            for (int c = 0; c < nc; ++c) {
-                tc_produce(ring, tt++, &tmQ, col0 + c * CW, row0, L, CW, lane);
-                tc_produce(ring, tt++, &tmK, col0 + c * CW, row0, L, CW, lane);
-            }
-            for (int c = 0; c < nc; ++c) tc_produce(ring, tt++, &tmV, col0 + c * CW, row0, L, CW, lane);
-        }
-        return;
-    }
+    // contiguous items per warp: the heads of a sequence and consecutive sequences stream through the same SM
+    const long long n_warps = (long long)gridDim.x * NW;
+    const long long per_warp = (n_items + n_warps - 1) / n_warps;
+    const long long item_lo = ((long long)blockIdx.x * NW + warp) * per_warp;
+    const long long item_hi = min(n_items, item_lo + per_warp);
+    if (item_lo >= item_hi) return;
     const int g = lane >> 2, t = lane & 3;
     const Philox ph(A.seed);
     const unsigned thr = drop_threshold(A.p_drop);
     const float inv_keep = 1.0f / (1.0f - A.p_drop);
-    long long n = 0;
-    for (long long item = item_lo; item < item_hi; ++item, ++n) {
-        if ((int)(n % NCW) != warp) continue;
+    auto coords = [&](long long item, int& row0, int& col0) {
+        const long long b = item / A.h;
+        row0 = (int)(b * L);
+        col0 = (int)(item - b * A.h) * A.dh;
+    };
+    {   // prologue: first item's Q, K (chunk 0) and V (chunk 0)
+        int r0, c0;
+        coords(item_lo, r0, c0);
+        wb.issue(0, &tmQ, c0, r0, L, CW, box_bytes, lane);
+        wb.issue(1, &tmK, c0, r0, L, CW, box_bytes, lane);
+        wb.issue(2, &tmV, c0, r0, L, CW, box_bytes, lane);
+    }
+    for (long long item = item_lo; item < item_hi; ++item) {
         const long long bb = item / A.h;
         const int hd = (int)(item - bb * A.h);
-        const long long t0 = n * T;
+        int row0, col0, nrow0 = 0, ncol0 = 0;
+        coords(item, row0, col0);
+        const bool has_next = item + 1 < item_hi;
+        if (has_next) coords(item + 1, nrow0, ncol0);
         float acc[MT][NT][4];
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
             for (int nj = 0; nj < NT; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = acc[mi][nj][2] = acc[mi][nj][3] = 0.f;
         for (int c = 0; c < nc; ++c) {
-            const float* Qs = ring.wait_full(t0 + 2 * c);
-            const float* Ks = ring.wait_full(t0 + 2 * c + 1);
-            tc_rowrow<MT, NT>(Qs, Ks, box_words, CW, g, t, acc);
-            ring.release(t0 + 2 * c, lane);
-            ring.release(t0 + 2 * c + 1, lane);
+            wb.wait(0);
+            wb.wait(1);
+            tc_rowrow<MT, NT>(wb.buf[0], wb.buf[1], box_words, CW, g, t, acc);
+            __syncwarp();                                    // every lane is done reading before the buffers are refilled
+            if (c + 1 < nc) {
+                wb.issue(0, &tmQ, col0 + (c + 1) * CW, row0, L, CW, box_bytes, lane);
+                wb.issue(1, &tmK, col0 + (c + 1) * CW, row0, L, CW, box_bytes, lane);
+            } else if (has_next) {                           // next item's Q, K load while this item does softmax + P V
+                wb.issue(0, &tmQ, ncol0, nrow0, L, CW, box_bytes, lane);
+                wb.issue(1, &tmK, ncol0, nrow0, L, CW, box_bytes, lane);
+            }
         }
         // ---- mask + softmax on the accumulator fragments: thread holds rows {16mi+g, +8}, cols 8nj + 2t + {0,1}
         bool kvalid[NT][2];
@@ -290,7 +277,7 @@ __global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_fwd_
 #pragma unroll
             for (int hrow = 0; hrow < 2; ++hrow) {
                 const int i = 16 * mi + g + 8 * hrow;
-                float s[NT][2];
+                float sc[NT][2];
                 float mx = -INFINITY;
 #pragma unroll
                 for (int nj = 0; nj < NT; ++nj)
@@ -300,7 +287,7 @@ __global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_fwd_
                         const bool ok = kvalid[nj][e] && (!A.causal || j <= i);
                         float x = acc[mi][nj][2 * hrow + e] * A.inv_sqrt + (ok ? 0.0f : -1e9f);
                         if (j >= L) x = -INFINITY;
-                        s[nj][e] = x;
+                        sc[nj][e] = x;
                         mx = fmaxf(mx, x);
                     }
                 mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
@@ -310,8 +297,8 @@ __global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_fwd_
                 for (int nj = 0; nj < NT; ++nj)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const float ex = (8 * nj + 2 * t + e < L) ? expf(s[nj][e] - mx) : 0.f;
-                        s[nj][e] = ex;
+                        const float ex = (8 * nj + 2 * t + e < L) ? expf(sc[nj][e] - mx) : 0.f;
+                        sc[nj][e] = ex;
                         sum += ex;
                     }
                 sum += __shfl_xor_sync(0xffffffffu, sum, 1);
@@ -322,7 +309,7 @@ __global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_fwd_
 #pragma unroll
                 for (int nj = 0; nj < NT; ++nj) {
                     const int j = 8 * nj + 2 * t;
-                    const float p0 = s[nj][0] * inv, p1 = s[nj][1] * inv;
+                    const float p0 = sc[nj][0] * inv, p1 = sc[nj][1] * inv;
                     if (i < L) {
                         float* pr = A.probs + (item * L + i) * L + j;
                         if (j < L) pr[0] = p0;
@@ -340,84 +327,83 @@ __global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_fwd_
             }
         // ---- O = drop(P) V, chunk by chunk
         for (int c = 0; c < nc; ++c) {
-            const long long tv = t0 + 2 * nc + c;
-            const float* Vs = ring.wait_full(tv);
+            wb.wait(2);
             float* out = A.ctx + bb * L * (long long)(A.h * A.dh) + (long long)hd * A.dh + c * CW;
-            tc_frag_times_tile<MT, NT>(pf, Vs, box_words, CW, L, g, t, out, (long long)A.h * A.dh);
-            ring.release(tv, lane);
+            tc_frag_times_tile<MT, NT>(pf, wb.buf[2], box_words, CW, L, g, t, out, (long long)A.h * A.dh);
+            __syncwarp();
+            if (c + 1 < nc) wb.issue(2, &tmV, col0 + (c + 1) * CW, row0, L, CW, box_bytes, lane);
+            else if (has_next) wb.issue(2, &tmV, ncol0, nrow0, L, CW, box_bytes, lane);
         }
     }
 }
 
 // =============================================================================================== backward
-template <int MT, int NT>
-__global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                                                       const __grid_constant__ CUtensorMap tmK,
-                                                                                       const __grid_constant__ CUtensorMap tmV,
-                                                                                       const __grid_constant__ CUtensorMap tmDO,
-                                                                                       const TcArgs A) {
+//   buffers: 0 = dO (kept for both phases when nc == 1), 1 = V then K, 2 = Q
+template <int MT, int NT, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                 const __grid_constant__ CUtensorMap tmK,
+                                                                 const __grid_constant__ CUtensorMap tmV,
+                                                                 const __grid_constant__ CUtensorMap tmDO, const TcArgs A) {
     using C = TcCfg<MT, NT>;
-    constexpr int NCW = C::NCW, LS = C::LS, PR = C::PR;
+    constexpr int LS = C::LS, PR = C::PR;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int CW = min(A.dh, 128);
-    constexpr int box_words = C::ROWS * 32;
-    unsigned char* priv;
-    const TcRing ring = tc_ring_setup(smem, A.stages, (uint32_t)((CW / 32) * box_words * 4), (uint32_t)(box_words * 4),
-                                      (size_t)NCW * 2 * PR * LS * 4, &priv);
+    constexpr int box_words = C::ROWS * 32, box_bytes = box_words * 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int L = A.L, nc = A.nc, T = 5 * nc;
+    unsigned char* priv;
+    WarpBuf wb = warp_setup<NW>(smem, (CW / 32) * box_bytes, (size_t)2 * PR * LS * 4, &priv, warp);
+    const int L = A.L, nc = A.nc;
     const long long n_items = (long long)A.B * A.h;
-    // contiguous block of items per CTA: the h heads of a sequence (adjacent 512-byte pieces of the same rows) and
-    // consecutive sequences are read by the same SM back to back -> DRAM pages / L2 lines are reused while hot
-    // (a round-robin assignment scattered every row over 12 SMs and ran at 0.28 of the HBM roofline)
-    const long long items_per_cta = (n_items + gridDim.x - 1) / gridDim.x;
-    const long long item_lo = (long long)blockIdx.x * items_per_cta;
-    const long long item_hi = min(n_items, item_lo + items_per_cta);
-    if (warp == NCW) {
-        long long tt = 0;
-        for (long long item = item_lo; item < item_hi; ++item) {
-            const long long b = item / A.h;
-            const int hd = (int)(item - b * A.h);
-            const int row0 = (int)(b * L), col0 = hd * A.dh;
-            for (int c = 0; c < nc; ++c) {
-                tc_produce(ring, tt++, &tmDO, col0 + c * CW, row0, L, CW, lane);
-                tc_produce(ring, tt++, &tmV, col0 + c * CW, row0, L, CW, lane);
-            }
-            for (int c = 0; c < nc; ++c) {
-                tc_produce(ring, tt++, &tmDO, col0 + c * CW, row0, L, CW, lane);
-                tc_produce(ring, tt++, &tmK, col0 + c * CW, row0, L, CW, lane);
-                tc_produce(ring, tt++, &tmQ, col0 + c * CW, row0, L, CW, lane);
-            }
-        }
-        return;
-    }
-    float* Pd_s = reinterpret_cast<float*>(priv) + (size_t)warp * 2 * PR * LS;   // Pd_s[i][j]   (i < 8NT rows, j < 16MT cols)
+    const long long n_warps = (long long)gridDim.x * NW;
+    const long long per_warp = (n_items + n_warps - 1) / n_warps;
+    const long long item_lo = ((long long)blockIdx.x * NW + warp) * per_warp;
+    const long long item_hi = min(n_items, item_lo + per_warp);
+    if (item_lo >= item_hi) return;
+    float* Pd_s = reinterpret_cast<float*>(priv);             // Pd_s[i][j]   (i < 8NT rows, j < 16MT cols)
     float* dS_s = Pd_s + PR * LS;
     const int g = lane >> 2, t = lane & 3;
     const Philox ph(A.seed);
     const unsigned thr = drop_threshold(A.p_drop);
     const float inv_keep = 1.0f / (1.0f - A.p_drop);
-    long long n = 0;
-    for (long long item = item_lo; item < item_hi; ++item, ++n) {
-        if ((int)(n % NCW) != warp) continue;
+    auto coords = [&](long long item, int& row0, int& col0) {
+        const long long b = item / A.h;
+        row0 = (int)(b * L);
+        col0 = (int)(item - b * A.h) * A.dh;
+    };
+    {
+        int r0, c0;
+        coords(item_lo, r0, c0);
+        wb.issue(0, &tmDO, c0, r0, L, CW, box_bytes, lane);
+        wb.issue(1, &tmV, c0, r0, L, CW, box_bytes, lane);
+        wb.issue(2, &tmQ, c0, r0, L, CW, box_bytes, lane);
+    }
+    for (long long item = item_lo; item < item_hi; ++item) {
         const long long bb = item / A.h;
         const int hd = (int)(item - bb * A.h);
-        const long long t0 = n * T;
+        int row0, col0, nrow0 = 0, ncol0 = 0;
+        coords(item, row0, col0);
+        const bool has_next = item + 1 < item_hi;
+        if (has_next) coords(item + 1, nrow0, ncol0);
         float acc[MT][NT][4];
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
             for (int nj = 0; nj < NT; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = acc[mi][nj][2] = acc[mi][nj][3] = 0.f;
         for (int c = 0; c < nc; ++c) {              // dPd = dO V^T
-            const float* dOs = ring.wait_full(t0 + 2 * c);
-            const float* Vs = ring.wait_full(t0 + 2 * c + 1);
-            tc_rowrow<MT, NT>(dOs, Vs, box_words, CW, g, t, acc);
-            ring.release(t0 + 2 * c, lane);
-            ring.release(t0 + 2 * c + 1, lane);
+            wb.wait(0);
+            wb.wait(1);
+            tc_rowrow<MT, NT>(wb.buf[0], wb.buf[1], box_words, CW, g, t, acc);
+            __syncwarp();
+            if (c + 1 < nc) {
+                wb.issue(0, &tmDO, col0 + (c + 1) * CW, row0, L, CW, box_bytes, lane);
+                wb.issue(1, &tmV, col0 + (c + 1) * CW, row0, L, CW, box_bytes, lane);
+            } else {
+                if (nc > 1) wb.issue(0, &tmDO, col0, row0, L, CW, box_bytes, lane);   // chunk 0 of dO again for phase 2
+                wb.issue(1, &tmK, col0, row0, L, CW, box_bytes, lane);                 // K chunk 0 replaces V
+            }
         }
         uint32_t dsf[MT][NT][4];                    // dS as A fragments (key-permuted) for dQ = dS K
-        __syncwarp();                               // previous item's transposed reads are done
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
@@ -463,18 +449,25 @@ __global__ void __launch_bounds__((TcCfg<MT, NT>::NCW + 1) * 32, 1) attn_tc_bwd_
         uint32_t pT[MT][NT][4], dsT[MT][NT][4];
         tc_load_transposed<MT, NT>(Pd_s, LS, g, t, pT);       // A = Pd^T  (rows = keys j, contraction over queries i)
         tc_load_transposed<MT, NT>(dS_s, LS, g, t, dsT);      // A = dS^T
+        __syncwarp();                                         // private tiles may be overwritten by the next item
         for (int c = 0; c < nc; ++c) {
-            const long long tb = t0 + 2 * nc + 3 * c;
             const long long go = bb * L * A.ld_grad + (long long)hd * A.dh + c * CW;
-            const float* dOs = ring.wait_full(tb);
-            tc_frag_times_tile<MT, NT>(pT, dOs, box_words, CW, L, g, t, A.dv + go, A.ld_grad);     // dV = Pd^T dO
-            ring.release(tb, lane);
-            const float* Ks = ring.wait_full(tb + 1);
-            tc_frag_times_tile<MT, NT>(dsf, Ks, box_words, CW, L, g, t, A.dq + go, A.ld_grad);     // dQ = dS K
-            ring.release(tb + 1, lane);
-            const float* Qs = ring.wait_full(tb + 2);
-            tc_frag_times_tile<MT, NT>(dsT, Qs, box_words, CW, L, g, t, A.dk + go, A.ld_grad);     // dK = dS^T Q
-            ring.release(tb + 2, lane);
+            const bool last = (c + 1 == nc);
+            if (nc > 1 || c > 0) wb.wait(0);                   // (nc == 1: dO of phase 1 is still resident)
+            tc_frag_times_tile<MT, NT>(pT, wb.buf[0], box_words, CW, L, g, t, A.dv + go, A.ld_grad);     // dV = Pd^T dO
+            __syncwarp();
+            if (!last) wb.issue(0, &tmDO, col0 + (c + 1) * CW, row0, L, CW, box_bytes, lane);
+            else if (has_next) wb.issue(0, &tmDO, ncol0, nrow0, L, CW, box_bytes, lane);
+            wb.wait(1);
+            tc_frag_times_tile<MT, NT>(dsf, wb.buf[1], box_words, CW, L, g, t, A.dq + go, A.ld_grad);    // dQ = dS K
+            __syncwarp();
+            if (!last) wb.issue(1, &tmK, col0 + (c + 1) * CW, row0, L, CW, box_bytes, lane);
+            else if (has_next) wb.issue(1, &tmV, ncol0, nrow0, L, CW, box_bytes, lane);
+            wb.wait(2);
+            tc_frag_times_tile<MT, NT>(dsT, wb.buf[2], box_words, CW, L, g, t, A.dk + go, A.ld_grad);    // dK = dS^T Q
+            __syncwarp();
+            if (!last) wb.issue(2, &tmQ, col0 + (c + 1) * CW, row0, L, CW, box_bytes, lane);
+            else if (has_next) wb.issue(2, &tmQ, ncol0, nrow0, L, CW, box_bytes, lane);
         }
     }
 }
@@ -514,20 +507,13 @@ static int tc_make_map(CUtensorMap* tm, const float* base, long long rows, long 
     return PR_OK;
 }
 
-template <int MT, int NT, bool BWD>
-static int launch_tc(TcArgs& A, cudaStream_t stream) {
+template <int MT, int NT, int NW, bool BWD>
+static int launch_tc_nw(TcArgs& A, cudaStream_t stream) {
     using C = TcCfg<MT, NT>;
     const int CW = std::min(A.dh, 128);
     const size_t tile = (size_t)(CW / 32) * C::ROWS * 128;
-    const size_t priv = BWD ? (size_t)C::NCW * 2 * C::PR * C::LS * 4 : 0;
-    const size_t bars = (size_t)2 * TC_MAX_STAGES * 8 + 16;
-    const size_t budget = 220 * 1024;
-    PR_CHECK_ARG(priv + bars + 4 * tile + 1024 <= budget, "attention(tf32): L=%d dh=%d does not fit shared memory", A.L, A.dh);
-    int S = (int)((budget - priv - bars - 1024) / tile);
-    S = std::min(S, TC_MAX_STAGES);
-    S = std::min(S, std::max(4, (BWD ? 5 : 3) * A.nc * C::NCW * 2));
-    A.stages = S;
-    const size_t smem = (size_t)S * tile + priv + bars + 1024;
+    const size_t priv = BWD ? (size_t)2 * C::PR * C::LS * 4 : 0;
+    const size_t smem = (size_t)NW * (3 * tile + priv) + (size_t)3 * NW * 8 + 1024;
     const long long rows = (long long)A.B * A.L, cols = (long long)A.h * A.dh;
     CUtensorMap tmQ, tmK, tmV, tmDO;
     int rc;
@@ -535,23 +521,32 @@ static int launch_tc(TcArgs& A, cudaStream_t stream) {
     if ((rc = tc_make_map(&tmK, A.k, rows, cols, A.ld, A.L))) return rc;
     if ((rc = tc_make_map(&tmV, A.v, rows, cols, A.ld, A.L))) return rc;
     const long long n_items = (long long)A.B * A.h;
-    // contiguous block of items per CTA: the h heads of a sequence (adjacent 512-byte pieces of the same rows) and
-    // consecutive sequences are read by the same SM back to back -> DRAM pages / L2 lines are reused while hot
-    // (a round-robin assignment scattered every row over 12 SMs and ran at 0.28 of the HBM roofline)
-    const long long items_per_cta = (n_items + gridDim.x - 1) / gridDim.x;
-    const long long item_lo = (long long)blockIdx.x * items_per_cta;
-    const long long item_hi = min(n_items, item_lo + items_per_cta);
-    const int grid = (int)std::max<long long>(1, std::min<long long>((n_items + C::NCW - 1) / C::NCW, sm_count()));
+    const int grid = (int)std::max<long long>(1, std::min<long long>((n_items + NW - 1) / NW, sm_count()));
     if (BWD) {
         if ((rc = tc_make_map(&tmDO, A.dctx, rows, cols, cols, A.L))) return rc;
-        PR_CUDA_CALL(cudaFuncSetAttribute(attn_tc_bwd_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_tc_bwd_kernel<MT, NT><<<grid, (C::NCW + 1) * 32, smem, stream>>>(tmQ, tmK, tmV, tmDO, A);
+        PR_CUDA_CALL(cudaFuncSetAttribute(attn_tc_bwd_kernel<MT, NT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attn_tc_bwd_kernel<MT, NT, NW><<<grid, NW * 32, smem, stream>>>(tmQ, tmK, tmV, tmDO, A);
     } else {
-        PR_CUDA_CALL(cudaFuncSetAttribute(attn_tc_fwd_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_tc_fwd_kernel<MT, NT><<<grid, (C::NCW + 1) * 32, smem, stream>>>(tmQ, tmK, tmV, A);
+        PR_CUDA_CALL(cudaFuncSetAttribute(attn_tc_fwd_kernel<MT, NT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attn_tc_fwd_kernel<MT, NT, NW><<<grid, NW * 32, smem, stream>>>(tmQ, tmK, tmV, A);
     }
     PR_CUDA_LAUNCH_CHECK(BWD ? "attn_tc_bwd_kernel" : "attn_tc_fwd_kernel");
     return PR_OK;
+}
+
+// warps per CTA: as many private pipelines as 220 KiB of shared memory hold (3 tiles [+ 2 private L x L tiles] per warp)
+template <int MT, int NT, bool BWD>
+static int launch_tc(TcArgs& A, cudaStream_t stream) {
+    using C = TcCfg<MT, NT>;
+    const int CW = std::min(A.dh, 128);
+    const size_t per_warp = (size_t)3 * (CW / 32) * C::ROWS * 128 + (BWD ? (size_t)2 * C::PR * C::LS * 4 : 0) + 24;
+    const int fit = (int)((220 * 1024 - 1024) / per_warp);
+    PR_CHECK_ARG(fit >= 2, "attention(tf32): L=%d dh=%d does not fit shared memory", A.L, A.dh);
+    if (fit >= 8) return launch_tc_nw<MT, NT, 8, BWD>(A, stream);
+    if (fit >= 6) return launch_tc_nw<MT, NT, 6, BWD>(A, stream);
+    if (fit >= 5) return launch_tc_nw<MT, NT, 5, BWD>(A, stream);
+    if (fit >= 4) return launch_tc_nw<MT, NT, 4, BWD>(A, stream);
+    return launch_tc_nw<MT, NT, 2, BWD>(A, stream);
 }
 
 template <bool BWD>
