@@ -213,7 +213,12 @@ def run_ours(args, out):
     resident = [(a.to(dev), b.to(dev)) for a, b in host]
     h2d = host[0][0].numel() * 8 + host[0][1].numel() * 8
 
-    def step(batch):
+    side = torch.cuda.Stream(device=dev)
+
+    def step(batch, nxt=None):
+        if nxt is not None and world > 1:
+            with torch.cuda.stream(side):    # index-exchange plan of the NEXT batch, overlapped with this step
+                model.prefetch(nxt)
         opt.zero_grad()
         loss = model(batch)
         loss.backward()
@@ -246,7 +251,7 @@ def run_ours(args, out):
     ops.PROFILE.update(on=True, names={"gather_rows"}, events={})
     launches0 = ops.LAUNCHES["count"]
     clocks.start()
-    ms = timed(lambda i: step(resident[i % POOL]), args.steps)
+    ms = timed(lambda i: step(resident[i % POOL], resident[(i + 1) % POOL]), args.steps)
     clk = clocks.stop()
     launches = ops.LAUNCHES["count"] - launches0
     gather_n, gather_ms = ops.profile_summary().get("gather_rows", (0, float("nan")))
@@ -254,9 +259,19 @@ def run_ours(args, out):
     value = B * world * args.steps / (ms / 1e3)
 
     # ---- timed region 2 (e2e): pinned-host batches copied in each step, loss read back each step
+    e2e_next = {}
+
+    from pixelrec_b200.trainer.trainer import Lookahead
+    look = Lookahead(model, dev)             # the public Trainer's own lookahead (H2D + plan of the next batch on a side stream)
+
     def e2e_step(i):
-        a, b = host[i % POOL]
-        loss = step((a.to(dev, non_blocking=True), b.to(dev, non_blocking=True)))
+        staged = e2e_next.pop(i, None) or look.stage(host[i % POOL])
+        cur = look.acquire(staged)
+        e2e_next[i + 1] = look.stage(host[(i + 1) % POOL])
+        opt.zero_grad()
+        loss = model(cur)
+        loss.backward()
+        opt.step()
         return loss.item()
     for i in range(2):
         e2e_step(i)

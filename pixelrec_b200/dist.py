@@ -101,7 +101,7 @@ class ExchangePlan:
 class ShardedGatherFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, W_local, idx, table):
-        plan = ExchangePlan(idx, table.world, table.group, table.padding_idx)
+        plan = table.take_plan(idx)
         D = W_local.shape[1]
         rows_send = ROWS.gather(W_local, plan.recv_rows)                              # owner-side gather
         rows_recv = torch.empty(plan.U, D, dtype=W_local.dtype, device=W_local.device)
@@ -155,6 +155,41 @@ class ShardedTableEmbedding(nn.Module):
         if self.sink.row2slot is None:
             self.sink.enable_sparse()
         return ShardedGatherFn.apply(self.weight, idx.contiguous(), self)
+
+    # ---- index-plan prefetch -----------------------------------------------------------------------------------
+    # The exchange plan (unique ids, owner bucketing, split sizes, index all_to_all) depends only on the batch's
+    # indices, not on the weights, and it needs a host sync for NCCL's split sizes.  Computed inline it drains the
+    # GPU at the top of every step; computed one batch ahead on a side stream the sync overlaps with the previous
+    # step's kernels.  Every rank must call prefetch / forward in the same order (they issue collectives).
+    @staticmethod
+    def _key(idx):
+        return (idx.data_ptr(), tuple(idx.shape), idx._version)
+
+    def prefetch(self, idx):
+        """Build the exchange plan of a FUTURE batch on the CURRENT stream (call it inside a side-stream context,
+        see trainer.Lookahead); forward() picks it up and makes its own stream wait for it."""
+        if not idx.is_cuda:
+            return
+        idx = idx.contiguous()
+        if getattr(self, "_plans", None) is None:
+            self._plans = {}
+        plan = ExchangePlan(idx, self.world, self.group, self.padding_idx)
+        plan.ready = torch.cuda.Event()
+        plan.ready.record(torch.cuda.current_stream(idx.device))
+        plan.keepalive = idx
+        if len(self._plans) > 4:
+            self._plans.clear()
+        self._plans[self._key(idx)] = plan
+
+    def take_plan(self, idx):
+        plans = getattr(self, "_plans", None)
+        plan = plans.pop(self._key(idx), None) if plans else None
+        if plan is None:
+            return ExchangePlan(idx, self.world, self.group, self.padding_idx)
+        torch.cuda.current_stream(idx.device).wait_event(plan.ready)
+        for tns in (plan.inverse, plan.perm, plan.expand, plan.recv_rows):   # allocated on the side stream, used on this one
+            tns.record_stream(torch.cuda.current_stream(idx.device))
+        return plan
 
     @torch.no_grad()
     def full_weight(self):

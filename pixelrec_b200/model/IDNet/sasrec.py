@@ -78,6 +78,11 @@ class SASRec(BaseModel):
         # pos/neg dot products + log-sigmoid loss                  sasrec.py:88-92 (targets read in place from E)
         return ops.bpr_loss(out, E, masked_index, slab)
 
+    def prefetch(self, interaction):
+        """Optional hint with the NEXT batch (same tensors that will be passed to forward): lets a row-sharded table
+        overlap its index exchange with the current step (Trainer._train_epoch and bench.py call it)."""
+        self.item_embedding.prefetch(interaction[0])
+
     @torch.no_grad()
     def predict(self, item_seq, item_feature):
         """sasrec.py:94-113: scores [B_e, N] = encoder(item_seq)[:, -1] @ item_feature.T"""

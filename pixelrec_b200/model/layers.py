@@ -51,6 +51,9 @@ class TableEmbedding(nn.Module):
     def forward(self, idx):
         return ops.GatherFn.apply(self.weight, idx.contiguous(), self.padding_idx, self.sink, self.gather_impl)
 
+    def prefetch(self, idx):
+        """no-op on one GPU (dist.ShardedTableEmbedding pre-computes its exchange plan here)"""
+
     def extra_repr(self):
         return f"{self.num_embeddings}, {self.embedding_dim}, padding_idx={self.padding_idx}"
 

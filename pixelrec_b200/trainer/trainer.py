@@ -28,6 +28,39 @@ def unwrap(model):
     return model.module if hasattr(model, "module") else model
 
 
+class Lookahead:
+    """One-batch lookahead on a side stream: the next batch's host->device copy and (for a row-sharded table) its
+    index-exchange plan -- which needs a host sync for NCCL's split sizes -- run while the current step's kernels
+    execute, instead of draining the GPU at the top of every step."""
+
+    def __init__(self, model, device):
+        self.model = model
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None
+
+    def stage(self, batch):
+        """host batch -> (device batch, ready event)"""
+        if self.stream is None:
+            return batch, None
+        with torch.cuda.stream(self.stream):
+            dev = tuple(t.to(self.device, non_blocking=True) for t in batch) if isinstance(batch, (tuple, list)) \
+                else batch.to(self.device, non_blocking=True)
+            if hasattr(self.model, "prefetch"):
+                self.model.prefetch(dev)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return dev, ev
+
+    def acquire(self, staged):
+        dev, ev = staged
+        if ev is not None:
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
+            for t in (dev if isinstance(dev, (tuple, list)) else (dev,)):
+                t.record_stream(cur)
+        return dev
+
+
 class Trainer:
     def __init__(self, config, model):
         self.config = config
@@ -87,9 +120,16 @@ class Trainer:
     def _train_epoch(self, train_data, epoch_idx, loss_func=None, show_progress=False):
         self.model.train()
         total = torch.zeros((), device=self.device)
-        for data in train_data:
+        look = Lookahead(unwrap(self.model), self.device)
+        it = iter(train_data)
+        nxt = next(it, None)
+        staged = look.stage(nxt) if nxt is not None else None
+        while staged is not None:
+            data = look.acquire(staged)
+            nxt = next(it, None)
+            staged = look.stage(nxt) if nxt is not None else None     # overlaps with this step's kernels
             self.optimizer.zero_grad()
-            losses = self.model(self.to_device(data))
+            losses = self.model(data)
             total += losses.detach()
             losses.backward()
             if self.clip_grad_norm:

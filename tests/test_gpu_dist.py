@@ -73,8 +73,14 @@ def _worker(rank, world, port, state, q):
         opt = FusedAdamW(m.parameters(), lr=1e-3, weight_decay=0.1, tables=[m.item_embedding])
         items, mask = _batch(world)
         sl = slice(rank * B, (rank + 1) * B)
+        batch = (torch.from_numpy(items[sl]).to(dev), torch.from_numpy(mask[sl]).to(dev))
+        side = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(side):                   # exchange plan built ahead of time on a side stream
+            m.prefetch(batch)
+        assert len(m.item_embedding._plans) == 1
         opt.zero_grad()
-        loss = m((torch.from_numpy(items[sl]).to(dev), torch.from_numpy(mask[sl]).to(dev)))
+        loss = m(batch)
+        assert len(m.item_embedding._plans) == 0        # forward consumed the prefetched plan
         loss.backward()
         opt.step()
         lt = loss.detach().clone()
