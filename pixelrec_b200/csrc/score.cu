@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_topk_kernel(const __grid_
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ __align__(8) uint64_t full_bar[SC_STAGES], empty_bar[SC_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_slot;
+    float* cand_smem = reinterpret_cast<float*>(smem + (size_t)SC_STAGES * SC_STAGE_BYTES);   // [128 epilogue threads][33]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.x % a.m_tiles, split = blockIdx.x / a.m_tiles;
     const int t_begin = split * a.tiles_per_split;
@@ -218,10 +219,19 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_topk_kernel(const __grid_
                     mx = fmaxf(mx, v[j]);
                 }
                 if (mx > val[K - 1]) {
+                    // rare path (after the first tiles only a few chunks per row hold a candidate): park the chunk in this
+                    // thread's shared-memory row and walk it with ONE copy of the insertion code.  (Inlining 32 unrolled
+                    // insertions made the epilogue ~40 KB of SASS: ncu showed 32 % no_instruction stalls -- I-cache misses --
+                    // and the tensor pipe only 20 % active because the TMEM buffers were drained too slowly.)
                     const int c0 = tile * SC_BN + c * 32;
+                    float* myrow = cand_smem + (threadIdx.x - 64) * 33;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (v[j] > val[K - 1]) topk_insert<K>(val, idx, v[j], c0 + j);
+                    for (int j = 0; j < 32; ++j) myrow[j] = v[j];
+#pragma unroll 1
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = myrow[j];
+                        if (x > val[K - 1]) topk_insert<K>(val, idx, x, c0 + j);
+                    }
                 }
             }
             tc_fence_before();
@@ -415,7 +425,7 @@ extern "C" int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float*
     a.kblocks = (int)(D / SC_BK);
     a.m_tiles = p.m_tiles; a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.n_splits = p.n_splits;
     a.n_words = p.n_words; a.mask = mask; a.cand_val = cand_val; a.cand_idx = cand_idx;
-    const size_t smem = (size_t)SC_STAGES * SC_STAGE_BYTES + 1024;     // +1 KiB slack for the 1024-byte alignment
+    const size_t smem = (size_t)SC_STAGES * SC_STAGE_BYTES + 128 * 33 * 4 + 1024;     // ring + candidate rows + 1 KiB alignment slack
     const int grid = p.m_tiles * p.n_splits;
     if (p.K == 16) {
         PR_CUDA_CALL(cudaFuncSetAttribute(score_topk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
