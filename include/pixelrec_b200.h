@@ -139,12 +139,24 @@ PR_API int pr_add_ln_bwd_f32(const float* dy, const float* h, int64_t h_seq_stri
                       int64_t D, float p_pre, float p_post, uint64_t seed, uint32_t stream_pre, uint32_t stream_post,
                       float* dh, int64_t dh_seq_stride, int dh_accumulate, float* dres, float* partials,
                       int n_partials, pr_stream_t stream);
+/* Same as pr_add_ln_bwd_f32 plus a third partial matrix: column sums of dh = bias gradient of the Linear that produced h
+ * (layers.py:613 `dense`, :669 `dense_2`): partials [3, n_partials, D] = (dgamma, dbeta, dbias).  Saves one full re-read
+ * of dh per Linear (ATen's sum(0) in the autograd path). */
+PR_API int pr_add_ln_bwd_bias_f32(const float* dy, const float* h, int64_t h_seq_stride, int64_t rows_per_seq, const float* res,
+                      int64_t res_period, const float* gamma, const float* mean, const float* rstd, int64_t rows,
+                      int64_t D, float p_pre, float p_post, uint64_t seed, uint32_t stream_pre, uint32_t stream_post,
+                      float* dh, int64_t dh_seq_stride, int dh_accumulate, float* dres, float* partials,
+                      int n_partials, pr_stream_t stream);
 /* out[m, c] = sum_p partials[m, p, c]   (m < n_mats, p < n_partials), fixed order */
 PR_API int pr_colsum_f32(const float* partials, int n_mats, int n_partials, int64_t D, float* out, pr_stream_t stream);
 
 /* activation of the feed-forward layer: layers.py:640-660,667   y = act(x) ; dx = act'(x) * dy */
 PR_API int pr_act_fwd_f32(const float* x, int64_t n, int act, float* y, pr_stream_t stream);
 PR_API int pr_act_bwd_f32(const float* x, const float* dy, int64_t n, int act, float* dx, pr_stream_t stream);
+/* row-wise variant that also emits per-CTA partial column sums of dx [n_partials, cols] (bias grad of dense_1, layers.py:666) */
+PR_API int pr_act_bwd_bias_partials(int64_t rows, int64_t cols);
+PR_API int pr_act_bwd_bias_f32(const float* x, const float* dy, int64_t rows, int64_t cols, int act, float* dx, float* partials,
+                        int n_partials, pr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K4+K6  causal self-attention core.   replaces get_attention_mask sasrec.py:119-126 and

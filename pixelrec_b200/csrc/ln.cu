@@ -121,13 +121,13 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 4 : 1) add_ln_fwd_kernel(LnA
 
 // backward.  dgamma/dbeta: per-lane register accumulators over the rows of this warp, then a
 // fixed-order sum over the CTA's warps in shared memory -> partials[{0,1}][blockIdx.x][D]
-template <int VPL>
-__global__ void __launch_bounds__(256, (VPL <= 4) ? 3 : 1) add_ln_bwd_kernel(LnArgs a, const float* __restrict__ dy,
+template <int VPL, bool DBIAS>
+__global__ void __launch_bounds__(256, (VPL <= 4) ? 2 : 1) add_ln_bwd_kernel(LnArgs a, const float* __restrict__ dy,
                                                          const float* __restrict__ mean_in,
                                                          const float* __restrict__ rstd_in, float* __restrict__ dh,
                                                          long long dh_seq_stride, int dh_accumulate,
                                                          float* __restrict__ dres, float* __restrict__ partials) {
-    extern __shared__ float4 sm_acc[];  // [2][D4]
+    extern __shared__ float4 sm_acc[];  // [2 or 3][D4]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const long long warp = (long long)blockIdx.x * nw + wid;
     const long long nwarps = (long long)gridDim.x * nw;
@@ -136,9 +136,11 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 3 : 1) add_ln_bwd_kernel(LnA
     const float ik_pre = 1.0f / (1.0f - a.p_pre), ik_post = 1.0f / (1.0f - a.p_post);
     const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
     const float invD = 1.0f / (float)(a.D4 * 4);
-    float4 accg[VPL], accb[VPL];
+    float4 accg[VPL], accb[VPL], accd[DBIAS ? VPL : 1];      // accd: column sums of dh = bias grad of the producing Linear
 #pragma unroll
     for (int j = 0; j < VPL; ++j) accg[j] = accb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < (DBIAS ? VPL : 1); ++j) accd[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     for (long long row = warp; row < a.rows; row += nwarps) {
         float4 z[VPL];
@@ -191,6 +193,7 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 3 : 1) add_ln_bwd_kernel(LnA
                 dz.w = rstd * (dxh[j].w - s1 - z[j].w * s2);
                 if (dr4) dr4[c] = dz;
                 if (a.p_pre > 0.f) dz = apply_keep(dz, mk_pre[j >> 1] >> (4 * (j & 1)), ik_pre);
+                if (DBIAS) { accd[DBIAS ? j : 0].x += dz.x; accd[DBIAS ? j : 0].y += dz.y; accd[DBIAS ? j : 0].z += dz.z; accd[DBIAS ? j : 0].w += dz.w; }
                 if (dh_accumulate) {
                     const float4 o = dh4[c];
                     dz.x += o.x; dz.y += o.y; dz.z += o.z; dz.w += o.w;
@@ -209,7 +212,13 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 3 : 1) add_ln_bwd_kernel(LnA
                     if (w == 0) {
                         sm_acc[c] = accg[j];
                         sm_acc[a.D4 + c] = accb[j];
+                        if (DBIAS) sm_acc[2 * a.D4 + c] = accd[DBIAS ? j : 0];
                     } else {
+                        if (DBIAS) {
+                            float4 u = sm_acc[2 * a.D4 + c];
+                            u.x += accd[DBIAS ? j : 0].x; u.y += accd[DBIAS ? j : 0].y; u.z += accd[DBIAS ? j : 0].z; u.w += accd[DBIAS ? j : 0].w;
+                            sm_acc[2 * a.D4 + c] = u;
+                        }
                         float4 t = sm_acc[c];
                         t.x += accg[j].x; t.y += accg[j].y; t.z += accg[j].z; t.w += accg[j].w;
                         sm_acc[c] = t;
@@ -224,9 +233,11 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 3 : 1) add_ln_bwd_kernel(LnA
     }
     float4* pg = reinterpret_cast<float4*>(partials) + (long long)blockIdx.x * a.D4;
     float4* pb = reinterpret_cast<float4*>(partials) + ((long long)gridDim.x + blockIdx.x) * a.D4;
+    float4* pd = reinterpret_cast<float4*>(partials) + (2 * (long long)gridDim.x + blockIdx.x) * a.D4;
     for (int c = threadIdx.x; c < a.D4; c += blockDim.x) {
         pg[c] = sm_acc[c];
         pb[c] = sm_acc[a.D4 + c];
+        if (DBIAS) pd[c] = sm_acc[2 * a.D4 + c];
     }
 }
 
@@ -313,6 +324,54 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
     for (long long i = (n4 << 2) + i0; i < n; i += stride) dx[i] = dy[i] * act_df(x[i], act);
 }
 
+// dx = act'(x) * dy and per-CTA partial column sums of dx (= bias grad of the Linear that produced x): warp per row
+template <int VPL>
+__global__ void __launch_bounds__(256) act_bwd_bias_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                           long long rows, int C4, int act, float* __restrict__ dx,
+                                                           float* __restrict__ partials) {
+    extern __shared__ float4 sm_acc[];  // [C4]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const long long warp = (long long)blockIdx.x * nw + wid, nwarps = (long long)gridDim.x * nw;
+    float4 acc[VPL];
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long row = warp; row < rows; row += nwarps) {
+        const float4* x4 = reinterpret_cast<const float4*>(x) + row * C4;
+        const float4* d4 = reinterpret_cast<const float4*>(dy) + row * C4;
+        float4* o4 = reinterpret_cast<float4*>(dx) + row * C4;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const int c = lane + 32 * j;
+            if (c < C4) {
+                const float4 v = ldg_stream(x4 + c);
+                float4 d = ldg_stream(d4 + c);
+                d.x *= act_df(v.x, act); d.y *= act_df(v.y, act); d.z *= act_df(v.z, act); d.w *= act_df(v.w, act);
+                o4[c] = d;
+                acc[j].x += d.x; acc[j].y += d.y; acc[j].z += d.z; acc[j].w += d.w;
+            }
+        }
+    }
+    for (int w = 0; w < nw; ++w) {
+        if (wid == w) {
+#pragma unroll
+            for (int j = 0; j < VPL; ++j) {
+                const int c = lane + 32 * j;
+                if (c < C4) {
+                    if (w == 0) sm_acc[c] = acc[j];
+                    else {
+                        float4 t = sm_acc[c];
+                        t.x += acc[j].x; t.y += acc[j].y; t.z += acc[j].z; t.w += acc[j].w;
+                        sm_acc[c] = t;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    float4* p = reinterpret_cast<float4*>(partials) + (long long)blockIdx.x * C4;
+    for (int c = threadIdx.x; c < C4; c += blockDim.x) p[c] = sm_acc[c];
+}
+
 static int ln_grid(long long rows) {
     const long long by_rows = (rows + 7) / 8;
     return (int)std::max<long long>(1, std::min<long long>(by_rows, (long long)sm_count() * 8));
@@ -373,7 +432,7 @@ extern "C" int pr_add_ln_bwd_partials(int64_t rows, int64_t D) {
     return ln_bwd_grid(rows);
 }
 
-extern "C" int pr_add_ln_bwd_f32(const float* dy, const float* h, int64_t h_seq_stride, int64_t rows_per_seq,
+static int add_ln_bwd_impl(bool want_dbias, const float* dy, const float* h, int64_t h_seq_stride, int64_t rows_per_seq,
                                  const float* res, int64_t res_period, const float* gamma, const float* mean,
                                  const float* rstd, int64_t rows, int64_t D, float p_pre, float p_post, uint64_t seed,
                                  uint32_t stream_pre, uint32_t stream_post, float* dh, int64_t dh_seq_stride,
@@ -387,7 +446,7 @@ extern "C" int pr_add_ln_bwd_f32(const float* dy, const float* h, int64_t h_seq_
     PR_CHECK_ARG(n_partials == (rows > 0 ? grid : 1), "pr_add_ln_bwd_f32: n_partials=%d, expected %d (pr_add_ln_bwd_partials)",
                  n_partials, rows > 0 ? grid : 1);
     if (rows == 0) {
-        PR_CUDA_CALL(cudaMemsetAsync(partials, 0, sizeof(float) * 2 * (size_t)D, stream));
+        PR_CUDA_CALL(cudaMemsetAsync(partials, 0, sizeof(float) * (want_dbias ? 3 : 2) * (size_t)D, stream));
         return PR_OK;
     }
     PR_CHECK_ARG(dy && mean && rstd && dh, "pr_add_ln_bwd_f32: null pointer");
@@ -397,12 +456,34 @@ extern "C" int pr_add_ln_bwd_f32(const float* dy, const float* h, int64_t h_seq_
                  "pr_add_ln_bwd_f32: pointers must be 16-byte aligned");
     LnArgs a{h, h_seq_stride, rows_per_seq, res, res_period, gamma, nullptr, 0.f, rows, (int)(D / 4),
              p_pre, p_post, seed, stream_pre, stream_post};
-    const size_t smem = (size_t)2 * D * sizeof(float);
-#define CALL(V) add_ln_bwd_kernel<V><<<grid, 256, smem, stream>>>(a, dy, mean, rstd, dh, dh_seq_stride, dh_accumulate, dres, partials)
+    const size_t smem = (size_t)(want_dbias ? 3 : 2) * D * sizeof(float);
+#define CALL(V)                                                                                                     \
+    do {                                                                                                            \
+        if (want_dbias) add_ln_bwd_kernel<V, true><<<grid, 256, smem, stream>>>(a, dy, mean, rstd, dh, dh_seq_stride, dh_accumulate, dres, partials); \
+        else add_ln_bwd_kernel<V, false><<<grid, 256, smem, stream>>>(a, dy, mean, rstd, dh, dh_seq_stride, dh_accumulate, dres, partials); \
+    } while (0)
     PR_DISPATCH_VPL(a.D4, CALL);
 #undef CALL
     PR_CUDA_LAUNCH_CHECK("add_ln_bwd_kernel");
     return PR_OK;
+}
+
+extern "C" int pr_add_ln_bwd_f32(const float* dy, const float* h, int64_t h_seq_stride, int64_t rows_per_seq,
+                                 const float* res, int64_t res_period, const float* gamma, const float* mean,
+                                 const float* rstd, int64_t rows, int64_t D, float p_pre, float p_post, uint64_t seed,
+                                 uint32_t stream_pre, uint32_t stream_post, float* dh, int64_t dh_seq_stride,
+                                 int dh_accumulate, float* dres, float* partials, int n_partials, pr_stream_t stream_) {
+    return add_ln_bwd_impl(false, dy, h, h_seq_stride, rows_per_seq, res, res_period, gamma, mean, rstd, rows, D, p_pre, p_post,
+                           seed, stream_pre, stream_post, dh, dh_seq_stride, dh_accumulate, dres, partials, n_partials, stream_);
+}
+
+extern "C" int pr_add_ln_bwd_bias_f32(const float* dy, const float* h, int64_t h_seq_stride, int64_t rows_per_seq,
+                                      const float* res, int64_t res_period, const float* gamma, const float* mean,
+                                      const float* rstd, int64_t rows, int64_t D, float p_pre, float p_post, uint64_t seed,
+                                      uint32_t stream_pre, uint32_t stream_post, float* dh, int64_t dh_seq_stride,
+                                      int dh_accumulate, float* dres, float* partials, int n_partials, pr_stream_t stream_) {
+    return add_ln_bwd_impl(true, dy, h, h_seq_stride, rows_per_seq, res, res_period, gamma, mean, rstd, rows, D, p_pre, p_post,
+                           seed, stream_pre, stream_post, dh, dh_seq_stride, dh_accumulate, dres, partials, n_partials, stream_);
 }
 
 extern "C" int pr_colsum_f32(const float* partials, int n_mats, int n_partials, int64_t D, float* out,
@@ -434,5 +515,36 @@ extern "C" int pr_act_bwd_f32(const float* x, const float* dy, int64_t n, int ac
     const int grid = (int)std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, (long long)sm_count() * 16));
     act_bwd_kernel<<<grid, 256, 0, stream>>>(x, dy, n, act, dx);
     PR_CUDA_LAUNCH_CHECK("act_bwd_kernel");
+    return PR_OK;
+}
+
+extern "C" int pr_act_bwd_bias_partials(int64_t rows, int64_t cols) {
+    (void)cols;
+    if (rows <= 0) return 1;
+    return (int)std::max<long long>(1, std::min<long long>((rows + 7) / 8, (long long)sm_count() * 4));
+}
+
+extern "C" int pr_act_bwd_bias_f32(const float* x, const float* dy, int64_t rows, int64_t cols, int act, float* dx,
+                                   float* partials, int n_partials, pr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PR_CHECK_ARG(rows > 0 && cols > 0 && cols % 4 == 0 && cols <= 8192, "pr_act_bwd_bias_f32: bad shape rows=%lld cols=%lld", (long long)rows,
+                 (long long)cols);
+    PR_CHECK_ARG(act >= 0 && act <= PR_ACT_QUICK_GELU, "pr_act_bwd_bias_f32: bad act");
+    PR_CHECK_ARG(x && dy && dx && partials && aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(partials),
+                 "pr_act_bwd_bias_f32: null/unaligned pointer");
+    const int grid = pr_act_bwd_bias_partials(rows, cols);
+    PR_CHECK_ARG(n_partials == grid, "pr_act_bwd_bias_f32: n_partials=%d, expected %d", n_partials, grid);
+    const int C4 = (int)(cols / 4);
+    const size_t smem = (size_t)cols * sizeof(float);
+#define CALLA(V) act_bwd_bias_kernel<V><<<grid, 256, smem, stream>>>(x, dy, rows, C4, act, dx, partials)
+    if (C4 <= 32) CALLA(1);
+    else if (C4 <= 64) CALLA(2);
+    else if (C4 <= 128) CALLA(4);
+    else if (C4 <= 256) CALLA(8);
+    else if (C4 <= 512) CALLA(16);
+    else if (C4 <= 1024) CALLA(32);
+    else CALLA(64);
+#undef CALLA
+    PR_CUDA_LAUNCH_CHECK("act_bwd_bias_kernel");
     return PR_OK;
 }

@@ -32,6 +32,10 @@ SIGNATURES = {
     "pr_add_ln_bwd_partials": (_I, [_I64, _I64]),
     "pr_add_ln_bwd_f32": (_I, [_P, _P, _I64, _I64, _P, _I64, _P, _P, _P, _I64, _I64, _F, _F, _U64, _U32, _U32, _P, _I64, _I,
                                _P, _P, _I, _P]),
+    "pr_add_ln_bwd_bias_f32": (_I, [_P, _P, _I64, _I64, _P, _I64, _P, _P, _P, _I64, _I64, _F, _F, _U64, _U32, _U32, _P, _I64, _I,
+                                    _P, _P, _I, _P]),
+    "pr_act_bwd_bias_partials": (_I, [_I64, _I64]),
+    "pr_act_bwd_bias_f32": (_I, [_P, _P, _I64, _I64, _I, _P, _P, _I, _P]),
     "pr_colsum_f32": (_I, [_P, _I, _I, _I64, _P, _P]),
     "pr_act_fwd_f32": (_I, [_P, _I64, _I, _P, _P]),
     "pr_act_bwd_f32": (_I, [_P, _P, _I64, _I, _P, _P]),

@@ -4,12 +4,18 @@ kernels (pixelrec_b200/ops.py); the Linear layers are cuBLAS calls (TF32 by defa
 them on Ampere -- set matmul_precision: fp32 in the yaml for strict fp32).
 """
 import copy
+import os
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
+
+
+# One hand-written autograd node per encoder layer (ops.TransformerLayerFn) instead of ~12 nodes; PR_FUSED_LAYER=0 selects
+# the op-by-op composition (identical kernels and numerics up to summation order of the bias gradients).
+FUSED_LAYER = os.environ.get("PR_FUSED_LAYER", "1") != "0"
 
 
 class TableGradSink:
@@ -121,6 +127,15 @@ class TransformerLayer(nn.Module):
         self.feed_forward = FeedForward(hidden_size, intermediate_size, hidden_dropout_prob, hidden_act, layer_norm_eps)
 
     def forward(self, x, key_ids, causal, seed, site):
+        if FUSED_LAYER and x.is_cuda:
+            m, f = self.multi_head_attention, self.feed_forward
+            p_attn = m.attn_dropout_prob if self.training else 0.0
+            p_hid = m.hidden_dropout_prob if self.training else 0.0
+            return ops.TransformerLayerFn.apply(
+                x.contiguous(), key_ids, m.query.weight, m.query.bias, m.key.weight, m.key.bias, m.value.weight, m.value.bias,
+                m.dense.weight, m.dense.bias, m.LayerNorm.weight, m.LayerNorm.bias, f.dense_1.weight, f.dense_1.bias,
+                f.dense_2.weight, f.dense_2.bias, f.LayerNorm.weight, f.LayerNorm.bias, m.num_attention_heads, bool(causal),
+                float(m.layer_norm_eps), float(p_attn), float(p_hid), ops.ACT_IDS[f.hidden_act], int(seed), int(site))
         return self.feed_forward(self.multi_head_attention(x, key_ids, causal, seed, site), seed, site)
 
 

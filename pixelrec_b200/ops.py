@@ -428,6 +428,126 @@ class GatherFn(torch.autograd.Function):
         return G, None, None, None, None
 
 
+# ------------------------------------------------------------------------------------------- fused transformer layer
+# One autograd node per encoder layer (REC/model/layers.py:676-703).  Same kernels and the same cuBLAS GEMMs as the
+# op-by-op path above, but the backward is written out by hand, which removes what autograd adds around them:
+#   * the two residual-gradient adds per layer become the beta=1 epilogue of the input-gradient GEMMs (addmm),
+#   * the bias gradients of dense / dense_2 / dense_1 come out of pr_add_ln_bwd_bias_f32 / pr_act_bwd_bias_f32 as
+#     per-CTA partial column sums instead of ATen sum(0) passes that re-read the whole gradient tensor,
+#   * q/k/v weight gradients are produced by ONE GEMM into a [3D, D] buffer and returned as views.
+def _raw_add_ln_fwd(h, res, gamma, beta, eps, p_pre, seed, stream_pre):
+    rows, D = h.numel() // gamma.numel(), gamma.numel()
+    y = torch.empty_like(h)
+    mean = torch.empty(rows, device=h.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=h.device, dtype=torch.float32)
+    with _prof("add_ln_fwd", h):
+        _lib.check(_L().pr_add_ln_fwd_f32(_p(h), 0, rows, _p(res), 0, _p(gamma), _p(beta), eps, rows, D, p_pre, 0.0, seed,
+                                          stream_pre, 0, _p(y), _p(mean), _p(rstd), _stream(h)), "pr_add_ln_fwd_f32")
+    _count()
+    return y, mean, rstd
+
+
+def _raw_add_ln_bwd_bias(dy, h, res, gamma, mean, rstd, p_pre, seed, stream_pre):
+    """-> dh (dropout applied), dres (== dh when p_pre == 0), dgamma, dbeta, dbias (column sums of dh)"""
+    rows, D = h.numel() // gamma.numel(), gamma.numel()
+    n_part = _L().pr_add_ln_bwd_partials(rows, D)
+    partials = torch.empty(3, n_part, D, device=dy.device, dtype=torch.float32)
+    dh = torch.empty_like(h)
+    dres = torch.empty_like(h) if p_pre > 0.0 else None
+    with _prof("add_ln_bwd", dy):
+        _lib.check(_L().pr_add_ln_bwd_bias_f32(_p(dy), _p(h), 0, rows, _p(res), 0, _p(gamma), _p(mean), _p(rstd), rows, D,
+                                               p_pre, 0.0, seed, stream_pre, 0, _p(dh), 0, 0, _p(dres), _p(partials), n_part,
+                                               _stream(dy)), "pr_add_ln_bwd_bias_f32")
+    out = torch.empty(3, D, device=dy.device, dtype=torch.float32)
+    with _prof("colsum", dy):
+        _lib.check(_L().pr_colsum_f32(_p(partials), 3, n_part, D, _p(out), _stream(dy)), "pr_colsum_f32")
+    _count(2)
+    return dh, (dres if dres is not None else dh), out[0], out[1], out[2]
+
+
+def _raw_act_bwd_bias(x, dy, act):
+    rows, cols = x.numel() // x.shape[-1], x.shape[-1]
+    n_part = _L().pr_act_bwd_bias_partials(rows, cols)
+    partials = torch.empty(n_part, cols, device=x.device, dtype=torch.float32)
+    dx = torch.empty_like(x)
+    with _prof("act_bwd", x):
+        _lib.check(_L().pr_act_bwd_bias_f32(_p(x), _p(dy), rows, cols, act, _p(dx), _p(partials), n_part, _stream(x)),
+                   "pr_act_bwd_bias_f32")
+    db = torch.empty(1, cols, device=x.device, dtype=torch.float32)
+    with _prof("colsum", x):
+        _lib.check(_L().pr_colsum_f32(_p(partials), 1, n_part, cols, _p(db), _stream(x)), "pr_colsum_f32")
+    _count(2)
+    return dx, db[0]
+
+
+class TransformerLayerFn(torch.autograd.Function):
+    """x [B,L,D] -> FeedForward(MultiHeadAttention(x))  (layers.py:700-703), one autograd node."""
+
+    @staticmethod
+    def forward(ctx, x, key_ids, wq, bq, wk, bk, wv, bv, wo, bo, g1, be1, w1, b1, w2, b2, g2, be2, n_heads, causal, eps,
+                p_attn, p_hid, act, seed, site):
+        _req(x, torch.float32, "x")
+        B, L, D = x.shape
+        x2 = x.view(B * L, D)
+        wqkv = torch.cat([wq, wk, wv], 0)
+        bqkv = torch.cat([bq, bk, bv], 0)
+        qkv = torch.addmm(bqkv, x2, wqkv.t()).view(B, L, 3 * D)                      # layers.py:586-588
+        tf32 = bool(torch.backends.cuda.matmul.allow_tf32) and L <= 32 and (D // n_heads) % 32 == 0 and \
+            ((D // n_heads) <= 128 or (D // n_heads) % 128 == 0)
+        ctxt = torch.empty(B, L, D, device=x.device, dtype=torch.float32)
+        probs = torch.empty(B, n_heads, L, L, device=x.device, dtype=torch.float32)
+        base = qkv.data_ptr()
+        fwd = _L().pr_sasrec_attn_fwd_tf32 if tf32 else _L().pr_sasrec_attn_fwd_f32
+        with _prof("attn_fwd", qkv):
+            _lib.check(fwd(base, base + 4 * D, base + 8 * D, 3 * D, _p(key_ids), B, L, n_heads, D // n_heads, int(causal), p_attn,
+                           seed, site, _p(ctxt), _p(probs), _stream(qkv)), "pr_sasrec_attn_fwd")
+        _count()
+        h = torch.addmm(bo, ctxt.view(B * L, D), wo.t())                               # :613
+        a, mean1, rstd1 = _raw_add_ln_fwd(h, x2, g1, be1, eps, p_hid, seed, site + 1)  # :614-615
+        h1 = torch.addmm(b1, a, w1.t())                                                # :666
+        gl = torch.empty_like(h1)
+        with _prof("act_fwd", h1):
+            _lib.check(_L().pr_act_fwd_f32(_p(h1), h1.numel(), act, _p(gl), _stream(h1)), "pr_act_fwd_f32")
+        _count()
+        h2 = torch.addmm(b2, gl, w2.t())                                               # :669
+        y, mean2, rstd2 = _raw_add_ln_fwd(h2, a, g2, be2, eps, p_hid, seed, site + 2)  # :670-671
+        ctx.save_for_backward(x, qkv, probs, ctxt, h, a, mean1, rstd1, h1, gl, h2, mean2, rstd2, wqkv, wo, w1, w2, g1, g2)
+        ctx.cfg = (B, L, D, n_heads, int(causal), eps, p_attn, p_hid, act, seed, site, tf32)
+        return y.view(B, L, D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, qkv, probs, ctxt, h, a, mean1, rstd1, h1, gl, h2, mean2, rstd2, wqkv, wo, w1, w2, g1, g2 = ctx.saved_tensors
+        B, L, D, n_heads, causal, eps, p_attn, p_hid, act, seed, site, tf32 = ctx.cfg
+        M = B * L
+        dy = dy.contiguous().view(M, D)
+        x2 = x.view(M, D)
+        # ---- feed-forward block
+        dh2, da_res, dg2, dbe2, db2 = _raw_add_ln_bwd_bias(dy, h2, a, g2, mean2, rstd2, p_hid, seed, site + 2)
+        dw2 = dh2.t().mm(gl)
+        dgl = dh2.mm(w2)
+        dh1, db1 = _raw_act_bwd_bias(h1, dgl, act)
+        dw1 = dh1.t().mm(a)
+        da = torch.addmm(da_res, dh1, w1)                                  # residual grad folded into the GEMM (beta = 1)
+        # ---- attention block
+        dh, dx_res, dg1, dbe1, dbo = _raw_add_ln_bwd_bias(da, h, x2, g1, mean1, rstd1, p_hid, seed, site + 1)
+        dwo = dh.t().mm(ctxt.view(M, D))
+        dctx = dh.mm(wo)
+        dqkv = torch.empty_like(qkv)
+        base, gbase = qkv.data_ptr(), dqkv.data_ptr()
+        bwd = _L().pr_sasrec_attn_bwd_tf32 if tf32 else _L().pr_sasrec_attn_bwd_f32
+        with _prof("attn_bwd", qkv):
+            _lib.check(bwd(base, base + 4 * D, base + 8 * D, 3 * D, _p(probs), _p(dctx), B, L, n_heads, D // n_heads, causal,
+                           p_attn, seed, site, gbase, gbase + 4 * D, gbase + 8 * D, 3 * D, _stream(qkv)), "pr_sasrec_attn_bwd")
+        _count()
+        dqkv2 = dqkv.view(M, 3 * D)
+        dwqkv = dqkv2.t().mm(x2)                                           # one GEMM for the three projections
+        dbqkv = dqkv2.sum(0)
+        dx = torch.addmm(dx_res, dqkv2, wqkv).view(B, L, D)                # residual grad folded into the GEMM
+        return (dx, None, dwqkv[:D], dbqkv[:D], dwqkv[D:2 * D], dbqkv[D:2 * D], dwqkv[2 * D:], dbqkv[2 * D:], dwo, dbo, dg1, dbe1,
+                dw1, db1, dw2, db2, dg2, dbe2, None, None, None, None, None, None, None, None)
+
+
 # ------------------------------------------------------------------------------------------- K9 score + top-k
 def score_topk(seq_out, item_feature, k, hist_u=None, hist_i=None, mask_col0=True):
     """Fused  (seq_out @ item_feature.T) -> mask(col 0, history) -> top-k  on tcgen05 tensor cores.

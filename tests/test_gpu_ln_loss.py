@@ -150,3 +150,67 @@ def test_bpr_loss_saturation_no_nan():
     loss.backward()
     assert torch.isfinite(loss) and abs(loss.item() - L * -np.log(1e-8)) < 1e-3    # the reference's +1e-8 floor
     assert torch.isfinite(out.grad).all()
+
+
+@pytest.mark.parametrize("rows,D,p", [(333, 512, 0.1), (100, 128, 0.0), (65, 1024, 0.1)])
+def test_add_ln_bwd_with_bias_grad_partials(rows, D, p):
+    """pr_add_ln_bwd_bias_f32: the extra partial matrix is the column sum of dh (bias grad of the producing Linear)."""
+    from pixelrec_b200 import ops
+    g = np.random.default_rng(rows + D)
+    h = g.standard_normal((rows, D)).astype(np.float32)
+    res = g.standard_normal((rows, D)).astype(np.float32)
+    gamma = (1 + 0.1 * g.standard_normal(D)).astype(np.float32)
+    beta = (0.1 * g.standard_normal(D)).astype(np.float32)
+    dy = g.standard_normal((rows, D)).astype(np.float32)
+    mpre = PH.rowwise_keep_scale(rows, D, p, 42, 7)
+    y_ref, cache = _ln_ref(h, res, gamma, beta, 1e-12, mpre, np.ones_like(mpre))
+    dz, dg, db = O.layernorm_bwd(dy.astype(np.float64), gamma.astype(np.float64), cache)
+    y, mean, rstd = ops._raw_add_ln_fwd(t(h), t(res), t(gamma), t(beta), 1e-12, p, 42, 7)
+    assert rel(y.cpu().numpy(), y_ref) < TOL
+    dh, dres, dgam, dbet, dbias = ops._raw_add_ln_bwd_bias(t(dy), t(h), t(res), t(gamma), mean, rstd, p, 42, 7)
+    assert rel(dh.cpu().numpy(), dz * mpre) < TOL and rel(dres.cpu().numpy(), dz) < TOL
+    assert rel(dgam.cpu().numpy(), dg) < TOL and rel(dbet.cpu().numpy(), db) < TOL
+    assert rel(dbias.cpu().numpy(), (dz * mpre).sum(0)) < TOL
+
+
+@pytest.mark.parametrize("rows,cols,act", [(500, 1024, "gelu"), (33, 256, "relu"), (7, 4096, "gelu"), (129, 36, "swish")])
+def test_act_bwd_with_bias_grad(rows, cols, act):
+    from pixelrec_b200 import ops
+    g = np.random.default_rng(rows)
+    x = (2 * g.standard_normal((rows, cols))).astype(np.float32)
+    dy = g.standard_normal((rows, cols)).astype(np.float32)
+    tx = t(x).requires_grad_()
+    ops.activation(tx, act).backward(t(dy))
+    dx, db = ops._raw_act_bwd_bias(t(x), t(dy), ops.ACT_IDS[act])
+    assert rel(dx.cpu().numpy(), tx.grad.cpu().numpy()) < 1e-6
+    assert rel(db.cpu().numpy(), tx.grad.cpu().numpy().astype(np.float64).sum(0)) < 2e-5
+
+
+def test_fused_layer_equals_op_by_op_layer():
+    """ops.TransformerLayerFn (hand-written backward) == the op-by-op composition of the same kernels."""
+    import pixelrec_b200.model.layers as Lm
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    layer = Lm.TransformerLayer(4, 128, 256, 0.1, 0.1, "gelu", 1e-12).to(dev()).train()
+    for p_ in layer.parameters():
+        if p_.ndim == 1:
+            p_.data.add_(0.05 * torch.randn_like(p_))
+    x = torch.randn(6, 20, 128, device=dev())
+    ids = torch.ones(6, 20, dtype=torch.int64, device=dev())
+    ids[0, :5] = 0
+    dyv = torch.randn(6, 20, 128, device=dev())
+    outs = {}
+    for fused in (True, False):
+        Lm.FUSED_LAYER = fused
+        layer.zero_grad()
+        xi = x.clone().requires_grad_()
+        y = layer(xi, ids, True, 123, 1)
+        y.backward(dyv)
+        outs[fused] = (y.detach(), xi.grad.clone(), {k: v.grad.clone() for k, v in layer.named_parameters()})
+    Lm.FUSED_LAYER = True
+    assert torch.allclose(outs[True][0], outs[False][0], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(outs[True][1], outs[False][1], rtol=1e-4, atol=1e-6)
+    for k in outs[True][2]:
+        a, b = outs[True][2][k], outs[False][2][k]
+        assert (a - b).abs().max().item() <= 1e-4 * max(b.abs().max().item(), 1e-3), k
+    torch.backends.cuda.matmul.allow_tf32 = True
