@@ -521,7 +521,7 @@ extern "C" int pr_act_bwd_f32(const float* x, const float* dy, int64_t n, int ac
 extern "C" int pr_act_bwd_bias_partials(int64_t rows, int64_t cols) {
     (void)cols;
     if (rows <= 0) return 1;
-    return (int)std::max<long long>(1, std::min<long long>((rows + 7) / 8, (long long)sm_count() * 4));
+    return (int)std::max<long long>(1, std::min<long long>((rows + 7) / 8, (long long)sm_count() * 8));
 }
 
 extern "C" int pr_act_bwd_bias_f32(const float* x, const float* dy, int64_t rows, int64_t cols, int act, float* dx,
