@@ -220,6 +220,17 @@ PR_API int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float* W, 
                              float* topk_val, int64_t* topk_idx, void* workspace, size_t workspace_bytes,
                              pr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * A1  on-device batch construction.   replaces SEQTrainDataset.__getitem__ + default collate,
+ *                                     REC/data/dataset/trainset.py:40-75 (python loops in 10 DataLoader workers)
+ *   padded [n_seq, W] int64: training windows left-padded with 0 (W = MAX_ITEM_LIST_LENGTH + 1), resident in HBM;
+ *   sel [B] int64: which windows form this batch.  Outputs items [B,2,W] (positives | aligned uniform negatives
+ *   rejected against the sequence's own items, 0 where there is no transition) and mask [B,W-1] (masked_index).
+ *   Deterministic in (seed, b, t): Philox4x32-10, see csrc/sampler.cu.  status bit 0: a sel index out of range.
+ */
+PR_API int pr_seq_batch_build(const int64_t* padded, int64_t n_seq, int W, const int64_t* sel, int64_t B, int64_t item_num,
+                       uint64_t seed, int64_t* items, int64_t* mask, int32_t* status, pr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

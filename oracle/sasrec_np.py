@@ -427,3 +427,32 @@ def seq_train_sample(item_seq, item_num, max_item_list_length, rng):
     pad = lambda xs, n: ([0] * (n - len(xs)) + list(xs))[-n:]
     items = np.array([pad(seq, Lp1), pad(negs, Lp1)], dtype=np.int64)
     return items, np.array(pad(mask, Lp1 - 1), dtype=np.int64)
+
+
+def seq_batch_build(padded, sel, item_num, seed):
+    """Restates pixelrec_b200/csrc/sampler.cu (the on-device form of trainset.py:52-75) with the same Philox stream, so the
+    GPU batch builder is checked bit for bit; statistical properties are those of seq_train_sample above."""
+    from oracle.philox_np import philox4x32_10
+    padded = np.asarray(padded)
+    sel = np.asarray(sel)
+    W = padded.shape[1]
+    B = len(sel)
+    items = np.zeros((B, 2, W), dtype=np.int64)
+    mask = np.zeros((B, W - 1), dtype=np.int64)
+    rng_range = np.uint64(item_num - 1)
+    for b in range(B):
+        row = padded[sel[b]]
+        items[b, 0] = row
+        nz = np.flatnonzero(row != 0)
+        first = int(nz[0]) if len(nz) else W
+        present = set(row[first:].tolist())
+        for t in range(first + 1, W):
+            for attempt in range(64):
+                ctr = np.array([np.uint64((b * W + t) * 64 + attempt)], dtype=np.uint64)
+                x = np.uint64(philox4x32_10(ctr, 0x5eed, seed)[0, 0])
+                neg = 1 + int((x * rng_range) >> np.uint64(32))
+                if neg not in present:
+                    break
+            items[b, 1, t] = neg
+            mask[b, t - 1] = 1
+    return items, mask

@@ -42,6 +42,54 @@ class NonConsecutiveSequentialDistributedSampler(torch.utils.data.Sampler):
         return self.num_samples
 
 
+class _EpochSampler:
+    def __init__(self, dataset):
+        self.dataset = dataset
+        self.epoch = 0
+
+    def set_epoch(self, epoch):
+        self.epoch = epoch
+
+
+class DeviceSeqLoader:
+    """Train loader whose batches are assembled ON THE GPU (pr_seq_batch_build): the padded training windows stay
+    resident in HBM, an epoch is a seeded permutation partitioned over ranks exactly like DistributedSampler
+    (pad to a multiple of world, rank r takes r, r+W, ...), and every step is one kernel launch instead of
+    B python `__getitem__` calls in DataLoader workers (REC/data/utils.py:88-112, trainset.py:40-75).
+    Enabled with `device_sampler: True` in the yaml (SEQ models)."""
+
+    def __init__(self, dataset, batch_size, device, rank=0, world=1, seed=0):
+        from .. import ops
+        self._ops = ops
+        self.dataset = dataset
+        self.batch_size = int(batch_size)
+        self.device = device
+        self.rank, self.world, self.seed = rank, world, int(seed)
+        self.sampler = _EpochSampler(dataset)
+        self.padded = torch.from_numpy(dataset.padded).to(device)
+        n = len(dataset)
+        self.num_samples = math.ceil(n / world)
+        self._step = 0
+
+    def __len__(self):
+        return math.ceil(self.num_samples / self.batch_size)
+
+    def __iter__(self):
+        n = len(self.dataset)
+        g = torch.Generator()
+        g.manual_seed(self.seed + self.sampler.epoch)
+        perm = torch.randperm(n, generator=g)
+        total = self.num_samples * self.world
+        if total > n:
+            perm = torch.cat([perm, perm[: total - n]])
+        mine = perm[self.rank:total:self.world].to(self.device)
+        for i in range(0, self.num_samples, self.batch_size):
+            self._step += 1
+            sel = mine[i:i + self.batch_size].contiguous()
+            yield self._ops.seq_batch_build(self.padded, sel, self.dataset.item_num,
+                                            (self.seed * 1000003 + self.sampler.epoch) * 1000003 + self._step * self.world + self.rank)
+
+
 def _worker_init(worker_id, num_workers, rank, seed):
     s = (num_workers * rank + worker_id + seed) % (2 ** 32)
     np.random.seed(s)
@@ -65,8 +113,12 @@ def bulid_dataloader(config, dataload):
     workers = config["num_workers"] if config["num_workers"] is not None else 10
     init_fn = partial(_worker_init, num_workers=workers, rank=rank, seed=torch.initial_seed())
     pin = torch.cuda.is_available()
-    train_loader = DataLoader(train_data, batch_size=config["train_batch_size"], num_workers=workers, pin_memory=pin,
-                              sampler=train_sampler, worker_init_fn=init_fn)
+    if config["device_sampler"] and torch.cuda.is_available() and config["device"] is not None:
+        train_loader = DeviceSeqLoader(train_data, config["train_batch_size"], config["device"], rank, world,
+                                       seed=config["seed"] or 0)
+    else:
+        train_loader = DataLoader(train_data, batch_size=config["train_batch_size"], num_workers=workers, pin_memory=pin,
+                                  sampler=train_sampler, worker_init_fn=init_fn)
     mk = lambda ds: DataLoader(ds, batch_size=config["eval_batch_size"], num_workers=workers, pin_memory=pin,
                                sampler=NonConsecutiveSequentialDistributedSampler(ds), collate_fn=collate)
     return train_loader, mk(valid_data), mk(test_data)

@@ -574,5 +574,20 @@ def score_topk(seq_out, item_feature, k, hist_u=None, hist_i=None, mask_col0=Tru
     return val, idx
 
 
+# ------------------------------------------------------------------------------------------- A1 on-device batches
+def seq_batch_build(padded, sel, item_num, seed, status=None):
+    """items [B,2,W], masked_index [B,W-1] for the windows `sel` of `padded` [n_seq, W] (trainset.py:52-75 on the GPU)."""
+    _req(padded, torch.int64, "padded"); _req(sel, torch.int64, "sel")
+    n_seq, W = padded.shape
+    B = sel.numel()
+    items = torch.empty(B, 2, W, device=padded.device, dtype=torch.int64)
+    mask = torch.empty(B, W - 1, device=padded.device, dtype=torch.int64)
+    with _prof("seq_batch_build", padded):
+        _lib.check(_L().pr_seq_batch_build(_p(padded), n_seq, W, _p(sel), B, int(item_num), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                           _p(items), _p(mask), _p(status), _stream(padded)), "pr_seq_batch_build")
+    _count()
+    return items, mask
+
+
 def inv_sqrt(x):
     return 1.0 / math.sqrt(x)

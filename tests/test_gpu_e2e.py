@@ -10,14 +10,16 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_run_loop_trains_and_evaluates(tmp_path, monkeypatch):
+@pytest.mark.parametrize("device_sampler", [False, True])
+def test_run_loop_trains_and_evaluates(tmp_path, monkeypatch, device_sampler):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA")
     monkeypatch.chdir(tmp_path)
     from run import run_loop
     cfg = dict(dataset="synthetic", synthetic_users=600, synthetic_items=300, MAX_ITEM_LIST_LENGTH=10,
                embedding_size=64, train_batch_size=64, eval_batch_size=128, epochs=3, num_workers=0, stopping_step=5,
-               checkpoint_dir=str(tmp_path / "saved"), optim_args={"learning_rate": 0.003, "weight_decay": 0.01})
+               checkpoint_dir=str(tmp_path / "saved"), optim_args={"learning_rate": 0.003, "weight_decay": 0.01},
+               device_sampler=device_sampler)
     files = [os.path.join(ROOT, "configs/IDNet/sasrec.yaml"), os.path.join(ROOT, "configs/overall/ID.yaml")]
     out = run_loop(0, files, saved=True, config_dict=cfg)
     assert set(out["test_result"]) == {"recall@5", "recall@10", "ndcg@5", "ndcg@10"}

@@ -186,3 +186,29 @@ def test_adamw_dense_vs_oracle(n):
         step_dev.fill_(step)
         ops.adamw_dense(dw, dg, dm, dv, 1e-3, 0.9, 0.999, 1e-8, 0.01, 0, step_dev=step_dev)   # step read from device
         assert np.abs(dw.cpu().numpy() - w).max() < 1e-6
+
+
+@pytest.mark.parametrize("n_seq,L,N,B", [(50, 10, 40, 64), (500, 20, 5000, 300), (7, 5, 8, 20)])
+def test_on_device_batch_builder_bit_exact(n_seq, L, N, B):
+    """A1: pr_seq_batch_build == oracle restatement (same Philox stream), and the batch has SEQTrainDataset's layout:
+    negatives never collide with the sequence, neg/mask are 0 up to and including the first real item."""
+    from pixelrec_b200 import ops
+    g = np.random.default_rng(n_seq + B)
+    W = L + 1
+    padded = np.zeros((n_seq, W), dtype=np.int64)
+    for i in range(n_seq):
+        n = int(g.integers(1, W + 1))
+        padded[i, W - n:] = g.integers(1, N, size=n)
+    sel = g.integers(0, n_seq, size=B).astype(np.int64)
+    ref_items, ref_mask = O.seq_batch_build(padded, sel, N, 777)
+    items, mask = ops.seq_batch_build(t(padded), t(sel), N, 777)
+    assert np.array_equal(items.cpu().numpy(), ref_items) and np.array_equal(mask.cpu().numpy(), ref_mask)
+    it, mk = ref_items, ref_mask
+    for b in range(B):
+        pos, neg = it[b, 0], it[b, 1]
+        n = int((pos != 0).sum())
+        assert mk[b].sum() == max(n - 1, 0) and (neg != 0).sum() == max(n - 1, 0)
+        assert not (set(neg[neg != 0].tolist()) & set(pos[pos != 0].tolist()))
+        assert ((neg >= 0) & (neg < N)).all()
+    other, _ = ops.seq_batch_build(t(padded), t(sel), N, 778)
+    assert not torch.equal(other, items)                      # a new seed draws new negatives
