@@ -57,6 +57,10 @@ PR_API int pr_sm_count(void);
 /* Makes `device` current for this library's CUDA runtime on the calling thread.  The host side calls
  * it with the device of the tensors it passes (one process per GPU: once, with LOCAL_RANK). */
 PR_API int pr_set_device(int device);
+/* Kernel-variant switches for A/B measurement (bit mask; also read once from the environment variable PR_TUNE):
+ *   1 = LayerNorm backward as per-warp bulk-copy row pipelines, 2 = L2 prefetch of the next row in the register LN kernels.
+ * mask < 0 only queries.  Returns the mask in effect.  Results are identical under every mask. */
+PR_API int pr_set_tuning(int mask);
 
 /* ------------------------------------------------------------------------------------------
  * K1  embedding row gather.     replaces nn.Embedding.forward: REC/model/IDNet/sasrec.py:31,68

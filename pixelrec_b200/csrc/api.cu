@@ -1,5 +1,6 @@
 // pixelrec_b200 -- ABI housekeeping: version, thread-local error string, cached device attributes.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -27,6 +28,19 @@ int sm_count() {
     return cached[dev];
 }
 
+// kernel-variant switches (bit mask), overridable with PR_TUNE for A/B measurements on the GPU box:
+//   1 = add_ln backward as per-warp TMA row pipelines, 2 = L2 prefetch of a warp's next row in the register LN kernels
+static int g_tune = -1;
+int tune() {
+    if (g_tune < 0) {
+        const char* e = getenv("PR_TUNE");
+        g_tune = e ? atoi(e) : PR_TUNE_DEFAULT;
+        if (g_tune < 0) g_tune = 0;
+    }
+    return g_tune;
+}
+void set_tune(int mask) { g_tune = mask; }
+
 }  // namespace pr
 
 extern "C" int pr_version(void) { return PR_ABI_VERSION; }
@@ -38,6 +52,10 @@ extern "C" int pr_sm_count(void) {
         return PR_ERR_UNSUPPORTED;
     }
     return pr::sm_count();
+}
+extern "C" int pr_set_tuning(int mask) {
+    if (mask >= 0) pr::set_tune(mask);
+    return pr::tune();
 }
 extern "C" int pr_set_device(int device) {
     cudaError_t e = cudaSetDevice(device);

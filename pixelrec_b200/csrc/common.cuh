@@ -11,6 +11,12 @@ namespace pr {
 // ---------------------------------------------------------------- error plumbing (api.cu)
 void set_last_error(const char* fmt, ...);
 int sm_count();
+int tune();                      // PR_TUNE bit mask (api.cu)
+#define PR_TUNE_LN_BWD_PIPE 1
+#define PR_TUNE_LN_L2_PREFETCH 2
+#ifndef PR_TUNE_DEFAULT
+#define PR_TUNE_DEFAULT 0
+#endif
 
 #define PR_CHECK_ARG(cond, ...)                 \
     do {                                        \
@@ -108,6 +114,10 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
                  "r"(bytes)
                  : "memory");
+}
+// L2 prefetch of a contiguous span (no smem, no completion tracking); bytes % 16 == 0, 16-B aligned
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>

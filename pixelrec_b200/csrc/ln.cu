@@ -16,6 +16,7 @@ struct LnArgs {
     const float* gamma; const float* beta; float eps;
     long long rows; int D4;
     float p_pre, p_post; unsigned long long seed; unsigned stream_pre, stream_post;
+    int l2_prefetch;   // PR_TUNE_LN_L2_PREFETCH: pull the warp's next row into L2 while this one is processed
 };
 
 // keep bits of one row for this lane: chunk j (= float4 column lane + 32*j) uses bits [4*(j&1), +4) of
@@ -59,6 +60,19 @@ __device__ __forceinline__ void load_z(const LnArgs& a, long long row, int lane,
     }
 }
 
+// lanes 0..2 each ask the copy engine to pull one array's next row into L2 (no smem, nothing to wait for)
+__device__ __forceinline__ void prefetch_row_l2(const LnArgs& a, long long row, int lane, const float* dy) {
+    const unsigned bytes = (unsigned)a.D4 * 16u;
+    if (lane == 0) {
+        const long long s = row / a.rows_per_seq, t = row - s * a.rows_per_seq;
+        l2_prefetch_bulk(a.h + s * a.h_seq_stride + t * (long long)a.D4 * 4, bytes);
+    } else if (lane == 1) {
+        if (a.res && a.res_period <= 0) l2_prefetch_bulk(a.res + row * (long long)a.D4 * 4, bytes);
+    } else if (lane == 2) {
+        if (dy) l2_prefetch_bulk(dy + row * (long long)a.D4 * 4, bytes);
+    }
+}
+
 template <int VPL>
 __device__ __forceinline__ void row_stats(const float4 (&z)[VPL], int lane, int D4, float& mean, float& var) {
     float s = 0.f;
@@ -91,6 +105,7 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 4 : 1) add_ln_fwd_kernel(LnA
     for (long long row = warp; row < a.rows; row += nwarps) {
         float4 z[VPL];
         unsigned mk_pre[(VPL + 1) / 2], mk_post[(VPL + 1) / 2];
+        if (a.l2_prefetch && row + nwarps < a.rows) prefetch_row_l2(a, row + nwarps, lane, nullptr);
         if (a.p_pre > 0.f) row_keep_bits<VPL>(ph, a.stream_pre, thr_pre, row, a.D4, lane, mk_pre);
         if (a.p_post > 0.f) row_keep_bits<VPL>(ph, a.stream_post, thr_post, row, a.D4, lane, mk_post);
         load_z<VPL>(a, row, lane, mk_pre, ik_pre, z);
@@ -116,6 +131,50 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 4 : 1) add_ln_fwd_kernel(LnA
             mean_out[row] = mean;
             rstd_out[row] = rstd;
         }
+    }
+}
+
+// fixed-order sum of the warps' register accumulators through shared memory -> partials[{0,1,2}][blockIdx.x][D]
+template <int VPL, bool DBIAS>
+__device__ __forceinline__ void cta_reduce_partials(const float4 (&accg)[VPL], const float4 (&accb)[VPL],
+                                                    const float4 (&accd)[DBIAS ? VPL : 1], float4* sm_acc, int D4,
+                                                    float* __restrict__ partials) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w) {
+        if (wid == w) {
+#pragma unroll
+            for (int j = 0; j < VPL; ++j) {
+                const int c = lane + 32 * j;
+                if (c < D4) {
+                    if (w == 0) {
+                        sm_acc[c] = accg[j];
+                        sm_acc[D4 + c] = accb[j];
+                        if (DBIAS) sm_acc[2 * D4 + c] = accd[DBIAS ? j : 0];
+                    } else {
+                        if (DBIAS) {
+                            float4 u = sm_acc[2 * D4 + c];
+                            u.x += accd[DBIAS ? j : 0].x; u.y += accd[DBIAS ? j : 0].y; u.z += accd[DBIAS ? j : 0].z; u.w += accd[DBIAS ? j : 0].w;
+                            sm_acc[2 * D4 + c] = u;
+                        }
+                        float4 t = sm_acc[c];
+                        t.x += accg[j].x; t.y += accg[j].y; t.z += accg[j].z; t.w += accg[j].w;
+                        sm_acc[c] = t;
+                        t = sm_acc[D4 + c];
+                        t.x += accb[j].x; t.y += accb[j].y; t.z += accb[j].z; t.w += accb[j].w;
+                        sm_acc[D4 + c] = t;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    float4* pg = reinterpret_cast<float4*>(partials) + (long long)blockIdx.x * D4;
+    float4* pb = reinterpret_cast<float4*>(partials) + ((long long)gridDim.x + blockIdx.x) * D4;
+    float4* pd = reinterpret_cast<float4*>(partials) + (2 * (long long)gridDim.x + blockIdx.x) * D4;
+    for (int c = threadIdx.x; c < D4; c += blockDim.x) {
+        pg[c] = sm_acc[c];
+        pb[c] = sm_acc[D4 + c];
+        if (DBIAS) pd[c] = sm_acc[2 * D4 + c];
     }
 }
 
@@ -145,6 +204,7 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 2 : 1) add_ln_bwd_kernel(LnA
     for (long long row = warp; row < a.rows; row += nwarps) {
         float4 z[VPL];
         unsigned mk_pre[(VPL + 1) / 2], mk_post[(VPL + 1) / 2];
+        if (a.l2_prefetch && row + nwarps < a.rows) prefetch_row_l2(a, row + nwarps, lane, dy);
         if (a.p_pre > 0.f) row_keep_bits<VPL>(ph, a.stream_pre, thr_pre, row, a.D4, lane, mk_pre);
         if (a.p_post > 0.f) row_keep_bits<VPL>(ph, a.stream_post, thr_post, row, a.D4, lane, mk_post);
         load_z<VPL>(a, row, lane, mk_pre, ik_pre, z);
@@ -202,43 +262,139 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 2 : 1) add_ln_bwd_kernel(LnA
             }
         }
     }
-    // CTA reduction in fixed warp order
-    for (int w = 0; w < nw; ++w) {
-        if (wid == w) {
+    cta_reduce_partials<VPL, DBIAS>(accg, accb, accd, sm_acc, a.D4, partials);
+}
+
+// Same backward as per-warp TMA row pipelines (PR_TUNE_LN_BWD_PIPE; needs D == 128*VPL so every lane column is live):
+// each warp owns STAGES shared-memory stages of [dy | h | res] rows, lane 0 keeps STAGES rows of bulk copies in
+// flight (cp.async.bulk + mbarrier complete_tx) while the warp works on the oldest one, so the bytes in flight per SM
+// no longer depend on how many rows fit in registers.  Row -> warp mapping, arithmetic and summation order are those
+// of add_ln_bwd_kernel.
+template <int VPL, bool DBIAS, int STAGES>
+__global__ void __launch_bounds__(256, (VPL <= 4) ? 2 : 1) add_ln_bwd_pipe_kernel(
+    LnArgs a, const float* __restrict__ dy, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+    float* __restrict__ dh, long long dh_seq_stride, int dh_accumulate, float* __restrict__ dres,
+    float* __restrict__ partials) {
+    extern __shared__ __align__(128) float4 sm_dyn[];
+    constexpr int RF4 = VPL * 32;                       // float4 per row
+    constexpr unsigned ROW_BYTES = RF4 * 16u;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float4* ring = sm_dyn + (size_t)wid * STAGES * 3 * RF4;
+    float4* sm_acc = sm_dyn + (size_t)nw * STAGES * 3 * RF4;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_acc + 3 * RF4) + wid * STAGES;
+    const long long warp = (long long)blockIdx.x * nw + wid;
+    const long long nwarps = (long long)gridDim.x * nw;
+    const bool has_res = a.res != nullptr;
+    if (lane == 0) {
 #pragma unroll
-            for (int j = 0; j < VPL; ++j) {
-                const int c = lane + 32 * j;
-                if (c < a.D4) {
-                    if (w == 0) {
-                        sm_acc[c] = accg[j];
-                        sm_acc[a.D4 + c] = accb[j];
-                        if (DBIAS) sm_acc[2 * a.D4 + c] = accd[DBIAS ? j : 0];
-                    } else {
-                        if (DBIAS) {
-                            float4 u = sm_acc[2 * a.D4 + c];
-                            u.x += accd[DBIAS ? j : 0].x; u.y += accd[DBIAS ? j : 0].y; u.z += accd[DBIAS ? j : 0].z; u.w += accd[DBIAS ? j : 0].w;
-                            sm_acc[2 * a.D4 + c] = u;
-                        }
-                        float4 t = sm_acc[c];
-                        t.x += accg[j].x; t.y += accg[j].y; t.z += accg[j].z; t.w += accg[j].w;
-                        sm_acc[c] = t;
-                        t = sm_acc[a.D4 + c];
-                        t.x += accb[j].x; t.y += accb[j].y; t.z += accb[j].z; t.w += accb[j].w;
-                        sm_acc[a.D4 + c] = t;
-                    }
-                }
-            }
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    auto issue = [&](int s, long long row) {            // lane 0 only
+        const long long sq = row / a.rows_per_seq, tt = row - sq * a.rows_per_seq;
+        float4* st = ring + (size_t)s * 3 * RF4;
+        mbar_arrive_expect_tx(&bars[s], (has_res ? 3u : 2u) * ROW_BYTES);
+        bulk_g2s(st, dy + row * (long long)(RF4 * 4), ROW_BYTES, &bars[s]);
+        bulk_g2s(st + RF4, a.h + sq * a.h_seq_stride + tt * (long long)(RF4 * 4), ROW_BYTES, &bars[s]);
+        if (has_res) {
+            const long long rrow = a.res_period > 0 ? (row % a.res_period) : row;
+            bulk_g2s(st + 2 * RF4, a.res + rrow * (long long)(RF4 * 4), ROW_BYTES, &bars[s]);
         }
-        __syncthreads();
+    };
+    const long long mine = warp < a.rows ? (a.rows - warp + nwarps - 1) / nwarps : 0;
+    if (lane == 0)
+        for (int s = 0; s < STAGES && s < mine; ++s) issue(s, warp + s * nwarps);
+
+    const Philox ph(a.seed);
+    const unsigned thr_pre = drop_threshold(a.p_pre), thr_post = drop_threshold(a.p_post);
+    const float ik_pre = 1.0f / (1.0f - a.p_pre), ik_post = 1.0f / (1.0f - a.p_post);
+    const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
+    const float invD = 1.0f / (float)(RF4 * 4);
+    float4 accg[VPL], accb[VPL], accd[DBIAS ? VPL : 1];
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) accg[j] = accb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < (DBIAS ? VPL : 1); ++j) accd[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    int s = 0;
+    unsigned parity = 0;
+    for (long long k = 0; k < mine; ++k) {
+        const long long row = warp + k * nwarps;
+        unsigned mk_pre[(VPL + 1) / 2], mk_post[(VPL + 1) / 2];
+        if (a.p_pre > 0.f) row_keep_bits<VPL>(ph, a.stream_pre, thr_pre, row, RF4, lane, mk_pre);
+        if (a.p_post > 0.f) row_keep_bits<VPL>(ph, a.stream_post, thr_post, row, RF4, lane, mk_post);
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        mbar_wait(&bars[s], parity);
+        const float4* st = ring + (size_t)s * 3 * RF4;
+        float4 d[VPL], z[VPL];
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const int c = lane + 32 * j;
+            d[j] = st[c];
+            float4 v = st[RF4 + c];
+            if (a.p_pre > 0.f) v = apply_keep(v, mk_pre[j >> 1] >> (4 * (j & 1)), ik_pre);
+            if (has_res) {
+                const float4 r = st[2 * RF4 + c];
+                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            }
+            z[j] = v;
+        }
+        __syncwarp();                                   // every lane has its copy: the stage may be refilled
+        if (lane == 0 && k + STAGES < mine) {
+            fence_proxy_async();
+            issue(s, row + (long long)STAGES * nwarps);
+        }
+        if (++s == STAGES) { s = 0; parity ^= 1u; }
+
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const int c = lane + 32 * j;
+            float4 dd = d[j];
+            if (a.p_post > 0.f) dd = apply_keep(dd, mk_post[j >> 1] >> (4 * (j & 1)), ik_post);
+            const float4 g = __ldg(g4 + c);
+            float4 xh;
+            xh.x = (z[j].x - mean) * rstd; xh.y = (z[j].y - mean) * rstd;
+            xh.z = (z[j].z - mean) * rstd; xh.w = (z[j].w - mean) * rstd;
+            z[j] = xh;
+            accg[j].x += dd.x * xh.x; accg[j].y += dd.y * xh.y; accg[j].z += dd.z * xh.z; accg[j].w += dd.w * xh.w;
+            accb[j].x += dd.x; accb[j].y += dd.y; accb[j].z += dd.z; accb[j].w += dd.w;
+            dd.x *= g.x; dd.y *= g.y; dd.z *= g.z; dd.w *= g.w;
+            d[j] = dd;
+            s1 += (dd.x + dd.y) + (dd.z + dd.w);
+            s2 += (dd.x * xh.x + dd.y * xh.y) + (dd.z * xh.z + dd.w * xh.w);
+        }
+        s1 = warp_sum(s1) * invD;
+        s2 = warp_sum(s2) * invD;
+        float4* dh4;
+        if (dh_seq_stride > 0) {
+            const long long sq = row / a.rows_per_seq, tt = row - sq * a.rows_per_seq;
+            dh4 = reinterpret_cast<float4*>(dh + sq * dh_seq_stride) + tt * RF4;
+        } else {
+            dh4 = reinterpret_cast<float4*>(dh) + row * RF4;
+        }
+        float4* dr4 = dres ? reinterpret_cast<float4*>(dres) + row * RF4 : nullptr;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const int c = lane + 32 * j;
+            float4 dz;
+            dz.x = rstd * (d[j].x - s1 - z[j].x * s2);
+            dz.y = rstd * (d[j].y - s1 - z[j].y * s2);
+            dz.z = rstd * (d[j].z - s1 - z[j].z * s2);
+            dz.w = rstd * (d[j].w - s1 - z[j].w * s2);
+            if (dr4) dr4[c] = dz;
+            if (a.p_pre > 0.f) dz = apply_keep(dz, mk_pre[j >> 1] >> (4 * (j & 1)), ik_pre);
+            if (DBIAS) { accd[DBIAS ? j : 0].x += dz.x; accd[DBIAS ? j : 0].y += dz.y; accd[DBIAS ? j : 0].z += dz.z; accd[DBIAS ? j : 0].w += dz.w; }
+            if (dh_accumulate) {
+                const float4 o = dh4[c];
+                dz.x += o.x; dz.y += o.y; dz.z += o.z; dz.w += o.w;
+            }
+            dh4[c] = dz;
+        }
     }
-    float4* pg = reinterpret_cast<float4*>(partials) + (long long)blockIdx.x * a.D4;
-    float4* pb = reinterpret_cast<float4*>(partials) + ((long long)gridDim.x + blockIdx.x) * a.D4;
-    float4* pd = reinterpret_cast<float4*>(partials) + (2 * (long long)gridDim.x + blockIdx.x) * a.D4;
-    for (int c = threadIdx.x; c < a.D4; c += blockDim.x) {
-        pg[c] = sm_acc[c];
-        pb[c] = sm_acc[a.D4 + c];
-        if (DBIAS) pd[c] = sm_acc[2 * a.D4 + c];
-    }
+    __syncthreads();
+    cta_reduce_partials<VPL, DBIAS>(accg, accb, accd, sm_acc, RF4, partials);
 }
 
 // out[m][c] = sum_p partials[m][p][c].  32 columns x 32 row-groups per CTA; group y adds rows p = y, y+32, ...
@@ -299,37 +455,71 @@ __device__ __forceinline__ float act_df(float x, int act) {
     }
 }
 
-__global__ void __launch_bounds__(256) act_fwd_kernel(const float* __restrict__ x, long long n, int act,
-                                                      float* __restrict__ y) {
+// ACT is a template parameter so the switch folds away; each thread keeps UNR independent 16-B loads in flight
+template <int ACT, int UNR>
+__global__ void __launch_bounds__(256) act_fwd_kernel(const float* __restrict__ x, long long n, float* __restrict__ y) {
     const long long n4 = n >> 2, stride = (long long)gridDim.x * blockDim.x;
     const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (long long i = i0; i < n4; i += stride) {
-        float4 v = reinterpret_cast<const float4*>(x)[i];
-        v.x = act_f(v.x, act); v.y = act_f(v.y, act); v.z = act_f(v.z, act); v.w = act_f(v.w, act);
-        reinterpret_cast<float4*>(y)[i] = v;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    long long i = i0;
+    for (; i + (UNR - 1) * stride < n4; i += UNR * stride) {
+        float4 v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) v[u] = ldg_stream(x4 + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            v[u].x = act_f(v[u].x, ACT); v[u].y = act_f(v[u].y, ACT); v[u].z = act_f(v[u].z, ACT); v[u].w = act_f(v[u].w, ACT);
+            y4[i + u * stride] = v[u];
+        }
     }
-    for (long long i = (n4 << 2) + i0; i < n; i += stride) y[i] = act_f(x[i], act);
+    for (; i < n4; i += stride) {
+        float4 v = x4[i];
+        v.x = act_f(v.x, ACT); v.y = act_f(v.y, ACT); v.z = act_f(v.z, ACT); v.w = act_f(v.w, ACT);
+        y4[i] = v;
+    }
+    for (long long t = (n4 << 2) + i0; t < n; t += stride) y[t] = act_f(x[t], ACT);
 }
 
+template <int ACT, int UNR>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                      long long n, int act, float* __restrict__ dx) {
+                                                      long long n, float* __restrict__ dx) {
     const long long n4 = n >> 2, stride = (long long)gridDim.x * blockDim.x;
     const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (long long i = i0; i < n4; i += stride) {
-        const float4 v = reinterpret_cast<const float4*>(x)[i];
-        float4 d = reinterpret_cast<const float4*>(dy)[i];
-        d.x *= act_df(v.x, act); d.y *= act_df(v.y, act); d.z *= act_df(v.z, act); d.w *= act_df(v.w, act);
-        reinterpret_cast<float4*>(dx)[i] = d;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* d4 = reinterpret_cast<const float4*>(dy);
+    float4* o4 = reinterpret_cast<float4*>(dx);
+    long long i = i0;
+    for (; i + (UNR - 1) * stride < n4; i += UNR * stride) {
+        float4 v[UNR], d[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            v[u] = ldg_stream(x4 + i + u * stride);
+            d[u] = ldg_stream(d4 + i + u * stride);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            d[u].x *= act_df(v[u].x, ACT); d[u].y *= act_df(v[u].y, ACT); d[u].z *= act_df(v[u].z, ACT); d[u].w *= act_df(v[u].w, ACT);
+            o4[i + u * stride] = d[u];
+        }
     }
-    for (long long i = (n4 << 2) + i0; i < n; i += stride) dx[i] = dy[i] * act_df(x[i], act);
+    for (; i < n4; i += stride) {
+        const float4 v = x4[i];
+        float4 d = d4[i];
+        d.x *= act_df(v.x, ACT); d.y *= act_df(v.y, ACT); d.z *= act_df(v.z, ACT); d.w *= act_df(v.w, ACT);
+        o4[i] = d;
+    }
+    for (long long t = (n4 << 2) + i0; t < n; t += stride) dx[t] = dy[t] * act_df(x[t], ACT);
 }
 
-// dx = act'(x) * dy and per-CTA partial column sums of dx (= bias grad of the Linear that produced x): warp per row
-template <int VPL>
-__global__ void __launch_bounds__(256) act_bwd_bias_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                           long long rows, int C4, int act, float* __restrict__ dx,
+// dx = act'(x) * dy and per-CTA partial column sums of dx (= bias grad of the Linear that produced x): warp per row,
+// the row is walked in chunks of CH float4 per lane with every load of a chunk issued before its math
+template <int ACT, int VPL>
+__global__ void __launch_bounds__(256, (VPL <= 8) ? 2 : 1) act_bwd_bias_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                           long long rows, int C4, float* __restrict__ dx,
                                                            float* __restrict__ partials) {
     extern __shared__ float4 sm_acc[];  // [C4]
+    constexpr int CH = VPL < 8 ? VPL : 8;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const long long warp = (long long)blockIdx.x * nw + wid, nwarps = (long long)gridDim.x * nw;
     float4 acc[VPL];
@@ -340,14 +530,26 @@ __global__ void __launch_bounds__(256) act_bwd_bias_kernel(const float* __restri
         const float4* d4 = reinterpret_cast<const float4*>(dy) + row * C4;
         float4* o4 = reinterpret_cast<float4*>(dx) + row * C4;
 #pragma unroll
-        for (int j = 0; j < VPL; ++j) {
-            const int c = lane + 32 * j;
-            if (c < C4) {
-                const float4 v = ldg_stream(x4 + c);
-                float4 d = ldg_stream(d4 + c);
-                d.x *= act_df(v.x, act); d.y *= act_df(v.y, act); d.z *= act_df(v.z, act); d.w *= act_df(v.w, act);
-                o4[c] = d;
-                acc[j].x += d.x; acc[j].y += d.y; acc[j].z += d.z; acc[j].w += d.w;
+        for (int jb = 0; jb < VPL; jb += CH) {
+            float4 v[CH], d[CH];
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                const int c = lane + 32 * (jb + u);
+                v[u] = d[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < C4) {
+                    v[u] = ldg_stream(x4 + c);
+                    d[u] = ldg_stream(d4 + c);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                const int c = lane + 32 * (jb + u);
+                if (c < C4) {
+                    float4 t = d[u];
+                    t.x *= act_df(v[u].x, ACT); t.y *= act_df(v[u].y, ACT); t.z *= act_df(v[u].z, ACT); t.w *= act_df(v[u].w, ACT);
+                    o4[c] = t;
+                    acc[jb + u].x += t.x; acc[jb + u].y += t.y; acc[jb + u].z += t.z; acc[jb + u].w += t.w;
+                }
             }
         }
     }
@@ -376,9 +578,14 @@ static int ln_grid(long long rows) {
     const long long by_rows = (rows + 7) / 8;
     return (int)std::max<long long>(1, std::min<long long>(by_rows, (long long)sm_count() * 8));
 }
-static int ln_bwd_grid(long long rows) {
+// the pipelined backward needs every lane column live (D = 128 * VPL) and 2 stages of 3 rows per warp in smem
+static bool ln_bwd_pipe_ok(long long D) {
+    return (tune() & PR_TUNE_LN_BWD_PIPE) && (D == 128 || D == 256 || D == 512 || D == 1024);
+}
+static int ln_bwd_grid(long long rows, long long D) {
     const long long by_rows = (rows + 7) / 8;
-    return (int)std::max<long long>(1, std::min<long long>(by_rows, (long long)sm_count() * 4));
+    const long long per_sm = ln_bwd_pipe_ok(D) ? (D <= 512 ? 2 : 1) : 4;   // pipelined: persistent, all CTAs resident
+    return (int)std::max<long long>(1, std::min<long long>(by_rows, (long long)sm_count() * per_sm));
 }
 
 static int check_ln_common(const char* who, const void* h, const void* gamma, long long rows, long long D,
@@ -394,6 +601,18 @@ static int check_ln_common(const char* who, const void* h, const void* gamma, lo
 }  // namespace pr
 
 using namespace pr;
+
+#define PR_DISPATCH_ACT(act, CALL)                              \
+    do {                                                        \
+        switch (act) {                                          \
+            case PR_ACT_GELU: CALL(PR_ACT_GELU); break;         \
+            case PR_ACT_RELU: CALL(PR_ACT_RELU); break;         \
+            case PR_ACT_SWISH: CALL(PR_ACT_SWISH); break;       \
+            case PR_ACT_TANH: CALL(PR_ACT_TANH); break;         \
+            case PR_ACT_QUICK_GELU: CALL(PR_ACT_QUICK_GELU); break; \
+            default: CALL(PR_ACT_SIGMOID); break;               \
+        }                                                       \
+    } while (0)
 
 #define PR_DISPATCH_VPL(D4, CALL)         \
     do {                                  \
@@ -417,7 +636,7 @@ extern "C" int pr_add_ln_fwd_f32(const float* h, int64_t h_seq_stride, int64_t r
     PR_CHECK_ARG(aligned16(h) && aligned16(res) && aligned16(gamma) && aligned16(beta) && aligned16(y),
                  "pr_add_ln_fwd_f32: pointers must be 16-byte aligned");
     LnArgs a{h, h_seq_stride, rows_per_seq, res, res_period, gamma, beta, eps, rows, (int)(D / 4),
-             p_pre, p_post, seed, stream_pre, stream_post};
+             p_pre, p_post, seed, stream_pre, stream_post, (tune() & PR_TUNE_LN_L2_PREFETCH) ? 1 : 0};
     const int grid = ln_grid(rows);
 #define CALL(V) add_ln_fwd_kernel<V><<<grid, 256, 0, stream>>>(a, y, mean, rstd)
     PR_DISPATCH_VPL(a.D4, CALL);
@@ -427,9 +646,8 @@ extern "C" int pr_add_ln_fwd_f32(const float* h, int64_t h_seq_stride, int64_t r
 }
 
 extern "C" int pr_add_ln_bwd_partials(int64_t rows, int64_t D) {
-    (void)D;
     if (rows <= 0) return 1;
-    return ln_bwd_grid(rows);
+    return ln_bwd_grid(rows, D);
 }
 
 static int add_ln_bwd_impl(bool want_dbias, const float* dy, const float* h, int64_t h_seq_stride, int64_t rows_per_seq,
@@ -442,7 +660,7 @@ static int add_ln_bwd_impl(bool want_dbias, const float* dy, const float* h, int
     int rc = check_ln_common("pr_add_ln_bwd_f32", h, gamma, rows, D, rows_per_seq, h_seq_stride, p_pre, p_post);
     if (rc) return rc;
     PR_CHECK_ARG(partials, "pr_add_ln_bwd_f32: partials is null");
-    const int grid = ln_bwd_grid(rows);
+    const int grid = ln_bwd_grid(rows, D);
     PR_CHECK_ARG(n_partials == (rows > 0 ? grid : 1), "pr_add_ln_bwd_f32: n_partials=%d, expected %d (pr_add_ln_bwd_partials)",
                  n_partials, rows > 0 ? grid : 1);
     if (rows == 0) {
@@ -455,7 +673,25 @@ static int add_ln_bwd_impl(bool want_dbias, const float* dy, const float* h, int
                      aligned16(partials),
                  "pr_add_ln_bwd_f32: pointers must be 16-byte aligned");
     LnArgs a{h, h_seq_stride, rows_per_seq, res, res_period, gamma, nullptr, 0.f, rows, (int)(D / 4),
-             p_pre, p_post, seed, stream_pre, stream_post};
+             p_pre, p_post, seed, stream_pre, stream_post, 0};
+    a.l2_prefetch = (tune() & PR_TUNE_LN_L2_PREFETCH) ? 1 : 0;
+    if (ln_bwd_pipe_ok(D)) {
+#define PIPE(V, S)                                                                                                   \
+    do {                                                                                                             \
+        const size_t sm = (size_t)8 * S * 3 * D * 4 + (size_t)3 * D * 4 + 8 * S * sizeof(uint64_t);                   \
+        auto kt = add_ln_bwd_pipe_kernel<V, true, S>;                                                                \
+        auto kf = add_ln_bwd_pipe_kernel<V, false, S>;                                                               \
+        PR_CUDA_CALL(cudaFuncSetAttribute(want_dbias ? kt : kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+        (want_dbias ? kt : kf)<<<grid, 256, sm, stream>>>(a, dy, mean, rstd, dh, dh_seq_stride, dh_accumulate, dres, partials); \
+    } while (0)
+        if (D == 128) PIPE(1, 8);
+        else if (D == 256) PIPE(2, 4);
+        else if (D == 512) PIPE(4, 2);
+        else PIPE(8, 2);
+#undef PIPE
+        PR_CUDA_LAUNCH_CHECK("add_ln_bwd_pipe_kernel");
+        return PR_OK;
+    }
     const size_t smem = (size_t)(want_dbias ? 3 : 2) * D * sizeof(float);
 #define CALL(V)                                                                                                     \
     do {                                                                                                            \
@@ -502,7 +738,9 @@ extern "C" int pr_act_fwd_f32(const float* x, int64_t n, int act, float* y, pr_s
     if (n == 0) return PR_OK;
     PR_CHECK_ARG(x && y && aligned16(x) && aligned16(y), "pr_act_fwd_f32: null/unaligned pointer");
     const int grid = (int)std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, (long long)sm_count() * 16));
-    act_fwd_kernel<<<grid, 256, 0, stream>>>(x, n, act, y);
+#define CALLF(A) act_fwd_kernel<A, 4><<<grid, 256, 0, stream>>>(x, n, y)
+    PR_DISPATCH_ACT(act, CALLF);
+#undef CALLF
     PR_CUDA_LAUNCH_CHECK("act_fwd_kernel");
     return PR_OK;
 }
@@ -513,7 +751,9 @@ extern "C" int pr_act_bwd_f32(const float* x, const float* dy, int64_t n, int ac
     if (n == 0) return PR_OK;
     PR_CHECK_ARG(x && dy && dx && aligned16(x) && aligned16(dy) && aligned16(dx), "pr_act_bwd_f32: null/unaligned pointer");
     const int grid = (int)std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, (long long)sm_count() * 16));
-    act_bwd_kernel<<<grid, 256, 0, stream>>>(x, dy, n, act, dx);
+#define CALLB(A) act_bwd_kernel<A, 4><<<grid, 256, 0, stream>>>(x, dy, n, dx)
+    PR_DISPATCH_ACT(act, CALLB);
+#undef CALLB
     PR_CUDA_LAUNCH_CHECK("act_bwd_kernel");
     return PR_OK;
 }
@@ -536,14 +776,19 @@ extern "C" int pr_act_bwd_bias_f32(const float* x, const float* dy, int64_t rows
     PR_CHECK_ARG(n_partials == grid, "pr_act_bwd_bias_f32: n_partials=%d, expected %d", n_partials, grid);
     const int C4 = (int)(cols / 4);
     const size_t smem = (size_t)cols * sizeof(float);
-#define CALLA(V) act_bwd_bias_kernel<V><<<grid, 256, smem, stream>>>(x, dy, rows, C4, act, dx, partials)
-    if (C4 <= 32) CALLA(1);
-    else if (C4 <= 64) CALLA(2);
-    else if (C4 <= 128) CALLA(4);
-    else if (C4 <= 256) CALLA(8);
-    else if (C4 <= 512) CALLA(16);
-    else if (C4 <= 1024) CALLA(32);
-    else CALLA(64);
+#define CALLV(A, V) act_bwd_bias_kernel<A, V><<<grid, 256, smem, stream>>>(x, dy, rows, C4, dx, partials)
+#define CALLA(A)                         \
+    do {                                 \
+        if (C4 <= 32) CALLV(A, 1);       \
+        else if (C4 <= 64) CALLV(A, 2);  \
+        else if (C4 <= 128) CALLV(A, 4); \
+        else if (C4 <= 256) CALLV(A, 8); \
+        else if (C4 <= 512) CALLV(A, 16);\
+        else if (C4 <= 1024) CALLV(A, 32);\
+        else CALLV(A, 64);               \
+    } while (0)
+    PR_DISPATCH_ACT(act, CALLA);
+#undef CALLV
 #undef CALLA
     PR_CUDA_LAUNCH_CHECK("act_bwd_bias_kernel");
     return PR_OK;

@@ -12,6 +12,17 @@ pytestmark = pytest.mark.gpu
 TOL = 2e-5
 
 
+@pytest.fixture(params=[0, 1, 2], ids=["tune0", "tune_pipe", "tune_l2pf"])
+def ln_tune(request):
+    """runs a test under each LayerNorm kernel variant (pr_set_tuning); results must not depend on it"""
+    from pixelrec_b200 import lib
+    L_ = lib.load()
+    before = L_.pr_set_tuning(-1)
+    L_.pr_set_tuning(request.param)
+    yield request.param
+    L_.pr_set_tuning(before)
+
+
 def _ln_ref(h, res, gamma, beta, eps, mpre, mpost):
     z = h * mpre + res
     y, cache = O.layernorm_fwd(z.astype(np.float64), gamma.astype(np.float64), beta.astype(np.float64), eps)
@@ -20,7 +31,7 @@ def _ln_ref(h, res, gamma, beta, eps, mpre, mpost):
 
 @pytest.mark.parametrize("rows,D", [(1, 4), (37, 64), (100, 128), (333, 512), (17, 768), (65, 1024), (40, 2048), (9, 4096), (50, 36)])
 @pytest.mark.parametrize("p_pre,p_post", [(0.0, 0.0), (0.1, 0.0), (0.0, 0.5)])
-def test_add_ln_fwd_bwd(rows, D, p_pre, p_post):
+def test_add_ln_fwd_bwd(rows, D, p_pre, p_post, ln_tune):
     from pixelrec_b200 import ops
     g = np.random.default_rng(rows * D)
     h = g.standard_normal((rows, D)).astype(np.float32)
@@ -51,7 +62,7 @@ def test_add_ln_fwd_bwd(rows, D, p_pre, p_post):
 
 @pytest.mark.parametrize("B,L,D", [(3, 10, 128), (5, 20, 512), (2, 7, 64)])
 @pytest.mark.parametrize("p", [0.0, 0.25])
-def test_embed_ln_strided_layout_and_posemb(B, L, D, p):
+def test_embed_ln_strided_layout_and_posemb(B, L, D, p, ln_tune):
     """sasrec.py:72,77-83: LN(E[:,0,:-1] + P[0:L]) read in place from the [B,2,L+1,D] gather output;
     grad wrt E lands only on rows (b,0,t<L); grad wrt P is the sum over the batch."""
     from pixelrec_b200 import ops
@@ -152,8 +163,10 @@ def test_bpr_loss_saturation_no_nan():
     assert torch.isfinite(out.grad).all()
 
 
-@pytest.mark.parametrize("rows,D,p", [(333, 512, 0.1), (100, 128, 0.0), (65, 1024, 0.1)])
-def test_add_ln_bwd_with_bias_grad_partials(rows, D, p):
+@pytest.mark.parametrize("rows,D,p", [(333, 512, 0.1), (100, 128, 0.0), (65, 1024, 0.1),
+                                      # long enough that every warp of the pipelined variant refills its stages several times
+                                      (12001, 512, 0.1), (40000, 128, 0.1), (30000, 256, 0.0), (9000, 1024, 0.1)])
+def test_add_ln_bwd_with_bias_grad_partials(rows, D, p, ln_tune):
     """pr_add_ln_bwd_bias_f32: the extra partial matrix is the column sum of dh (bias grad of the producing Linear)."""
     from pixelrec_b200 import ops
     g = np.random.default_rng(rows + D)
@@ -171,6 +184,11 @@ def test_add_ln_bwd_with_bias_grad_partials(rows, D, p):
     assert rel(dh.cpu().numpy(), dz * mpre) < TOL and rel(dres.cpu().numpy(), dz) < TOL
     assert rel(dgam.cpu().numpy(), dg) < TOL and rel(dbet.cpu().numpy(), db) < TOL
     assert rel(dbias.cpu().numpy(), (dz * mpre).sum(0)) < TOL
+    if ln_tune:   # same arithmetic per row under every variant: dh / dres are bit-identical to the register kernel
+        from pixelrec_b200 import lib
+        lib.load().pr_set_tuning(0)
+        dh0, dres0, *_ = ops._raw_add_ln_bwd_bias(t(dy), t(h), t(res), t(gamma), mean, rstd, p, 42, 7)
+        assert torch.equal(dh0, dh) and torch.equal(dres0, dres)
 
 
 @pytest.mark.parametrize("rows,cols,act", [(500, 1024, "gelu"), (33, 256, "relu"), (7, 4096, "gelu"), (129, 36, "swish")])
