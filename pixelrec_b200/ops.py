@@ -7,6 +7,7 @@ libpixelrec_b200.so and raises if given anything but CUDA tensors -- there is no
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -480,6 +481,21 @@ def _raw_act_bwd_bias(x, dy, act):
     return dx, db[0]
 
 
+WGRAD_SPLIT = int(os.environ.get("PR_WGRAD_SPLIT", "8"))
+
+
+def _wgrad(dy2, x2):
+    """dW = dy2^T @ x2 for dy2 [M, out], x2 [M, in] (M = B*L is the contraction).  The output is a few hundred tiles at
+    most, so one cuBLAS GEMM leaves most SMs idle or falls back to a slow split; an explicit split-K (batched GEMM over
+    WGRAD_SPLIT slabs of M + one fixed-order sum) measured 1.3-2.0x faster at M = 81920 (profiles/r01h_rowkernels_ab.md)
+    and stays deterministic."""
+    M = dy2.shape[0]
+    S = WGRAD_SPLIT
+    if S > 1 and M % S == 0 and M // S >= 2048:
+        return torch.bmm(dy2.view(S, M // S, -1).transpose(1, 2), x2.view(S, M // S, -1)).sum(0)
+    return dy2.t().mm(x2)
+
+
 class TransformerLayerFn(torch.autograd.Function):
     """x [B,L,D] -> FeedForward(MultiHeadAttention(x))  (layers.py:700-703), one autograd node."""
 
@@ -524,14 +540,14 @@ class TransformerLayerFn(torch.autograd.Function):
         x2 = x.view(M, D)
         # ---- feed-forward block
         dh2, da_res, dg2, dbe2, db2 = _raw_add_ln_bwd_bias(dy, h2, a, g2, mean2, rstd2, p_hid, seed, site + 2)
-        dw2 = dh2.t().mm(gl)
+        dw2 = _wgrad(dh2, gl)
         dgl = dh2.mm(w2)
         dh1, db1 = _raw_act_bwd_bias(h1, dgl, act)
-        dw1 = dh1.t().mm(a)
+        dw1 = _wgrad(dh1, a)
         da = torch.addmm(da_res, dh1, w1)                                  # residual grad folded into the GEMM (beta = 1)
         # ---- attention block
         dh, dx_res, dg1, dbe1, dbo = _raw_add_ln_bwd_bias(da, h, x2, g1, mean1, rstd1, p_hid, seed, site + 1)
-        dwo = dh.t().mm(ctxt.view(M, D))
+        dwo = _wgrad(dh, ctxt.view(M, D))
         dctx = dh.mm(wo)
         dqkv = torch.empty_like(qkv)
         base, gbase = qkv.data_ptr(), dqkv.data_ptr()
@@ -541,7 +557,7 @@ class TransformerLayerFn(torch.autograd.Function):
                            p_attn, seed, site, gbase, gbase + 4 * D, gbase + 8 * D, 3 * D, _stream(qkv)), "pr_sasrec_attn_bwd")
         _count()
         dqkv2 = dqkv.view(M, 3 * D)
-        dwqkv = dqkv2.t().mm(x2)                                           # one GEMM for the three projections
+        dwqkv = _wgrad(dqkv2, x2)                                           # one GEMM for the three projections
         dbqkv = dqkv2.sum(0)
         dx = torch.addmm(dx_res, dqkv2, wqkv).view(B, L, D)                # residual grad folded into the GEMM
         return (dx, None, dwqkv[:D], dbqkv[:D], dwqkv[D:2 * D], dbqkv[D:2 * D], dwqkv[2 * D:], dbqkv[2 * D:], dwo, dbo, dg1, dbe1,

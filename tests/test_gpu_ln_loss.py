@@ -232,3 +232,23 @@ def test_fused_layer_equals_op_by_op_layer():
         a, b = outs[True][2][k], outs[False][2][k]
         assert (a - b).abs().max().item() <= 1e-4 * max(b.abs().max().item(), 1e-3), k
     torch.backends.cuda.matmul.allow_tf32 = True
+
+
+def test_weight_grad_split_k_matches_single_gemm():
+    """ops._wgrad: the explicit split-K form (used when M = B*L is large) equals dy^T @ x."""
+    from pixelrec_b200 import ops
+    g = np.random.default_rng(5)
+    M, o, i = 8 * 2048, 96, 64
+    dy = g.standard_normal((M, o)).astype(np.float32)
+    x = g.standard_normal((M, i)).astype(np.float32)
+    ref = dy.astype(np.float64).T @ x.astype(np.float64)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        assert ops.WGRAD_SPLIT > 1 and M % ops.WGRAD_SPLIT == 0 and M // ops.WGRAD_SPLIT >= 2048
+        got = ops._wgrad(t(dy), t(x))
+        small = ops._wgrad(t(dy[:1000]), t(x[:1000]))          # below the threshold: plain GEMM
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    assert got.shape == (o, i) and rel(got.cpu().numpy(), ref) < TOL
+    assert rel(small.cpu().numpy(), dy[:1000].astype(np.float64).T @ x[:1000].astype(np.float64)) < TOL

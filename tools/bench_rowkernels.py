@@ -13,7 +13,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pixelrec_b200 import ops  # noqa: E402
 
 
-def timeit(fn, flush, iters=12, warm=3):
+ITERS, WARM = 12, 3
+
+
+def timeit(fn, flush):
+    iters, warm = ITERS, WARM
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -37,7 +41,11 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--gemm", action="store_true")
     ap.add_argument("--tunes", default="0,1,2,3")
+    ap.add_argument("--once", action="store_true", help="one launch per case, no warm-up (for ncu captures)")
     a = ap.parse_args()
+    global ITERS, WARM
+    if a.once:
+        ITERS, WARM = 1, 0
     dev = torch.device("cuda", 0)
     torch.backends.cuda.matmul.allow_tf32 = True
     B, L, D = a.B, a.L, a.D
