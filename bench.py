@@ -231,12 +231,16 @@ def run_ours(args, out):
             dist.barrier()
             torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(fn, K):
         sync_all()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
+        h0 = time.perf_counter()
         for i in range(K):
             fn(i)
+        host_ms[0] = (time.perf_counter() - h0) * 1e3 / max(K, 1)   # host time to ENQUEUE one step (no sync inside)
         e.record()
         sync_all()
         ms = torch.tensor([s.elapsed_time(e)], device=dev)
@@ -253,6 +257,7 @@ def run_ours(args, out):
     clocks.start()
     ms = timed(lambda i: step(resident[i % POOL], resident[(i + 1) % POOL]), args.steps)
     clk = clocks.stop()
+    host_enqueue_ms = host_ms[0]
     launches = ops.LAUNCHES["count"] - launches0
     gather_n, gather_ms = ops.profile_summary().get("gather_rows", (0, float("nan")))
     ops.PROFILE.update(on=False, events={})
@@ -318,10 +323,15 @@ def run_ours(args, out):
         "e2e": {"value": e2e, "unit": "sequences/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
+        "host_enqueue_ms_per_step": host_enqueue_ms,
         "clocks": clk,
         "roofline": {"kernel": "gather_rows_bulk_kernel (pr_gather_rows_f32, K1)", "bound": "hbm",
                      "achieved": gather_gbps, "peak": hbm, "unit": "GB/s",
-                     "frac": (gather_gbps / hbm) if gather_gbps else None, "traffic": None,
+                     "frac": (gather_gbps / hbm) if gather_gbps else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload (B=4096/GPU, N=1), one
+                     # `ncu --set full` capture: profiles/r01a_ncu_full_summary.md (146.17 MB read + 297.61 MB written; below
+                     # the algorithmic bytes because repeated ids hit L2 and part of the output is still in L2 at kernel end)
+                     "traffic": 443776512 if (B == 4096 and world == 1) else None,
                      "algorithmic_bytes_per_launch": alg["gather_rows"], "launch_ms": gather_ms if gather_n else None,
                      "launches_timed": gather_n, "peak_source": peak_src,
                      "note": "long-tail ids repeat inside a step, so part of the table reads hit L2: achieved can exceed the DRAM copy peak"},

@@ -58,7 +58,8 @@ PR_API int pr_sm_count(void);
  * it with the device of the tensors it passes (one process per GPU: once, with LOCAL_RANK). */
 PR_API int pr_set_device(int device);
 /* Kernel-variant switches for A/B measurement (bit mask; also read once from the environment variable PR_TUNE):
- *   1 = LayerNorm backward as per-warp bulk-copy row pipelines, 2 = L2 prefetch of the next row in the register LN kernels.
+ *   1 = LayerNorm backward as per-warp bulk-copy row pipelines, 2 = L2 prefetch of the next row in the register LN kernels,
+ *   4 = LayerNorm forward as per-warp bulk-copy row pipelines.
  * mask < 0 only queries.  Returns the mask in effect.  Results are identical under every mask. */
 PR_API int pr_set_tuning(int mask);
 

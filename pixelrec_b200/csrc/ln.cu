@@ -134,6 +134,94 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 4 : 1) add_ln_fwd_kernel(LnA
     }
 }
 
+// Forward as per-warp TMA row pipelines (PR_TUNE_LN_FWD_PIPE; D == 128*VPL): stage = [h | res] rows, same arithmetic
+template <int VPL, int STAGES>
+__global__ void __launch_bounds__(256, (VPL <= 4) ? 2 : 1) add_ln_fwd_pipe_kernel(LnArgs a, float* __restrict__ y,
+                                                                                float* __restrict__ mean_out,
+                                                                                float* __restrict__ rstd_out) {
+    extern __shared__ __align__(128) float4 sm_dyn[];
+    constexpr int RF4 = VPL * 32;
+    constexpr unsigned ROW_BYTES = RF4 * 16u;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float4* ring = sm_dyn + (size_t)wid * STAGES * 2 * RF4;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_dyn + (size_t)nw * STAGES * 2 * RF4) + wid * STAGES;
+    const long long warp = (long long)blockIdx.x * nw + wid;
+    const long long nwarps = (long long)gridDim.x * nw;
+    const bool has_res = a.res != nullptr;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    auto issue = [&](int s, long long row) {            // lane 0 only
+        const long long sq = row / a.rows_per_seq, tt = row - sq * a.rows_per_seq;
+        float4* st = ring + (size_t)s * 2 * RF4;
+        mbar_arrive_expect_tx(&bars[s], (has_res ? 2u : 1u) * ROW_BYTES);
+        bulk_g2s(st, a.h + sq * a.h_seq_stride + tt * (long long)(RF4 * 4), ROW_BYTES, &bars[s]);
+        if (has_res) {
+            const long long rrow = a.res_period > 0 ? (row % a.res_period) : row;
+            bulk_g2s(st + RF4, a.res + rrow * (long long)(RF4 * 4), ROW_BYTES, &bars[s]);
+        }
+    };
+    const long long mine = warp < a.rows ? (a.rows - warp + nwarps - 1) / nwarps : 0;
+    if (lane == 0)
+        for (int s = 0; s < STAGES && s < mine; ++s) issue(s, warp + s * nwarps);
+    const Philox ph(a.seed);
+    const unsigned thr_pre = drop_threshold(a.p_pre), thr_post = drop_threshold(a.p_post);
+    const float ik_pre = 1.0f / (1.0f - a.p_pre), ik_post = 1.0f / (1.0f - a.p_post);
+    const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(a.beta);
+    int s = 0;
+    unsigned parity = 0;
+    for (long long k = 0; k < mine; ++k) {
+        const long long row = warp + k * nwarps;
+        unsigned mk_pre[(VPL + 1) / 2], mk_post[(VPL + 1) / 2];
+        if (a.p_pre > 0.f) row_keep_bits<VPL>(ph, a.stream_pre, thr_pre, row, RF4, lane, mk_pre);
+        if (a.p_post > 0.f) row_keep_bits<VPL>(ph, a.stream_post, thr_post, row, RF4, lane, mk_post);
+        mbar_wait(&bars[s], parity);
+        const float4* st = ring + (size_t)s * 2 * RF4;
+        float4 z[VPL];
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const int c = lane + 32 * j;
+            float4 v = st[c];
+            if (a.p_pre > 0.f) v = apply_keep(v, mk_pre[j >> 1] >> (4 * (j & 1)), ik_pre);
+            if (has_res) {
+                const float4 r = st[RF4 + c];
+                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            }
+            z[j] = v;
+        }
+        __syncwarp();
+        if (lane == 0 && k + STAGES < mine) {
+            fence_proxy_async();
+            issue(s, row + (long long)STAGES * nwarps);
+        }
+        if (++s == STAGES) { s = 0; parity ^= 1u; }
+        float mean, var;
+        row_stats<VPL>(z, lane, RF4, mean, var);
+        const float rstd = 1.0f / sqrtf(var + a.eps);
+        float4* y4 = reinterpret_cast<float4*>(y) + row * RF4;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const int c = lane + 32 * j;
+            const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
+            float4 o;
+            o.x = (z[j].x - mean) * rstd * g.x + b.x;
+            o.y = (z[j].y - mean) * rstd * g.y + b.y;
+            o.z = (z[j].z - mean) * rstd * g.z + b.z;
+            o.w = (z[j].w - mean) * rstd * g.w + b.w;
+            if (a.p_post > 0.f) o = apply_keep(o, mk_post[j >> 1] >> (4 * (j & 1)), ik_post);
+            y4[c] = o;
+        }
+        if (lane == 0) {
+            mean_out[row] = mean;
+            rstd_out[row] = rstd;
+        }
+    }
+}
+
 // fixed-order sum of the warps' register accumulators through shared memory -> partials[{0,1,2}][blockIdx.x][D]
 template <int VPL, bool DBIAS>
 __device__ __forceinline__ void cta_reduce_partials(const float4 (&accg)[VPL], const float4 (&accb)[VPL],
@@ -637,6 +725,22 @@ extern "C" int pr_add_ln_fwd_f32(const float* h, int64_t h_seq_stride, int64_t r
                  "pr_add_ln_fwd_f32: pointers must be 16-byte aligned");
     LnArgs a{h, h_seq_stride, rows_per_seq, res, res_period, gamma, beta, eps, rows, (int)(D / 4),
              p_pre, p_post, seed, stream_pre, stream_post, (tune() & PR_TUNE_LN_L2_PREFETCH) ? 1 : 0};
+    if ((tune() & PR_TUNE_LN_FWD_PIPE) && (D == 128 || D == 256 || D == 512 || D == 1024)) {
+        const int pgrid = (int)std::max<long long>(1, std::min<long long>((rows + 7) / 8, (long long)sm_count() * (D <= 512 ? 2 : 1)));
+#define FPIPE(V, S)                                                                                            \
+    do {                                                                                                       \
+        const size_t sm = (size_t)8 * S * 2 * D * 4 + 8 * S * sizeof(uint64_t);                                 \
+        PR_CUDA_CALL(cudaFuncSetAttribute(add_ln_fwd_pipe_kernel<V, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+        add_ln_fwd_pipe_kernel<V, S><<<pgrid, 256, sm, stream>>>(a, y, mean, rstd);                            \
+    } while (0)
+        if (D == 128) FPIPE(1, 12);
+        else if (D == 256) FPIPE(2, 6);
+        else if (D == 512) FPIPE(4, 3);
+        else FPIPE(8, 3);
+#undef FPIPE
+        PR_CUDA_LAUNCH_CHECK("add_ln_fwd_pipe_kernel");
+        return PR_OK;
+    }
     const int grid = ln_grid(rows);
 #define CALL(V) add_ln_fwd_kernel<V><<<grid, 256, 0, stream>>>(a, y, mean, rstd)
     PR_DISPATCH_VPL(a.D4, CALL);
