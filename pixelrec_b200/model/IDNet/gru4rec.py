@@ -4,7 +4,6 @@ section 2 row 13 scopes it).  Table lookup, gradient scatter-add, loss and optim
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 from torch.nn.init import xavier_normal_, xavier_uniform_
 
 from ... import ops

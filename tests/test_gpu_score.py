@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import sasrec_np as O
-from tests.gpu_util import dev, rel, t
+from tests.gpu_util import t
 
 pytestmark = pytest.mark.gpu
 
