@@ -59,7 +59,7 @@ PR_API int pr_sm_count(void);
 PR_API int pr_set_device(int device);
 /* Kernel-variant switches for A/B measurement (bit mask; also read once from the environment variable PR_TUNE):
  *   1 = LayerNorm backward as per-warp bulk-copy row pipelines, 2 = L2 prefetch of the next row in the register LN kernels,
- *   4 = LayerNorm forward as per-warp bulk-copy row pipelines.
+ *   4 = LayerNorm forward as per-warp bulk-copy row pipelines, 8 = tensor-core attention with two warps per item pipeline.
  * mask < 0 only queries.  Returns the mask in effect.  Results are identical under every mask. */
 PR_API int pr_set_tuning(int mask);
 

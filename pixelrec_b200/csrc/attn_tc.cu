@@ -73,9 +73,10 @@ struct WarpBuf {
     float* buf[3];            // three [ROWS x CW] swizzled tiles
     uint64_t* bar[3];         // one mbarrier per tile
     unsigned phase[3];        // parity to wait for next
+    // `leader`: the one thread of the pipeline that talks to the TMA engine (lane 0 of the warp, or of the pair's first warp)
     __device__ __forceinline__ void issue(int i, const CUtensorMap* tm, int col0, int row0, int L, int CW, int box_bytes,
-                                          int lane) {
-        if (lane == 0) {
+                                          bool leader) {
+        if (leader) {
             mbar_arrive_expect_tx(bar[i], (uint32_t)(CW * 4) * (uint32_t)L);
             for (int bx = 0; bx < CW / 32; ++bx)
                 tma_box_2d(reinterpret_cast<unsigned char*>(buf[i]) + (size_t)bx * box_bytes, tm, col0 + 32 * bx, row0, bar[i]);
@@ -87,7 +88,15 @@ struct WarpBuf {
     }
 };
 
+// all threads of one pipeline: a warp, or (PAIR) the two warps that share the pipeline's buffers -- named barrier 1 + pipe
+template <bool PAIR>
+__device__ __forceinline__ void pipe_sync(int pipe) {
+    if (PAIR) asm volatile("bar.sync %0, 64;" ::"r"(pipe + 1) : "memory");
+    else __syncwarp();
+}
+
 // carve per-warp buffers out of dynamic smem, zero them (rows >= L must read as 0), init the barriers
+// (NW = pipelines per CTA, `warp` = index of this thread's pipeline: a warp, or a pair of warps sharing the buffers)
 template <int NW>
 __device__ __forceinline__ WarpBuf warp_setup(unsigned char* smem, int tile_bytes, size_t private_bytes_per_warp,
                                               unsigned char** priv, int warp) {
@@ -115,7 +124,7 @@ __device__ __forceinline__ WarpBuf warp_setup(unsigned char* smem, int tile_byte
 // acc[mi][nj] += X[16mi + {g, g+8}][d] * Y[8nj + g][d]  over one CW-wide tile pair  ("row x row" product)
 template <int MT, int NT>
 __device__ __forceinline__ void tc_rowrow(const float* __restrict__ Xs, const float* __restrict__ Ys, int box_words, int CW,
-                                          int g, int t, float (&acc)[MT][NT][4]) {
+                                          int g, int t, float (&acc)[MT][NT][4], int m0 = 0) {   // X rows start at m-tile m0
     // every row used here has (row & 7) == g, so the swizzle term is shared by all of them
 #pragma unroll 4
     for (int ks = 0; ks < CW; ks += 8) {
@@ -124,9 +133,9 @@ __device__ __forceinline__ void tc_rowrow(const float* __restrict__ Xs, const fl
         uint32_t a[MT][4], b[NT][2];
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi) {
-            const float* r0 = Xs + base + (16 * mi + g) * 32;
+            const float* r0 = Xs + base + (16 * (mi + m0) + g) * 32;
             // query rows >= 8*NT do not exist in the tile (and are >= L): alias them, their results are discarded
-            const float* r1 = (16 * mi + 8 < 8 * NT) ? r0 + 8 * 32 : r0;
+            const float* r1 = (16 * (mi + m0) + 8 < 8 * NT) ? r0 + 8 * 32 : r0;
             a[mi][0] = to_tf32(r0[ch0]);
             a[mi][1] = to_tf32(r1[ch0]);
             a[mi][2] = to_tf32(r0[ch1]);
@@ -149,7 +158,8 @@ __device__ __forceinline__ void tc_rowrow(const float* __restrict__ Xs, const fl
 // are stored.  Afrag holds A fragments with the permuted contraction index (k = t <-> row 2t, k = t+4 <-> row 2t+1).
 template <int MT, int KT>
 __device__ __forceinline__ void tc_frag_times_tile(const uint32_t (&af)[MT][KT][4], const float* __restrict__ Xs, int box_words,
-                                                   int CW, int L, int g, int t, float* __restrict__ out, long long out_ld) {
+                                                   int CW, int L, int g, int t, float* __restrict__ out, long long out_ld,
+                                                   int m0 = 0) {
     for (int nd = 0; nd < CW; nd += 8) {
         // column nd + g: 16-byte chunk ((nd>>2) + (g>>2)) & 7, word g & 3; rows 2t / 2t+1 (+8ks): (row & 7) = 2t / 2t+1
         const int cbase = (nd >> 5) * box_words + (g & 3);
@@ -168,7 +178,7 @@ __device__ __forceinline__ void tc_frag_times_tile(const uint32_t (&af)[MT][KT][
         }
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi) {
-            const int r0 = 16 * mi + g, r1 = r0 + 8;
+            const int r0 = 16 * (mi + m0) + g, r1 = r0 + 8;
             if (r0 < L) *reinterpret_cast<float2*>(out + (long long)r0 * out_ld + nd + 2 * t) = make_float2(acc[mi][0], acc[mi][1]);
             if (r1 < L) *reinterpret_cast<float2*>(out + (long long)r1 * out_ld + nd + 2 * t) = make_float2(acc[mi][2], acc[mi][3]);
         }
@@ -177,12 +187,13 @@ __device__ __forceinline__ void tc_frag_times_tile(const uint32_t (&af)[MT][KT][
 
 // A fragments of M^T from a private smem matrix M[r][c] (row stride LS): out rows = c, contraction over r (permuted)
 template <int MT, int KT>
-__device__ __forceinline__ void tc_load_transposed(const float* __restrict__ M, int LS, int g, int t, uint32_t (&af)[MT][KT][4]) {
+__device__ __forceinline__ void tc_load_transposed(const float* __restrict__ M, int LS, int g, int t, uint32_t (&af)[MT][KT][4],
+                                                   int m0 = 0) {
 #pragma unroll
     for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
         for (int ks = 0; ks < KT; ++ks) {
-            const float* r0 = M + (8 * ks + 2 * t) * LS + 16 * mi + g;
+            const float* r0 = M + (8 * ks + 2 * t) * LS + 16 * (mi + m0) + g;
             const float* r1 = r0 + LS;
             af[mi][ks][0] = to_tf32(r0[0]);      // (row c = 16mi+g,   k = t   <-> r = 8ks+2t)
             af[mi][ks][1] = to_tf32(r0[8]);      // (row c = 16mi+g+8, k = t)
@@ -201,8 +212,11 @@ __device__ __forceinline__ void tc_keep(const Philox& ph, unsigned stream, long 
 }
 
 // =============================================================================================== forward
-template <int MT, int NT, int NW>
-__global__ void __launch_bounds__(NW * 32, 1) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ,
+// PAIR: two warps share one pipeline (one set of tiles, one set of mbarriers) and each owns one 16-row query tile of the
+// item -- every product of the forward is row-local, so the pair only meets at the buffer hand-overs (pipe_sync).  Twice
+// the warps per SM at the same shared-memory footprint; the kernel is latency-bound at 6 warps/SM (profiles/r01h_attention_ncu.md).
+template <int MT, int NT, int NW, bool PAIR>
+__global__ void __launch_bounds__(NW * (PAIR ? 64 : 32), 1) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                  const __grid_constant__ CUtensorMap tmK,
                                                                  const __grid_constant__ CUtensorMap tmV, const TcArgs A) {
     using C = TcCfg<MT, NT>;
@@ -210,7 +224,12 @@ __global__ void __launch_bounds__(NW * 32, 1) attn_tc_fwd_kernel(const __grid_co
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzled boxes need 1 KiB alignment
     const int CW = min(A.dh, 128);
     constexpr int box_words = C::ROWS * 32, box_bytes = box_words * 4;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    static_assert(!PAIR || MT == 2, "a pair splits exactly two query tiles");
+    constexpr int MW = PAIR ? MT / 2 : MT;                    // query tiles per warp
+    const int lane = threadIdx.x & 31;
+    const int warp = PAIR ? (threadIdx.x >> 6) : (threadIdx.x >> 5);          // pipeline index inside the CTA
+    const int m0 = PAIR ? ((threadIdx.x >> 5) & 1) : 0;                       // first query tile of this warp
+    const bool leader = (lane == 0) && (m0 == 0);
     unsigned char* priv;
     WarpBuf wb = warp_setup<NW>(smem, (CW / 32) * box_bytes, 0, &priv, warp);
     const int L = A.L, nc = A.nc;
@@ -233,9 +252,9 @@ __global__ void __launch_bounds__(NW * 32, 1) attn_tc_fwd_kernel(const __grid_co
     {   // prologue: first item's Q, K (chunk 0) and V (chunk 0)
         int r0, c0;
         coords(item_lo, r0, c0);
-        wb.issue(0, &tmQ, c0, r0, L, CW, box_bytes, lane);
-        wb.issue(1, &tmK, c0, r0, L, CW, box_bytes, lane);
-        wb.issue(2, &tmV, c0, r0, L, CW, box_bytes, lane);
+        wb.issue(0, &tmQ, c0, r0, L, CW, box_bytes, leader);
+        wb.issue(1, &tmK, c0, r0, L, CW, box_bytes, leader);
+        wb.issue(2, &tmV, c0, r0, L, CW, box_bytes, leader);
     }
     for (long long item = item_lo; item < item_hi; ++item) {
         const long long bb = item / A.h;
@@ -244,22 +263,22 @@ __global__ void __launch_bounds__(NW * 32, 1) attn_tc_fwd_kernel(const __grid_co
         coords(item, row0, col0);
         const bool has_next = item + 1 < item_hi;
         if (has_next) coords(item + 1, nrow0, ncol0);
-        float acc[MT][NT][4];
+        float acc[MW][NT][4];
 #pragma unroll
-        for (int mi = 0; mi < MT; ++mi)
+        for (int mi = 0; mi < MW; ++mi)
 #pragma unroll
             for (int nj = 0; nj < NT; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = acc[mi][nj][2] = acc[mi][nj][3] = 0.f;
         for (int c = 0; c < nc; ++c) {
             wb.wait(0);
             wb.wait(1);
-            tc_rowrow<MT, NT>(wb.buf[0], wb.buf[1], box_words, CW, g, t, acc);
-            __syncwarp();                                    // every lane is done reading before the buffers are refilled
+            tc_rowrow<MW, NT>(wb.buf[0], wb.buf[1], box_words, CW, g, t, acc, m0);
+            pipe_sync<PAIR>(warp);                           // everyone is done reading before the buffers are refilled
             if (c + 1 < nc) {
-                wb.issue(0, &tmQ, col0 + (c + 1) * CW, row0, L, CW, box_bytes, lane);
-                wb.issue(1, &tmK, col0 + (c + 1) * CW, row0, L, CW, box_bytes, lane);
+                wb.issue(0, &tmQ, col0 + (c + 1) * CW, row0, L, CW, box_bytes, leader);
+                wb.issue(1, &tmK, col0 + (c + 1) * CW, row0, L, CW, box_bytes, leader);
             } else if (has_next) {                           // next item's Q, K load while this item does softmax + P V
-                wb.issue(0, &tmQ, ncol0, nrow0, L, CW, box_bytes, lane);
-                wb.issue(1, &tmK, ncol0, nrow0, L, CW, box_bytes, lane);
+                wb.issue(0, &tmQ, ncol0, nrow0, L, CW, box_bytes, leader);
+                wb.issue(1, &tmK, ncol0, nrow0, L, CW, box_bytes, leader);
             }
         }
         // ---- mask + softmax on the accumulator fragments: thread holds rows {16mi+g, +8}, cols 8nj + 2t + {0,1}
@@ -271,12 +290,12 @@ __global__ void __launch_bounds__(NW * 32, 1) attn_tc_fwd_kernel(const __grid_co
                 const int j = 8 * nj + 2 * t + e;
                 kvalid[nj][e] = (j < L) && (A.key_ids == nullptr || A.key_ids[bb * L + j] != 0);
             }
-        uint32_t pf[MT][NT][4];          // dropped P as A fragments of the next product
+        uint32_t pf[MW][NT][4];          // dropped P as A fragments of the next product
 #pragma unroll
-        for (int mi = 0; mi < MT; ++mi)
+        for (int mi = 0; mi < MW; ++mi)
 #pragma unroll
             for (int hrow = 0; hrow < 2; ++hrow) {
-                const int i = 16 * mi + g + 8 * hrow;
+                const int i = 16 * (mi + m0) + g + 8 * hrow;
                 float sc[NT][2];
                 float mx = -INFINITY;
 #pragma unroll
@@ -329,18 +348,20 @@ __global__ void __launch_bounds__(NW * 32, 1) attn_tc_fwd_kernel(const __grid_co
         for (int c = 0; c < nc; ++c) {
             wb.wait(2);
             float* out = A.ctx + bb * L * (long long)(A.h * A.dh) + (long long)hd * A.dh + c * CW;
-            tc_frag_times_tile<MT, NT>(pf, wb.buf[2], box_words, CW, L, g, t, out, (long long)A.h * A.dh);
-            __syncwarp();
-            if (c + 1 < nc) wb.issue(2, &tmV, col0 + (c + 1) * CW, row0, L, CW, box_bytes, lane);
-            else if (has_next) wb.issue(2, &tmV, ncol0, nrow0, L, CW, box_bytes, lane);
+            tc_frag_times_tile<MW, NT>(pf, wb.buf[2], box_words, CW, L, g, t, out, (long long)A.h * A.dh, m0);
+            pipe_sync<PAIR>(warp);
+            if (c + 1 < nc) wb.issue(2, &tmV, col0 + (c + 1) * CW, row0, L, CW, box_bytes, leader);
+            else if (has_next) wb.issue(2, &tmV, ncol0, nrow0, L, CW, box_bytes, leader);
         }
     }
 }
 
 // =============================================================================================== backward
 //   buffers: 0 = dO (kept for both phases when nc == 1), 1 = V then K, 2 = Q
-template <int MT, int NT, int NW>
-__global__ void __launch_bounds__(NW * 32, 1) attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ,
+//   PAIR: as in the forward; dP/dS/dQ are split by query tile, dV/dK by key tile (they contract over ALL queries, which
+//   the pair exchanges through the pipeline's private Pd / dS tiles -- one extra pipe_sync after they are written)
+template <int MT, int NT, int NW, bool PAIR>
+__global__ void __launch_bounds__(NW * (PAIR ? 64 : 32), 1) attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                  const __grid_constant__ CUtensorMap tmK,
                                                                  const __grid_constant__ CUtensorMap tmV,
                                                                  const __grid_constant__ CUtensorMap tmDO, const TcArgs A) {
@@ -350,7 +371,12 @@ __global__ void __launch_bounds__(NW * 32, 1) attn_tc_bwd_kernel(const __grid_co
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int CW = min(A.dh, 128);
     constexpr int box_words = C::ROWS * 32, box_bytes = box_words * 4;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    static_assert(!PAIR || MT == 2, "a pair splits exactly two query / key tiles");
+    constexpr int MW = PAIR ? MT / 2 : MT;
+    const int lane = threadIdx.x & 31;
+    const int warp = PAIR ? (threadIdx.x >> 6) : (threadIdx.x >> 5);
+    const int m0 = PAIR ? ((threadIdx.x >> 5) & 1) : 0;
+    const bool leader = (lane == 0) && (m0 == 0);
     unsigned char* priv;
     WarpBuf wb = warp_setup<NW>(smem, (CW / 32) * box_bytes, (size_t)2 * PR * LS * 4, &priv, warp);
     const int L = A.L, nc = A.nc;
@@ -374,9 +400,9 @@ __global__ void __launch_bounds__(NW * 32, 1) attn_tc_bwd_kernel(const __grid_co
     {
         int r0, c0;
         coords(item_lo, r0, c0);
-        wb.issue(0, &tmDO, c0, r0, L, CW, box_bytes, lane);
-        wb.issue(1, &tmV, c0, r0, L, CW, box_bytes, lane);
-        wb.issue(2, &tmQ, c0, r0, L, CW, box_bytes, lane);
+        wb.issue(0, &tmDO, c0, r0, L, CW, box_bytes, leader);
+        wb.issue(1, &tmV, c0, r0, L, CW, box_bytes, leader);
+        wb.issue(2, &tmQ, c0, r0, L, CW, box_bytes, leader);
     }
     for (long long item = item_lo; item < item_hi; ++item) {
         const long long bb = item / A.h;
@@ -385,30 +411,30 @@ __global__ void __launch_bounds__(NW * 32, 1) attn_tc_bwd_kernel(const __grid_co
         coords(item, row0, col0);
         const bool has_next = item + 1 < item_hi;
         if (has_next) coords(item + 1, nrow0, ncol0);
-        float acc[MT][NT][4];
+        float acc[MW][NT][4];
 #pragma unroll
-        for (int mi = 0; mi < MT; ++mi)
+        for (int mi = 0; mi < MW; ++mi)
 #pragma unroll
             for (int nj = 0; nj < NT; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = acc[mi][nj][2] = acc[mi][nj][3] = 0.f;
         for (int c = 0; c < nc; ++c) {              // dPd = dO V^T
             wb.wait(0);
             wb.wait(1);
-            tc_rowrow<MT, NT>(wb.buf[0], wb.buf[1], box_words, CW, g, t, acc);
-            __syncwarp();
+            tc_rowrow<MW, NT>(wb.buf[0], wb.buf[1], box_words, CW, g, t, acc, m0);
+            pipe_sync<PAIR>(warp);
             if (c + 1 < nc) {
-                wb.issue(0, &tmDO, col0 + (c + 1) * CW, row0, L, CW, box_bytes, lane);
-                wb.issue(1, &tmV, col0 + (c + 1) * CW, row0, L, CW, box_bytes, lane);
+                wb.issue(0, &tmDO, col0 + (c + 1) * CW, row0, L, CW, box_bytes, leader);
+                wb.issue(1, &tmV, col0 + (c + 1) * CW, row0, L, CW, box_bytes, leader);
             } else {
-                if (nc > 1) wb.issue(0, &tmDO, col0, row0, L, CW, box_bytes, lane);   // chunk 0 of dO again for phase 2
-                wb.issue(1, &tmK, col0, row0, L, CW, box_bytes, lane);                 // K chunk 0 replaces V
+                if (nc > 1) wb.issue(0, &tmDO, col0, row0, L, CW, box_bytes, leader);   // chunk 0 of dO again for phase 2
+                wb.issue(1, &tmK, col0, row0, L, CW, box_bytes, leader);                 // K chunk 0 replaces V
             }
         }
-        uint32_t dsf[MT][NT][4];                    // dS as A fragments (key-permuted) for dQ = dS K
+        uint32_t dsf[MW][NT][4];                    // dS as A fragments (key-permuted) for dQ = dS K
 #pragma unroll
-        for (int mi = 0; mi < MT; ++mi)
+        for (int mi = 0; mi < MW; ++mi)
 #pragma unroll
             for (int hrow = 0; hrow < 2; ++hrow) {
-                const int i = 16 * mi + g + 8 * hrow;
+                const int i = 16 * (mi + m0) + g + 8 * hrow;
                 unsigned kb[2] = {0xffu, 0xffu};
                 if (A.p_drop > 0.f) tc_keep<NT>(ph, A.rng_stream, item, L, i, t, thr, kb);
                 float p[NT][2], dp[NT][2];
@@ -445,29 +471,29 @@ __global__ void __launch_bounds__(NW * 32, 1) attn_tc_bwd_kernel(const __grid_co
                     }
                 }
             }
-        __syncwarp();
-        uint32_t pT[MT][NT][4], dsT[MT][NT][4];
-        tc_load_transposed<MT, NT>(Pd_s, LS, g, t, pT);       // A = Pd^T  (rows = keys j, contraction over queries i)
-        tc_load_transposed<MT, NT>(dS_s, LS, g, t, dsT);      // A = dS^T
-        __syncwarp();                                         // private tiles may be overwritten by the next item
+        pipe_sync<PAIR>(warp);                                // all query rows of Pd / dS are in the private tiles
+        uint32_t pT[MW][NT][4], dsT[MW][NT][4];
+        tc_load_transposed<MW, NT>(Pd_s, LS, g, t, pT, m0);   // A = Pd^T  (rows = keys j, contraction over queries i)
+        tc_load_transposed<MW, NT>(dS_s, LS, g, t, dsT, m0);  // A = dS^T
+        pipe_sync<PAIR>(warp);                                // private tiles may be overwritten by the next item
         for (int c = 0; c < nc; ++c) {
             const long long go = bb * L * A.ld_grad + (long long)hd * A.dh + c * CW;
             const bool last = (c + 1 == nc);
             if (nc > 1 || c > 0) wb.wait(0);                   // (nc == 1: dO of phase 1 is still resident)
-            tc_frag_times_tile<MT, NT>(pT, wb.buf[0], box_words, CW, L, g, t, A.dv + go, A.ld_grad);     // dV = Pd^T dO
-            __syncwarp();
-            if (!last) wb.issue(0, &tmDO, col0 + (c + 1) * CW, row0, L, CW, box_bytes, lane);
-            else if (has_next) wb.issue(0, &tmDO, ncol0, nrow0, L, CW, box_bytes, lane);
+            tc_frag_times_tile<MW, NT>(pT, wb.buf[0], box_words, CW, L, g, t, A.dv + go, A.ld_grad, m0);     // dV = Pd^T dO
+            pipe_sync<PAIR>(warp);
+            if (!last) wb.issue(0, &tmDO, col0 + (c + 1) * CW, row0, L, CW, box_bytes, leader);
+            else if (has_next) wb.issue(0, &tmDO, ncol0, nrow0, L, CW, box_bytes, leader);
             wb.wait(1);
-            tc_frag_times_tile<MT, NT>(dsf, wb.buf[1], box_words, CW, L, g, t, A.dq + go, A.ld_grad);    // dQ = dS K
-            __syncwarp();
-            if (!last) wb.issue(1, &tmK, col0 + (c + 1) * CW, row0, L, CW, box_bytes, lane);
-            else if (has_next) wb.issue(1, &tmV, ncol0, nrow0, L, CW, box_bytes, lane);
+            tc_frag_times_tile<MW, NT>(dsf, wb.buf[1], box_words, CW, L, g, t, A.dq + go, A.ld_grad, m0);    // dQ = dS K
+            pipe_sync<PAIR>(warp);
+            if (!last) wb.issue(1, &tmK, col0 + (c + 1) * CW, row0, L, CW, box_bytes, leader);
+            else if (has_next) wb.issue(1, &tmV, ncol0, nrow0, L, CW, box_bytes, leader);
             wb.wait(2);
-            tc_frag_times_tile<MT, NT>(dsT, wb.buf[2], box_words, CW, L, g, t, A.dk + go, A.ld_grad);    // dK = dS^T Q
-            __syncwarp();
-            if (!last) wb.issue(2, &tmQ, col0 + (c + 1) * CW, row0, L, CW, box_bytes, lane);
-            else if (has_next) wb.issue(2, &tmQ, ncol0, nrow0, L, CW, box_bytes, lane);
+            tc_frag_times_tile<MW, NT>(dsT, wb.buf[2], box_words, CW, L, g, t, A.dk + go, A.ld_grad, m0);    // dK = dS^T Q
+            pipe_sync<PAIR>(warp);
+            if (!last) wb.issue(2, &tmQ, col0 + (c + 1) * CW, row0, L, CW, box_bytes, leader);
+            else if (has_next) wb.issue(2, &tmQ, ncol0, nrow0, L, CW, box_bytes, leader);
         }
     }
 }
@@ -507,7 +533,7 @@ static int tc_make_map(CUtensorMap* tm, const float* base, long long rows, long 
     return PR_OK;
 }
 
-template <int MT, int NT, int NW, bool BWD>
+template <int MT, int NT, int NW, bool BWD, bool PAIR>
 static int launch_tc_nw(TcArgs& A, cudaStream_t stream) {
     using C = TcCfg<MT, NT>;
     const int CW = std::min(A.dh, 128);
@@ -524,11 +550,11 @@ static int launch_tc_nw(TcArgs& A, cudaStream_t stream) {
     const int grid = (int)std::max<long long>(1, std::min<long long>((n_items + NW - 1) / NW, sm_count()));
     if (BWD) {
         if ((rc = tc_make_map(&tmDO, A.dctx, rows, cols, cols, A.L))) return rc;
-        PR_CUDA_CALL(cudaFuncSetAttribute(attn_tc_bwd_kernel<MT, NT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_tc_bwd_kernel<MT, NT, NW><<<grid, NW * 32, smem, stream>>>(tmQ, tmK, tmV, tmDO, A);
+        PR_CUDA_CALL(cudaFuncSetAttribute(attn_tc_bwd_kernel<MT, NT, NW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attn_tc_bwd_kernel<MT, NT, NW, PAIR><<<grid, NW * (PAIR ? 64 : 32), smem, stream>>>(tmQ, tmK, tmV, tmDO, A);
     } else {
-        PR_CUDA_CALL(cudaFuncSetAttribute(attn_tc_fwd_kernel<MT, NT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attn_tc_fwd_kernel<MT, NT, NW><<<grid, NW * 32, smem, stream>>>(tmQ, tmK, tmV, A);
+        PR_CUDA_CALL(cudaFuncSetAttribute(attn_tc_fwd_kernel<MT, NT, NW, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attn_tc_fwd_kernel<MT, NT, NW, PAIR><<<grid, NW * (PAIR ? 64 : 32), smem, stream>>>(tmQ, tmK, tmV, A);
     }
     PR_CUDA_LAUNCH_CHECK(BWD ? "attn_tc_bwd_kernel" : "attn_tc_fwd_kernel");
     return PR_OK;
@@ -542,11 +568,19 @@ static int launch_tc(TcArgs& A, cudaStream_t stream) {
     const size_t per_warp = (size_t)3 * (CW / 32) * C::ROWS * 128 + (BWD ? (size_t)2 * C::PR * C::LS * 4 : 0) + 24;
     const int fit = (int)((220 * 1024 - 1024) / per_warp);
     PR_CHECK_ARG(fit >= 2, "attention(tf32): L=%d dh=%d does not fit shared memory", A.L, A.dh);
-    if (fit >= 8) return launch_tc_nw<MT, NT, 8, BWD>(A, stream);
-    if (fit >= 6) return launch_tc_nw<MT, NT, 6, BWD>(A, stream);
-    if (fit >= 5) return launch_tc_nw<MT, NT, 5, BWD>(A, stream);
-    if (fit >= 4) return launch_tc_nw<MT, NT, 4, BWD>(A, stream);
-    return launch_tc_nw<MT, NT, 2, BWD>(A, stream);
+    constexpr bool CAN_PAIR = (MT == 2);
+    if (CAN_PAIR && (tune() & PR_TUNE_ATTN_PAIR)) {          // two warps per pipeline (named barriers 1..NW: NW <= 8)
+        if (fit >= 8) return launch_tc_nw<MT, NT, 8, BWD, CAN_PAIR>(A, stream);
+        if (fit >= 6) return launch_tc_nw<MT, NT, 6, BWD, CAN_PAIR>(A, stream);
+        if (fit >= 5) return launch_tc_nw<MT, NT, 5, BWD, CAN_PAIR>(A, stream);
+        if (fit >= 4) return launch_tc_nw<MT, NT, 4, BWD, CAN_PAIR>(A, stream);
+        return launch_tc_nw<MT, NT, 2, BWD, CAN_PAIR>(A, stream);
+    }
+    if (fit >= 8) return launch_tc_nw<MT, NT, 8, BWD, false>(A, stream);
+    if (fit >= 6) return launch_tc_nw<MT, NT, 6, BWD, false>(A, stream);
+    if (fit >= 5) return launch_tc_nw<MT, NT, 5, BWD, false>(A, stream);
+    if (fit >= 4) return launch_tc_nw<MT, NT, 4, BWD, false>(A, stream);
+    return launch_tc_nw<MT, NT, 2, BWD, false>(A, stream);
 }
 
 template <bool BWD>

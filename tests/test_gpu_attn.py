@@ -119,11 +119,22 @@ def test_attention_rejects_bad_shapes():
 TOL_TF32 = 2e-3      # TF32 operands (10-bit mantissa), fp32 accumulate; north_star tolerance is 1e-3 on loss/logits
 
 
+@pytest.fixture(params=[0, 8], ids=["warp_per_item", "warp_pair_per_item"])
+def attn_tune(request):
+    """tensor-core attention variants (pr_set_tuning bit 8: two warps share one item pipeline); same results required"""
+    from pixelrec_b200 import lib
+    L_ = lib.load()
+    before = L_.pr_set_tuning(-1)
+    L_.pr_set_tuning((before & ~8) | request.param)
+    yield request.param
+    L_.pr_set_tuning(before)
+
+
 @pytest.mark.parametrize("B,L,h,dh", [(3, 10, 4, 32), (5, 20, 4, 128), (2, 7, 2, 128), (4, 20, 4, 16), (2, 12, 4, 64),
                                       (3, 20, 4, 512), (2, 10, 2, 256), (3, 32, 2, 64), (70, 20, 4, 128), (2, 1, 4, 32),
-                                      (300, 20, 4, 128), (4, 16, 4, 96), (3, 24, 2, 128)])
+                                      (300, 20, 4, 128), (4, 16, 4, 96), (3, 24, 2, 128), (33, 17, 4, 32), (9, 32, 4, 256)])
 @pytest.mark.parametrize("p", [0.0, 0.1])
-def test_attention_tensor_core_path(B, L, h, dh, p):
+def test_attention_tensor_core_path(B, L, h, dh, p, attn_tune):
     """mma.sync TF32 attention core vs the fp64 oracle (same masks, same Philox dropout bits as the fp32 kernel)."""
     from pixelrec_b200 import ops
     if dh % 32:
@@ -141,7 +152,7 @@ def test_attention_tensor_core_path(B, L, h, dh, p):
     assert rel(tq.grad.cpu().numpy(), dqkv_ref) < TOL_TF32 * 2
 
 
-def test_attention_tensor_core_exact_on_tf32_representable_inputs():
+def test_attention_tensor_core_exact_on_tf32_representable_inputs(attn_tune):
     """With operands exactly representable in TF32 the tensor-core path must agree with the fp32 FFMA kernel to fp32
     rounding (1e-6), which pins the fragment layouts independently of TF32 rounding noise."""
     from pixelrec_b200 import ops
@@ -155,3 +166,24 @@ def test_attention_tensor_core_exact_on_tf32_representable_inputs():
     valid = torch.from_numpy(ids.astype(bool)).to(a.device)
     # S = QK^T is exact; P is fp32 -> rounded to TF32 before P V, so O carries ~2^-11 relative error
     assert (a - b)[valid].abs().max().item() < 2e-3 * a.abs().max().item()
+
+
+@pytest.mark.parametrize("B,L,h,dh,p", [(300, 20, 4, 128, 0.1), (40, 32, 2, 64, 0.0), (25, 20, 4, 512, 0.1)])
+def test_attention_warp_pair_variant_is_bit_identical(B, L, h, dh, p):
+    """Splitting an item between two warps changes who computes a query tile, not the arithmetic: ctx, probs-based grads equal."""
+    from pixelrec_b200 import lib, ops
+    L_ = lib.load()
+    before = L_.pr_set_tuning(-1)
+    qkv, ids, dctx, *_ = _case(B, L, h, dh, p, 5)
+    outs = []
+    try:
+        for mask in (before & ~8, before | 8):
+            L_.pr_set_tuning(mask)
+            tq = t(qkv).requires_grad_()
+            ctx = ops.attention(tq, t(ids), h, True, p, 5, 5, tf32=True)
+            ctx.backward(t(dctx))
+            torch.cuda.synchronize()
+            outs.append((ctx.detach().clone(), tq.grad.clone()))
+    finally:
+        L_.pr_set_tuning(before)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
