@@ -17,7 +17,7 @@ int tune();                      // PR_TUNE bit mask (api.cu)
 #define PR_TUNE_LN_FWD_PIPE 4
 #define PR_TUNE_ATTN_PAIR 8
 #ifndef PR_TUNE_DEFAULT
-#define PR_TUNE_DEFAULT PR_TUNE_LN_BWD_PIPE   /* measured: profiles/r01h_rowkernels_ab.md */
+#define PR_TUNE_DEFAULT (PR_TUNE_LN_BWD_PIPE | PR_TUNE_ATTN_PAIR)   /* measured: profiles/r01h_rowkernels_ab.md, r01l_attention_pair.md */
 #endif
 
 #define PR_CHECK_ARG(cond, ...)                 \
