@@ -13,13 +13,14 @@ W1 = np.uint64(0xBB67AE85)
 MASK = np.uint64(0xFFFFFFFF)
 
 
-def philox4x32_10(ctr, stream, seed):
-    """ctr: uint64 array; returns uint32 array [..., 4]."""
+def philox4x32_10(ctr, stream, seed, c3=0):
+    """ctr: uint64 array (counter words 0,1); stream = counter word 2; c3 = counter word 3 (the kernels always use 0; the
+    argument exists so the Random123 known-answer vectors can be checked).  Returns uint32 array [..., 4]."""
     ctr = np.asarray(ctr, dtype=np.uint64)
     c0 = ctr & MASK
     c1 = (ctr >> np.uint64(32)) & MASK
     c2 = np.full_like(c0, np.uint64(stream))
-    c3 = np.zeros_like(c0)
+    c3 = np.full_like(c0, np.uint64(c3))
     k0 = np.uint64(seed & 0xFFFFFFFF)
     k1 = np.uint64((seed >> 32) & 0xFFFFFFFF)
     for _ in range(10):
