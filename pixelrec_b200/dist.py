@@ -105,7 +105,8 @@ class ShardedGatherFn(torch.autograd.Function):
         D = W_local.shape[1]
         rows_send = ROWS.gather(W_local, plan.recv_rows)                              # owner-side gather
         rows_recv = torch.empty(plan.U, D, dtype=W_local.dtype, device=W_local.device)
-        dist.all_to_all_single(rows_recv, rows_send, plan.send_splits, plan.recv_splits, group=table.group)
+        with ops._prof("exchange_fwd_a2a", rows_send):                                # event-timed by bench.py at N > 1
+            dist.all_to_all_single(rows_recv, rows_send, plan.send_splits, plan.recv_splits, group=table.group)
         out = ROWS.gather(rows_recv, plan.expand)                                     # unique rows -> request order
         ctx.plan = plan
         ctx.table = table
@@ -120,7 +121,8 @@ class ShardedGatherFn(torch.autograd.Function):
         d_u = ROWS.scatter_slots(dE, plan.inverse.contiguous(), plan.U, plan.pad_slot)
         d_send = ROWS.gather(d_u, plan.perm)
         d_recv = torch.empty(len(plan.recv_rows), D, dtype=dE.dtype, device=dE.device)
-        dist.all_to_all_single(d_recv, d_send, plan.recv_splits, plan.send_splits, group=table.group)
+        with ops._prof("exchange_bwd_a2a", d_send):
+            dist.all_to_all_single(d_recv, d_send, plan.recv_splits, plan.send_splits, group=table.group)
         splan = ROWS.plan(plan.recv_rows, table.n_local, table.local_padding_idx, row2slot=table.sink.row2slot)
         rows = ROWS.scatter(d_recv, splan)                                            # duplicates ACROSS ranks reduced here
         table.sink.deposit(splan, rows)

@@ -102,7 +102,8 @@ class FusedAdamW(torch.optim.Optimizer):
         if self.world > 1:
             for f in self._flat:
                 if f is not None:
-                    torch.distributed.all_reduce(f["g"])
+                    with ops._prof("dense_grad_allreduce", f["g"]):
+                        torch.distributed.all_reduce(f["g"])
         for gi, group in enumerate(self.param_groups):
             b1, b2 = group["betas"]
             f = self._flat[gi]
