@@ -15,6 +15,18 @@
 //     written to memory.
 //   * grid = m_tiles x n_splits (<= #SMs); every CTA walks its share of the N tiles; a small second kernel merges
 //     the n_splits candidate lists per row (ties -> lower item id, like a stable sort).
+//
+// v2 (score_topk2_kernel, PR_TUNE_SCORE_V2; + PR_TUNE_SCORE_MCAST) -- same MMA pipeline, different epilogue and operand feed:
+//   * v1's epilogue is what bounds it (ncu: tensor pipe 16-20 % active, L2 15 %): every candidate insertion is a divergent
+//     branch that serialises the warp (~3.5 K insert events per warp and CTA), and one epilogue warp per scheduler cannot
+//     hide the latency of the shared-memory candidate walk.  v2 builds a 32-bit candidate word per 32-column chunk with
+//     compares only, then runs a WARP-UNIFORM loop (trip count = max candidates of any lane, ~1-2 per chunk) whose body
+//     is a predicated register select tree + predicated sorted insert: no branches, no shared memory.  8 epilogue warps
+//     (two per TMEM lane quadrant, 128 columns each) double the issue slots; every thread keeps its own list.
+//   * MCAST: the m-tiles of an eval batch (8 at B_e=1024) all need the same [256 x 32] table tile.  They form a thread
+//     block cluster; CTA r loads rows [r*256/CL, (r+1)*256/CL) of the tile and TMA-multicasts them into every CTA of
+//     the cluster (empty barriers collect one tcgen05.commit.multicast arrive per CTA before a stage is overwritten).
+//     L2->SM operand traffic per k-block drops from 48 KiB to 16 + 32/CL KiB (CL=8: 20 KiB).
 #include <cuda.h>
 
 #include <algorithm>
@@ -39,8 +51,9 @@ struct ScoreArgs {
     int m_tiles, n_tiles, tiles_per_split, n_splits;
     int n_words;          // mask words per row = n_tiles * 8
     const uint32_t* mask; // [m_tiles*128][n_words]
-    float* cand_val;      // [m_tiles*128][n_splits][K]
+    float* cand_val;      // [m_tiles*128][n_splits][K]   (v2: [m_tiles*128][n_splits*2][K])
     int* cand_idx;
+    int cluster;          // v2: CTAs per cluster sharing each table tile by TMA multicast (1 = none)
 };
 
 // ---- PTX wrappers (tcgen05 / TMA) --------------------------------------------------------------------------
@@ -248,6 +261,184 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_topk_kernel(const __grid_
     if (warp == 1) tmem_dealloc(tmem_base, SC_TMEM_COLS);
 }
 
+
+// ================================================================================================ v2
+constexpr int SC2_EPI_WARPS = 8;
+constexpr int SC2_THREADS = 64 + 32 * SC2_EPI_WARPS;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// box -> the same shared-memory offset of every CTA in `mask`; complete_tx lands on the same-offset mbarrier of each
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar,
+                                                  uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+        "[%2], %5;" ::"r"(smem_u32(smem_dst)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+// one arrive on the same-offset mbarrier of every CTA in `mask` once this thread's earlier tcgen05.mma have completed
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+// v[j] for a per-lane j without local memory: 31 selects
+__device__ __forceinline__ float pick32(const float (&v)[32], int j) {
+    float a[16], b[8], c[4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+    const float d0 = (j & 8) ? c[1] : c[0], d1 = (j & 8) ? c[3] : c[2];
+    return (j & 16) ? d1 : d0;
+}
+
+template <int K>
+__global__ void __launch_bounds__(SC2_THREADS, 1) score_topk2_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                     const __grid_constant__ CUtensorMap tmB,
+                                                                     const ScoreArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ __align__(8) uint64_t full_bar[SC_STAGES], empty_bar[SC_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x % a.m_tiles, split = blockIdx.x / a.m_tiles;
+    const int t_begin = split * a.tiles_per_split;
+    const int t_end = min(a.n_tiles, t_begin + a.tiles_per_split);
+    const int n_my = t_end - t_begin;                      // identical in every CTA of a cluster (same split)
+    const int CL = a.cluster;
+    const uint16_t cl_mask = (uint16_t)((1u << CL) - 1u);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (uint32_t)CL); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], SC2_EPI_WARPS); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, SC_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    if (CL > 1) cluster_sync_all();                        // peers' barriers are initialised before any remote arrive / multicast
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            const int rank = (CL > 1) ? (int)cluster_ctarank() : 0;
+            const int slice_rows = SC_BN / CL;
+            const int slice_bytes = SC_B_BYTES / CL;
+            long long it = 0;
+            for (int t = 0; t < n_my; ++t) {
+                const int n0 = (t_begin + t) * SC_BN;
+                for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
+                    const int s = (int)(it % SC_STAGES);
+                    // CL arrivals: every CTA of the cluster has finished reading stage s of the previous round
+                    mbar_wait(&empty_bar[s], (uint32_t)(((it / SC_STAGES) & 1) ^ 1));
+                    mbar_arrive_expect_tx(&full_bar[s], SC_STAGE_BYTES);    // own A box + CL slices of the table tile
+                    unsigned char* st = smem + (size_t)s * SC_STAGE_BYTES;
+                    tma_load_2d(st, &tmA, kb * SC_BK, m_tile * SC_BM, &full_bar[s]);
+                    if (CL > 1)
+                        tma_load_2d_mcast(st + SC_A_BYTES + rank * slice_bytes, &tmB, kb * SC_BK, n0 + rank * slice_rows,
+                                          &full_bar[s], cl_mask);
+                    else
+                        tma_load_2d(st + SC_A_BYTES, &tmB, kb * SC_BK, n0, &full_bar[s]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = tf32_idesc(SC_BM, SC_BN);
+            long long it = 0;
+            for (int t = 0; t < n_my; ++t) {
+                const int buf = t & 1;
+                mbar_wait(&tempty_bar[buf], (uint32_t)(((t >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * SC_BN;
+                for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
+                    const int s = (int)(it % SC_STAGES);
+                    mbar_wait(&full_bar[s], (uint32_t)((it / SC_STAGES) & 1));
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)s * SC_STAGE_BYTES);
+                    const uint64_t adesc = sw128_kmajor_desc(sa), bdesc = sw128_kmajor_desc(sa + SC_A_BYTES);
+#pragma unroll
+                    for (int k4 = 0; k4 < SC_BK / 8; ++k4)
+                        umma_tf32(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) ? 1u : 0u);
+                    if (CL > 1) umma_commit_mcast(&empty_bar[s], cl_mask);   // frees stage s in every CTA that writes into it
+                    else umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tfull_bar[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue warps 2..9
+        // thread == (user row, column half): warp%4 = TMEM lane quadrant, (warp-2)/4 = which 128 of the tile's 256 columns
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = m_tile * SC_BM + q * 32 + lane;
+        float val[K];
+        int idx[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) { val[i] = -INFINITY; idx[i] = -1; }
+        const uint32_t* mrow = a.mask + (size_t)row * a.n_words + half * 4;
+        for (int t = 0; t < n_my; ++t) {
+            const int buf = t & 1;
+            const int tile = t_begin + t;
+            const uint4 mw = *reinterpret_cast<const uint4*>(mrow + tile * 8);
+            mbar_wait(&tfull_bar[buf], (uint32_t)((t >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * SC_BN + half * 128);
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                float v[32];
+                __syncwarp();                                   // tcgen05.ld is warp-collective (.sync.aligned)
+                tmem_ld32(taddr + c * 32, v);
+                const uint32_t w = (c == 0) ? mw.x : (c == 1) ? mw.y : (c == 2) ? mw.z : mw.w;
+                const float thr = val[K - 1];
+                uint32_t bits = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) bits |= (v[j] > thr) ? (1u << j) : 0u;
+                bits &= ~w;                                     // pad column, history, columns >= N
+                if (__any_sync(0xffffffffu, bits != 0u)) {
+                    const int c0 = tile * SC_BN + half * 128 + c * 32;
+                    do {                                        // warp-uniform trip count; lanes without a candidate insert -inf (no-op)
+                        const bool has = bits != 0u;
+                        const int j = has ? (__ffs((int)bits) - 1) : 0;
+                        bits &= bits - 1u;
+                        const float x = has ? pick32(v, j) : -INFINITY;
+                        topk_insert<K>(val, idx, x, c0 + j);    // ascending j: on ties the lower column stays ahead
+                    } while (__any_sync(0xffffffffu, bits != 0u));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        }
+        const size_t list = (size_t)row * (a.n_splits * 2) + (size_t)(split * 2 + half);
+        float* cv = a.cand_val + list * K;
+        int* ci = a.cand_idx + list * K;
+#pragma unroll
+        for (int i = 0; i < K; ++i) { cv[i] = val[i]; ci[i] = idx[i]; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (CL > 1) cluster_sync_all();       // no CTA may exit while a peer can still arrive on its barriers
+    if (warp == 1) tmem_dealloc(tmem_base, SC_TMEM_COLS);
+}
+
 // merge the n_splits sorted candidate lists of a row: k rounds of warp arg-max (value desc, then item id asc)
 __global__ void __launch_bounds__(128) score_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
                                                           int n_cand, long long B_e, int k, float* __restrict__ out_val,
@@ -372,9 +563,60 @@ static ScorePlan score_plan(long long B_e, long long N, int k) {
     p.n_words = p.n_tiles * 8;
     const size_t rows = (size_t)p.m_tiles * SC_BM;
     p.mask_bytes = (rows * p.n_words * 4 + 255) / 256 * 256;
-    p.cand_bytes = (rows * p.n_splits * p.K * 4 + 255) / 256 * 256;
+    // sized for either kernel variant (the tuning mask may change between the workspace query and the call):
+    // v1 keeps n_splits lists per row, v2 two lists (column halves) for each of <= n_splits splits
+    p.cand_bytes = (rows * p.n_splits * 2 * p.K * 4 + 255) / 256 * 256;
     p.total = p.mask_bytes + 2 * p.cand_bytes;
     return p;
+}
+
+// v2 launch: 8 epilogue warps, optional cluster multicast of the table tile across the m-tiles
+template <int K>
+static int launch_v2(const CUtensorMap& tmA, const float* W, long long N, long long D, ScoreArgs a, const ScorePlan& p,
+                     bool mcast, cudaStream_t stream, int* n_lists) {
+    auto kern = score_topk2_kernel<K>;
+    const size_t smem = (size_t)SC_STAGES * SC_STAGE_BYTES + 1024;          // ring + 1 KiB alignment slack
+    PR_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int splits = std::min(p.n_splits, 1024 / (2 * K));                      // two lists per split and row
+    int CL = 1;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(SC2_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (mcast) {
+        for (int c = 8; c > 1; c >>= 1)
+            if (p.m_tiles % c == 0) { CL = c; break; }
+        if (CL > 1) {
+            // all clusters co-resident in one wave: the multicast couples the CTAs of a cluster, a second wave would idle SMs
+            at[0].val.clusterDim.x = CL;
+            cfg.gridDim = dim3(p.m_tiles * splits);
+            int max_clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < p.m_tiles / CL) {
+                (void)cudaGetLastError();
+                CL = 1;                                                     // cluster shape not schedulable here: plain v2
+            } else {
+                splits = std::max(1, std::min(splits, max_clusters / (p.m_tiles / CL)));
+            }
+        }
+    }
+    a.cluster = CL;
+    a.tiles_per_split = (p.n_tiles + splits - 1) / splits;
+    a.n_splits = (p.n_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
+    *n_lists = a.n_splits * 2;
+    CUtensorMap tmB;
+    int rc = make_map(&tmB, W, N, D, SC_BN / CL);                           // box = this CTA's slice of the table tile
+    if (rc) return rc;
+    at[0].val.clusterDim.x = CL;
+    cfg.gridDim = dim3(p.m_tiles * a.n_splits);
+    PR_CUDA_CALL(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, a));
+    PR_CUDA_LAUNCH_CHECK("score_topk2_kernel");
+    return PR_OK;
 }
 
 }  // namespace pr
@@ -418,24 +660,32 @@ extern "C" int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float*
     CUtensorMap tmA, tmB;
     int rc = make_map(&tmA, seq_out, B_e, D, SC_BM);
     if (rc) return rc;
-    rc = make_map(&tmB, W, N, D, SC_BN);
-    if (rc) return rc;
 
     ScoreArgs a;
     a.kblocks = (int)(D / SC_BK);
     a.m_tiles = p.m_tiles; a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.n_splits = p.n_splits;
-    a.n_words = p.n_words; a.mask = mask; a.cand_val = cand_val; a.cand_idx = cand_idx;
-    const size_t smem = (size_t)SC_STAGES * SC_STAGE_BYTES + 128 * 33 * 4 + 1024;     // ring + candidate rows + 1 KiB alignment slack
-    const int grid = p.m_tiles * p.n_splits;
-    if (p.K == 16) {
-        PR_CUDA_CALL(cudaFuncSetAttribute(score_topk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        score_topk_kernel<16><<<grid, SC_THREADS, smem, stream>>>(tmA, tmB, a);
+    a.n_words = p.n_words; a.mask = mask; a.cand_val = cand_val; a.cand_idx = cand_idx; a.cluster = 1;
+    int n_lists = p.n_splits;
+    if (tune() & PR_TUNE_SCORE_V2) {
+        const bool mcast = (tune() & PR_TUNE_SCORE_MCAST) != 0;
+        rc = (p.K == 16) ? launch_v2<16>(tmA, W, N, D, a, p, mcast, stream, &n_lists)
+                         : launch_v2<32>(tmA, W, N, D, a, p, mcast, stream, &n_lists);
+        if (rc) return rc;
     } else {
-        PR_CUDA_CALL(cudaFuncSetAttribute(score_topk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        score_topk_kernel<32><<<grid, SC_THREADS, smem, stream>>>(tmA, tmB, a);
+        rc = make_map(&tmB, W, N, D, SC_BN);
+        if (rc) return rc;
+        const size_t smem = (size_t)SC_STAGES * SC_STAGE_BYTES + 128 * 33 * 4 + 1024;     // ring + candidate rows + 1 KiB alignment slack
+        const int grid = p.m_tiles * p.n_splits;
+        if (p.K == 16) {
+            PR_CUDA_CALL(cudaFuncSetAttribute(score_topk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            score_topk_kernel<16><<<grid, SC_THREADS, smem, stream>>>(tmA, tmB, a);
+        } else {
+            PR_CUDA_CALL(cudaFuncSetAttribute(score_topk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            score_topk_kernel<32><<<grid, SC_THREADS, smem, stream>>>(tmA, tmB, a);
+        }
+        PR_CUDA_LAUNCH_CHECK("score_topk_kernel");
     }
-    PR_CUDA_LAUNCH_CHECK("score_topk_kernel");
-    score_merge_kernel<<<(int)((B_e + 3) / 4), 128, 0, stream>>>(cand_val, cand_idx, p.n_splits * p.K, B_e, k, topk_val,
+    score_merge_kernel<<<(int)((B_e + 3) / 4), 128, 0, stream>>>(cand_val, cand_idx, n_lists * p.K, B_e, k, topk_val,
                                                                  (long long*)topk_idx);
     PR_CUDA_LAUNCH_CHECK("score_merge_kernel");
     return PR_OK;

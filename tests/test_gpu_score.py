@@ -1,5 +1,7 @@
 """GPU parity: K9 fused scoring GEMM (tcgen05, TF32) + mask + top-k vs the oracle's
 full_sort_topk (trainer.py:334-336 + collector.py:133)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -8,6 +10,21 @@ from oracle import sasrec_np as O
 from tests.gpu_util import t
 
 pytestmark = pytest.mark.gpu
+
+# Kernel variants of pr_score_topk_f32 (pr_set_tuning bits 16 / 32, csrc/score.cu "v2").  The default kernel always runs;
+# the staged variants were written without GPU access and stay opt-in (PR_EXPERIMENTAL=1, run under a timeout: see
+# tools/round2_gpu.sh) until a B200 run has confirmed them.
+_VARIANTS = [0] + ([16, 48] if os.environ.get("PR_EXPERIMENTAL") == "1" else [])
+
+
+@pytest.fixture(params=_VARIANTS, ids=lambda v: {0: "v1", 16: "v2", 48: "v2_mcast"}[v], autouse=True)
+def score_variant(request):
+    from pixelrec_b200 import lib
+    L_ = lib.load()
+    before = L_.pr_set_tuning(-1)
+    L_.pr_set_tuning((before & ~48) | request.param)
+    yield request.param
+    L_.pr_set_tuning(before)
 
 
 def _hist(g, B_e, N, n_per):

@@ -46,10 +46,25 @@ for tf32 in (True, False):
     out[f"reference_path_tf32={tf32}_ms"] = timeit(ref_path)
 out["fused_tcgen05_ms"] = timeit(lambda: ops.score_topk(seq, W, k, hu, hi))
 out["fused_TFLOPs"] = 2 * B_e * N * D / out["fused_tcgen05_ms"] / 1e9
+# A/B of the kernel variants (pr_set_tuning bits 16 = v2 epilogue, 32 = + cluster multicast): SCORE_TUNES=0,16,48
+if os.environ.get("SCORE_TUNES"):
+    from pixelrec_b200 import lib
+    L_ = lib.load()
+    base = L_.pr_set_tuning(-1)
+    i0 = ops.score_topk(seq, W, k, hu, hi)[1].clone()
+    for tn in [int(x) for x in os.environ["SCORE_TUNES"].split(",")]:
+        L_.pr_set_tuning((base & ~48) | tn)
+        ms = timeit(lambda: ops.score_topk(seq, W, k, hu, hi))
+        same = bool((ops.score_topk(seq, W, k, hu, hi)[1] == i0).all())
+        out[f"tune{tn}_ms"] = ms
+        out[f"tune{tn}_TFLOPs"] = 2 * B_e * N * D / ms / 1e9
+        out[f"tune{tn}_ids_equal_v1"] = same
+    L_.pr_set_tuning(base)
 torch.backends.cuda.matmul.allow_tf32 = False
 v1, i1 = ref_path()
 v2, i2 = ops.score_topk(seq, W, k, hu, hi)
 out["idx_agreement_vs_fp32"] = float((i1 == i2).float().mean())
 out["max_abs_val_diff"] = float((v1 - v2).abs().max())
 print(json.dumps(out))
+os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/bench_score.json", "w"), indent=1)
