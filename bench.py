@@ -153,13 +153,15 @@ def run_reference(args, out):
     out.emit(json.dumps(line))
 
 
-def workload_config(B, world, note=None):
+def workload_config(B, world, note=None, exchange=None):
     c = C2
     cfg = {"workload": f"C2 IDNet/sasrec Pixel200K-shape: N={c['N']} items, emb_dim={c['D']}, seq_len={c['L']}, "
                        f"{c['heads']} heads, {c['layers']} layers, inner {c['inner']}x, dropout {c['dropout']}, "
                        f"AdamW(lr {c['lr']}, wd {c['wd']}) dense semantics, batch {B}/GPU",
            "batch_per_gpu": B, "global_batch": B * world, "seq_len": c["L"],
-           "parallelism": f"dp{world} + item table row-sharded {world}-way" if world > 1 else "single GPU",
+           "parallelism": (f"dp{world} + item table row-sharded {world}-way, row exchange: "
+                           + ("peer-memory kernels over NVLink (P2P)" if exchange == "p2p" else "NCCL all_to_all"))
+           if world > 1 else "single GPU",
            "l2": "working set (table+Adam state 597 MB, activations > 2 GB per step) >> 126 MB L2; a pool of distinct batches rotates"}
     if note:
         cfg["note"] = note
@@ -183,6 +185,8 @@ def run_ours(args, out):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.exchange:
+        os.environ["PR_EXCHANGE"] = args.exchange
     from pixelrec_b200 import ops
     from pixelrec_b200.dist import broadcast_dense_params
     from pixelrec_b200.model.IDNet.sasrec import SASRec
@@ -291,6 +295,9 @@ def run_ours(args, out):
     prof = ops.profile_summary()
     ops.PROFILE.update(on=False, events={})
 
+    xs = getattr(model.item_embedding, "exchange_status", lambda: 0)()
+    if xs:
+        raise SystemExit(f"peer exchange flagged status {xs} (bit 1: receive region overflow -- raise PR_P2P_CAP_FACTOR)")
     hbm, _, peak_src = peaks()
     L, D, N = c["L"], c["D"], c["N"]
     R_u = B * (2 * L + 1)                                   # rows actually consumed
@@ -319,7 +326,7 @@ def run_ours(args, out):
         "metric": METRIC, "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (tf32 tensor-core linear layers, fp32 everywhere else)", "data": "synthetic",
-        "config": workload_config(B, world),
+        "config": workload_config(B, world, exchange=getattr(model.item_embedding, "exchange", None)),
         "e2e": {"value": e2e, "unit": "sequences/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
@@ -378,6 +385,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="sequences per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default=None, choices=["nccl", "p2p"],
+                    help="N>1 row exchange of the sharded table: NCCL all_to_all (default) or peer-memory kernels (staged)")
     args = ap.parse_args()
     with StdoutGuard() as out:
         if args.impl == "reference":

@@ -59,7 +59,8 @@ PR_API int pr_sm_count(void);
 PR_API int pr_set_device(int device);
 /* Kernel-variant switches for A/B measurement (bit mask; also read once from the environment variable PR_TUNE):
  *   1 = LayerNorm backward as per-warp bulk-copy row pipelines, 2 = L2 prefetch of the next row in the register LN kernels,
- *   4 = LayerNorm forward as per-warp bulk-copy row pipelines, 8 = tensor-core attention with two warps per item pipeline.
+ *   4 = LayerNorm forward as per-warp bulk-copy row pipelines, 8 = tensor-core attention with two warps per item pipeline,
+ *   16 = score_topk with the branch-free 8-warp epilogue, 32 = (with 16) table tile TMA-multicast across a cluster.
  * mask < 0 only queries.  Returns the mask in effect.  Results are identical under every mask. */
 PR_API int pr_set_tuning(int mask);
 
@@ -235,6 +236,32 @@ PR_API int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float* W, 
  */
 PR_API int pr_seq_batch_build(const int64_t* padded, int64_t n_seq, int W, const int64_t* sel, int64_t B, int64_t item_num,
                        uint64_t seed, int64_t* items, int64_t* mask, int32_t* status, pr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Peer-memory exchange of the ROW-SHARDED item table (one process per GPU, NVLink / NVSwitch P2P).
+ *   replaces  the table replicated per GPU + the dense [N,D] gradient all-reduce of DDP, REC/run.py:40 around
+ *             nn.Embedding REC/model/IDNet/sasrec.py:31,68; SURVEY.md section 8e (owner(i) = i % G, local row i / G).
+ * pr_shared_alloc / pr_shared_free: device memory of the CURRENT device that other processes may map (cudaMalloc +
+ *   CUDA IPC); handle64 receives an opaque 64-byte handle to ship to the peers (e.g. all_gather_object).
+ * pr_shared_open / pr_shared_close: map / unmap a peer's allocation into the current device's address space (peer access
+ *   is enabled on demand).  Call it in a process OTHER than the one that allocated; open each handle once per process.
+ * pr_gather_rows_peers_f32: out[r, :] = shards[idx[r] % G][idx[r] / G, :] -- lookup and exchange in one kernel; shards is
+ *   a DEVICE array of G device pointers (own shard included), N the global row count.  status bit 0: idx outside [0,N).
+ * pr_push_rows_peers_f32: for every u < U with ids[u] != skip_id: claims slot p = counters[ids[u] % G]++ and writes
+ *   rows[u, :] to recv_rows[owner][rank*cap + p, :] and ids[u] / G to recv_ids[owner][rank*cap + p].  recv_rows[g] is
+ *   rank g's receive buffer [G*cap, D], recv_ids[g] its id buffer [G*cap] (the owner pre-fills it with -1 = unused);
+ *   counters [G] int32 must be zero on entry.  ids must be distinct.  status bit 1: a region overflowed (row dropped).
+ *   The caller orders these kernels against the owners' use of the buffers (a barrier collective on the stream).
+ */
+PR_API int pr_shared_alloc(size_t bytes, void** dptr, unsigned char* handle64);
+PR_API int pr_shared_free(void* dptr);
+PR_API int pr_shared_open(const unsigned char* handle64, void** dptr);
+PR_API int pr_shared_close(void* dptr);
+PR_API int pr_gather_rows_peers_f32(const float* const* shards, int G, int64_t N, int64_t D, const int64_t* idx, int64_t R,
+                                    float* out, int32_t* status, pr_stream_t stream);
+PR_API int pr_push_rows_peers_f32(const float* rows, const int64_t* ids, int64_t U, int64_t D, int G, int rank, int64_t cap,
+                                  int64_t skip_id, float* const* recv_rows, int64_t* const* recv_ids, int32_t* counters,
+                                  int32_t* status, pr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -12,10 +12,21 @@ NVLink/NVSwitch) ONLY at the shard boundary.
     dense-semantics AdamW.  There is no dense [N,D] gradient and no dense all-reduce of the table anywhere
     (the reference all-reduces N*D*4 bytes every step).
 
-The row kernels are reached through `ROWS` so that the exchange logic can be unit-tested on CPU/gloo with an
-oracle-backed stand-in (tests/test_dist_gloo.py); the product default is the CUDA library and nothing else.
+  * `exchange="p2p"` (PR_EXCHANGE=p2p; staged, opt-in until confirmed on a multi-GPU box): the two row all_to_alls,
+    the owner-side gather into a send buffer, the index all_to_all and its host sync are replaced by peer-memory
+    kernels (csrc/peer.cu).  Every rank maps its peers' shards and receive buffers (CUDA IPC); the lookup reads each
+    distinct row straight out of its owner's shard over NVLink (pr_gather_rows_peers_f32), the backward writes the
+    locally reduced gradient rows straight into the owner's receive region (pr_push_rows_peers_f32).  NCCL is left
+    with two 4-byte all_reduces per step that order those kernels against the owners' optimizer step.
+
+The row kernels are reached through `ROWS` (and the peer-memory ones through `PEER`) so that the exchange logic can be
+unit-tested on CPU/gloo with oracle-backed stand-ins (tests/test_dist_gloo.py); the product default is the CUDA
+library and nothing else.
 """
 from __future__ import annotations
+
+import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -51,6 +62,33 @@ class CudaRows:
 
 
 ROWS = CudaRows
+
+
+class CudaPeer:
+    """Default peer-memory backend: CUDA IPC allocations + the kernels of csrc/peer.cu."""
+
+    @staticmethod
+    def alloc(nbytes, device):
+        return ops.SharedBuffer(nbytes, device)          # .ref (device address), .handle, .tensor(shape, dtype)
+
+    @staticmethod
+    def open(handle, device):
+        return ops.shared_open(handle, device)           # device address of the peer's buffer, mapped here
+
+    @staticmethod
+    def table(refs, device):
+        return torch.tensor(refs, dtype=torch.int64, device=device)
+
+    @staticmethod
+    def gather(shard_table, G, N, D, idx):
+        return ops.gather_rows_peers(shard_table, G, N, D, idx)
+
+    @staticmethod
+    def push(rows, ids, G, rank, cap, skip_id, rows_table, ids_table, counters, status):
+        ops.push_rows_peers(rows, ids, G, rank, cap, skip_id, rows_table, ids_table, counters, status)
+
+
+PEER = CudaPeer
 
 
 def world_info(group=None):
@@ -97,6 +135,9 @@ class ExchangePlan:
         self.recv_rows = torch.empty(sum(self.recv_splits), dtype=torch.int64, device=flat.device)
         dist.all_to_all_single(self.recv_rows, local_rows, self.recv_splits, self.send_splits, group=group)
 
+    def tensors(self):
+        return (self.inverse, self.perm, self.expand, self.recv_rows)
+
 
 class ShardedGatherFn(torch.autograd.Function):
     @staticmethod
@@ -129,14 +170,113 @@ class ShardedGatherFn(torch.autograd.Function):
         return None, None, None
 
 
+class PeerPlan:
+    """Index plan of one lookup for the peer-memory exchange: the distinct ids (each row crosses NVLink once per
+    direction) and the map back to request order.  No collective and no split sizes -- it can be built on any stream."""
+
+    def __init__(self, idx, padding_idx=None):
+        flat = idx.reshape(-1)
+        self.R = flat.numel()
+        self.uniq, inverse = torch.unique(flat, sorted=True, return_inverse=True)
+        self.inverse = inverse.contiguous()
+        self.U = self.uniq.numel()
+        self.pad_slot = -1
+        if padding_idx is not None and self.U:
+            hit = (self.uniq == padding_idx).nonzero()
+            if hit.numel():
+                self.pad_slot = int(hit[0])
+
+    def tensors(self):
+        return (self.uniq, self.inverse)
+
+
+class PeerExchange:
+    """Peer-mapped state of one ShardedTableEmbedding: the shard itself (moved into shareable memory), this rank's
+    receive buffers, and device tables of every rank's addresses."""
+
+    def __init__(self, table, R):
+        G, rank, D = table.world, table.rank, table.embedding_dim
+        dev = table.weight.device
+        factor = float(os.environ.get("PR_P2P_CAP_FACTOR", "2.0"))
+        self.R = int(R)
+        self.cap = int(max(1, min(R, max(64, math.ceil(factor * R / G)))))    # rows one source may send one owner per step
+        self.G, self.rank = G, rank
+        # the shard moves into shareable memory; the Parameter object (and its optimizer state) stay the same
+        self._w = PEER.alloc(max(table.n_local, 1) * D * 4, dev)
+        w = self._w.tensor((table.n_local, D), torch.float32)
+        with torch.no_grad():
+            w.copy_(table.weight.data)
+            table.weight.data = w
+        self._rows = PEER.alloc(G * self.cap * D * 4, dev)
+        self._ids = PEER.alloc(G * self.cap * 8, dev)
+        self.recv_rows = self._rows.tensor((G * self.cap, D), torch.float32)
+        self.recv_ids = self._ids.tensor((G * self.cap,), torch.int64)
+        self.recv_ids.fill_(-1)                                                # -1 = unused slot (dropped by the plan)
+        mine = (self._w.handle, self._rows.handle, self._ids.handle, self.cap)
+        everyone = [None] * G
+        dist.all_gather_object(everyone, mine, group=table.group)
+        if any(e[3] != self.cap for e in everyone):
+            raise ops._lib.PixelRecB200Error("peer exchange: ranks disagree on the receive capacity (unequal batch sizes?)")
+        own = (self._w.ref, self._rows.ref, self._ids.ref)
+        refs = [[own[k] if r == rank else PEER.open(everyone[r][k], dev) for r in range(G)] for k in range(3)]
+        self.w_table, self.rows_table, self.ids_table = (PEER.table(x, dev) for x in refs)
+        self.counters = torch.zeros(G, dtype=torch.int32, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._sync = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.group = table.group
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+        dist.barrier(group=table.group)          # every shard copied and every id buffer initialised before the first pull
+
+    def barrier(self):
+        """Orders the peer kernels of all ranks on their streams (4-byte all_reduce; asynchronous w.r.t. the host)."""
+        with ops._prof("exchange_barrier", self._sync):
+            dist.all_reduce(self._sync, group=self.group)
+
+
+class PeerGatherFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, W_local, idx, table):
+        plan = table.take_plan(idx)
+        px = table.peer_exchange(plan.R)
+        D = table.embedding_dim
+        px.barrier()                          # S1: every owner has finished the optimizer step of the previous batch
+        rows_u = PEER.gather(px.w_table, table.world, table.num_embeddings, D, plan.uniq)   # lookup + exchange, one kernel
+        out = ROWS.gather(rows_u, plan.inverse)                                             # distinct rows -> request order
+        ctx.plan, ctx.table, ctx.px = plan, table, px
+        return out.view(*idx.shape, D)
+
+    @staticmethod
+    def backward(ctx, dE):
+        plan, table, px = ctx.plan, ctx.table, ctx.px
+        D = table.embedding_dim
+        if plan.R > px.R:
+            raise ops._lib.PixelRecB200Error(f"peer exchange sized for {px.R} lookups per step, got {plan.R}")
+        dE = dE.contiguous().view(plan.R, D)
+        d_u = ROWS.scatter_slots(dE, plan.inverse, plan.U, plan.pad_slot)       # local duplicates reduced first
+        px.counters.zero_()
+        PEER.push(d_u, plan.uniq, table.world, table.rank, px.cap, table.padding_idx, px.rows_table, px.ids_table,
+                  px.counters, px.status)
+        px.barrier()                          # S2: every rank's rows have landed in the owners' receive buffers
+        splan = ROWS.plan(px.recv_ids, table.n_local, None, row2slot=table.sink.row2slot)
+        rows = ROWS.scatter(px.recv_rows, splan)            # duplicates ACROSS ranks reduced here, in ascending source rank
+        table.sink.deposit(splan, rows)
+        px.recv_ids.fill_(-1)                 # ready for the next step (peers push again only after the next S1)
+        return None, None, None
+
+
 class ShardedTableEmbedding(nn.Module):
     """Row-sharded drop-in for model.layers.TableEmbedding.  `weight` holds only the local shard
     [ceil((N-rank)/world), D]; state_dict()/load_state_dict() speak the reference's full `weight` [N, D]."""
 
-    def __init__(self, num_embeddings, embedding_dim, padding_idx=None, group=None):
+    def __init__(self, num_embeddings, embedding_dim, padding_idx=None, group=None, exchange=None):
         super().__init__()
         from .model.layers import TableGradSink
         self.group = group
+        self.exchange = (exchange or os.environ.get("PR_EXCHANGE", "nccl")).lower()    # "nccl" (all_to_all) | "p2p" (peer memory)
+        if self.exchange not in ("nccl", "p2p"):
+            raise ValueError(f"exchange must be 'nccl' or 'p2p', got {self.exchange!r}")
+        self._px = None
         self.world, self.rank = world_info(group)
         self.num_embeddings = num_embeddings
         self.embedding_dim = embedding_dim
@@ -156,7 +296,24 @@ class ShardedTableEmbedding(nn.Module):
     def forward(self, idx):
         if self.sink.row2slot is None:
             self.sink.enable_sparse()
-        return ShardedGatherFn.apply(self.weight, idx.contiguous(), self)
+        fn = PeerGatherFn if self.exchange == "p2p" else ShardedGatherFn
+        return fn.apply(self.weight, idx.contiguous(), self)
+
+    def _make_plan(self, idx):
+        if self.exchange == "p2p":
+            return PeerPlan(idx, self.padding_idx)
+        return ExchangePlan(idx, self.world, self.group, self.padding_idx)
+
+    def peer_exchange(self, R):
+        """Peer-mapped buffers, created at the first lookup (collective: every rank gets here in the same step)."""
+        if self._px is None:
+            self._px = PeerExchange(self, R)
+        return self._px
+
+    def exchange_status(self):
+        """Host-synchronising check of the peer exchange's device flags (bit 0: bad id, bit 1: a receive region
+        overflowed -- raise PR_P2P_CAP_FACTOR).  0 when the all_to_all exchange is in use."""
+        return 0 if self._px is None else int(self._px.status.item())
 
     # ---- index-plan prefetch -----------------------------------------------------------------------------------
     # The exchange plan (unique ids, owner bucketing, split sizes, index all_to_all) depends only on the batch's
@@ -175,7 +332,7 @@ class ShardedTableEmbedding(nn.Module):
         idx = idx.contiguous()
         if getattr(self, "_plans", None) is None:
             self._plans = {}
-        plan = ExchangePlan(idx, self.world, self.group, self.padding_idx)
+        plan = self._make_plan(idx)
         plan.ready = torch.cuda.Event()
         plan.ready.record(torch.cuda.current_stream(idx.device))
         plan.keepalive = idx
@@ -187,9 +344,9 @@ class ShardedTableEmbedding(nn.Module):
         plans = getattr(self, "_plans", None)
         plan = plans.pop(self._key(idx), None) if plans else None
         if plan is None:
-            return ExchangePlan(idx, self.world, self.group, self.padding_idx)
+            return self._make_plan(idx)
         torch.cuda.current_stream(idx.device).wait_event(plan.ready)
-        for tns in (plan.inverse, plan.perm, plan.expand, plan.recv_rows):   # allocated on the side stream, used on this one
+        for tns in plan.tensors():                                          # allocated on the side stream, used on this one
             tns.record_stream(torch.cuda.current_stream(idx.device))
         return plan
 

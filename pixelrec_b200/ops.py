@@ -590,6 +590,92 @@ def score_topk(seq_out, item_feature, k, hist_u=None, hist_i=None, mask_col0=Tru
     return val, idx
 
 
+# ------------------------------------------------------------------------------------------- peer-memory exchange
+_CAI_TYPESTR = {torch.float32: "<f4", torch.int64: "<i8", torch.int32: "<i4", torch.uint8: "|u1"}
+
+
+class _DevArray:
+    """__cuda_array_interface__ view of raw device memory, so torch can alias it without owning it."""
+
+    def __init__(self, ptr, shape, dtype, owner):
+        self.owner = owner               # keeps the allocation alive as long as a tensor aliases it
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": _CAI_TYPESTR[dtype],
+                                         "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+class SharedBuffer:
+    """Device memory that the other ranks of the box can map (pr_shared_alloc: cudaMalloc + CUDA IPC handle).
+    `.ref` is its device address in THIS process, `.handle` the 64 bytes to ship to the peers."""
+
+    def __init__(self, nbytes, device):
+        import ctypes as C
+        self.device = torch.device(device)
+        self.nbytes = int(nbytes)
+        _lib.check(_L().pr_set_device(self.device.index), "pr_set_device")
+        _cur_dev[0] = self.device.index
+        ptr = C.c_void_p()
+        h = C.create_string_buffer(64)
+        _lib.check(_L().pr_shared_alloc(self.nbytes, C.byref(ptr), h), "pr_shared_alloc")
+        self.ref = int(ptr.value)
+        self.handle = h.raw
+
+    def tensor(self, shape, dtype):
+        n = 1
+        for x in shape:
+            n *= int(x)
+        if n * torch.empty((), dtype=dtype).element_size() > self.nbytes:
+            raise ValueError("SharedBuffer.tensor: view larger than the allocation")
+        return torch.as_tensor(_DevArray(self.ref, shape, dtype, self), device=self.device)
+
+    def __del__(self):
+        try:
+            if getattr(self, "ref", None):
+                _L().pr_shared_free(self.ref)
+        except Exception:      # interpreter shutdown
+            pass
+
+
+def shared_open(handle, device):
+    """Maps a peer's SharedBuffer (its 64-byte handle) into this process; returns the device address."""
+    import ctypes as C
+    device = torch.device(device)
+    _lib.check(_L().pr_set_device(device.index), "pr_set_device")
+    _cur_dev[0] = device.index
+    ptr = C.c_void_p()
+    _lib.check(_L().pr_shared_open(bytes(handle), C.byref(ptr)), "pr_shared_open")
+    return int(ptr.value)
+
+
+def gather_rows_peers(shard_table, G, N, D, idx, status=None):
+    """out[r] = shard[idx[r] % G][idx[r] // G] read straight from the owners' memory (lookup + exchange in one kernel).
+    shard_table: int64 CUDA tensor [G] of device addresses (own shard and the peers' mapped shards)."""
+    _req(shard_table, torch.int64, "shard_table")
+    _req(idx, torch.int64, "idx")
+    R = idx.numel()
+    out = torch.empty(*idx.shape, D, device=idx.device, dtype=torch.float32)
+    with _prof("gather_rows_peers", idx):
+        _lib.check(_L().pr_gather_rows_peers_f32(_p(shard_table), int(G), int(N), int(D), _p(idx), R, _p(out), _p(status),
+                                                 _stream(idx)), "pr_gather_rows_peers_f32")
+    _count()
+    return out
+
+
+def push_rows_peers(rows, ids, G, rank, cap, skip_id, recv_rows_table, recv_ids_table, counters, status=None):
+    """rows[u] -> the owner's receive region of this rank (see include/pixelrec_b200.h); counters [G] int32 zero on entry."""
+    _req(rows, torch.float32, "rows")
+    _req(ids, torch.int64, "ids")
+    _req(counters, torch.int32, "counters")
+    U, D = rows.shape
+    if ids.numel() != U:
+        raise ValueError("push_rows_peers: one id per row")
+    with _prof("push_rows_peers", rows):
+        _lib.check(_L().pr_push_rows_peers_f32(_p(rows), _p(ids), U, D, int(G), int(rank), int(cap),
+                                               -1 if skip_id is None else int(skip_id), _p(recv_rows_table),
+                                               _p(recv_ids_table), _p(counters), _p(status), _stream(rows)),
+                   "pr_push_rows_peers_f32")
+    _count()
+
+
 # ------------------------------------------------------------------------------------------- A1 on-device batches
 def seq_batch_build(padded, sel, item_num, seed, status=None):
     """items [B,2,W], masked_index [B,W-1] for the windows `sel` of `padded` [n_seq, W] (trainset.py:52-75 on the GPU)."""

@@ -137,6 +137,11 @@ class Trainer:
             self.optimizer.step()
         total_loss = float(total.item())        # ONE device->host sync per epoch
         self._check_nan(total_loss)
+        for m in unwrap(self.model).modules():  # peer-memory exchange (exchange: p2p): device flags, read once per epoch
+            status = getattr(m, "exchange_status", None)
+            if status is not None and status():
+                raise RuntimeError("row exchange flagged an error (bit 0: id out of range, bit 1: a peer receive region "
+                                   "overflowed and gradient rows were dropped -- raise PR_P2P_CAP_FACTOR)")
         return total_loss
 
     @staticmethod

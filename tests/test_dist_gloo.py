@@ -35,6 +35,56 @@ class OracleRows:
         return torch.from_numpy(O.scatter_add_rows(dOut.numpy(), slot_idx.numpy(), U, pad_slot))
 
 
+class ShmBuf:
+    """CPU stand-in for ops.SharedBuffer: a /dev/shm file both gloo processes map (test infrastructure only)."""
+
+    def __init__(self, nbytes, device):
+        self.path = f"/dev/shm/pr_b200_test_{os.getpid()}_{id(self)}"
+        self.mm = np.memmap(self.path, dtype=np.uint8, mode="w+", shape=(int(nbytes),))
+        self.ref = torch.from_numpy(self.mm)
+        self.handle = self.path.encode()
+
+    def tensor(self, shape, dtype):
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        return self.ref[:n].view(dtype).view(*shape)
+
+
+class ShmPeer:
+    """CPU stand-in for pixelrec_b200.dist.CudaPeer: same slot protocol as csrc/peer.cu, python loops."""
+    alloc = ShmBuf
+
+    @staticmethod
+    def open(handle, device):
+        return torch.from_numpy(np.memmap(handle.decode(), dtype=np.uint8, mode="r+"))
+
+    @staticmethod
+    def table(refs, device):
+        return list(refs)
+
+    @staticmethod
+    def gather(shard_table, G, N, D, idx):
+        out = torch.empty(idx.numel(), D)
+        for r, i in enumerate(idx.reshape(-1).tolist()):
+            assert 0 <= i < N
+            out[r] = shard_table[i % G].view(torch.float32).view(-1, D)[i // G]
+        return out.view(*idx.shape, D)
+
+    @staticmethod
+    def push(rows, ids, G, rank, cap, skip_id, rows_table, ids_table, counters, status):
+        for u, i in enumerate(ids.tolist()):
+            if i == skip_id:
+                continue
+            o = i % G
+            pos = int(counters[o])
+            counters[o] += 1
+            if pos >= cap:
+                status[0] |= 2
+                continue
+            slot = rank * cap + pos
+            rows_table[o].view(torch.float32).view(-1, rows.shape[1])[slot] = rows[u]
+            ids_table[o].view(torch.int64)[slot] = i // G
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -82,6 +132,124 @@ def _worker(rank, world, port, N, D, out_q):
         out_q.put((rank, traceback.format_exc()))
     finally:
         dist.destroy_process_group()
+
+
+def _worker_p2p(rank, world, port, N, D, cap_factor, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["PR_P2P_CAP_FACTOR"] = str(cap_factor)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pixelrec_b200 import dist as pd
+        pd.ROWS = OracleRows
+        pd.PEER = ShmPeer
+        g = np.random.default_rng(321)
+        W = g.standard_normal((N, D)).astype(np.float32)
+        table = pd.ShardedTableEmbedding(N, D, padding_idx=0, exchange="p2p")
+        table.sink.row2slot = torch.zeros(1)            # oracle backend ignores it
+        table.load_state_dict({"weight": torch.from_numpy(W)})
+        Wcur = W.copy()
+        for step in range(3):                           # several steps: slot reset, barriers, peers see updated rows
+            idx_all = g.integers(0, N, size=(world, 6, 2, 5)).astype(np.int64)
+            idx_all[:, :, 1, 0] = 0
+            idx_all[0, 0, 0, :] = [0, 1, 2, 3, N - 1]
+            idx_all[1, 1, 0, :2] = idx_all[0, 2, 0, :2]                              # same ids requested from both ranks
+            dE_all = g.standard_normal((world, 6, 2, 5, D)).astype(np.float32)
+            idx = torch.from_numpy(idx_all[rank])
+            if step == 1:                               # plan built ahead of time, as trainer.Lookahead does
+                plan = table._make_plan(idx)
+                assert isinstance(plan, pd.PeerPlan) and plan.U == len(np.unique(idx_all[rank]))
+            E = table(idx)
+            assert torch.equal(E.detach(), torch.from_numpy(Wcur[idx_all[rank]]))    # bit-exact gather across shards
+            E.backward(torch.from_numpy(dE_all[rank]))
+            (splan, G_local), = table.sink.pending
+            table.sink.pending.clear()
+            G_full = O.scatter_add_rows(dE_all.reshape(-1, D), idx_all.reshape(-1), N, 0)
+            assert np.allclose(G_local.numpy(), G_full[rank::world], rtol=1e-5, atol=1e-6)
+            if rank == 0:
+                assert (G_local.numpy()[0] == 0).all()                               # global pad id 0 lives here
+            assert table.exchange_status() == 0
+            assert (table._px.recv_ids == -1).all()                                  # receive slots released
+            with torch.no_grad():                       # stand-in for the optimizer step on the owned shard
+                table.weight.data -= 0.5 * G_local
+            Wnew = table.full_weight().numpy()          # all_gather path: independent of the peer-memory reads
+            assert np.allclose(Wnew, Wcur - 0.5 * G_full, rtol=1e-5, atol=1e-6)
+            Wcur = Wnew.copy()
+        assert torch.equal(table.full_weight(), torch.from_numpy(Wcur))
+        sd = table.state_dict()
+        assert torch.equal(sd["weight"], torch.from_numpy(Wcur))
+        dist.barrier()
+        out_q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        out_q.put((rank, traceback.format_exc()))
+    finally:
+        px = getattr(locals().get("table"), "_px", None)
+        if px is not None:
+            for b in (px._w, px._rows, px._ids):
+                try:
+                    os.unlink(b.path)
+                except OSError:
+                    pass
+        dist.destroy_process_group()
+
+
+def _worker_p2p_overflow(rank, world, port, out_q):
+    """a receive region too small for the step: rows are dropped, never written out of bounds, and the flag is raised"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), PR_P2P_CAP_FACTOR="0.01")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pixelrec_b200 import dist as pd
+        pd.ROWS = OracleRows
+        pd.PEER = ShmPeer
+        N, D = 4001, 4
+        table = pd.ShardedTableEmbedding(N, D, padding_idx=0, exchange="p2p")
+        table.sink.row2slot = torch.zeros(1)
+        idx = torch.arange(1 + rank, 1 + rank + 2 * 400, 2).view(20, 20)    # 400 distinct ids, all owned by ONE rank; cap = 64
+        E = table(idx)
+        E.backward(torch.ones_like(E))
+        assert table._px.cap == 64
+        st = torch.tensor([table.exchange_status()])
+        dist.all_reduce(st, op=dist.ReduceOp.MAX)
+        assert int(st) == 2
+        dist.barrier()
+        out_q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        out_q.put((rank, traceback.format_exc()))
+    finally:
+        px = getattr(locals().get("table"), "_px", None)
+        if px is not None:
+            for b in (px._w, px._rows, px._ids):
+                try:
+                    os.unlink(b.path)
+                except OSError:
+                    pass
+        dist.destroy_process_group()
+
+
+def _spawn(target, world, *args):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=target, args=(r, world, port) + args + (q,)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(30)
+    assert all(r[1] == "ok" for r in res), res
+
+
+@pytest.mark.parametrize("N,D,cap_factor", [(11, 8, 2.0), (64, 16, 2.0), (257, 4, 1.2)])
+def test_sharded_table_peer_exchange_world2_gloo(N, D, cap_factor):
+    """exchange='p2p' host logic (plans, slot protocol, barriers, buffer reuse over several steps) with /dev/shm standing
+    in for peer-mapped HBM and the oracle for the row kernels"""
+    _spawn(_worker_p2p, 2, N, D, cap_factor)
+
+
+def test_peer_exchange_overflow_is_flagged_world2_gloo():
+    _spawn(_worker_p2p_overflow, 2)
 
 
 @pytest.mark.parametrize("N,D", [(11, 8), (64, 16)])

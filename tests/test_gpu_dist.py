@@ -56,8 +56,8 @@ def _single(world, state):
     return loss.item(), {k: v.detach().cpu() for k, v in m.state_dict().items()}
 
 
-def _worker(rank, world, port, state, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+def _worker(rank, world, port, state, q, exchange="nccl"):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), PR_EXCHANGE=exchange, PR_P2P_CAP_FACTOR=str(world))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -67,7 +67,7 @@ def _worker(rank, world, port, state, q):
         from pixelrec_b200.trainer.optim import FusedAdamW
         torch.backends.cuda.matmul.allow_tf32 = False
         m = SASRec(CFG, _Dl())
-        assert isinstance(m.item_embedding, ShardedTableEmbedding)
+        assert isinstance(m.item_embedding, ShardedTableEmbedding) and m.item_embedding.exchange == exchange
         m.load_state_dict(state)
         m = m.to(dev).train()
         opt = FusedAdamW(m.parameters(), lr=1e-3, weight_decay=0.1, tables=[m.item_embedding])
@@ -83,6 +83,7 @@ def _worker(rank, world, port, state, q):
         assert len(m.item_embedding._plans) == 0        # forward consumed the prefetched plan
         loss.backward()
         opt.step()
+        assert m.item_embedding.exchange_status() == 0
         lt = loss.detach().clone()
         dist.all_reduce(lt)
         sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}        # collective (gathers the table)
@@ -99,8 +100,13 @@ def _worker(rank, world, port, state, q):
         dist.destroy_process_group()
 
 
+# "p2p" (peer-memory kernels + CUDA IPC, csrc/peer.cu) was written without multi-GPU access: opt-in until confirmed
+_EXCHANGES = ["nccl"] + (["p2p"] if os.environ.get("PR_EXPERIMENTAL") == "1" else [])
+
+
+@pytest.mark.parametrize("exchange", _EXCHANGES)
 @pytest.mark.parametrize("world", [2])
-def test_sharded_dp_step_equals_single_gpu(world):
+def test_sharded_dp_step_equals_single_gpu(world, exchange):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     from pixelrec_b200.model.IDNet.sasrec import SASRec
@@ -110,7 +116,7 @@ def test_sharded_dp_step_equals_single_gpu(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, state, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, state, q, exchange)) for r in range(world)]
     for p in procs:
         p.start()
     status, loss, sd = q.get(timeout=300)
