@@ -238,6 +238,22 @@ PR_API int pr_seq_batch_build(const int64_t* padded, int64_t n_seq, int W, const
                        uint64_t seed, int64_t* items, int64_t* mask, int32_t* status, pr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K6b attention core for LONG sequences, 64 < L <= 256 (any L <= 256 is accepted), strict fp32.
+ *   replaces  the attention core of the ViT item encoder when it has more than 64 tokens (ViT-B/16: 197 tokens, 12 heads,
+ *             dh 64): HF CLIPVisionModel encoder layers built by REC/model/load.py:90-99, used at
+ *             REC/model/PixelNet/mosasrec.py:69; and REC/model/layers.py:590-612 for MAX_ITEM_LIST_LENGTH > 64.
+ *   Same operand layout and mask semantics as pr_sasrec_attn_*_f32 (fused q|k|v rows with leading dimension ld, key_ids
+ *   optional, additive -1e9 mask); no dropout (the CLIP encoder has none).  dh must be a power of two in [4, 128].
+ *   Outputs ctx [B, L, h*dh] and lse [B*h, L] (log-sum-exp of the masked, scaled scores): the [L, L] probabilities are
+ *   never written; the backward recomputes them from lse.  delta_ws: [B*h, L] fp32 scratch.
+ */
+PR_API int pr_attn_long_fwd_f32(const float* q, const float* k, const float* v, int64_t ld, const int64_t* key_ids, int B, int L,
+                                int h, int dh, int causal, float* ctx, float* lse, pr_stream_t stream);
+PR_API int pr_attn_long_bwd_f32(const float* q, const float* k, const float* v, int64_t ld, const int64_t* key_ids,
+                                const float* ctx, const float* lse, const float* dctx, int B, int L, int h, int dh, int causal,
+                                float* dq, float* dk, float* dv, int64_t ld_grad, float* delta_ws, pr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Peer-memory exchange of the ROW-SHARDED item table (one process per GPU, NVLink / NVSwitch P2P).
  *   replaces  the table replicated per GPU + the dense [N,D] gradient all-reduce of DDP, REC/run.py:40 around
  *             nn.Embedding REC/model/IDNet/sasrec.py:31,68; SURVEY.md section 8e (owner(i) = i % G, local row i / G).

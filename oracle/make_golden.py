@@ -165,17 +165,19 @@ if __name__ == "__main__" and (len(sys.argv) == 1 or "gru4rec_small" in sys.argv
     make_gru_case()
 
 
-def make_vit_case():
+def make_vit_case(case="vit_small", image_size=96, patch_size=32, n_img=5):
     """CLIP ViT item encoder golden: HF transformers CLIPVisionModel (the class the reference instantiates,
     REC/model/load.py:94; random init -- no hub access) + the reference's own MeanItemEncoder wrapper
-    (REC/model/layers.py:121-128) on a small config: output vectors and parameter gradients."""
+    (REC/model/layers.py:121-128) on a small config: output vectors and parameter gradients.
+    vit_small: 10 tokens (patch 32 on 96x96); vit_long197: 197 tokens (patch 8 on 112x112) -- the sequence length of
+    ViT-B/16 at 224x224 (BASELINE.json configs[3]) at a fixture-sized width."""
     from transformers import CLIPVisionConfig, CLIPVisionModel
     from oracle.refload import load_reference
     load_reference()
     from REC.model.layers import Identity, MeanItemEncoder
     torch.manual_seed(3)
-    cfg = CLIPVisionConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4, image_size=96,
-                           patch_size=32)
+    cfg = CLIPVisionConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=3, num_attention_heads=4,
+                           image_size=image_size, patch_size=patch_size)
     m = CLIPVisionModel(cfg)
     with torch.no_grad():
         for p in m.parameters():
@@ -186,7 +188,7 @@ def make_vit_case():
             p.requires_grad = False
     m.vision_model.post_layernorm = Identity()
     enc = MeanItemEncoder(item_encoder=m, input_dim=64, output_dim=48, act_name="relu", dnn_layers=[])
-    x = torch.randn(5, 3, 96, 96)
+    x = torch.randn(n_img, 3, image_size, image_size)
     out = enc(x)
     g = torch.randn_like(out)
     out.backward(g)
@@ -196,9 +198,11 @@ def make_vit_case():
     for k, p in enc.named_parameters():
         if p.grad is not None:
             d["grad/" + k] = p.grad.numpy().copy()
-    np.savez_compressed(os.path.join(OUT, "vit_small.npz"), **d)
-    print("vit_small", out.shape, len([k for k in d if k.startswith("grad/")]), "grads")
+    np.savez_compressed(os.path.join(OUT, case + ".npz"), **d)
+    print(case, out.shape, len([k for k in d if k.startswith("grad/")]), "grads")
 
 
 if __name__ == "__main__" and (len(sys.argv) == 1 or "vit_small" in sys.argv[1:]):
     make_vit_case()
+if __name__ == "__main__" and (len(sys.argv) == 1 or "vit_long197" in sys.argv[1:]):
+    make_vit_case("vit_long197", image_size=112, patch_size=8, n_img=3)

@@ -427,12 +427,6 @@ static int launch_attn(AttnArgs& A, cudaStream_t stream) {
     auto kern = BWD ? attn_bwd_kernel<LMAX, CW4> : attn_fwd_kernel<LMAX, CW4>;
     PR_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long n_items = (long long)A.B * A.h;
-    // contiguous block of items per CTA: the h heads of a sequence (adjacent 512-byte pieces of the same rows) and
-    // consecutive sequences are read by the same SM back to back -> DRAM pages / L2 lines are reused while hot
-    // (a round-robin assignment scattered every row over 12 SMs and ran at 0.28 of the HBM roofline)
-    const long long items_per_cta = (n_items + gridDim.x - 1) / gridDim.x;
-    const long long item_lo = (long long)blockIdx.x * items_per_cta;
-    const long long item_hi = min(n_items, item_lo + items_per_cta);
     const int grid = (int)std::max<long long>(1, std::min<long long>((n_items + NCW - 1) / NCW, sm_count()));
     kern<<<grid, (NCW + 1) * 32, smem, stream>>>(A);
     PR_CUDA_LAUNCH_CHECK(BWD ? "attn_bwd_kernel" : "attn_fwd_kernel");

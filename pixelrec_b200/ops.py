@@ -343,8 +343,54 @@ class AttnFn(torch.autograd.Function):
         return dqkv, None, None, None, None, None, None, None
 
 
+class LongAttnFn(torch.autograd.Function):
+    """Same contract as AttnFn for 64 < L <= 256 (ViT-B/16's 197 tokens): strict fp32, no dropout, probabilities are
+    recomputed in the backward from the saved log-sum-exp (pr_attn_long_*_f32, csrc/attn_long.cuh)."""
+
+    @staticmethod
+    def forward(ctx, qkv, key_ids, n_heads, causal):
+        _req(qkv, torch.float32, "qkv")
+        B, Lq, D3 = qkv.shape
+        D = D3 // 3
+        dh = D // n_heads
+        if key_ids is not None:
+            _req(key_ids, torch.int64, "key_ids")
+        out = torch.empty(B, Lq, D, device=qkv.device, dtype=torch.float32)
+        lse = torch.empty(B * n_heads, Lq, device=qkv.device, dtype=torch.float32)
+        base = qkv.data_ptr()
+        with _prof("attn_long_fwd", qkv):
+            _lib.check(_L().pr_attn_long_fwd_f32(base, base + 4 * D, base + 8 * D, D3, _p(key_ids), B, Lq, n_heads, dh,
+                                                 int(causal), _p(out), _p(lse), _stream(qkv)), "pr_attn_long_fwd_f32")
+        _count()
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.key_ids = key_ids
+        ctx.cfg = (B, Lq, n_heads, dh, int(causal))
+        return out
+
+    @staticmethod
+    def backward(ctx, dctx):
+        qkv, out, lse = ctx.saved_tensors
+        B, Lq, h, dh, causal = ctx.cfg
+        D = h * dh
+        dctx = dctx.contiguous()
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty_like(lse)
+        base, gbase = qkv.data_ptr(), dqkv.data_ptr()
+        with _prof("attn_long_bwd", qkv):
+            _lib.check(_L().pr_attn_long_bwd_f32(base, base + 4 * D, base + 8 * D, 3 * D, _p(ctx.key_ids), _p(out), _p(lse),
+                                                 _p(dctx), B, Lq, h, dh, causal, gbase, gbase + 4 * D, gbase + 8 * D, 3 * D,
+                                                 _p(delta), _stream(qkv)), "pr_attn_long_bwd_f32")
+        _count(2)
+        return dqkv, None, None, None
+
+
 def attention(qkv, key_ids, n_heads, causal=True, p_drop=0.0, seed=0, rng_stream=0, tf32=None):
-    """tf32: None = follow torch.backends.cuda.matmul.allow_tf32 (the linear layers' policy), True/False to force."""
+    """tf32: None = follow torch.backends.cuda.matmul.allow_tf32 (the linear layers' policy), True/False to force.
+    Sequences longer than 64 (ViT-B/16 item encoder) take the long-sequence kernels, which have no dropout."""
+    if qkv.dim() == 3 and qkv.shape[1] > 64:
+        if p_drop:
+            raise _lib.PixelRecB200Error(f"attention: dropout is not supported for L={qkv.shape[1]} > 64")
+        return LongAttnFn.apply(qkv, key_ids, int(n_heads), bool(causal))
     return AttnFn.apply(qkv, key_ids, int(n_heads), bool(causal), float(p_drop), int(seed), int(rng_stream), tf32)
 
 

@@ -1,0 +1,135 @@
+"""CPU check of SIMT kernel LOGIC without a GPU: the device code of csrc/attn_long.cuh and csrc/peer.cuh is compiled for the
+host on a thread-per-CUDA-thread emulation layer (tests/emu/emu_cuda.h: pthread barriers for __syncthreads / warp
+collectives) and compared with the oracle.  This pins indexing, masking, reductions and the slot protocol; it says nothing
+about performance or about PTX-level behaviour -- the GPU parity tests (tests/test_gpu_*.py) remain the gate."""
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import sasrec_np as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_P, _I, _LL = C.c_void_p, C.c_int, C.c_longlong
+
+
+@pytest.fixture(scope="module")
+def emu():
+    out = os.path.join(tempfile.mkdtemp(prefix="pr_emu_"), "libemu.so")
+    src = os.path.join(ROOT, "tests", "emu", "emu_kernels.cpp")
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", out, src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lib = C.CDLL(out)
+    lib.emu_attn_long_fwd.argtypes = [_P, _P, _P, _LL, _P, _I, _I, _I, _I, _I, _P, _P, _I]
+    lib.emu_attn_long_bwd.argtypes = [_P, _P, _P, _LL, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _LL, _P, _I]
+    lib.emu_gather_rows_peers.argtypes = [_P, _I, _LL, _I, _P, _LL, _P, _P, _I]
+    lib.emu_push_rows_peers.argtypes = [_P, _P, _LL, _I, _I, _I, _LL, _LL, _P, _P, _P, _P, _I]
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _mask(key_ids, causal, B, L):
+    valid = np.ones((B, L), bool) if key_ids is None else (key_ids != 0)
+    tri = np.tril(np.ones((L, L), bool)) if causal else np.ones((L, L), bool)
+    return np.where(valid[:, None, None, :] & tri[None, None], 0.0, -1e9)
+
+
+@pytest.mark.parametrize("B,L,h,dh,causal,padded", [(1, 70, 2, 16, 0, False), (2, 197, 1, 8, 0, False), (1, 100, 2, 32, 1, True),
+                                                  (1, 65, 1, 64, 0, True), (1, 33, 3, 4, 1, False), (1, 130, 1, 128, 0, False)])
+def test_attn_long_fwd_bwd_emulated(emu, B, L, h, dh, causal, padded):
+    g = np.random.default_rng(L * dh)
+    D = h * dh
+    qkv = g.standard_normal((B, L, 3 * D)).astype(np.float32)
+    key_ids = None
+    if padded:
+        key_ids = g.integers(1, 50, size=(B, L)).astype(np.int64)
+        key_ids[:, :L // 5] = 0                                   # left padding, as SEQTrainDataset produces
+    q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+    mask = _mask(key_ids, causal, B, L)
+    ref, cache = O.attn_core_fwd(q.astype(np.float64), k.astype(np.float64), v.astype(np.float64), mask, h)
+    ctx = np.zeros((B, L, D), np.float32)
+    lse = np.zeros((B * h, L), np.float32)
+    kp = _ptr(key_ids) if key_ids is not None else None
+    base = qkv.ctypes.data
+    emu.emu_attn_long_fwd(base, base + 4 * D, base + 8 * D, 3 * D, kp, B, L, h, dh, causal, _ptr(ctx), _ptr(lse), 2)
+    # query rows with no visible key (left padding under the causal mask) are don't-care: the reference's additive -1e9
+    # makes them uniform in fp32 but not in the fp64 oracle; they never reach the loss
+    live = (mask == 0).any(-1)[:, 0]                              # [B, L]
+    assert live.any() and np.isfinite(ctx).all()
+    assert np.abs(ctx - ref)[live].max() < 2e-5 * max(1.0, np.abs(ref).max())
+    s = np.einsum("bihd,bjhd->bhij", q.reshape(B, L, h, dh).astype(np.float64), k.reshape(B, L, h, dh).astype(np.float64))
+    s = s / np.sqrt(dh) + mask
+    lse_ref = np.log(np.exp(s - s.max(-1, keepdims=True)).sum(-1)) + s.max(-1)
+    lv = np.broadcast_to(live[:, None, :], (B, h, L))
+    assert np.allclose(lse.reshape(B, h, L)[lv], lse_ref[lv], rtol=1e-5, atol=1e-4)
+    dout = g.standard_normal((B, L, D)).astype(np.float32) * live[..., None]
+    dq_r, dk_r, dv_r = O.attn_core_bwd(dout.astype(np.float64), cache)
+    dqkv = np.zeros_like(qkv)
+    delta = np.zeros((B * h, L), np.float32)
+    gb = dqkv.ctypes.data
+    emu.emu_attn_long_bwd(base, base + 4 * D, base + 8 * D, 3 * D, kp, _ptr(ctx), _ptr(lse), _ptr(dout), B, L, h, dh, causal,
+                          gb, gb + 4 * D, gb + 8 * D, 3 * D, _ptr(delta), 2)
+    for got, want, name in ((dqkv[..., :D], dq_r, "dq"), (dqkv[..., D:2 * D], dk_r, "dk"), (dqkv[..., 2 * D:], dv_r, "dv")):
+        err = np.abs(got - want).max() / max(np.abs(want).max(), 1e-6)
+        assert err < 5e-5, (name, err)
+
+
+@pytest.mark.parametrize("G,N,D,R", [(1, 20, 8, 9), (2, 101, 16, 300), (4, 77, 36, 130), (8, 1003, 8, 2100)])
+def test_gather_rows_peers_emulated(emu, G, N, D, R):
+    g = np.random.default_rng(G * N)
+    W = g.standard_normal((N, D)).astype(np.float32)
+    shards = [np.ascontiguousarray(W[r::G]) if len(range(r, N, G)) else np.zeros((1, D), np.float32) for r in range(G)]
+    table = (C.c_void_p * G)(*[s.ctypes.data for s in shards])
+    idx = g.integers(0, N, size=R).astype(np.int64)
+    idx[:2] = [0, N - 1]
+    out = np.full((R, D), 7.0, np.float32)
+    status = np.zeros(1, np.int32)
+    emu.emu_gather_rows_peers(table, G, N, D, _ptr(idx), R, _ptr(out), _ptr(status), 3)
+    assert np.array_equal(out, O.gather_rows(W, idx)) and status[0] == 0
+    idx[1] = N + 3
+    emu.emu_gather_rows_peers(table, G, N, D, _ptr(idx), R, _ptr(out), _ptr(status), 3)
+    assert status[0] == 1 and (out[1] == 0).all() and np.array_equal(out[2:], W[idx[2:]])
+
+
+@pytest.mark.parametrize("G,N,D,U,cap", [(2, 101, 8, 60, 60), (4, 1003, 16, 300, 300), (3, 50, 4, 40, 5)])
+def test_push_rows_peers_emulated(emu, G, N, D, U, cap):
+    """slot protocol of csrc/peer.cuh: every row lands exactly once in its owner's region of the sending rank (or is
+    dropped and flagged when that region is full), ids are local rows, nothing is written outside the region"""
+    g = np.random.default_rng(N + U)
+    recv_rows = [np.full((G * cap, D), np.nan, np.float32) for _ in range(G)]
+    recv_ids = [np.full(G * cap, -1, np.int64) for _ in range(G)]
+    rt = (C.c_void_p * G)(*[a.ctypes.data for a in recv_rows])
+    it = (C.c_void_p * G)(*[a.ctypes.data for a in recv_ids])
+    status = np.zeros(1, np.int32)
+    sent = {}
+    for rank in range(G):
+        ids = np.sort(g.choice(N, size=U, replace=False)).astype(np.int64)
+        ids[0] = 0
+        rows = g.standard_normal((U, D)).astype(np.float32)
+        counters = np.zeros(G, np.int32)
+        emu.emu_push_rows_peers(_ptr(rows), _ptr(ids), U, D, G, rank, cap, 0, rt, it, _ptr(counters), _ptr(status), 2)
+        for o in range(G):
+            assert counters[o] == ((ids[1:] % G) == o).sum()
+        sent[rank] = (ids, rows, counters.copy())
+    overflow = any((c > cap).any() for _, _, c in sent.values())
+    assert bool(status[0] & 2) == overflow
+    for o in range(G):
+        for rank in range(G):
+            ids, rows, counters = sent[rank]
+            n = min(int(counters[o]), cap)
+            reg_ids = recv_ids[o][rank * cap:(rank + 1) * cap]
+            reg_rows = recv_rows[o][rank * cap:(rank + 1) * cap]
+            assert (reg_ids[n:] == -1).all() and np.isnan(reg_rows[n:]).all()
+            mine = {int(i): rows[u] for u, i in enumerate(ids) if i != 0 and i % G == o}
+            got = set()
+            for slot in range(n):
+                gid = int(reg_ids[slot]) * G + o
+                assert gid in mine and gid not in got and np.array_equal(reg_rows[slot], mine[gid])
+                got.add(gid)
+            assert len(got) == n and (n == len(mine) or overflow)
