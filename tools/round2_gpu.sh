@@ -1,0 +1,47 @@
+#!/bin/bash
+# Validation of the code staged without GPU access (score_topk v2 / multicast, long-sequence attention, peer kernels, p2p
+# exchange).  Every stage runs under its own timeout so a hung kernel cannot hold the box; logs -> gpurun_out/.
+#
+#   gpurun --timeout 1500 -- 'bash tools/round2_gpu.sh stage1'            # 1 GPU: staged kernels, parity + A/B timing
+#   gpurun --gpus 2 --timeout 1200 -- 'bash tools/round2_gpu.sh stage2'   # 2 GPUs: peer-memory exchange vs NCCL
+#
+# Order matters: parity first (cheap, tells which variant may become a default), timing after.
+set -u
+mkdir -p gpurun_out
+export PR_EXPERIMENTAL=1
+stage=${1:-stage1}
+run() {  # run <seconds> <log name> <command...>
+  local secs=$1 name=$2; shift 2
+  timeout --signal=KILL "$secs" "$@" > "gpurun_out/$name.log" 2>&1
+  local rc=$?
+  echo "$name rc=$rc $(tail -1 gpurun_out/$name.log | cut -c1-200)"
+  grep -E "FAILED|Timeout|rror" "gpurun_out/$name.log" | head -6
+  return $rc
+}
+PYT="python -u -m pytest -q -m gpu --timeout=120 --timeout-method=thread -p no:cacheprovider"
+
+if [ "$stage" = stage1 ]; then
+  nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+  # 1. SIMT kernels whose logic is already pinned by the CPU emulation (lowest risk first)
+  run 300 r2_attn_long   $PYT tests/test_gpu_attn_long.py
+  run 300 r2_vit         $PYT tests/test_gpu_vit.py
+  run 300 r2_peer        $PYT tests/test_gpu_peer.py
+  # 2. score_topk variants: v2 epilogue (tune 16), then + cluster multicast (tune 48); each variant in its own process
+  run 300 r2_score_v2    $PYT tests/test_gpu_score.py -k "v2 and not mcast"
+  run 300 r2_score_mcast $PYT tests/test_gpu_score.py -k "v2_mcast"
+  # 3. timing (only meaningful if the parity runs above passed)
+  run 300 r2_bench_score env SCORE_TUNES=0,16,48 python tools/bench_score.py
+  cp gpurun_out/bench_score.json gpurun_out/r2_bench_score.json 2>/dev/null
+  # 4. the whole default suite + bench, as the driver runs them
+  run 900 r2_pytest_default env -u PR_EXPERIMENTAL python -m pytest tests -x -q -m gpu
+  run 600 r2_bench_n1 python bench.py --steps 20 --warmup 5
+  tail -1 gpurun_out/r2_bench_n1.log > gpurun_out/r2_bench_n1.json
+elif [ "$stage" = stage2 ]; then
+  run 600 r2_dist $PYT tests/test_gpu_dist.py
+  for ex in nccl p2p; do
+    run 420 r2_bench_n2_$ex python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu --exchange $ex
+    tail -1 gpurun_out/r2_bench_n2_$ex.log > gpurun_out/r2_bench_n2_$ex.json
+  done
+fi
+exit 0
