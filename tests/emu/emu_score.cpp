@@ -1,0 +1,51 @@
+// Host build of csrc/score_kernels.cuh (v2 scoring kernel, candidate merge, mask kernels) on the emulated Blackwell pipeline
+// (emu_tc.h).  emu_score_topk_v2 mirrors the launch sequence of pr_score_topk_f32 with an explicit split count and cluster
+// size.  Loaded by tests/test_emu_kernels.py through ctypes.  Test infrastructure only.
+#include "emu_tc.h"
+
+#include "../../pixelrec_b200/csrc/score_kernels.cuh"
+
+using namespace pr;
+
+template <int K>
+static void run_v2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ScoreArgs& a, int grid, int cluster) {
+    const size_t smem = (size_t)SC_STAGES * SC_STAGE_BYTES + SC2_BAR_BYTES + 1024;
+    emu::after_launch_hook() = emu::join_async;
+    emu::launch_cluster(grid, cluster, SC2_THREADS, smem, [&]() { score_topk2_kernel<K>(tmA, tmB, a); });
+    emu::after_launch_hook() = nullptr;
+}
+
+extern "C" int emu_score_topk_v2(const float* seq, long long B_e, const float* W, long long N, long long D, const long long* hist_u,
+                                 const long long* hist_i, long long n_hist, int mask_col0, int k, int splits_req, int cluster,
+                                 float* out_val, long long* out_idx) {
+    const int K = (k <= 16) ? 16 : 32;
+    ScoreArgs a{};
+    a.kblocks = (int)(D / SC_BK);
+    a.m_tiles = (int)((B_e + SC_BM - 1) / SC_BM);
+    a.n_tiles = (int)((N + SC_BN - 1) / SC_BN);
+    if (a.m_tiles % cluster) return -1;
+    a.tiles_per_split = (a.n_tiles + splits_req - 1) / splits_req;
+    a.n_splits = (a.n_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
+    a.n_words = a.n_tiles * 8;
+    a.cluster = cluster;
+    const long long rows = (long long)a.m_tiles * SC_BM;
+    std::vector<uint32_t> mask((size_t)rows * a.n_words);
+    const int n_lists = a.n_splits * 2;
+    std::vector<float> cand_val((size_t)rows * n_lists * K, -1234.5f);
+    std::vector<int> cand_idx((size_t)rows * n_lists * K, -77);
+    a.mask = mask.data();
+    a.cand_val = cand_val.data();
+    a.cand_idx = cand_idx.data();
+    const long long nmask = rows * a.n_words;
+    emu::launch((int)((nmask + 255) / 256), 256, 0, [&]() { score_mask_base_kernel(mask.data(), rows, a.n_words, N, mask_col0); });
+    if (n_hist > 0)
+        emu::launch((int)((n_hist + 255) / 256), 256, 0,
+                    [&]() { score_mask_hist_kernel(mask.data(), a.n_words, B_e, N, hist_u, hist_i, n_hist); });
+    const CUtensorMap tmA{seq, B_e, D, SC_BM}, tmB{W, N, D, SC_BN / cluster};
+    if (K == 16) run_v2<16>(tmA, tmB, a, a.m_tiles * a.n_splits, cluster);
+    else run_v2<32>(tmA, tmB, a, a.m_tiles * a.n_splits, cluster);
+    emu::launch((int)((B_e + 3) / 4), 128, 0, [&]() {
+        score_merge_kernel(cand_val.data(), cand_idx.data(), n_lists * K, B_e, k, out_val, out_idx);
+    });
+    return a.n_splits;
+}

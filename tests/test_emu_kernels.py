@@ -30,6 +30,18 @@ def emu():
     return lib
 
 
+@pytest.fixture(scope="module")
+def emu_score():
+    """csrc/score_kernels.cuh on the emulated Blackwell pipeline (tests/emu/emu_tc.h)"""
+    out = os.path.join(tempfile.mkdtemp(prefix="pr_emu_"), "libemu_score.so")
+    src = os.path.join(ROOT, "tests", "emu", "emu_score.cpp")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", out, src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lib = C.CDLL(out)
+    lib.emu_score_topk_v2.argtypes = [_P, _LL, _P, _LL, _LL, _P, _P, _LL, _I, _I, _I, _I, _P, _P]
+    return lib
+
+
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -133,3 +145,27 @@ def test_push_rows_peers_emulated(emu, G, N, D, U, cap):
                 assert gid in mine and gid not in got and np.array_equal(reg_rows[slot], mine[gid])
                 got.add(gid)
             assert len(got) == n and (n == len(mine) or overflow)
+
+
+@pytest.mark.parametrize("B_e,N,D,k,splits,cluster", [(100, 300, 64, 10, 1, 1),       # one CTA, 2 tiles
+                                                     (200, 1700, 160, 10, 2, 2),     # ring wraps 2.5x, TMEM buffers reused, cluster of 2
+                                                     (130, 1000, 96, 20, 3, 2),      # K = 32 lists, ragged last tile / split
+                                                     (500, 600, 64, 10, 2, 4)])      # cluster of 4 (B_e = 500: 4 m-tiles)
+def test_score_topk_v2_pipeline_emulated(emu_score, B_e, N, D, k, splits, cluster):
+    """score_topk2_kernel (branch-free 8-warp epilogue, optional table-tile multicast across a cluster) + merge + mask kernels
+    on emulated mbarriers / asynchronous TMA / deferred MMAs / TMEM, against the oracle's full_sort_topk on integer operands
+    (exact, massive ties).  A protocol error shows up as a wrong result, an over-arrival abort or a deadlock timeout."""
+    g = np.random.default_rng(B_e + N)
+    seq = g.integers(-3, 4, size=(B_e, D)).astype(np.float32)
+    W = g.integers(-3, 4, size=(N, D)).astype(np.float32)
+    hu = np.repeat(np.arange(B_e), 5).astype(np.int64)
+    hi = g.integers(1, N, size=B_e * 5).astype(np.int64)
+    scores = seq.astype(np.float64) @ W.astype(np.float64).T
+    v_ref, i_ref = O.full_sort_topk(scores, hu, hi, k)
+    val = np.zeros((B_e, k), np.float32)
+    idx = np.zeros((B_e, k), np.int64)
+    ns = emu_score.emu_score_topk_v2(_ptr(seq), B_e, _ptr(W), N, D, _ptr(hu), _ptr(hi), len(hu), 1, k, splits, cluster,
+                                     _ptr(val), _ptr(idx))
+    assert ns >= 1
+    assert np.array_equal(idx, i_ref)
+    assert np.array_equal(val.astype(np.float64), v_ref)
