@@ -226,6 +226,19 @@ PR_API int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float* W, 
                              float* topk_val, int64_t* topk_idx, void* workspace, size_t workspace_bytes,
                              pr_stream_t stream);
 
+/* full-catalog softmax cross-entropy on the same tcgen05 pipeline (north_star: "scoring ... fused with the softmax/CE").
+ *   EXTENSION -- the reference trains with sampled negatives (REC/model/IDNet/sasrec.py:88-92) and has no full-softmax
+ *   loss; the oracle is a restatement of F.cross_entropy(seq_out @ W.T, target) (oracle/sasrec_np.py full_catalog_ce).
+ *   For every row: lse = log sum_c exp(<seq_out[row], W[c]>) over the catalog (column 0 excluded when mask_col0 != 0),
+ *   tgt_logit = <seq_out[row], W[target[row]]>, nll = lse - tgt_logit.  Any of lse / tgt_logit / nll may be NULL (not all);
+ *   target may be NULL when only lse is wanted.  The logits are never written (online max / sum in the GEMM epilogue).
+ *   Forward only.
+ */
+PR_API size_t pr_score_ce_workspace_bytes(int64_t B_e, int64_t N);
+PR_API int pr_score_ce_f32(const float* seq_out, int64_t B_e, const float* W, int64_t N, int64_t D, const int64_t* target,
+                           int mask_col0, float* lse, float* tgt_logit, float* nll, void* workspace, size_t workspace_bytes,
+                           pr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * A1  on-device batch construction.   replaces SEQTrainDataset.__getitem__ + default collate,
  *                                     REC/data/dataset/trainset.py:40-75 (python loops in 10 DataLoader workers)

@@ -376,6 +376,20 @@ def full_sort_topk(scores, hist_u, hist_i, k):
     return np.take_along_axis(s, order, 1), order
 
 
+def full_catalog_ce(scores, target, mask_col0=True):
+    """EXTENSION, parity unpinned by the reference (it trains with sampled negatives, sasrec.py:88-92): softmax
+    cross-entropy of `target` [B] over the whole catalog, restating torch's F.cross_entropy(scores, target, reduction='none')
+    with column 0 ([PAD]) removed from the softmax as trainer.py:334 removes it from the ranking.
+    Returns (lse [B], target logit [B], nll [B] = lse - target logit)."""
+    s = np.array(scores, dtype=np.float64, copy=True)
+    if mask_col0:
+        s[:, 0] = -np.inf
+    m = s.max(1, keepdims=True)
+    lse = (m + np.log(np.exp(s - m).sum(1, keepdims=True)))[:, 0]
+    tl = s[np.arange(s.shape[0]), np.asarray(target)]
+    return lse, tl, lse - tl
+
+
 def topk_hits(topk_idx, positive_u, positive_i, n_users):
     """collector.py:134-139: pos_idx[u, r] = 1 iff topk_idx[u, r] is u's positive item; pos_len = #positives."""
     pos = np.zeros(topk_idx.shape, dtype=np.int32)

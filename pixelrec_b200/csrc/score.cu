@@ -308,10 +308,10 @@ static ScorePlan score_plan(long long B_e, long long N, int k) {
 }
 
 // v2 launch: 8 epilogue warps, optional cluster multicast of the table tile across the m-tiles
-template <int K>
+template <int K, int MODE>
 static int launch_v2(const CUtensorMap& tmA, const float* W, long long N, long long D, ScoreArgs a, const ScorePlan& p,
                      bool mcast, cudaStream_t stream, int* n_lists) {
-    auto kern = score_topk2_kernel<K>;
+    auto kern = score_topk2_kernel<K, MODE>;
     const size_t smem = (size_t)SC_STAGES * SC_STAGE_BYTES + SC2_BAR_BYTES + 1024;   // ring + barriers + 1 KiB alignment slack
     PR_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int splits = std::min(p.n_splits, 1024 / (2 * K));                      // two lists per split and row
@@ -402,11 +402,12 @@ extern "C" int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float*
     a.kblocks = (int)(D / SC_BK);
     a.m_tiles = p.m_tiles; a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.n_splits = p.n_splits;
     a.n_words = p.n_words; a.mask = mask; a.cand_val = cand_val; a.cand_idx = cand_idx; a.cluster = 1;
+    a.target = nullptr; a.n_rows = B_e; a.ce_part = nullptr;
     int n_lists = p.n_splits;
     if (tune() & PR_TUNE_SCORE_V2) {
         const bool mcast = (tune() & PR_TUNE_SCORE_MCAST) != 0;
-        rc = (p.K == 16) ? launch_v2<16>(tmA, W, N, D, a, p, mcast, stream, &n_lists)
-                         : launch_v2<32>(tmA, W, N, D, a, p, mcast, stream, &n_lists);
+        rc = (p.K == 16) ? launch_v2<16, 0>(tmA, W, N, D, a, p, mcast, stream, &n_lists)
+                         : launch_v2<32, 0>(tmA, W, N, D, a, p, mcast, stream, &n_lists);
         if (rc) return rc;
     } else {
         rc = make_map(&tmB, W, N, D, SC_BN);
@@ -425,5 +426,51 @@ extern "C" int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float*
     score_merge_kernel<<<(int)((B_e + 3) / 4), 128, 0, stream>>>(cand_val, cand_idx, n_lists * p.K, B_e, k, topk_val,
                                                                  (long long*)topk_idx);
     PR_CUDA_LAUNCH_CHECK("score_merge_kernel");
+    return PR_OK;
+}
+
+// ---- full-catalog softmax cross-entropy (extension: the reference trains with sampled negatives, sasrec.py:88-92) ---------
+extern "C" size_t pr_score_ce_workspace_bytes(int64_t B_e, int64_t N) {
+    if (B_e <= 0 || N <= 0) return 0;
+    const ScorePlan p = score_plan(B_e, N, 1);
+    const size_t rows = (size_t)p.m_tiles * SC_BM;
+    return p.mask_bytes + (rows * p.n_splits * 2 * 4 * 4 + 255) / 256 * 256;
+}
+
+extern "C" int pr_score_ce_f32(const float* seq_out, int64_t B_e, const float* W, int64_t N, int64_t D, const int64_t* target,
+                               int mask_col0, float* lse, float* tgt_logit, float* nll, void* workspace, size_t workspace_bytes,
+                               pr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PR_CHECK_ARG(B_e > 0 && N > 0 && D > 0, "pr_score_ce_f32: bad shape B_e=%lld N=%lld D=%lld", (long long)B_e, (long long)N,
+                 (long long)D);
+    PR_CHECK_ARG(D % SC_BK == 0, "pr_score_ce_f32: D=%lld must be a multiple of %d", (long long)D, SC_BK);
+    PR_CHECK_ARG(N < (1LL << 31) - 512, "pr_score_ce_f32: N too large");
+    PR_CHECK_ARG(seq_out && W && workspace && (lse || nll), "pr_score_ce_f32: null pointer");
+    PR_CHECK_ARG(target || !(tgt_logit || nll), "pr_score_ce_f32: tgt_logit / nll need target ids");
+    PR_CHECK_ARG(aligned16(seq_out) && aligned16(W), "pr_score_ce_f32: seq_out / W must be 16-byte aligned");
+    PR_CHECK_ARG(workspace_bytes >= pr_score_ce_workspace_bytes(B_e, N), "pr_score_ce_f32: workspace %zu < required %zu",
+                 workspace_bytes, pr_score_ce_workspace_bytes(B_e, N));
+    PR_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "pr_score_ce_f32: workspace must be 256-byte aligned");
+    const ScorePlan p = score_plan(B_e, N, 1);
+    char* ws = (char*)workspace;
+    uint32_t* mask = (uint32_t*)ws;
+    float* part = (float*)(ws + p.mask_bytes);
+    const long long rows = (long long)p.m_tiles * SC_BM;
+    const long long nmask = rows * p.n_words;
+    score_mask_base_kernel<<<(int)((nmask + 255) / 256), 256, 0, stream>>>(mask, rows, p.n_words, N, mask_col0);
+    PR_CUDA_LAUNCH_CHECK("score_mask_base_kernel");
+    CUtensorMap tmA;
+    int rc = make_map(&tmA, seq_out, B_e, D, SC_BM);
+    if (rc) return rc;
+    ScoreArgs a;
+    a.kblocks = (int)(D / SC_BK);
+    a.m_tiles = p.m_tiles; a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.n_splits = p.n_splits;
+    a.n_words = p.n_words; a.mask = mask; a.cand_val = nullptr; a.cand_idx = nullptr; a.cluster = 1;
+    a.target = (const long long*)target; a.n_rows = B_e; a.ce_part = part;
+    int n_lists = 0;
+    rc = launch_v2<16, 1>(tmA, W, N, D, a, p, (tune() & PR_TUNE_SCORE_MCAST) != 0, stream, &n_lists);
+    if (rc) return rc;
+    score_ce_merge_kernel<<<(int)((B_e + 3) / 4), 128, 0, stream>>>(part, n_lists, B_e, lse, tgt_logit, nll);
+    PR_CUDA_LAUNCH_CHECK("score_ce_merge_kernel");
     return PR_OK;
 }

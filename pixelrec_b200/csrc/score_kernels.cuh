@@ -26,6 +26,9 @@ struct ScoreArgs {
     float* cand_val;      // [m_tiles*128][n_splits][K]   (v2: [m_tiles*128][n_splits*2][K])
     int* cand_idx;
     int cluster;          // v2: CTAs per cluster sharing each table tile by TMA multicast (1 = none)
+    const long long* target;   // CE mode: [B_e] target item per row
+    long long n_rows;          // CE mode: B_e
+    float* ce_part;            // CE mode: [m_tiles*128][n_splits*2][4] = (running max, sum of exp, target logit or -inf, unused)
 };
 
 constexpr int SC2_EPI_WARPS = 8;
@@ -75,7 +78,9 @@ __device__ __forceinline__ float pick32(const float (&v)[32], int j) {
     return (j & 16) ? d1 : d0;
 }
 
-template <int K>
+// MODE 0: masked per-row top-k (eval ranking).  MODE 1: online log-sum-exp over the unmasked catalog + the target item's
+// logit = full-catalog softmax cross-entropy (K unused).
+template <int K, int MODE = 0>
 __global__ void __launch_bounds__(SC2_THREADS, 1) score_topk2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                      const __grid_constant__ CUtensorMap tmB,
                                                                      const ScoreArgs a) {
@@ -165,11 +170,12 @@ __global__ void __launch_bounds__(SC2_THREADS, 1) score_topk2_kernel(const __gri
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         const int row = m_tile * SC_BM + q * 32 + lane;
+        const uint32_t* mrow = a.mask + (size_t)row * a.n_words + half * 4;
+        if constexpr (MODE == 0) {
         float val[K];
         int idx[K];
 #pragma unroll
         for (int i = 0; i < K; ++i) { val[i] = -INFINITY; idx[i] = -1; }
-        const uint32_t* mrow = a.mask + (size_t)row * a.n_words + half * 4;
         for (int t = 0; t < n_my; ++t) {
             const int buf = t & 1;
             const int tile = t_begin + t;
@@ -208,6 +214,48 @@ __global__ void __launch_bounds__(SC2_THREADS, 1) score_topk2_kernel(const __gri
         int* ci = a.cand_idx + list * K;
 #pragma unroll
         for (int i = 0; i < K; ++i) { cv[i] = val[i]; ci[i] = idx[i]; }
+        } else {
+        // ---- CE mode: running (max, sum of exp) over this thread's columns, and the target's logit if it is among them
+        float mx = -INFINITY, sum = 0.f, tlogit = -INFINITY;
+        const long long tgt = (row < a.n_rows && a.target) ? a.target[row] : -1;      // rows >= B_e are tile padding
+        for (int t = 0; t < n_my; ++t) {
+            const int buf = t & 1;
+            const int tile = t_begin + t;
+            const uint4 mw = *reinterpret_cast<const uint4*>(mrow + tile * 8);
+            mbar_wait(&tfull_bar[buf], (uint32_t)((t >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * SC_BN + half * 128);
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                float v[32];
+                __syncwarp();
+                tmem_ld32(taddr + c * 32, v);
+                const uint32_t w = (c == 0) ? mw.x : (c == 1) ? mw.y : (c == 2) ? mw.z : mw.w;
+                const long long c0 = (long long)tile * SC_BN + half * 128 + c * 32;
+                const long long tcol = tgt - c0;
+                if (tcol >= 0 && tcol < 32 && !((w >> (int)tcol) & 1u)) tlogit = pick32(v, (int)tcol);
+                float cm = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = ((w >> j) & 1u) ? -INFINITY : v[j];
+                    cm = fmaxf(cm, v[j]);
+                }
+                const float mnew = fmaxf(mx, cm);
+                if (mnew > -INFINITY) {                         // (all-masked chunks before the first live one: nothing to add)
+                    float part = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) part += expf(v[j] - mnew);      // exp(-inf) = 0 for masked columns
+                    sum = sum * expf(mx - mnew) + part;
+                    mx = mnew;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        }
+        const size_t list = (size_t)row * (a.n_splits * 2) + (size_t)(split * 2 + half);
+        *reinterpret_cast<float4*>(a.ce_part + list * 4) = make_float4(mx, sum, tlogit, 0.f);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -259,6 +307,40 @@ __global__ void __launch_bounds__(128) score_merge_kernel(const float* __restric
             out_val[row * k + r] = none ? -INFINITY : wv;
             out_idx[row * k + r] = none ? -1 : (long long)wi;
         }
+    }
+}
+
+// CE merge: lse[row] = log sum_c exp(logit[row,c]) over the unmasked catalog from the n_lists partial (max, sum) pairs,
+// tgt[row] = the target's logit (-inf if the target is masked or out of range), nll = lse - tgt.  One warp per row.
+__global__ void __launch_bounds__(128) score_ce_merge_kernel(const float* __restrict__ part, int n_lists, long long B_e,
+                                                             float* __restrict__ lse, float* __restrict__ tgt,
+                                                             float* __restrict__ nll) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= B_e) return;
+    float m = -INFINITY, tl = -INFINITY;
+    for (int i = lane; i < n_lists; i += 32) {
+        const float4 p = *reinterpret_cast<const float4*>(part + ((size_t)row * n_lists + i) * 4);
+        m = fmaxf(m, p.x);
+        tl = fmaxf(tl, p.z);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        tl = fmaxf(tl, __shfl_xor_sync(0xffffffffu, tl, o));
+    }
+    float s = 0.f;
+    for (int i = lane; i < n_lists; i += 32) {
+        const float4 p = *reinterpret_cast<const float4*>(part + ((size_t)row * n_lists + i) * 4);
+        if (p.x > -INFINITY) s += p.y * expf(p.x - m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        const float l = m + logf(s);
+        if (lse) lse[row] = l;
+        if (tgt) tgt[row] = tl;
+        if (nll) nll[row] = l - tl;
     }
 }
 

@@ -636,6 +636,26 @@ def score_topk(seq_out, item_feature, k, hist_u=None, hist_i=None, mask_col0=Tru
     return val, idx
 
 
+def score_ce(seq_out, item_feature, target, mask_col0=True):
+    """Full-catalog softmax cross-entropy on the tcgen05 scoring pipeline (extension, forward only; include/pixelrec_b200.h):
+    returns (lse [B_e], target logit [B_e], nll [B_e]) without materialising the [B_e, N] logits."""
+    _req(seq_out, torch.float32, "seq_out")
+    _req(item_feature, torch.float32, "item_feature")
+    _req(target, torch.int64, "target")
+    B_e, D = seq_out.shape
+    N = item_feature.shape[0]
+    ws_bytes = _L().pr_score_ce_workspace_bytes(B_e, N)
+    if ws_bytes == 0:
+        raise _lib.PixelRecB200Error(f"score_ce: unsupported shape B_e={B_e} N={N}")
+    ws = torch.empty(ws_bytes, device=seq_out.device, dtype=torch.uint8)
+    out = torch.empty(3, B_e, device=seq_out.device, dtype=torch.float32)
+    with _prof("score_ce", seq_out):
+        _lib.check(_L().pr_score_ce_f32(_p(seq_out), B_e, _p(item_feature), N, D, _p(target), int(bool(mask_col0)), _p(out[0]),
+                                        _p(out[1]), _p(out[2]), _p(ws), ws_bytes, _stream(seq_out)), "pr_score_ce_f32")
+    _count(3)
+    return out[0], out[1], out[2]
+
+
 # ------------------------------------------------------------------------------------------- peer-memory exchange
 _CAI_TYPESTR = {torch.float32: "<f4", torch.int64: "<i8", torch.int32: "<i4", torch.uint8: "|u1"}
 

@@ -49,3 +49,33 @@ extern "C" int emu_score_topk_v2(const float* seq, long long B_e, const float* W
     });
     return a.n_splits;
 }
+
+extern "C" int emu_score_ce_v2(const float* seq, long long B_e, const float* W, long long N, long long D, const long long* target,
+                               int mask_col0, int splits_req, int cluster, float* lse, float* tgt, float* nll) {
+    ScoreArgs a{};
+    a.kblocks = (int)(D / SC_BK);
+    a.m_tiles = (int)((B_e + SC_BM - 1) / SC_BM);
+    a.n_tiles = (int)((N + SC_BN - 1) / SC_BN);
+    if (a.m_tiles % cluster) return -1;
+    a.tiles_per_split = (a.n_tiles + splits_req - 1) / splits_req;
+    a.n_splits = (a.n_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
+    a.n_words = a.n_tiles * 8;
+    a.cluster = cluster;
+    const long long rows = (long long)a.m_tiles * SC_BM;
+    std::vector<uint32_t> mask((size_t)rows * a.n_words);
+    const int n_lists = a.n_splits * 2;
+    std::vector<float> part((size_t)rows * n_lists * 4, -99.f);
+    a.mask = mask.data();
+    a.target = target;
+    a.n_rows = B_e;
+    a.ce_part = part.data();
+    const long long nmask = rows * a.n_words;
+    emu::launch((int)((nmask + 255) / 256), 256, 0, [&]() { score_mask_base_kernel(mask.data(), rows, a.n_words, N, mask_col0); });
+    const CUtensorMap tmA{seq, B_e, D, SC_BM}, tmB{W, N, D, SC_BN / cluster};
+    const size_t smem = (size_t)SC_STAGES * SC_STAGE_BYTES + SC2_BAR_BYTES + 1024;
+    emu::after_launch_hook() = emu::join_async;
+    emu::launch_cluster(a.m_tiles * a.n_splits, cluster, SC2_THREADS, smem, [&]() { score_topk2_kernel<16, 1>(tmA, tmB, a); });
+    emu::after_launch_hook() = nullptr;
+    emu::launch((int)((B_e + 3) / 4), 128, 0, [&]() { score_ce_merge_kernel(part.data(), n_lists, B_e, lse, tgt, nll); });
+    return a.n_splits;
+}

@@ -39,6 +39,7 @@ def emu_score():
     assert r.returncode == 0, r.stderr
     lib = C.CDLL(out)
     lib.emu_score_topk_v2.argtypes = [_P, _LL, _P, _LL, _LL, _P, _P, _LL, _I, _I, _I, _I, _P, _P]
+    lib.emu_score_ce_v2.argtypes = [_P, _LL, _P, _LL, _LL, _P, _I, _I, _I, _P, _P, _P]
     return lib
 
 
@@ -169,3 +170,21 @@ def test_score_topk_v2_pipeline_emulated(emu_score, B_e, N, D, k, splits, cluste
     assert ns >= 1
     assert np.array_equal(idx, i_ref)
     assert np.array_equal(val.astype(np.float64), v_ref)
+
+
+@pytest.mark.parametrize("B_e,N,D,splits,cluster", [(70, 300, 64, 1, 1), (200, 1500, 96, 3, 2)])
+def test_score_ce_pipeline_emulated(emu_score, B_e, N, D, splits, cluster):
+    """CE epilogue of the v2 scoring kernel (online max / sum of exp per thread, target-logit pick-up, partial merge) on the
+    emulated pipeline vs the oracle's full_catalog_ce (extension: restates F.cross_entropy, not a reference path)."""
+    g = np.random.default_rng(N + D)
+    seq = g.standard_normal((B_e, D)).astype(np.float32)
+    W = (0.3 * g.standard_normal((N, D))).astype(np.float32)
+    target = g.integers(1, N, size=B_e).astype(np.int64)
+    target[:3] = [1, N - 1, 255]
+    lse_r, tl_r, nll_r = O.full_catalog_ce(seq.astype(np.float64) @ W.astype(np.float64).T, target)
+    lse, tl, nll = (np.zeros(B_e, np.float32) for _ in range(3))
+    ns = emu_score.emu_score_ce_v2(_ptr(seq), B_e, _ptr(W), N, D, _ptr(target), 1, splits, cluster, _ptr(lse), _ptr(tl), _ptr(nll))
+    assert ns >= 1
+    assert np.allclose(lse, lse_r, rtol=2e-5, atol=2e-5)
+    assert np.allclose(tl, tl_r, rtol=2e-5, atol=2e-5)
+    assert np.allclose(nll, nll_r, rtol=1e-4, atol=1e-4)

@@ -112,3 +112,20 @@ def test_score_topk_fewer_valid_items_than_k_and_bad_args():
         ops.score_topk(t(np.zeros((2, 48), np.float32)), t(np.zeros((10, 48), np.float32)), 5)    # D % 32
     with pytest.raises(PixelRecB200Error):
         ops.score_topk(seq, W, 33)
+
+
+@pytest.mark.skipif(os.environ.get("PR_EXPERIMENTAL") != "1", reason="staged kernels: set PR_EXPERIMENTAL=1")
+@pytest.mark.parametrize("B_e,N,D", [(64, 3000, 128), (1024, 97001, 512), (5, 300, 32)])
+def test_score_ce_matches_oracle(B_e, N, D):
+    """full-catalog softmax CE on the v2 scoring pipeline (extension; oracle restates F.cross_entropy): TF32 operands, fp32
+    accumulation -> 2e-3 of max|logit| on lse / target logit"""
+    from pixelrec_b200 import ops
+    g = np.random.default_rng(N + 1)
+    seq = g.standard_normal((B_e, D)).astype(np.float32)
+    W = (0.05 * g.standard_normal((N, D))).astype(np.float32)
+    target = g.integers(1, N, size=B_e).astype(np.int64)
+    scores = seq.astype(np.float64) @ W.astype(np.float64).T
+    lse_r, tl_r, nll_r = O.full_catalog_ce(scores, target)
+    lse, tl, nll = (x.cpu().numpy() for x in ops.score_ce(t(seq), t(W), t(target)))
+    tol = 2e-3 * np.abs(scores).max()
+    assert np.abs(lse - lse_r).max() < tol and np.abs(tl - tl_r).max() < tol and np.abs(nll - nll_r).max() < 2 * tol

@@ -150,3 +150,19 @@ def test_torch_port_matches_reference_golden(golden):
     tv, ti = TP.predict_topk({k: v.detach() for k, v in P.items()}, torch.from_numpy(golden["eval_item_seq"]),
                              torch.from_numpy(golden["eval_hist_u"]), torch.from_numpy(golden["eval_hist_i"]), 10, c["layers"], c["h"])
     assert np.array_equal(ti.numpy(), golden["eval_topk_idx"])
+
+
+def test_full_catalog_ce_oracle_restates_torch_cross_entropy():
+    """the CE extension has no reference counterpart; its oracle is pinned to torch's F.cross_entropy instead"""
+    import torch
+    import torch.nn.functional as F
+    from oracle import sasrec_np as O
+    g = np.random.default_rng(5)
+    scores = g.standard_normal((17, 301))
+    target = g.integers(1, 301, size=17)
+    lse, tl, nll = O.full_catalog_ce(scores, target, mask_col0=False)
+    ref = F.cross_entropy(torch.from_numpy(scores), torch.from_numpy(target), reduction="none").numpy()
+    assert np.allclose(nll, ref, rtol=1e-12, atol=1e-12)
+    lse0, _, nll0 = O.full_catalog_ce(scores, target, mask_col0=True)
+    ref0 = F.cross_entropy(torch.from_numpy(scores[:, 1:]), torch.from_numpy(target - 1), reduction="none").numpy()
+    assert np.allclose(nll0, ref0, rtol=1e-12, atol=1e-12) and (lse0 <= lse + 1e-12).all()

@@ -29,6 +29,7 @@ if [ "$stage" = stage1 ]; then
   # 2. score_topk variants: v2 epilogue (tune 16), then + cluster multicast (tune 48); each variant in its own process
   run 300 r2_score_v2    $PYT tests/test_gpu_score.py -k "v2 and not mcast"
   run 300 r2_score_mcast $PYT tests/test_gpu_score.py -k "v2_mcast"
+  run 300 r2_score_ce    $PYT tests/test_gpu_score.py -k "score_ce"
   # 3. timing (only meaningful if the parity runs above passed)
   run 300 r2_bench_score env SCORE_TUNES=0,16,48 python tools/bench_score.py
   cp gpurun_out/bench_score.json gpurun_out/r2_bench_score.json 2>/dev/null
