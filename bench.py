@@ -13,7 +13,8 @@ L=20, 4 heads, 2 layers).  Batch per GPU is fixed (weak scaling); the table is r
 Prints ONE JSON line (rank 0).  `value` = whole-job sequences/s with inputs resident in HBM; `e2e` = the same
 through the public plugin API with pinned-HOST batches copied in every step and the loss read back every step;
 `roofline` = the embedding-gather kernel (BASELINE.json's named kernel) timed live with CUDA events inside the
-timed region; `roofline_kernels` = every kernel of ours, timed the same way in an extra pass; `cpu_baseline` =
+timed region; `roofline_kernels` = every kernel of ours, timed the same way in an extra pass; `roofline_score_topk` =
+the eval scoring call (tcgen05 GEMM + mask + top-k, the path's one tensor-bound kernel) timed alone; `cpu_baseline` =
 the oracle torch port of the reference step on the host cores (bounded sample).
 
 --impl reference: times the reference's CPU implementation of the same step (oracle/torch_port.py, the pinned
