@@ -198,7 +198,10 @@ class PeerExchange:
         G, rank, D = table.world, table.rank, table.embedding_dim
         dev = table.weight.device
         factor = float(os.environ.get("PR_P2P_CAP_FACTOR", "2.0"))
-        self.R = int(R)
+        r_all = torch.tensor([int(R)], dtype=torch.int64, device=dev)
+        dist.all_reduce(r_all, op=dist.ReduceOp.MAX, group=table.group)       # ranks may start on batches of different size
+        R = int(r_all.item())
+        self.R = R
         self.cap = int(max(1, min(R, max(64, math.ceil(factor * R / G)))))    # rows one source may send one owner per step
         self.G, self.rank = G, rank
         # the shard moves into shareable memory; the Parameter object (and its optimizer state) stay the same
