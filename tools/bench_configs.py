@@ -1,0 +1,140 @@
+"""Throughput of the BASELINE.json configurations that bench.py does not cover (bench.py measures configs[1], the one the
+headline metric is quoted on).  Same step definition (zero_grad -> forward -> backward -> fused AdamW, dropout as shipped),
+same timing rules (CUDA events, barrier + synchronize on both sides, max over ranks), one JSON line per run.
+
+    c3  IDNet/sasrec Pixel8M-shape: N=408375 items, emb_dim=2048, seq_len=20, table row-sharded over the launched ranks
+    c4  PixelNet/sasrec + CLIP ViT item encoder on synthetic 224x224 pixels (--patch 32: the reference yaml; 16: BASELINE text)
+    c5  IDNet/gru4rec Pixel1M-shape: N=100001 items, emb_dim=4096, seq_len=10 (gather / scatter stress; GRU body = cuDNN)
+
+    python tools/bench_configs.py --config c5 [--batch B] [--steps K] [--warmup W]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_configs.py --config c3
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+SHAPES = {
+    "c3": dict(model="SASRec", N=408375, D=2048, L=20, batch=1024),
+    "c4": dict(model="MOSASRec", N=97001, D=512, L=10, batch=16),
+    "c5": dict(model="GRU4Rec", N=100001, D=4096, L=10, batch=1024),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", required=True, choices=sorted(SHAPES))
+    ap.add_argument("--batch", type=int, default=0, help="sequences per GPU per step (default: per config)")
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--patch", type=int, default=32, choices=[16, 32], help="c4: ViT-B/<patch>")
+    ap.add_argument("--exchange", default=None, choices=["nccl", "p2p"])
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.exchange:
+        os.environ["PR_EXCHANGE"] = args.exchange
+    from pixelrec_b200.dist import broadcast_dense_params
+    from pixelrec_b200.trainer.optim import FusedAdamW
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    sh = SHAPES[args.config]
+    B = args.batch or sh["batch"]
+    N, D, L = sh["N"], sh["D"], sh["L"]
+    torch.manual_seed(2020)
+
+    class Dl:
+        item_num = N
+    g = np.random.default_rng(1000 + rank)
+    perm, p = bench.popularity(N)
+    if sh["model"] == "SASRec":
+        from pixelrec_b200.model.IDNet.sasrec import SASRec
+        cfg = dict(n_layers=2, n_heads=4, embedding_size=D, inner_size=2, hidden_dropout_prob=0.1, attn_dropout_prob=0.1,
+                   hidden_act="gelu", layer_norm_eps=1e-12, initializer_range=0.02, MAX_ITEM_LIST_LENGTH=L, seed=2020 + rank)
+        model = SASRec(cfg, Dl()).to(dev).train()
+        opt = FusedAdamW(model.parameters(), lr=1e-4, weight_decay=0.1, tables=[model.item_embedding])
+        what = f"IDNet/sasrec Pixel8M-shape: N={N} items, emb_dim={D}, seq_len={L}, 4 heads (dh={D // 4}), 2 layers, dropout 0.1"
+    elif sh["model"] == "GRU4Rec":
+        from pixelrec_b200.model.IDNet.gru4rec import GRU4Rec
+        cfg = dict(embedding_size=D, hidden_size=1, num_layers=1, dropout_prob=0.0, MAX_ITEM_LIST_LENGTH=L, seed=2020 + rank)
+        model = GRU4Rec(cfg, Dl()).to(dev).train()
+        opt = FusedAdamW(model.parameters(), lr=1e-4, weight_decay=0.01, tables=[model.item_embedding])
+        what = f"IDNet/gru4rec Pixel1M-shape: N={N} items, emb_dim={D}, seq_len={L}, 1 GRU layer (cuDNN)"
+    else:
+        from pixelrec_b200.config import Config
+        files = [os.path.join(ROOT, "configs/PixelNet/sasrec.yaml"), os.path.join(ROOT, "configs/overall/ViT.yaml")]
+        c = Config(files, config_dict=dict(encoder_name=f"clip-vit-base-patch{args.patch}", seed=2020 + rank))
+        model = c.model_class(c, Dl()).to(dev).train()
+        modal = [q for n, q in model.named_parameters() if q.requires_grad and "visual_encoder" in n]
+        rec = [q for n, q in model.named_parameters() if q.requires_grad and "visual_encoder" not in n]
+        opt = FusedAdamW([dict(params=modal, lr=1e-4, weight_decay=0.0), dict(params=rec, lr=1e-4, weight_decay=0.1)])
+        what = (f"PixelNet/sasrec + CLIP ViT-B/{args.patch} (random init, first 165 parameters frozen as overall/ViT.yaml) on synthetic "
+                f"224x224 pixels, emb_dim={D}, seq_len={L}")
+    broadcast_dense_params(model)
+
+    POOL = 3
+    batches = []
+    for _ in range(POOL):
+        items, mask = bench.synth_batch(g, B, N, L, perm, p)
+        if sh["model"] == "MOSASRec":
+            imgs = torch.randn(B, 2 * (L + 1), 3, 224, 224, device=dev)
+            batches.append((imgs, torch.from_numpy(mask).to(dev)))
+        else:
+            batches.append((torch.from_numpy(items).to(dev), torch.from_numpy(mask).to(dev)))
+
+    def step(i):
+        opt.zero_grad()
+        loss = model(batches[i % POOL])
+        loss.backward()
+        opt.step()
+        return loss
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    sync_all()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(args.steps):
+        loss = step(i)
+    e.record()
+    sync_all()
+    ms = torch.tensor([s.elapsed_time(e)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    xs = getattr(getattr(model, "item_embedding", None), "exchange_status", lambda: 0)()
+    if rank == 0:
+        print(json.dumps({
+            "metric": f"sequences/sec {args.config}", "value": B * world * args.steps / (ms / 1e3), "unit": "sequences/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "dtype": "f32 (tf32 tensor-core linear layers)", "data": "synthetic",
+            "config": {"workload": what, "batch_per_gpu": B, "global_batch": B * world,
+                       "parallelism": ("single GPU" if world == 1 else
+                                       f"dp{world}" + ("" if sh["model"] == "MOSASRec" else f" + item table row-sharded {world}-way"))},
+            "loss": float(loss), "exchange_status": xs,
+            "max_memory_GB": torch.cuda.max_memory_allocated(dev) / 2 ** 30}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -4,6 +4,7 @@
 #
 #   gpurun --timeout 1500 -- 'bash tools/round2_gpu.sh stage1'            # 1 GPU: staged kernels, parity + A/B timing
 #   gpurun --gpus 2 --timeout 1200 -- 'bash tools/round2_gpu.sh stage2'   # 2 GPUs: peer-memory exchange vs NCCL
+#   gpurun --timeout 1500 -- 'bash tools/round2_gpu.sh configs'           # 1 GPU: BASELINE configs 3, 4, 5
 #
 # Order matters: parity first (cheap, tells which variant may become a default), timing after.
 set -u
@@ -37,6 +38,14 @@ if [ "$stage" = stage1 ]; then
   run 900 r2_pytest_default env -u PR_EXPERIMENTAL python -m pytest tests -x -q -m gpu
   run 600 r2_bench_n1 python bench.py --steps 20 --warmup 5
   tail -1 gpurun_out/r2_bench_n1.log > gpurun_out/r2_bench_n1.json
+elif [ "$stage" = configs ]; then
+  # the BASELINE.json configurations bench.py does not cover, one GPU (c3 also fits one GPU: 3.35 GB table + Adam state)
+  for c in c5 c3; do
+    run 420 r2_cfg_$c python tools/bench_configs.py --config $c
+    tail -1 gpurun_out/r2_cfg_$c.log > gpurun_out/r2_cfg_$c.json
+  done
+  run 600 r2_cfg_c4_p32 python tools/bench_configs.py --config c4 --patch 32 --steps 5
+  run 600 r2_cfg_c4_p16 python tools/bench_configs.py --config c4 --patch 16 --steps 5
 elif [ "$stage" = stage2 ]; then
   run 600 r2_dist $PYT tests/test_gpu_dist.py
   for ex in nccl p2p; do
