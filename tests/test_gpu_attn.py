@@ -110,7 +110,7 @@ def test_attention_rejects_bad_shapes():
     from pixelrec_b200 import ops
     from pixelrec_b200.lib import PixelRecB200Error
     with pytest.raises(PixelRecB200Error):
-        ops.attention(torch.zeros(1, 65, 3 * 64, device=dev()), None, 2, True)      # L > 64
+        ops.attention(torch.zeros(1, 300, 3 * 64, device=dev()), None, 2, True)     # L > 256 (64 < L <= 256: long-sequence kernels)
     with pytest.raises(PixelRecB200Error):
         ops.attention(torch.zeros(1, 8, 3 * 96, device=dev()), None, 2, True)       # dh = 48
 
