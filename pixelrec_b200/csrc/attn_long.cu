@@ -9,6 +9,22 @@
 #define PR_DYN_SMEM_F4(name) extern __shared__ __align__(16) float4 name[]
 #include "attn_long.cuh"
 
+namespace pr {
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+// D = A(16x8, row) * B(8x8, col) + D, TF32 operands, fp32 accumulate
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+}  // namespace pr
+#include "attn_long_tc.cuh"
+
 using namespace pr;
 
 namespace {
@@ -21,6 +37,18 @@ int check_long(const char* who, const float* q, const float* k, const float* v, 
     PR_CHECK_ARG(ld % 4 == 0 && ld >= (long long)h * dh, "%s: ld=%lld must be a multiple of 4 and >= h*dh", who, ld);
     PR_CHECK_ARG(q && k && v && aligned16(q) && aligned16(k) && aligned16(v), "%s: q/k/v null or not 16-byte aligned", who);
     PR_CHECK_ARG(long_smem_float4(L, dh) * 16 <= 220 * 1024, "%s: L=%d dh=%d does not fit shared memory", who, L, dh);
+    return PR_OK;
+}
+
+template <int DH>
+int launch_long_tc(const LongAttnArgs& A, cudaStream_t stream) {
+    const size_t smem = long_tc_smem_floats<DH>(A.L) * 4;
+    if (smem > 220 * 1024) return PR_ERR_UNSUPPORTED;      // caller falls back to the fp32 kernel
+    PR_CUDA_CALL(cudaFuncSetAttribute(attn_long_tc_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long n_items = (long long)A.B * A.h;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(n_items, (long long)sm_count()));
+    attn_long_tc_fwd_kernel<DH><<<grid, ALT_THREADS, smem, stream>>>(A);
+    PR_CUDA_LAUNCH_CHECK("attn_long_tc_fwd_kernel");
     return PR_OK;
 }
 
@@ -48,6 +76,13 @@ extern "C" int pr_attn_long_fwd_f32(const float* q, const float* k, const float*
     A.B = B; A.L = L; A.h = h; A.dh = dh; A.causal = causal;
     A.scale = (float)(1.0 / sqrt((double)dh));
     A.ctx = ctx; A.lse = lse;
+    if (tune() & PR_TUNE_ATTN_LONG_TC) {                   // tensor-core forward (TF32); same outputs, the backward is unchanged
+        rc = PR_ERR_UNSUPPORTED;
+        if (dh == 32) rc = launch_long_tc<32>(A, (cudaStream_t)stream_);
+        else if (dh == 64) rc = launch_long_tc<64>(A, (cudaStream_t)stream_);
+        else if (dh == 128) rc = launch_long_tc<128>(A, (cudaStream_t)stream_);
+        if (rc != PR_ERR_UNSUPPORTED) return rc;
+    }
     return launch_long(attn_long_fwd_kernel, "attn_long_fwd_kernel", A, (cudaStream_t)stream_);
 }
 

@@ -1,8 +1,10 @@
 // Host build of the SIMT kernels in pixelrec_b200/csrc/{attn_long,peer}.cuh on the emulation layer (emu_cuda.h).
 // Loaded by tests/test_emu_kernels.py through ctypes.  Test infrastructure only.
 #include "emu_cuda.h"
+#include "emu_mma.h"
 
 #include "../../pixelrec_b200/csrc/attn_long.cuh"
+#include "../../pixelrec_b200/csrc/attn_long_tc.cuh"
 #include "../../pixelrec_b200/csrc/peer.cuh"
 
 using namespace pr;
@@ -21,6 +23,17 @@ extern "C" void emu_attn_long_fwd(const float* q, const float* k, const float* v
     LongAttnArgs A = make_args(q, k, v, ld, key_ids, B, L, h, dh, causal);
     A.ctx = ctx; A.lse = lse;
     emu::launch(grid, AL_THREADS, long_smem_float4(L, dh) * 16, [&]() { attn_long_fwd_kernel(A); });
+}
+
+extern "C" int emu_attn_long_tc_fwd(const float* q, const float* k, const float* v, long long ld, const long long* key_ids, int B,
+                                   int L, int h, int dh, int causal, float* ctx, float* lse, int grid) {
+    LongAttnArgs A = make_args(q, k, v, ld, key_ids, B, L, h, dh, causal);
+    A.ctx = ctx; A.lse = lse;
+    if (dh == 32) emu::launch(grid, ALT_THREADS, long_tc_smem_floats<32>(L) * 4, [&]() { attn_long_tc_fwd_kernel<32>(A); });
+    else if (dh == 64) emu::launch(grid, ALT_THREADS, long_tc_smem_floats<64>(L) * 4, [&]() { attn_long_tc_fwd_kernel<64>(A); });
+    else if (dh == 128) emu::launch(grid, ALT_THREADS, long_tc_smem_floats<128>(L) * 4, [&]() { attn_long_tc_fwd_kernel<128>(A); });
+    else return -1;
+    return 0;
 }
 
 extern "C" void emu_attn_long_bwd(const float* q, const float* k, const float* v, long long ld, const long long* key_ids,

@@ -25,6 +25,7 @@ def emu():
     lib = C.CDLL(out)
     lib.emu_attn_long_fwd.argtypes = [_P, _P, _P, _LL, _P, _I, _I, _I, _I, _I, _P, _P, _I]
     lib.emu_attn_long_bwd.argtypes = [_P, _P, _P, _LL, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _LL, _P, _I]
+    lib.emu_attn_long_tc_fwd.argtypes = [_P, _P, _P, _LL, _P, _I, _I, _I, _I, _I, _P, _P, _I]
     lib.emu_gather_rows_peers.argtypes = [_P, _I, _LL, _I, _P, _LL, _P, _P, _I]
     lib.emu_push_rows_peers.argtypes = [_P, _P, _LL, _I, _I, _I, _LL, _LL, _P, _P, _P, _P, _I]
     return lib
@@ -91,6 +92,36 @@ def test_attn_long_fwd_bwd_emulated(emu, B, L, h, dh, causal, padded):
     for got, want, name in ((dqkv[..., :D], dq_r, "dq"), (dqkv[..., D:2 * D], dk_r, "dk"), (dqkv[..., 2 * D:], dv_r, "dv")):
         err = np.abs(got - want).max() / max(np.abs(want).max(), 1e-6)
         assert err < 5e-5, (name, err)
+
+
+@pytest.mark.parametrize("B,L,h,dh,causal,padded", [(1, 70, 1, 32, 0, False), (1, 100, 2, 64, 1, True), (1, 197, 1, 64, 0, False)])
+def test_attn_long_tc_fwd_emulated(emu, B, L, h, dh, causal, padded):
+    """tensor-core forward (mma.sync TF32 emulated lane-exactly with the PTX fragment layouts): fragment index arithmetic,
+    the accumulator->A-fragment key permutation, online softmax over 64-key blocks, masks, lse -- vs the fp64 oracle at TF32
+    tolerance, and lse consistent with the fp32 kernels' (the backward consumes it)."""
+    g = np.random.default_rng(L + dh)
+    D = h * dh
+    qkv = g.standard_normal((B, L, 3 * D)).astype(np.float32)
+    key_ids = None
+    if padded:
+        key_ids = g.integers(1, 50, size=(B, L)).astype(np.int64)
+        key_ids[:, :L // 5] = 0
+    q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+    mask = _mask(key_ids, causal, B, L)
+    ref, _ = O.attn_core_fwd(q.astype(np.float64), k.astype(np.float64), v.astype(np.float64), mask, h)
+    live = (mask == 0).any(-1)[:, 0]
+    ctx = np.zeros((B, L, D), np.float32)
+    lse = np.zeros((B * h, L), np.float32)
+    kp = _ptr(key_ids) if key_ids is not None else None
+    base = qkv.ctypes.data
+    assert emu.emu_attn_long_tc_fwd(base, base + 4 * D, base + 8 * D, 3 * D, kp, B, L, h, dh, causal, _ptr(ctx), _ptr(lse), 1) == 0
+    assert np.isfinite(ctx).all()
+    assert np.abs(ctx - ref)[live].max() < 3e-3 * max(1.0, np.abs(ref).max())          # TF32 operands
+    ctx32 = np.zeros_like(ctx)
+    lse32 = np.zeros_like(lse)
+    emu.emu_attn_long_fwd(base, base + 4 * D, base + 8 * D, 3 * D, kp, B, L, h, dh, causal, _ptr(ctx32), _ptr(lse32), 1)
+    lv = np.broadcast_to(live[:, None, :], (B, h, L))
+    assert np.abs(lse - lse32).reshape(B, h, L)[lv].max() < 2e-2
 
 
 @pytest.mark.parametrize("G,N,D,R", [(1, 20, 8, 9), (2, 101, 16, 300), (4, 77, 36, 130), (8, 1003, 8, 2100)])
