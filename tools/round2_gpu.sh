@@ -32,6 +32,7 @@ if [ "$stage" = stage1 ]; then
   run 300 r2_score_mcast $PYT tests/test_gpu_score.py -k "v2_mcast"
   run 300 r2_score_ce    $PYT tests/test_gpu_score.py -k "score_ce"
   # 3. timing (only meaningful if the parity runs above passed)
+  run 300 r2_bench_attn_long python tools/bench_attn_long.py
   run 300 r2_bench_score env SCORE_TUNES=0,16,48 python tools/bench_score.py
   cp gpurun_out/bench_score.json gpurun_out/r2_bench_score.json 2>/dev/null
   # 4. the whole default suite + bench, as the driver runs them
