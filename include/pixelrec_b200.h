@@ -61,7 +61,8 @@ PR_API int pr_set_device(int device);
  *   1 = LayerNorm backward as per-warp bulk-copy row pipelines, 2 = L2 prefetch of the next row in the register LN kernels,
  *   4 = LayerNorm forward as per-warp bulk-copy row pipelines, 8 = tensor-core attention with two warps per item pipeline,
  *   16 = score_topk with the branch-free 8-warp epilogue, 32 = (with 16) table tile TMA-multicast across a cluster,
- *   64 = long-sequence attention forward on tensor cores (TF32 operands: results differ from the fp32 kernel within TF32 tolerance).
+ *   64 = long-sequence attention (forward; backward for dh <= 64) on tensor cores (TF32 operands: results differ from the
+ *        fp32 kernels within TF32 tolerance).
  * mask < 0 only queries.  Returns the mask in effect.  Results are identical under every mask except where noted. */
 PR_API int pr_set_tuning(int mask);
 

@@ -52,6 +52,21 @@ int launch_long_tc(const LongAttnArgs& A, cudaStream_t stream) {
     return PR_OK;
 }
 
+template <int DH>
+int launch_long_tc_bwd(const LongAttnArgs& A, cudaStream_t stream) {
+    const size_t smem = long_tc_bwd_smem_floats<DH>(A.L) * 4;
+    if (smem > 220 * 1024) return PR_ERR_UNSUPPORTED;
+    PR_CUDA_CALL(cudaFuncSetAttribute(attn_long_tc_bwd_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PR_CUDA_CALL(cudaFuncSetAttribute(attn_long_tc_bwd_dkv_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long n_items = (long long)A.B * A.h;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(n_items, (long long)sm_count()));
+    attn_long_tc_bwd_dq_kernel<DH><<<grid, ALT_THREADS, smem, stream>>>(A);
+    PR_CUDA_LAUNCH_CHECK("attn_long_tc_bwd_dq_kernel");
+    attn_long_tc_bwd_dkv_kernel<DH><<<grid, ALT_THREADS, smem, stream>>>(A);
+    PR_CUDA_LAUNCH_CHECK("attn_long_tc_bwd_dkv_kernel");
+    return PR_OK;
+}
+
 template <typename Kern>
 int launch_long(Kern kern, const char* name, const LongAttnArgs& A, cudaStream_t stream) {
     const size_t smem = long_smem_float4(A.L, A.dh) * 16;
@@ -102,6 +117,12 @@ extern "C" int pr_attn_long_bwd_f32(const float* q, const float* k, const float*
     A.scale = (float)(1.0 / sqrt((double)dh));
     A.lse = const_cast<float*>(lse); A.ctx_in = ctx; A.dctx = dctx; A.delta = delta_ws;
     A.dq = dq; A.dk = dk; A.dv = dv; A.ld_grad = ld_grad;
+    if (tune() & PR_TUNE_ATTN_LONG_TC) {
+        rc = PR_ERR_UNSUPPORTED;
+        if (dh == 32) rc = launch_long_tc_bwd<32>(A, (cudaStream_t)stream_);
+        else if (dh == 64) rc = launch_long_tc_bwd<64>(A, (cudaStream_t)stream_);      // dh = 128 would spill: fp32 kernels
+        if (rc != PR_ERR_UNSUPPORTED) return rc;
+    }
     rc = launch_long(attn_long_bwd_dq_kernel, "attn_long_bwd_dq_kernel", A, (cudaStream_t)stream_);
     if (rc) return rc;
     return launch_long(attn_long_bwd_dkv_kernel, "attn_long_bwd_dkv_kernel", A, (cudaStream_t)stream_);

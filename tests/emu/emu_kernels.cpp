@@ -36,6 +36,24 @@ extern "C" int emu_attn_long_tc_fwd(const float* q, const float* k, const float*
     return 0;
 }
 
+template <int DH>
+static void run_tc_bwd(const LongAttnArgs& A, int grid) {
+    emu::launch(grid, ALT_THREADS, long_tc_bwd_smem_floats<DH>(A.L) * 4, [&]() { attn_long_tc_bwd_dq_kernel<DH>(A); });
+    emu::launch(grid, ALT_THREADS, long_tc_bwd_smem_floats<DH>(A.L) * 4, [&]() { attn_long_tc_bwd_dkv_kernel<DH>(A); });
+}
+
+extern "C" int emu_attn_long_tc_bwd(const float* q, const float* k, const float* v, long long ld, const long long* key_ids,
+                                    const float* ctx, const float* lse, const float* dctx, int B, int L, int h, int dh, int causal,
+                                    float* dq, float* dk, float* dv, long long ld_grad, float* delta, int grid) {
+    LongAttnArgs A = make_args(q, k, v, ld, key_ids, B, L, h, dh, causal);
+    A.lse = const_cast<float*>(lse); A.ctx_in = ctx; A.dctx = dctx; A.delta = delta;
+    A.dq = dq; A.dk = dk; A.dv = dv; A.ld_grad = ld_grad;
+    if (dh == 32) run_tc_bwd<32>(A, grid);
+    else if (dh == 64) run_tc_bwd<64>(A, grid);
+    else return -1;
+    return 0;
+}
+
 extern "C" void emu_attn_long_bwd(const float* q, const float* k, const float* v, long long ld, const long long* key_ids,
                                   const float* ctx, const float* lse, const float* dctx, int B, int L, int h, int dh, int causal,
                                   float* dq, float* dk, float* dv, long long ld_grad, float* delta, int grid) {

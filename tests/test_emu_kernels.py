@@ -26,6 +26,7 @@ def emu():
     lib.emu_attn_long_fwd.argtypes = [_P, _P, _P, _LL, _P, _I, _I, _I, _I, _I, _P, _P, _I]
     lib.emu_attn_long_bwd.argtypes = [_P, _P, _P, _LL, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _LL, _P, _I]
     lib.emu_attn_long_tc_fwd.argtypes = [_P, _P, _P, _LL, _P, _I, _I, _I, _I, _I, _P, _P, _I]
+    lib.emu_attn_long_tc_bwd.argtypes = [_P, _P, _P, _LL, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _LL, _P, _I]
     lib.emu_gather_rows_peers.argtypes = [_P, _I, _LL, _I, _P, _LL, _P, _P, _I]
     lib.emu_push_rows_peers.argtypes = [_P, _P, _LL, _I, _I, _I, _LL, _LL, _P, _P, _P, _P, _I]
     return lib
@@ -122,6 +123,18 @@ def test_attn_long_tc_fwd_emulated(emu, B, L, h, dh, causal, padded):
     emu.emu_attn_long_fwd(base, base + 4 * D, base + 8 * D, 3 * D, kp, B, L, h, dh, causal, _ptr(ctx32), _ptr(lse32), 1)
     lv = np.broadcast_to(live[:, None, :], (B, h, L))
     assert np.abs(lse - lse32).reshape(B, h, L)[lv].max() < 2e-2
+    # tensor-core backward from the tensor-core forward's ctx / lse, vs the fp64 oracle
+    _, cache = O.attn_core_fwd(q.astype(np.float64), k.astype(np.float64), v.astype(np.float64), mask, h)
+    dout = g.standard_normal((B, L, D)).astype(np.float32) * live[..., None]
+    dq_r, dk_r, dv_r = O.attn_core_bwd(dout.astype(np.float64), cache)
+    dqkv = np.zeros_like(qkv)
+    delta = np.zeros((B * h, L), np.float32)
+    gb = dqkv.ctypes.data
+    assert emu.emu_attn_long_tc_bwd(base, base + 4 * D, base + 8 * D, 3 * D, kp, _ptr(ctx), _ptr(lse), _ptr(dout), B, L, h, dh,
+                                    causal, gb, gb + 4 * D, gb + 8 * D, 3 * D, _ptr(delta), 1) == 0
+    for got, want, name in ((dqkv[..., :D], dq_r, "dq"), (dqkv[..., D:2 * D], dk_r, "dk"), (dqkv[..., 2 * D:], dv_r, "dv")):
+        err = np.abs(got - want).max() / max(np.abs(want).max(), 1e-6)
+        assert err < 5e-3, (name, err)
 
 
 @pytest.mark.parametrize("G,N,D,R", [(1, 20, 8, 9), (2, 101, 16, 300), (4, 77, 36, 130), (8, 1003, 8, 2100)])

@@ -38,7 +38,7 @@ def _mask(key_ids, causal, B, L):
 def test_attn_long_fwd_bwd(B, L, h, dh, causal, padded, long_variant):
     from pixelrec_b200 import ops
     tc = bool(long_variant) and dh in (32, 64, 128)
-    ftol, gtol = (3e-3, 5e-3) if tc else (3e-5, 1e-4)          # TF32 operands in the forward / its lse feeding the fp32 backward
+    ftol, gtol = (3e-3, 5e-3) if tc else (3e-5, 1e-4)          # TF32 operands in the tensor-core forward and backward
     g = np.random.default_rng(L * dh + B)
     D = h * dh
     qkv = g.standard_normal((B, L, 3 * D)).astype(np.float32)
