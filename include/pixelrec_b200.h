@@ -228,6 +228,20 @@ PR_API int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float* W, 
                              float* topk_val, int64_t* topk_idx, void* workspace, size_t workspace_bytes,
                              pr_stream_t stream);
 
+/* K9 with fp16 operands (staged): fp16 has the 10 explicit mantissa bits of TF32 (and is rounded to nearest, where the TF32
+ *   datapath reads truncated fp32 words) but kind::f16 MMAs run at twice the TF32 rate on half the operand bytes.  The
+ *   exponent range is narrower: |x| > 65504 saturates and raises status bit 2; |x| < 6e-5 loses precision (absolute error
+ *   <= 3e-8).  LayerNorm outputs and N(0, 0.02^2)-scale tables are far inside that range.
+ * pr_score_prepare_f16: dst_f16[i] = fp16(src[i]), n % 4 == 0 -- convert the item table ONCE per evaluation.
+ * pr_score_topk_f16: as pr_score_topk_f32 with W16 = the converted [N, D] table (D % 64 == 0); seq_out is fp32 and converted
+ *   into the workspace.  Always runs the v2 kernel (pr_set_tuning bit 32 adds the cluster multicast).
+ */
+PR_API int pr_score_prepare_f16(const float* src, int64_t n, void* dst_f16, int32_t* status, pr_stream_t stream);
+PR_API size_t pr_score_topk_f16_workspace_bytes(int64_t B_e, int64_t N, int64_t D, int k);
+PR_API int pr_score_topk_f16(const float* seq_out, int64_t B_e, const void* W16, int64_t N, int64_t D, const int64_t* hist_u,
+                             const int64_t* hist_i, int64_t n_hist, int mask_col0, int k, float* topk_val, int64_t* topk_idx,
+                             void* workspace, size_t workspace_bytes, int32_t* status, pr_stream_t stream);
+
 /* full-catalog softmax cross-entropy on the same tcgen05 pipeline (north_star: "scoring ... fused with the softmax/CE").
  *   EXTENSION -- the reference trains with sampled negatives (REC/model/IDNet/sasrec.py:88-92) and has no full-softmax
  *   loss; the oracle is a restatement of F.cross_entropy(seq_out @ W.T, target) (oracle/sasrec_np.py full_catalog_ce).

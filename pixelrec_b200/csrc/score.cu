@@ -31,6 +31,7 @@
 
 #include <algorithm>
 #include <math.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -58,6 +59,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// the same with fp16 operands (K = 16 per instruction)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -282,6 +292,27 @@ static int make_map(CUtensorMap* tm, const float* base, long long rows, long lon
     return PR_OK;
 }
 
+// [rows, D] fp16 row-major -> boxes of [box_rows x 64 halves] (the same 128-byte swizzled rows as the fp32 map)
+static int make_map_f16(CUtensorMap* tm, const void* base, long long rows, long long D, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_last_error("cuTensorMapEncodeTiled entry point not available");
+        return PR_ERR_UNSUPPORTED;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)D * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled(fp16) failed with CUresult %d (rows=%lld D=%lld)", (int)r, rows, D);
+        return PR_ERR_INVALID_ARGUMENT;
+    }
+    return PR_OK;
+}
+
 struct ScorePlan {
     int m_tiles, n_tiles, n_splits, tiles_per_split, n_words, K;
     size_t mask_bytes, cand_bytes, total;
@@ -308,10 +339,10 @@ static ScorePlan score_plan(long long B_e, long long N, int k) {
 }
 
 // v2 launch: 8 epilogue warps, optional cluster multicast of the table tile across the m-tiles
-template <int K, int MODE>
-static int launch_v2(const CUtensorMap& tmA, const float* W, long long N, long long D, ScoreArgs a, const ScorePlan& p,
+template <int K, int MODE, bool F16 = false>
+static int launch_v2(const CUtensorMap& tmA, const void* W, long long N, long long D, ScoreArgs a, const ScorePlan& p,
                      bool mcast, cudaStream_t stream, int* n_lists) {
-    auto kern = score_topk2_kernel<K, MODE>;
+    auto kern = score_topk2_kernel<K, MODE, F16>;
     const size_t smem = (size_t)SC_STAGES * SC_STAGE_BYTES + SC2_BAR_BYTES + 1024;   // ring + barriers + 1 KiB alignment slack
     PR_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int splits = std::min(p.n_splits, 1024 / (2 * K));                      // two lists per split and row
@@ -347,7 +378,8 @@ static int launch_v2(const CUtensorMap& tmA, const float* W, long long N, long l
     a.n_splits = (p.n_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
     *n_lists = a.n_splits * 2;
     CUtensorMap tmB;
-    int rc = make_map(&tmB, W, N, D, SC_BN / CL);                           // box = this CTA's slice of the table tile
+    int rc = F16 ? make_map_f16(&tmB, W, N, D, SC_BN / CL)                  // box = this CTA's slice of the table tile
+                 : make_map(&tmB, (const float*)W, N, D, SC_BN / CL);
     if (rc) return rc;
     at[0].val.clusterDim.x = CL;
     cfg.gridDim = dim3(p.m_tiles * a.n_splits);
@@ -472,5 +504,74 @@ extern "C" int pr_score_ce_f32(const float* seq_out, int64_t B_e, const float* W
     if (rc) return rc;
     score_ce_merge_kernel<<<(int)((B_e + 3) / 4), 128, 0, stream>>>(part, n_lists, B_e, lse, tgt_logit, nll);
     PR_CUDA_LAUNCH_CHECK("score_ce_merge_kernel");
+    return PR_OK;
+}
+
+// ---- fp16-operand scoring (same mantissa width as TF32, twice the MMA rate, half the operand bytes) -----------------------
+extern "C" int pr_score_prepare_f16(const float* src, int64_t n, void* dst_f16, int32_t* status, pr_stream_t stream_) {
+    PR_CHECK_ARG(n >= 0 && n % 4 == 0, "pr_score_prepare_f16: n=%lld must be a non-negative multiple of 4", (long long)n);
+    if (n == 0) return PR_OK;
+    PR_CHECK_ARG(src && dst_f16 && aligned16(src) && (reinterpret_cast<uintptr_t>(dst_f16) & 7u) == 0,
+                 "pr_score_prepare_f16: null or unaligned pointer");
+    const long long n4 = n / 4;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((n4 + 255) / 256, (long long)sm_count() * 8));
+    score_to_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>((const float4*)src, n4, (uint2*)dst_f16, status);
+    PR_CUDA_LAUNCH_CHECK("score_to_f16_kernel");
+    return PR_OK;
+}
+
+static size_t f16_seq_bytes(int64_t B_e, int64_t D) { return ((size_t)B_e * D * 2 + 255) / 256 * 256; }
+
+extern "C" size_t pr_score_topk_f16_workspace_bytes(int64_t B_e, int64_t N, int64_t D, int k) {
+    if (B_e <= 0 || N <= 0 || D <= 0 || k <= 0 || k > 32) return 0;
+    return score_plan(B_e, N, k).total + f16_seq_bytes(B_e, D);
+}
+
+extern "C" int pr_score_topk_f16(const float* seq_out, int64_t B_e, const void* W16, int64_t N, int64_t D, const int64_t* hist_u,
+                                 const int64_t* hist_i, int64_t n_hist, int mask_col0, int k, float* topk_val, int64_t* topk_idx,
+                                 void* workspace, size_t workspace_bytes, int32_t* status, pr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PR_CHECK_ARG(B_e > 0 && N > 0 && D > 0, "pr_score_topk_f16: bad shape B_e=%lld N=%lld D=%lld", (long long)B_e, (long long)N,
+                 (long long)D);
+    PR_CHECK_ARG(D % 64 == 0, "pr_score_topk_f16: D=%lld must be a multiple of 64", (long long)D);
+    PR_CHECK_ARG(k >= 1 && k <= 32 && k <= N, "pr_score_topk_f16: k=%d outside [1, min(32, N)]", k);
+    PR_CHECK_ARG(N < (1LL << 31) - 512, "pr_score_topk_f16: N too large");
+    PR_CHECK_ARG(seq_out && W16 && topk_val && topk_idx && workspace, "pr_score_topk_f16: null pointer");
+    PR_CHECK_ARG(aligned16(seq_out) && aligned16(W16), "pr_score_topk_f16: seq_out / W16 must be 16-byte aligned");
+    PR_CHECK_ARG(n_hist >= 0 && (n_hist == 0 || (hist_u && hist_i)), "pr_score_topk_f16: bad history arguments");
+    const ScorePlan p = score_plan(B_e, N, k);
+    PR_CHECK_ARG(workspace_bytes >= p.total + f16_seq_bytes(B_e, D), "pr_score_topk_f16: workspace %zu < required %zu",
+                 workspace_bytes, p.total + f16_seq_bytes(B_e, D));
+    PR_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "pr_score_topk_f16: workspace must be 256-byte aligned");
+    char* ws = (char*)workspace;
+    uint32_t* mask = (uint32_t*)ws;
+    float* cand_val = (float*)(ws + p.mask_bytes);
+    int* cand_idx = (int*)(ws + p.mask_bytes + p.cand_bytes);
+    void* seq16 = ws + p.total;
+    int rc = pr_score_prepare_f16(seq_out, B_e * D, seq16, status, stream_);
+    if (rc) return rc;
+    const long long rows = (long long)p.m_tiles * SC_BM;
+    const long long nmask = rows * p.n_words;
+    score_mask_base_kernel<<<(int)((nmask + 255) / 256), 256, 0, stream>>>(mask, rows, p.n_words, N, mask_col0);
+    if (n_hist > 0)
+        score_mask_hist_kernel<<<(int)((n_hist + 255) / 256), 256, 0, stream>>>(mask, p.n_words, B_e, N, (const long long*)hist_u,
+                                                                                (const long long*)hist_i, n_hist);
+    PR_CUDA_LAUNCH_CHECK("score_mask kernels");
+    CUtensorMap tmA;
+    rc = make_map_f16(&tmA, seq16, B_e, D, SC_BM);
+    if (rc) return rc;
+    ScoreArgs a;
+    a.kblocks = (int)(D / 64);
+    a.m_tiles = p.m_tiles; a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.n_splits = p.n_splits;
+    a.n_words = p.n_words; a.mask = mask; a.cand_val = cand_val; a.cand_idx = cand_idx; a.cluster = 1;
+    a.target = nullptr; a.n_rows = B_e; a.ce_part = nullptr;
+    int n_lists = 0;
+    const bool mcast = (tune() & PR_TUNE_SCORE_MCAST) != 0;
+    rc = (p.K == 16) ? launch_v2<16, 0, true>(tmA, W16, N, D, a, p, mcast, stream, &n_lists)
+                     : launch_v2<32, 0, true>(tmA, W16, N, D, a, p, mcast, stream, &n_lists);
+    if (rc) return rc;
+    score_merge_kernel<<<(int)((B_e + 3) / 4), 128, 0, stream>>>(cand_val, cand_idx, n_lists * p.K, B_e, k, topk_val,
+                                                                 (long long*)topk_idx);
+    PR_CUDA_LAUNCH_CHECK("score_merge_kernel");
     return PR_OK;
 }

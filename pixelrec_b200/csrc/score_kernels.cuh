@@ -52,6 +52,52 @@ __host__ __device__ constexpr uint32_t tf32_idesc(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16 with fp16 A and B: format fields [7,10) and [10,13) are 0
+__host__ __device__ constexpr uint32_t f16_idesc(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// fp32 -> fp16 bit pattern, round to nearest even, saturating to +-65504 (sets *sat); plain integer code so that the host
+// emulation converts identically
+__host__ __device__ inline uint16_t f32_to_f16_rn(float f, bool* sat) {
+    uint32_t x;
+    memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    const uint32_t ax = x & 0x7fffffffu;
+    if (ax >= 0x7f800000u) return (uint16_t)(sign | (ax > 0x7f800000u ? 0x7e00u : 0x7c00u));      // nan / inf
+    if (ax >= 0x477ff000u) {                                  // rounds to >= 65520: saturate
+        if (sat) *sat = true;
+        return (uint16_t)(sign | 0x7bffu);
+    }
+    if (ax < 0x33000001u) return (uint16_t)sign;              // < 2^-25 (half of the smallest subnormal): zero
+    if (ax < 0x38800000u) {                                   // subnormal half: value = m * 2^-24
+        const int e = (int)(ax >> 23);                        // biased fp32 exponent, 102..112
+        const uint32_t m = (ax & 0x7fffffu) | 0x800000u;      // 24-bit significand
+        const int shift = 126 - e;                            // 14..24
+        uint32_t h = m >> shift;
+        const uint32_t rem = m & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+        if (rem > halfway || (rem == halfway && (h & 1u))) ++h;
+        return (uint16_t)(sign | h);
+    }
+    uint32_t h = ((ax >> 23) - 112u) << 10 | ((ax >> 13) & 0x3ffu);
+    const uint32_t rem = ax & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;    // carry may bump the exponent: still correct
+    return (uint16_t)(sign | h);
+}
+
+__global__ void __launch_bounds__(256) score_to_f16_kernel(const float4* __restrict__ src, long long n4, uint2* __restrict__ dst,
+                                                           int* __restrict__ status) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    bool sat = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = src[i];
+        uint2 o;
+        o.x = (uint32_t)f32_to_f16_rn(v.x, &sat) | ((uint32_t)f32_to_f16_rn(v.y, &sat) << 16);
+        o.y = (uint32_t)f32_to_f16_rn(v.z, &sat) | ((uint32_t)f32_to_f16_rn(v.w, &sat) << 16);
+        dst[i] = o;
+    }
+    if (sat && status) atomicOr(status, 4);
+}
+
 // sorted (descending) insert; strict '>' keeps the earlier (lower) column on ties
 template <int K>
 __device__ __forceinline__ void topk_insert(float (&val)[K], int (&idx)[K], float v, int c) {
@@ -80,7 +126,10 @@ __device__ __forceinline__ float pick32(const float (&v)[32], int j) {
 
 // MODE 0: masked per-row top-k (eval ranking).  MODE 1: online log-sum-exp over the unmasked catalog + the target item's
 // logit = full-catalog softmax cross-entropy (K unused).
-template <int K, int MODE = 0>
+// F16: operands are fp16 copies of seq_out / the table (pr_score_prepare_f16): same 10 explicit mantissa bits as TF32 -- and
+// rounded to nearest, where the TF32 datapath reads truncated fp32 words -- at twice the MMA rate and half the operand bytes.
+// A 128-byte swizzle row then holds 64 elements and one MMA covers K = 16; every byte offset of the pipeline is unchanged.
+template <int K, int MODE = 0, bool F16 = false>
 __global__ void __launch_bounds__(SC2_THREADS, 1) score_topk2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                      const __grid_constant__ CUtensorMap tmB,
                                                                      const ScoreArgs a) {
@@ -98,6 +147,7 @@ __global__ void __launch_bounds__(SC2_THREADS, 1) score_topk2_kernel(const __gri
     const int t_begin = split * a.tiles_per_split;
     const int t_end = min(a.n_tiles, t_begin + a.tiles_per_split);
     const int n_my = t_end - t_begin;                      // identical in every CTA of a cluster (same split)
+    constexpr int BKE = F16 ? 64 : SC_BK;                  // operand elements per 128-byte k-block
     const int CL = a.cluster;
     const uint16_t cl_mask = (uint16_t)((1u << CL) - 1u);
 
@@ -128,12 +178,12 @@ __global__ void __launch_bounds__(SC2_THREADS, 1) score_topk2_kernel(const __gri
                     mbar_wait(&empty_bar[s], (uint32_t)(((it / SC_STAGES) & 1) ^ 1));
                     mbar_arrive_expect_tx(&full_bar[s], SC_STAGE_BYTES);    // own A box + CL slices of the table tile
                     unsigned char* st = smem + (size_t)s * SC_STAGE_BYTES;
-                    tma_load_2d(st, &tmA, kb * SC_BK, m_tile * SC_BM, &full_bar[s]);
+                    tma_load_2d(st, &tmA, kb * BKE, m_tile * SC_BM, &full_bar[s]);
                     if (CL > 1)
-                        tma_load_2d_mcast(st + SC_A_BYTES + rank * slice_bytes, &tmB, kb * SC_BK, n0 + rank * slice_rows,
+                        tma_load_2d_mcast(st + SC_A_BYTES + rank * slice_bytes, &tmB, kb * BKE, n0 + rank * slice_rows,
                                           &full_bar[s], cl_mask);
                     else
-                        tma_load_2d(st + SC_A_BYTES, &tmB, kb * SC_BK, n0, &full_bar[s]);
+                        tma_load_2d(st + SC_A_BYTES, &tmB, kb * BKE, n0, &full_bar[s]);
                 }
             }
         }
@@ -141,7 +191,7 @@ __global__ void __launch_bounds__(SC2_THREADS, 1) score_topk2_kernel(const __gri
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
         if (lane == 0) {
-            constexpr uint32_t idesc = tf32_idesc(SC_BM, SC_BN);
+            constexpr uint32_t idesc = F16 ? f16_idesc(SC_BM, SC_BN) : tf32_idesc(SC_BM, SC_BN);
             long long it = 0;
             for (int t = 0; t < n_my; ++t) {
                 const int buf = t & 1;
@@ -155,8 +205,10 @@ __global__ void __launch_bounds__(SC2_THREADS, 1) score_topk2_kernel(const __gri
                     const uint32_t sa = smem_u32(smem + (size_t)s * SC_STAGE_BYTES);
                     const uint64_t adesc = sw128_kmajor_desc(sa), bdesc = sw128_kmajor_desc(sa + SC_A_BYTES);
 #pragma unroll
-                    for (int k4 = 0; k4 < SC_BK / 8; ++k4)
-                        umma_tf32(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) ? 1u : 0u);
+                    for (int k4 = 0; k4 < 4; ++k4) {                  // 4 MMAs of 32 operand bytes per 128-byte k-block
+                        if constexpr (F16) umma_f16(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) ? 1u : 0u);
+                        else umma_tf32(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) ? 1u : 0u);
+                    }
                     if (CL > 1) umma_commit_mcast(&empty_bar[s], cl_mask);   // frees stage s in every CTA that writes into it
                     else umma_commit(&empty_bar[s]);
                 }

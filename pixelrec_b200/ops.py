@@ -636,6 +636,44 @@ def score_topk(seq_out, item_feature, k, hist_u=None, hist_i=None, mask_col0=Tru
     return val, idx
 
 
+def score_prepare_f16(x, status=None):
+    """fp16 copy (round to nearest even, saturating; status bit 2 = a value was beyond +-65504) of an fp32 CUDA tensor:
+    the operand format of score_topk_f16.  Convert the item table once per evaluation, not per batch."""
+    _req(x, torch.float32, "x")
+    if x.numel() % 4:
+        raise ValueError("score_prepare_f16: element count must be a multiple of 4")
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    with _prof("score_prepare_f16", x):
+        _lib.check(_L().pr_score_prepare_f16(_p(x), x.numel(), _p(out), _p(status), _stream(x)), "pr_score_prepare_f16")
+    _count()
+    return out
+
+
+def score_topk_f16(seq_out, item_feature_f16, k, hist_u=None, hist_i=None, mask_col0=True, status=None):
+    """score_topk with fp16 operands (kind::f16 MMAs: the mantissa width of TF32 at twice the rate and half the operand
+    bytes).  seq_out stays fp32 (converted inside); item_feature_f16 comes from score_prepare_f16.  D % 64 == 0."""
+    _req(seq_out, torch.float32, "seq_out")
+    _req(item_feature_f16, torch.float16, "item_feature_f16")
+    B_e, D = seq_out.shape
+    N = item_feature_f16.shape[0]
+    n_hist = 0
+    if hist_u is not None and hist_u.numel():
+        _req(hist_u, torch.int64, "hist_u"); _req(hist_i, torch.int64, "hist_i")
+        n_hist = hist_u.numel()
+    ws_bytes = _L().pr_score_topk_f16_workspace_bytes(B_e, N, D, k)
+    if ws_bytes == 0:
+        raise _lib.PixelRecB200Error(f"score_topk_f16: unsupported shape B_e={B_e} N={N} D={D} k={k}")
+    ws = torch.empty(ws_bytes, device=seq_out.device, dtype=torch.uint8)
+    val = torch.empty(B_e, k, device=seq_out.device, dtype=torch.float32)
+    idx = torch.empty(B_e, k, device=seq_out.device, dtype=torch.int64)
+    with _prof("score_topk_f16", seq_out):
+        _lib.check(_L().pr_score_topk_f16(_p(seq_out), B_e, _p(item_feature_f16), N, D, _p(hist_u) if n_hist else None,
+                                          _p(hist_i) if n_hist else None, n_hist, int(bool(mask_col0)), int(k), _p(val),
+                                          _p(idx), _p(ws), ws_bytes, _p(status), _stream(seq_out)), "pr_score_topk_f16")
+    _count(5 if n_hist else 4)
+    return val, idx
+
+
 def score_ce(seq_out, item_feature, target, mask_col0=True):
     """Full-catalog softmax cross-entropy on the tcgen05 scoring pipeline (extension, forward only; include/pixelrec_b200.h):
     returns (lse [B_e], target logit [B_e], nll [B_e]) without materialising the [B_e, N] logits."""

@@ -90,6 +90,7 @@ class Trainer:
         self.eval_collector = Collector(config)
         self.evaluator = Evaluator(config)
         self.item_feature = None
+        self.item_feature_f16 = None
         self.tot_item_num = None
 
     # ------------------------------------------------------------------ optimizer (trainer.py:66-103)
@@ -247,19 +248,29 @@ class Trainer:
         hu = hi = None
         if history_index is not None:
             hu, hi = (x.to(self.device).contiguous() for x in history_index)
-        _, topk_idx = ops.score_topk(seq_out, self.item_feature.contiguous(), max(self.config["topk"]), hu, hi, mask_col0=True)
+        if self._scoring_mode() == "tcgen05_f16" and self.item_feature.shape[1] % 64 == 0:     # staged, opt-in
+            if self.item_feature_f16 is None:
+                self.item_feature_f16 = ops.score_prepare_f16(self.item_feature.contiguous())   # once per evaluate()
+            _, topk_idx = ops.score_topk_f16(seq_out, self.item_feature_f16, max(self.config["topk"]), hu, hi, mask_col0=True)
+        else:
+            _, topk_idx = ops.score_topk(seq_out, self.item_feature.contiguous(), max(self.config["topk"]), hu, hi,
+                                         mask_col0=True)
         return topk_idx, positive_u, positive_i
 
+    def _scoring_mode(self):
+        return (self.config["eval_scoring"] or "tcgen05").lower()
+
     def _use_fused_topk(self):
-        mode = (self.config["eval_scoring"] or "tcgen05").lower()
+        mode = self._scoring_mode()
         model = unwrap(self.model)
         D = self.item_feature.shape[1]
-        return (mode == "tcgen05" and hasattr(model, "encode_last") and D % 32 == 0 and max(self.config["topk"]) <= 32
-                and self.item_feature.is_cuda)
+        return (mode in ("tcgen05", "tcgen05_f16") and hasattr(model, "encode_last") and D % 32 == 0
+                and max(self.config["topk"]) <= 32 and self.item_feature.is_cuda)
 
     @torch.no_grad()
     def compute_item_feature(self, config, data):
         self.item_feature = unwrap(self.model).compute_item_all()
+        self.item_feature_f16 = None
 
     def distributed_concat(self, tensor, num_total_examples):
         if dist_ready():

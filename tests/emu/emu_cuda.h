@@ -17,6 +17,7 @@
 
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(8) uint2 { unsigned x, y; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
 

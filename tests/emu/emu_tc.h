@@ -20,8 +20,8 @@
 
 #include "emu_cuda.h"
 
-struct CUtensorMap {            // stand-in: [rows, cols] fp32 row-major, boxes of [box_rows x 32 floats]
-    const float* base; long long rows, cols; int box_rows;
+struct CUtensorMap {            // stand-in: [rows, cols] row-major of 4-byte (fp32) or 2-byte (fp16) elements, boxes of [box_rows x 128 bytes]
+    const void* base; long long rows, cols; int box_rows; int elem_bytes;
 };
 #define __grid_constant__
 
@@ -86,14 +86,33 @@ inline void join_async() {
     std::lock_guard<std::mutex> lk(g_m());
     bars().clear();
 }
-struct MmaOp { uint32_t d; uint64_t adesc, bdesc; uint32_t idesc, acc; };
+struct MmaOp { uint32_t d; uint64_t adesc, bdesc; uint32_t idesc, acc; bool f16; };
+inline float half_bits_to_float(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+    float f;
+    if (e == 0) {
+        f = std::ldexp((float)m, -24);
+    } else if (e == 31) {
+        f = m ? std::nanf("") : INFINITY;
+    } else {
+        f = std::ldexp((float)(m | 0x400u), (int)e - 25);
+    }
+    uint32_t bits;
+    memcpy(&bits, &f, 4);
+    bits |= sign;
+    memcpy(&f, &bits, 4);
+    return f;
+}
 inline thread_local std::vector<MmaOp> t_pending;
 inline void copy_box(unsigned char* dst, CUtensorMap tm, int c0, int c1) {
-    float* o = reinterpret_cast<float*>(dst);
+    const int eb = tm.elem_bytes, inner = 128 / eb;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(tm.base);
     for (int r = 0; r < tm.box_rows; ++r)
-        for (int c = 0; c < 32; ++c) {
+        for (int c = 0; c < inner; ++c) {
             const long long row = (long long)c1 + r, col = (long long)c0 + c;
-            o[r * 32 + c] = (row >= 0 && row < tm.rows && col >= 0 && col < tm.cols) ? tm.base[row * tm.cols + col] : 0.0f;
+            unsigned char* o = dst + (size_t)r * 128 + (size_t)c * eb;
+            if (row >= 0 && row < tm.rows && col >= 0 && col < tm.cols) memcpy(o, src + ((size_t)row * tm.cols + col) * eb, eb);
+            else memset(o, 0, eb);
         }
 }
 inline void run_pending_mmas() {
@@ -102,14 +121,24 @@ inline void run_pending_mmas() {
         const int M = (int)((op.idesc >> 24) & 0x1f) << 4, N = (int)((op.idesc >> 17) & 0x3f) << 3;
         if ((op.d >> 16) != 0 || M != 128) fail("emulated UMMA supports M = 128 at TMEM lane 0 only");
         const uint32_t a_addr = (uint32_t)(op.adesc & 0x3FFF) << 4, b_addr = (uint32_t)(op.bdesc & 0x3FFF) << 4;
-        const float* A = reinterpret_cast<const float*>(me->smem + (a_addr - 1024));
-        const float* B = reinterpret_cast<const float*>(me->smem + (b_addr - 1024));
+        const unsigned char* Ab = me->smem + (a_addr - 1024);
+        const unsigned char* Bb = me->smem + (b_addr - 1024);
         const int col0 = (int)(op.d & 0xffff);
         if (col0 + N > 512) fail("UMMA accumulator beyond 512 TMEM columns");
+        const bool fmt16 = ((op.idesc >> 7) & 7u) == 0 && ((op.idesc >> 10) & 7u) == 0;
+        if (fmt16 != op.f16) fail("instruction descriptor operand format does not match the MMA kind");
         for (int m = 0; m < M; ++m)
             for (int n = 0; n < N; ++n) {
                 float s = 0.f;
-                for (int k = 0; k < 8; ++k) s += A[m * 32 + k] * B[n * 32 + k];      // rows are 128 bytes apart
+                if (op.f16) {                                                   // K = 16 halves = 32 bytes; rows are 128 bytes apart
+                    const uint16_t* A = reinterpret_cast<const uint16_t*>(Ab + (size_t)m * 128);
+                    const uint16_t* B = reinterpret_cast<const uint16_t*>(Bb + (size_t)n * 128);
+                    for (int k = 0; k < 16; ++k) s += half_bits_to_float(A[k]) * half_bits_to_float(B[k]);
+                } else {                                                        // K = 8 fp32 words
+                    const float* A = reinterpret_cast<const float*>(Ab + (size_t)m * 128);
+                    const float* B = reinterpret_cast<const float*>(Bb + (size_t)n * 128);
+                    for (int k = 0; k < 8; ++k) s += A[k] * B[k];
+                }
                 float& d = me->tmem[(size_t)m * 512 + col0 + n];
                 d = op.acc ? d + s : s;
             }
@@ -176,7 +205,10 @@ inline void tmem_dealloc(uint32_t, uint32_t) { emu::warp_sync(); }
 inline void tc_fence_before() {}
 inline void tc_fence_after() {}
 inline void umma_tf32(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    emu::t_pending.push_back(emu::MmaOp{d, adesc, bdesc, idesc, acc});
+    emu::t_pending.push_back(emu::MmaOp{d, adesc, bdesc, idesc, acc, false});
+}
+inline void umma_f16(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    emu::t_pending.push_back(emu::MmaOp{d, adesc, bdesc, idesc, acc, true});
 }
 inline void umma_commit(uint64_t* bar) {
     emu::run_pending_mmas();

@@ -41,6 +41,7 @@ def emu_score():
     assert r.returncode == 0, r.stderr
     lib = C.CDLL(out)
     lib.emu_score_topk_v2.argtypes = [_P, _LL, _P, _LL, _LL, _P, _P, _LL, _I, _I, _I, _I, _P, _P]
+    lib.emu_score_topk_f16.argtypes = [_P, _LL, _P, _LL, _LL, _P, _P, _LL, _I, _I, _I, _I, _P, _P, _P]
     lib.emu_score_ce_v2.argtypes = [_P, _LL, _P, _LL, _LL, _P, _I, _I, _I, _P, _P, _P]
     return lib
 
@@ -232,3 +233,30 @@ def test_score_ce_pipeline_emulated(emu_score, B_e, N, D, splits, cluster):
     assert np.allclose(lse, lse_r, rtol=2e-5, atol=2e-5)
     assert np.allclose(tl, tl_r, rtol=2e-5, atol=2e-5)
     assert np.allclose(nll, nll_r, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("B_e,N,D,k,splits,cluster", [(100, 300, 64, 10, 1, 1), (200, 1700, 192, 10, 2, 2)])
+def test_score_topk_f16_pipeline_emulated(emu_score, B_e, N, D, k, splits, cluster):
+    """fp16-operand mode of the v2 scoring kernel (kind::f16: 64 elements per 128-byte k-block, K = 16 per MMA) incl. the
+    fp32 -> fp16 conversion kernel, on the emulated pipeline.  Small integers are exact in fp16, so results must equal the
+    oracle bit for bit; a value beyond the fp16 range must raise the saturation flag."""
+    g = np.random.default_rng(B_e * 3 + N)
+    seq = g.integers(-3, 4, size=(B_e, D)).astype(np.float32)
+    W = g.integers(-3, 4, size=(N, D)).astype(np.float32)
+    hu = np.repeat(np.arange(B_e), 5).astype(np.int64)
+    hi = g.integers(1, N, size=B_e * 5).astype(np.int64)
+    v_ref, i_ref = O.full_sort_topk(seq.astype(np.float64) @ W.astype(np.float64).T, hu, hi, k)
+    val = np.zeros((B_e, k), np.float32)
+    idx = np.zeros((B_e, k), np.int64)
+    status = np.zeros(1, np.int32)
+    ns = emu_score.emu_score_topk_f16(_ptr(seq), B_e, _ptr(W), N, D, _ptr(hu), _ptr(hi), len(hu), 1, k, splits, cluster,
+                                      _ptr(val), _ptr(idx), _ptr(status))
+    assert ns >= 1 and status[0] == 0
+    assert np.array_equal(idx, i_ref)
+    assert np.array_equal(val.astype(np.float64), v_ref)
+    if cluster == 1:
+        W2 = W.copy()
+        W2[5, 3] = 1e6
+        emu_score.emu_score_topk_f16(_ptr(seq), B_e, _ptr(W2), N, D, _ptr(hu), _ptr(hi), len(hu), 1, k, splits, cluster,
+                                     _ptr(val), _ptr(idx), _ptr(status))
+        assert status[0] == 4

@@ -129,3 +129,48 @@ def test_score_ce_matches_oracle(B_e, N, D):
     lse, tl, nll = (x.cpu().numpy() for x in ops.score_ce(t(seq), t(W), t(target)))
     tol = 2e-3 * np.abs(scores).max()
     assert np.abs(lse - lse_r).max() < tol and np.abs(tl - tl_r).max() < tol and np.abs(nll - nll_r).max() < 2 * tol
+
+
+@pytest.mark.skipif(os.environ.get("PR_EXPERIMENTAL") != "1", reason="staged kernels: set PR_EXPERIMENTAL=1")
+@pytest.mark.parametrize("B_e,N,D,k", [(5, 300, 64, 10), (300, 5003, 512, 10), (1024, 20011, 512, 10), (33, 777, 128, 20)])
+def test_score_topk_f16_exact_on_small_integers(B_e, N, D, k):
+    """fp16-operand scoring (kind::f16): small integers are exact in fp16 -> bit-exact ids, values and tie order"""
+    from pixelrec_b200 import ops
+    g = np.random.default_rng(B_e * 11 + N)
+    seq = g.integers(-3, 4, size=(B_e, D)).astype(np.float32)
+    W = g.integers(-3, 4, size=(N, D)).astype(np.float32)
+    hu, hi = _hist(g, B_e, N, 6)
+    v_ref, i_ref = O.full_sort_topk(seq.astype(np.float64) @ W.astype(np.float64).T, hu, hi, k)
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    W16 = ops.score_prepare_f16(t(W), status)
+    assert W16.dtype == torch.float16 and torch.equal(W16.float().cpu(), torch.from_numpy(W))
+    val, idx = ops.score_topk_f16(t(seq), W16, k, t(hu), t(hi), status=status)
+    assert np.array_equal(idx.cpu().numpy(), i_ref)
+    assert np.array_equal(val.cpu().numpy().astype(np.float64), v_ref)
+    assert int(status.item()) == 0
+
+
+@pytest.mark.skipif(os.environ.get("PR_EXPERIMENTAL") != "1", reason="staged kernels: set PR_EXPERIMENTAL=1")
+def test_score_topk_f16_gaussian_matches_tf32_quality_and_flags_overflow():
+    from pixelrec_b200 import ops
+    B_e, N, D, k = 1024, 97001, 512, 10
+    g = np.random.default_rng(7)
+    seq = g.standard_normal((B_e, D)).astype(np.float32)
+    W = (0.02 * g.standard_normal((N, D))).astype(np.float32)
+    hu, hi = _hist(g, B_e, N, 12)
+    scores = seq.astype(np.float64) @ W.astype(np.float64).T
+    v_ref, i_ref = O.full_sort_topk(scores, hu, hi, k)
+    W16 = ops.score_prepare_f16(t(W))
+    assert torch.equal(W16.cpu(), torch.from_numpy(W).half())                     # same rounding as torch's fp16 cast
+    val, idx = ops.score_topk_f16(t(seq), W16, k, t(hu), t(hi))
+    val, idx = val.cpu().numpy(), idx.cpu().numpy()
+    tol = 2e-3 * np.abs(scores).max()
+    masked = scores.copy()
+    masked[:, 0] = -np.inf
+    masked[hu, hi] = -np.inf
+    assert np.abs(val - np.take_along_axis(masked, idx, 1)).max() < tol
+    assert (val[:, -1] >= v_ref[:, -1] - tol).all() and (idx == i_ref).mean() > 0.97
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    big = t(np.full((4, 64), 1e6, np.float32))
+    out = ops.score_prepare_f16(big, status)
+    assert int(status.item()) == 4 and torch.isfinite(out).all()

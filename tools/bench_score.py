@@ -60,6 +60,15 @@ if os.environ.get("SCORE_TUNES"):
         out[f"tune{tn}_TFLOPs"] = 2 * B_e * N * D / ms / 1e9
         out[f"tune{tn}_ids_equal_v1"] = same
     L_.pr_set_tuning(base)
+# fp16-operand path (staged): SCORE_F16=1 [with PR_TUNE bit 32 for the multicast]
+if os.environ.get("SCORE_F16") == "1":
+    W16 = ops.score_prepare_f16(W)
+    out["prepare_f16_table_ms"] = timeit(lambda: ops.score_prepare_f16(W))
+    ms = timeit(lambda: ops.score_topk_f16(seq, W16, k, hu, hi))
+    out["f16_ms"] = ms
+    out["f16_TFLOPs"] = 2 * B_e * N * D / ms / 1e9
+    i16 = ops.score_topk_f16(seq, W16, k, hu, hi)[1]
+    out["f16_idx_agreement_vs_tf32"] = float((i16 == ops.score_topk(seq, W, k, hu, hi)[1]).float().mean())
 torch.backends.cuda.matmul.allow_tf32 = False
 v1, i1 = ref_path()
 v2, i2 = ops.score_topk(seq, W, k, hu, hi)

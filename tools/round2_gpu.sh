@@ -30,10 +30,13 @@ if [ "$stage" = stage1 ]; then
   # 2. score_topk variants: v2 epilogue (tune 16), then + cluster multicast (tune 48); each variant in its own process
   run 300 r2_score_v2    $PYT tests/test_gpu_score.py -k "v2 and not mcast"
   run 300 r2_score_mcast $PYT tests/test_gpu_score.py -k "v2_mcast"
-  run 300 r2_score_ce    $PYT tests/test_gpu_score.py -k "score_ce"
+  run 300 r2_score_ce    $PYT tests/test_gpu_score.py -k "score_ce and v1"
+  run 300 r2_score_f16   $PYT tests/test_gpu_score.py -k "f16 and v1"
+  run 300 r2_score_f16mc $PYT tests/test_gpu_score.py -k "f16 and v2_mcast"
   # 3. timing (only meaningful if the parity runs above passed)
   run 300 r2_bench_attn_long python tools/bench_attn_long.py
-  run 300 r2_bench_score env SCORE_TUNES=0,16,48 python tools/bench_score.py
+  run 300 r2_bench_score env SCORE_TUNES=0,16,48 SCORE_F16=1 python tools/bench_score.py
+  run 300 r2_bench_score_f16mc env PR_TUNE=$((9 | 32)) SCORE_F16=1 python tools/bench_score.py
   cp gpurun_out/bench_score.json gpurun_out/r2_bench_score.json 2>/dev/null
   # 4. the whole default suite + bench, as the driver runs them
   run 900 r2_pytest_default env -u PR_EXPERIMENTAL python -m pytest tests -x -q -m gpu
