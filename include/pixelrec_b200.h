@@ -61,6 +61,7 @@ PR_API int pr_set_device(int device);
  *   1 = LayerNorm backward as per-warp bulk-copy row pipelines, 2 = L2 prefetch of the next row in the register LN kernels,
  *   4 = LayerNorm forward as per-warp bulk-copy row pipelines, 8 = tensor-core attention with two warps per item pipeline,
  *   16 = score_topk with the branch-free 8-warp epilogue, 32 = (with 16) table tile TMA-multicast across a cluster,
+ *   128 = fp16 scoring keeps the 128 x D seq_out tile resident in shared memory (D <= 512),
  *   64 = long-sequence attention (forward; backward for dh <= 64) on tensor cores (TF32 operands: results differ from the
  *        fp32 kernels within TF32 tolerance).
  * mask < 0 only queries.  Returns the mask in effect.  Results are identical under every mask except where noted. */

@@ -18,6 +18,7 @@ int tune();                      // PR_TUNE bit mask (api.cu)
 #define PR_TUNE_ATTN_PAIR 8
 #define PR_TUNE_SCORE_V2 16      /* score_topk: branch-free 8-warp epilogue (staged, unmeasured) */
 #define PR_TUNE_ATTN_LONG_TC 64  /* long-sequence attention forward on mma.sync TF32 (staged, unmeasured) */
+#define PR_TUNE_SCORE_ARES 128    /* fp16 scoring: seq_out tile resident in shared memory (staged) */
 #define PR_TUNE_SCORE_MCAST 32   /* + table tile TMA-multicast across the m-tiles of a cluster (needs SCORE_V2) */
 #ifndef PR_TUNE_DEFAULT
 #define PR_TUNE_DEFAULT (PR_TUNE_LN_BWD_PIPE | PR_TUNE_ATTN_PAIR)   /* measured: profiles/r01h_rowkernels_ab.md, r01l_attention_pair.md */

@@ -339,11 +339,13 @@ static ScorePlan score_plan(long long B_e, long long N, int k) {
 }
 
 // v2 launch: 8 epilogue warps, optional cluster multicast of the table tile across the m-tiles
-template <int K, int MODE, bool F16 = false>
+template <int K, int MODE, bool F16 = false, bool ARES = false>
 static int launch_v2(const CUtensorMap& tmA, const void* W, long long N, long long D, ScoreArgs a, const ScorePlan& p,
                      bool mcast, cudaStream_t stream, int* n_lists) {
-    auto kern = score_topk2_kernel<K, MODE, F16>;
-    const size_t smem = (size_t)SC_STAGES * SC_STAGE_BYTES + SC2_BAR_BYTES + 1024;   // ring + barriers + 1 KiB alignment slack
+    auto kern = score_topk2_kernel<K, MODE, F16, ARES>;
+    // ring (+ resident seq_out tile) + barriers + 1 KiB alignment slack
+    const size_t smem = (ARES ? (size_t)a.kblocks * SC_A_BYTES + (size_t)3 * SC_B_BYTES : (size_t)SC_STAGES * SC_STAGE_BYTES) +
+                        SC2_BAR_BYTES + 1024;
     PR_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int splits = std::min(p.n_splits, 1024 / (2 * K));                      // two lists per split and row
     int CL = 1;
@@ -567,8 +569,12 @@ extern "C" int pr_score_topk_f16(const float* seq_out, int64_t B_e, const void* 
     a.target = nullptr; a.n_rows = B_e; a.ce_part = nullptr;
     int n_lists = 0;
     const bool mcast = (tune() & PR_TUNE_SCORE_MCAST) != 0;
-    rc = (p.K == 16) ? launch_v2<16, 0, true>(tmA, W16, N, D, a, p, mcast, stream, &n_lists)
-                     : launch_v2<32, 0, true>(tmA, W16, N, D, a, p, mcast, stream, &n_lists);
+    if ((tune() & PR_TUNE_SCORE_ARES) && D <= 512)       // seq_out tile resident in shared memory (<= 128 KiB)
+        rc = (p.K == 16) ? launch_v2<16, 0, true, true>(tmA, W16, N, D, a, p, mcast, stream, &n_lists)
+                         : launch_v2<32, 0, true, true>(tmA, W16, N, D, a, p, mcast, stream, &n_lists);
+    else
+        rc = (p.K == 16) ? launch_v2<16, 0, true>(tmA, W16, N, D, a, p, mcast, stream, &n_lists)
+                         : launch_v2<32, 0, true>(tmA, W16, N, D, a, p, mcast, stream, &n_lists);
     if (rc) return rc;
     score_merge_kernel<<<(int)((B_e + 3) / 4), 128, 0, stream>>>(cand_val, cand_idx, n_lists * p.K, B_e, k, topk_val,
                                                                  (long long*)topk_idx);

@@ -129,19 +129,28 @@ __device__ __forceinline__ float pick32(const float (&v)[32], int j) {
 // F16: operands are fp16 copies of seq_out / the table (pr_score_prepare_f16): same 10 explicit mantissa bits as TF32 -- and
 // rounded to nearest, where the TF32 datapath reads truncated fp32 words -- at twice the MMA rate and half the operand bytes.
 // A 128-byte swizzle row then holds 64 elements and one MMA covers K = 16; every byte offset of the pipeline is unchanged.
-template <int K, int MODE = 0, bool F16 = false>
+// ARES (needs F16, D <= 512): the CTA's 128 x D seq_out tile (<= 128 KiB in fp16) is loaded ONCE and stays resident; the
+// ring then carries only table tiles (3 stages of 32 KiB).  Without it the tile is re-streamed from L2 for every one of the
+// CTA's ~20 table tiles, which at the fp16 MMA rate would exceed the chip's L2 throughput.
+template <int K, int MODE = 0, bool F16 = false, bool ARES = false>
 __global__ void __launch_bounds__(SC2_THREADS, 1) score_topk2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                      const __grid_constant__ CUtensorMap tmB,
                                                                      const ScoreArgs a) {
     PR_DYN_SMEM_BYTES(smem_raw);
     // SWIZZLE_128B tiles (TMA destination == UMMA operand) must sit on 1024-byte boundaries
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    static_assert(!ARES || F16, "the resident seq_out tile only fits in fp16");
+    constexpr int NST = ARES ? 3 : SC_STAGES;                // ring stages
+    constexpr int STB = ARES ? SC_B_BYTES : SC_STAGE_BYTES;  // bytes per stage
+    constexpr int B_OFF = ARES ? 0 : SC_A_BYTES;             // table tile inside a stage
+    unsigned char* ring = smem + (ARES ? (size_t)a.kblocks * SC_A_BYTES : 0);      // resident A k-blocks come first
     // barriers live behind the ring, at the same offset in every CTA of a cluster (remote arrives address them by offset)
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)SC_STAGES * SC_STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + (size_t)NST * STB);
     uint64_t* empty_bar = full_bar + SC_STAGES;
     uint64_t* tfull_bar = empty_bar + SC_STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot_p = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* ares_bar = tempty_bar + 2;
+    uint32_t* tmem_slot_p = reinterpret_cast<uint32_t*>(ares_bar + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.x % a.m_tiles, split = blockIdx.x / a.m_tiles;
     const int t_begin = split * a.tiles_per_split;
@@ -152,8 +161,9 @@ __global__ void __launch_bounds__(SC2_THREADS, 1) score_topk2_kernel(const __gri
     const uint16_t cl_mask = (uint16_t)((1u << CL) - 1u);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < SC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (uint32_t)CL); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], (uint32_t)CL); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], SC2_EPI_WARPS); }
+        if (ARES) mbar_init(ares_bar, 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot_p, SC_TMEM_COLS);
@@ -170,20 +180,25 @@ __global__ void __launch_bounds__(SC2_THREADS, 1) score_topk2_kernel(const __gri
             const int slice_rows = SC_BN / CL;
             const int slice_bytes = SC_B_BYTES / CL;
             long long it = 0;
+            if (ARES && n_my > 0) {                                    // the whole seq_out tile, once
+                mbar_arrive_expect_tx(ares_bar, (uint32_t)a.kblocks * SC_A_BYTES);
+                for (int kb = 0; kb < a.kblocks; ++kb)
+                    tma_load_2d(smem + (size_t)kb * SC_A_BYTES, &tmA, kb * BKE, m_tile * SC_BM, ares_bar);
+            }
             for (int t = 0; t < n_my; ++t) {
                 const int n0 = (t_begin + t) * SC_BN;
                 for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
-                    const int s = (int)(it % SC_STAGES);
+                    const int s = (int)(it % NST);
                     // CL arrivals: every CTA of the cluster has finished reading stage s of the previous round
-                    mbar_wait(&empty_bar[s], (uint32_t)(((it / SC_STAGES) & 1) ^ 1));
-                    mbar_arrive_expect_tx(&full_bar[s], SC_STAGE_BYTES);    // own A box + CL slices of the table tile
-                    unsigned char* st = smem + (size_t)s * SC_STAGE_BYTES;
-                    tma_load_2d(st, &tmA, kb * BKE, m_tile * SC_BM, &full_bar[s]);
+                    mbar_wait(&empty_bar[s], (uint32_t)(((it / NST) & 1) ^ 1));
+                    mbar_arrive_expect_tx(&full_bar[s], STB);          // (own A box +) CL slices of the table tile
+                    unsigned char* st = ring + (size_t)s * STB;
+                    if (!ARES) tma_load_2d(st, &tmA, kb * BKE, m_tile * SC_BM, &full_bar[s]);
                     if (CL > 1)
-                        tma_load_2d_mcast(st + SC_A_BYTES + rank * slice_bytes, &tmB, kb * BKE, n0 + rank * slice_rows,
+                        tma_load_2d_mcast(st + B_OFF + rank * slice_bytes, &tmB, kb * BKE, n0 + rank * slice_rows,
                                           &full_bar[s], cl_mask);
                     else
-                        tma_load_2d(st + SC_A_BYTES, &tmB, kb * BKE, n0, &full_bar[s]);
+                        tma_load_2d(st + B_OFF, &tmB, kb * BKE, n0, &full_bar[s]);
                 }
             }
         }
@@ -193,17 +208,22 @@ __global__ void __launch_bounds__(SC2_THREADS, 1) score_topk2_kernel(const __gri
         if (lane == 0) {
             constexpr uint32_t idesc = F16 ? f16_idesc(SC_BM, SC_BN) : tf32_idesc(SC_BM, SC_BN);
             long long it = 0;
+            if (ARES && n_my > 0) {
+                mbar_wait(ares_bar, 0);
+                tc_fence_after();
+            }
             for (int t = 0; t < n_my; ++t) {
                 const int buf = t & 1;
                 mbar_wait(&tempty_bar[buf], (uint32_t)(((t >> 1) & 1) ^ 1));
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * SC_BN;
                 for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
-                    const int s = (int)(it % SC_STAGES);
-                    mbar_wait(&full_bar[s], (uint32_t)((it / SC_STAGES) & 1));
+                    const int s = (int)(it % NST);
+                    mbar_wait(&full_bar[s], (uint32_t)((it / NST) & 1));
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)s * SC_STAGE_BYTES);
-                    const uint64_t adesc = sw128_kmajor_desc(sa), bdesc = sw128_kmajor_desc(sa + SC_A_BYTES);
+                    const uint32_t sb = smem_u32(ring + (size_t)s * STB + B_OFF);
+                    const uint32_t sa = ARES ? smem_u32(smem + (size_t)kb * SC_A_BYTES) : smem_u32(ring + (size_t)s * STB);
+                    const uint64_t adesc = sw128_kmajor_desc(sa), bdesc = sw128_kmajor_desc(sb);
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {                  // 4 MMAs of 32 operand bytes per 128-byte k-block
                         if constexpr (F16) umma_f16(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) ? 1u : 0u);

@@ -83,7 +83,7 @@ extern "C" int emu_score_ce_v2(const float* seq, long long B_e, const float* W, 
 // fp16-operand variant: mirrors pr_score_prepare_f16 + pr_score_topk_f16
 extern "C" int emu_score_topk_f16(const float* seq, long long B_e, const float* W, long long N, long long D, const long long* hist_u,
                                   const long long* hist_i, long long n_hist, int mask_col0, int k, int splits_req, int cluster,
-                                  float* out_val, long long* out_idx, int* status) {
+                                  float* out_val, long long* out_idx, int* status, int ares) {
     const int K = (k <= 16) ? 16 : 32;
     std::vector<uint16_t> seq16((size_t)B_e * D), W16((size_t)N * D);
     emu::launch(4, 256, 0, [&]() { score_to_f16_kernel((const float4*)seq, B_e * D / 4, (uint2*)seq16.data(), status); });
@@ -112,10 +112,18 @@ extern "C" int emu_score_topk_f16(const float* seq, long long B_e, const float* 
         emu::launch((int)((n_hist + 255) / 256), 256, 0,
                     [&]() { score_mask_hist_kernel(mask.data(), a.n_words, B_e, N, hist_u, hist_i, n_hist); });
     const CUtensorMap tmA{seq16.data(), B_e, D, SC_BM, 2}, tmB{W16.data(), N, D, SC_BN / cluster, 2};
-    const size_t smem = (size_t)SC_STAGES * SC_STAGE_BYTES + SC2_BAR_BYTES + 1024;
+    const size_t smem = (ares ? (size_t)a.kblocks * SC_A_BYTES + (size_t)3 * SC_B_BYTES : (size_t)SC_STAGES * SC_STAGE_BYTES) +
+                        SC2_BAR_BYTES + 1024;
+    if (ares && D > 512) return -2;
     emu::after_launch_hook() = emu::join_async;
-    if (K == 16) emu::launch_cluster(a.m_tiles * a.n_splits, cluster, SC2_THREADS, smem, [&]() { score_topk2_kernel<16, 0, true>(tmA, tmB, a); });
-    else emu::launch_cluster(a.m_tiles * a.n_splits, cluster, SC2_THREADS, smem, [&]() { score_topk2_kernel<32, 0, true>(tmA, tmB, a); });
+    const int grid = a.m_tiles * a.n_splits;
+    if (ares) {
+        if (K == 16) emu::launch_cluster(grid, cluster, SC2_THREADS, smem, [&]() { score_topk2_kernel<16, 0, true, true>(tmA, tmB, a); });
+        else emu::launch_cluster(grid, cluster, SC2_THREADS, smem, [&]() { score_topk2_kernel<32, 0, true, true>(tmA, tmB, a); });
+    } else {
+        if (K == 16) emu::launch_cluster(grid, cluster, SC2_THREADS, smem, [&]() { score_topk2_kernel<16, 0, true>(tmA, tmB, a); });
+        else emu::launch_cluster(grid, cluster, SC2_THREADS, smem, [&]() { score_topk2_kernel<32, 0, true>(tmA, tmB, a); });
+    }
     emu::after_launch_hook() = nullptr;
     emu::launch((int)((B_e + 3) / 4), 128, 0, [&]() {
         score_merge_kernel(cand_val.data(), cand_idx.data(), n_lists * K, B_e, k, out_val, out_idx);

@@ -41,7 +41,7 @@ def emu_score():
     assert r.returncode == 0, r.stderr
     lib = C.CDLL(out)
     lib.emu_score_topk_v2.argtypes = [_P, _LL, _P, _LL, _LL, _P, _P, _LL, _I, _I, _I, _I, _P, _P]
-    lib.emu_score_topk_f16.argtypes = [_P, _LL, _P, _LL, _LL, _P, _P, _LL, _I, _I, _I, _I, _P, _P, _P]
+    lib.emu_score_topk_f16.argtypes = [_P, _LL, _P, _LL, _LL, _P, _P, _LL, _I, _I, _I, _I, _P, _P, _P, _I]
     lib.emu_score_ce_v2.argtypes = [_P, _LL, _P, _LL, _LL, _P, _I, _I, _I, _P, _P, _P]
     return lib
 
@@ -235,8 +235,9 @@ def test_score_ce_pipeline_emulated(emu_score, B_e, N, D, splits, cluster):
     assert np.allclose(nll, nll_r, rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("B_e,N,D,k,splits,cluster", [(100, 300, 64, 10, 1, 1), (200, 1700, 192, 10, 2, 2)])
-def test_score_topk_f16_pipeline_emulated(emu_score, B_e, N, D, k, splits, cluster):
+@pytest.mark.parametrize("B_e,N,D,k,splits,cluster,ares", [(100, 300, 64, 10, 1, 1, 0), (200, 1700, 192, 10, 2, 2, 0),
+                                                          (200, 1700, 192, 10, 2, 2, 1), (70, 1200, 512, 20, 1, 1, 1)])
+def test_score_topk_f16_pipeline_emulated(emu_score, B_e, N, D, k, splits, cluster, ares):
     """fp16-operand mode of the v2 scoring kernel (kind::f16: 64 elements per 128-byte k-block, K = 16 per MMA) incl. the
     fp32 -> fp16 conversion kernel, on the emulated pipeline.  Small integers are exact in fp16, so results must equal the
     oracle bit for bit; a value beyond the fp16 range must raise the saturation flag."""
@@ -250,7 +251,7 @@ def test_score_topk_f16_pipeline_emulated(emu_score, B_e, N, D, k, splits, clust
     idx = np.zeros((B_e, k), np.int64)
     status = np.zeros(1, np.int32)
     ns = emu_score.emu_score_topk_f16(_ptr(seq), B_e, _ptr(W), N, D, _ptr(hu), _ptr(hi), len(hu), 1, k, splits, cluster,
-                                      _ptr(val), _ptr(idx), _ptr(status))
+                                      _ptr(val), _ptr(idx), _ptr(status), ares)      # ares: seq_out tile resident, 3-stage table ring
     assert ns >= 1 and status[0] == 0
     assert np.array_equal(idx, i_ref)
     assert np.array_equal(val.astype(np.float64), v_ref)
@@ -258,5 +259,5 @@ def test_score_topk_f16_pipeline_emulated(emu_score, B_e, N, D, k, splits, clust
         W2 = W.copy()
         W2[5, 3] = 1e6
         emu_score.emu_score_topk_f16(_ptr(seq), B_e, _ptr(W2), N, D, _ptr(hu), _ptr(hi), len(hu), 1, k, splits, cluster,
-                                     _ptr(val), _ptr(idx), _ptr(status))
+                                     _ptr(val), _ptr(idx), _ptr(status), ares)
         assert status[0] == 4

@@ -133,9 +133,13 @@ def test_score_ce_matches_oracle(B_e, N, D):
 
 @pytest.mark.skipif(os.environ.get("PR_EXPERIMENTAL") != "1", reason="staged kernels: set PR_EXPERIMENTAL=1")
 @pytest.mark.parametrize("B_e,N,D,k", [(5, 300, 64, 10), (300, 5003, 512, 10), (1024, 20011, 512, 10), (33, 777, 128, 20)])
-def test_score_topk_f16_exact_on_small_integers(B_e, N, D, k):
-    """fp16-operand scoring (kind::f16): small integers are exact in fp16 -> bit-exact ids, values and tie order"""
-    from pixelrec_b200 import ops
+@pytest.mark.parametrize("ares", [0, 128], ids=["ring", "resident_seq"])
+def test_score_topk_f16_exact_on_small_integers(B_e, N, D, k, ares):
+    """fp16-operand scoring (kind::f16): small integers are exact in fp16 -> bit-exact ids, values and tie order.
+    ares (pr_set_tuning bit 128): the seq_out tile stays resident in shared memory, the ring carries table tiles only."""
+    from pixelrec_b200 import lib, ops
+    L_ = lib.load()
+    L_.pr_set_tuning((L_.pr_set_tuning(-1) & ~128) | ares)          # the autouse score_variant fixture restores the mask
     g = np.random.default_rng(B_e * 11 + N)
     seq = g.integers(-3, 4, size=(B_e, D)).astype(np.float32)
     W = g.integers(-3, 4, size=(N, D)).astype(np.float32)
