@@ -5,6 +5,7 @@
 #   gpurun --timeout 1500 -- 'bash tools/round2_gpu.sh stage1'            # 1 GPU: staged kernels, parity + A/B timing
 #   gpurun --gpus 2 --timeout 1200 -- 'bash tools/round2_gpu.sh stage2'   # 2 GPUs: peer-memory exchange vs NCCL
 #   gpurun --timeout 1500 -- 'bash tools/round2_gpu.sh configs'           # 1 GPU: BASELINE configs 3, 4, 5
+#   gpurun --timeout 1800 -- 'bash tools/round2_gpu.sh ncu'               # 1 GPU: ncu --set full of the staged kernels
 #
 # Order matters: parity first (cheap, tells which variant may become a default), timing after.
 set -u
@@ -43,6 +44,14 @@ if [ "$stage" = stage1 ]; then
   run 900 r2_pytest_default env -u PR_EXPERIMENTAL python -m pytest tests -x -q -m gpu
   run 600 r2_bench_n1 python bench.py --steps 20 --warmup 5
   tail -1 gpurun_out/r2_bench_n1.log > gpurun_out/r2_bench_n1.json
+elif [ "$stage" = ncu ]; then
+  # one full capture per staged kernel that passed stage1 (never a bench number: ncu replays every kernel ~40 times)
+  NCU="ncu --set full --clock-control none --import-source on"
+  run 600 r2_ncu_score_v2 env SCORE_TUNES=16 $NCU -k regex:score_topk2 -c 1 -o gpurun_out/r2_score_v2 python tools/bench_score.py
+  run 600 r2_ncu_score_mc env SCORE_TUNES=48 $NCU -k regex:score_topk2 -s 6 -c 1 -o gpurun_out/r2_score_mcast python tools/bench_score.py
+  run 600 r2_ncu_score_f16 env PR_TUNE=$((9 | 32 | 128)) SCORE_F16=1 $NCU -k regex:score_topk2 -c 1 -o gpurun_out/r2_score_f16 python tools/bench_score.py
+  run 600 r2_ncu_attn_long $NCU -k regex:attn_long -c 3 -o gpurun_out/r2_attn_long python tools/bench_attn_long.py --images 64
+  for f in gpurun_out/r2_*.ncu-rep; do [ -f "$f" ] && ncu -i "$f" --page raw --csv > "${f%.ncu-rep}.raw.csv" 2>/dev/null; done
 elif [ "$stage" = configs ]; then
   # the BASELINE.json configurations bench.py does not cover, one GPU (c3 also fits one GPU: 3.35 GB table + Adam state)
   for c in c5 c3; do
