@@ -24,7 +24,16 @@ def _i(*s):
     return torch.zeros(*s, dtype=torch.int64)
 
 
+def _long_attn_bwd(o):
+    class Ctx:                                   # what LongAttnFn.forward leaves behind
+        saved_tensors = (_f(1, 100, 3 * 64), _f(1, 100, 64), _f(2, 100))
+        key_ids = None
+        cfg = (1, 100, 2, 32, 0)
+    return o.LongAttnFn.backward(Ctx, _f(1, 100, 64))
+
+
 CASES = {
+    "attention_long_bwd": _long_attn_bwd,
     "gather_rows": lambda o: o.gather_rows(_f(10, 8), _i(5)),
     "scatter_plan": lambda o: o.ScatterPlan(_i(6), 10, 0),
     "adamw_dense": lambda o: o.adamw_dense(_f(8), _f(8), _f(8), _f(8), 1e-3, 0.9, 0.999, 1e-8, 0.1, 1),
