@@ -229,6 +229,16 @@ PR_API int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float* W, 
                              float* topk_val, int64_t* topk_idx, void* workspace, size_t workspace_bytes,
                              pr_stream_t stream);
 
+/* K5 (staged): linear layer on the tcgen05 pipeline of K9.   replaces nn.Linear [+ erf-GELU] of the encoder layers,
+ *   REC/model/layers.py:586-588 (query/key/value), :613 (dense), :666 + :651-660 (dense_1 + gelu), :669 (dense_2)
+ *   out[m, n] = act(sum_k x[m, k] * W[n, k] + bias[n]);  x [M, K], W [N, K] (nn.Linear layout), out [M, N], all fp32
+ *   row-major; TF32 operands, fp32 accumulation.  K % 32 == 0, N % 4 == 0.  bias may be NULL.  act: -1 none, PR_ACT_GELU,
+ *   PR_ACT_RELU.  pre (optional, [M, N]): the pre-activation values, which the backward of the activation needs.
+ *   pr_set_tuning bit 32 multicasts the W tiles across the m-tiles of a cluster.
+ */
+PR_API int pr_linear_tf32(const float* x, int64_t M, const float* W, int64_t N, int64_t K, const float* bias, int act, float* out,
+                          float* pre, pr_stream_t stream);
+
 /* K9 with fp16 operands (staged): fp16 has the 10 explicit mantissa bits of TF32 (and is rounded to nearest, where the TF32
  *   datapath reads truncated fp32 words) but kind::f16 MMAs run at twice the TF32 rate on half the operand bytes.  The
  *   exponent range is narrower: |x| > 65504 saturates and raises status bit 2; |x| < 6e-5 loses precision (absolute error

@@ -122,6 +122,7 @@ __device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) 
 }  // namespace pr
 
 #define PR_DYN_SMEM_BYTES(name) extern __shared__ __align__(1024) unsigned char name[]
+#define PR_LDG4(p) __ldg(p)
 #include "score_kernels.cuh"
 
 namespace pr {
@@ -367,12 +368,13 @@ static int launch_v2(const CUtensorMap& tmA, const void* W, long long N, long lo
             at[0].val.clusterDim.x = CL;
             cfg.gridDim = dim3(p.m_tiles * splits);
             int max_clusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < p.m_tiles / CL) {
+            const bool ok = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) == cudaSuccess;
+            if (!ok || max_clusters < 1 || (MODE != 2 && max_clusters < p.m_tiles / CL)) {
                 (void)cudaGetLastError();
                 CL = 1;                                                     // cluster shape not schedulable here: plain v2
-            } else {
+            } else if (MODE != 2) {
                 splits = std::max(1, std::min(splits, max_clusters / (p.m_tiles / CL)));
-            }
+            }                                                               // linear mode: one split, as many waves as it takes
         }
     }
     a.cluster = CL;
@@ -436,7 +438,7 @@ extern "C" int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float*
     a.kblocks = (int)(D / SC_BK);
     a.m_tiles = p.m_tiles; a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.n_splits = p.n_splits;
     a.n_words = p.n_words; a.mask = mask; a.cand_val = cand_val; a.cand_idx = cand_idx; a.cluster = 1;
-    a.target = nullptr; a.n_rows = B_e; a.ce_part = nullptr;
+    a.target = nullptr; a.n_rows = B_e; a.ce_part = nullptr; a.lin_out = nullptr; a.lin_pre = nullptr; a.lin_bias = nullptr;
     int n_lists = p.n_splits;
     if (tune() & PR_TUNE_SCORE_V2) {
         const bool mcast = (tune() & PR_TUNE_SCORE_MCAST) != 0;
@@ -580,4 +582,35 @@ extern "C" int pr_score_topk_f16(const float* seq_out, int64_t B_e, const void* 
                                                                  (long long*)topk_idx);
     PR_CUDA_LAUNCH_CHECK("score_merge_kernel");
     return PR_OK;
+}
+
+// ---- linear layers on the same pipeline (K5): y = act(x W^T + b) -----------------------------------------------------------
+extern "C" int pr_linear_tf32(const float* x, int64_t M, const float* W, int64_t N, int64_t Kd, const float* bias, int act,
+                              float* out, float* pre, pr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PR_CHECK_ARG(M > 0 && N > 0 && Kd > 0, "pr_linear_tf32: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)Kd);
+    PR_CHECK_ARG(Kd % SC_BK == 0 && N % 4 == 0, "pr_linear_tf32: K=%lld must be a multiple of %d and N=%lld of 4", (long long)Kd,
+                 SC_BK, (long long)N);
+    PR_CHECK_ARG(act == -1 || act == PR_ACT_GELU || act == PR_ACT_RELU, "pr_linear_tf32: act must be -1 (none), gelu or relu");
+    PR_CHECK_ARG(x && W && out, "pr_linear_tf32: null pointer");
+    PR_CHECK_ARG(aligned16(x) && aligned16(W) && aligned16(out) && aligned16(pre) && aligned16(bias), "pr_linear_tf32: alignment");
+    PR_CHECK_ARG(M < (1LL << 31) - 256 && N < (1LL << 31) - 512, "pr_linear_tf32: shape too large");
+    CUtensorMap tmA;
+    int rc = make_map(&tmA, x, M, Kd, SC_BM);
+    if (rc) return rc;
+    ScorePlan p;                                           // one split: every CTA owns an m-tile and walks all n-tiles
+    p.K = 16;
+    p.m_tiles = (int)((M + SC_BM - 1) / SC_BM);
+    p.n_tiles = (int)((N + SC_BN - 1) / SC_BN);
+    p.n_splits = 1;
+    p.tiles_per_split = p.n_tiles;
+    p.n_words = 0; p.mask_bytes = p.cand_bytes = p.total = 0;
+    ScoreArgs a;
+    a.kblocks = (int)(Kd / SC_BK);
+    a.m_tiles = p.m_tiles; a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.n_splits = 1;
+    a.n_words = 0; a.mask = nullptr; a.cand_val = nullptr; a.cand_idx = nullptr; a.cluster = 1;
+    a.target = nullptr; a.n_rows = M; a.ce_part = nullptr;
+    a.lin_out = out; a.lin_pre = pre; a.lin_bias = bias; a.lin_act = act; a.lin_M = M; a.lin_N = N;
+    int n_lists = 0;
+    return launch_v2<16, 2>(tmA, W, N, Kd, a, p, (tune() & PR_TUNE_SCORE_MCAST) != 0, stream, &n_lists);
 }

@@ -27,6 +27,8 @@ struct ScoreArgs {
     int* cand_idx;
     int cluster;          // v2: CTAs per cluster sharing each table tile by TMA multicast (1 = none)
     const long long* target;   // CE mode: [B_e] target item per row
+    // linear mode (MODE 2): out = act(A . B^T + bias) written as a dense [lin_M, lin_N] fp32 matrix, optional pre-activation copy
+    float* lin_out; float* lin_pre; const float* lin_bias; int lin_act; long long lin_M, lin_N;
     long long n_rows;          // CE mode: B_e
     float* ce_part;            // CE mode: [m_tiles*128][n_splits*2][4] = (running max, sum of exp, target logit or -inf, unused)
 };
@@ -124,6 +126,9 @@ __device__ __forceinline__ float pick32(const float (&v)[32], int j) {
     return (j & 16) ? d1 : d0;
 }
 
+// MODE 2: plain linear layer y = act(x W^T + b) (REC/model/layers.py:586-588,613,666,669 nn.Linear [+ erf-GELU :651-660]) on the
+// same pipeline: "users" = rows of x, "items" = rows of W (output features); the epilogue adds the bias, applies the
+// activation and stores the tile (each thread owns one row: 32 consecutive floats = one 128-byte line per tcgen05.ld).
 // MODE 0: masked per-row top-k (eval ranking).  MODE 1: online log-sum-exp over the unmasked catalog + the target item's
 // logit = full-catalog softmax cross-entropy (K unused).
 // F16: operands are fp16 copies of seq_out / the table (pr_score_prepare_f16): same 10 explicit mantissa bits as TF32 -- and
@@ -242,6 +247,49 @@ __global__ void __launch_bounds__(SC2_THREADS, 1) score_topk2_kernel(const __gri
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         const int row = m_tile * SC_BM + q * 32 + lane;
+        if constexpr (MODE == 2) {
+        for (int t = 0; t < n_my; ++t) {
+            const int buf = t & 1;
+            const int tile = t_begin + t;
+            mbar_wait(&tfull_bar[buf], (uint32_t)((t >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * SC_BN + half * 128);
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                float v[32];
+                __syncwarp();
+                tmem_ld32(taddr + c * 32, v);
+                const long long c0 = (long long)tile * SC_BN + half * 128 + c * 32;
+                if (row < a.lin_M && c0 < a.lin_N) {                  // lin_N % 4 == 0: float4 groups are all-in or all-out
+                    float* po = a.lin_out + (long long)row * a.lin_N + c0;
+                    float* pp = a.lin_pre ? a.lin_pre + (long long)row * a.lin_N + c0 : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (c0 + j < a.lin_N) {
+                            float4 x = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            if (a.lin_bias) {
+                                const float4 bb = PR_LDG4(reinterpret_cast<const float4*>(a.lin_bias + c0 + j));
+                                x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+                            }
+                            if (pp) *reinterpret_cast<float4*>(pp + j) = x;
+                            if (a.lin_act == 0) {                     // PR_ACT_GELU, erf form (csrc/ln.cu act_apply)
+                                x.x = x.x * 0.5f * (1.0f + erff(x.x * 0.70710678118654752440f));
+                                x.y = x.y * 0.5f * (1.0f + erff(x.y * 0.70710678118654752440f));
+                                x.z = x.z * 0.5f * (1.0f + erff(x.z * 0.70710678118654752440f));
+                                x.w = x.w * 0.5f * (1.0f + erff(x.w * 0.70710678118654752440f));
+                            } else if (a.lin_act == 1) {              // PR_ACT_RELU
+                                x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+                            }
+                            *reinterpret_cast<float4*>(po + j) = x;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        }
+        } else {
         const uint32_t* mrow = a.mask + (size_t)row * a.n_words + half * 4;
         if constexpr (MODE == 0) {
         float val[K];
@@ -327,6 +375,7 @@ __global__ void __launch_bounds__(SC2_THREADS, 1) score_topk2_kernel(const __gri
         }
         const size_t list = (size_t)row * (a.n_splits * 2) + (size_t)(split * 2 + half);
         *reinterpret_cast<float4*>(a.ce_part + list * 4) = make_float4(mx, sum, tlogit, 0.f);
+        }
         }
     }
     tc_fence_before();

@@ -528,6 +528,7 @@ def _raw_act_bwd_bias(x, dy, act):
 
 
 WGRAD_SPLIT = int(os.environ.get("PR_WGRAD_SPLIT", "8"))
+LINEAR_TC = os.environ.get("PR_LINEAR_TC", "0") == "1"      # staged: FFN dense_1 + GELU through pr_linear_tf32
 
 
 def _wgrad(dy2, x2):
@@ -566,11 +567,14 @@ class TransformerLayerFn(torch.autograd.Function):
         _count()
         h = torch.addmm(bo, ctxt.view(B * L, D), wo.t())                               # :613
         a, mean1, rstd1 = _raw_add_ln_fwd(h, x2, g1, be1, eps, p_hid, seed, site + 1)  # :614-615
-        h1 = torch.addmm(b1, a, w1.t())                                                # :666
-        gl = torch.empty_like(h1)
-        with _prof("act_fwd", h1):
-            _lib.check(_L().pr_act_fwd_f32(_p(h1), h1.numel(), act, _p(gl), _stream(h1)), "pr_act_fwd_f32")
-        _count()
+        if LINEAR_TC and torch.backends.cuda.matmul.allow_tf32 and act in (0, 1):     # staged: dense_1 + activation in one tcgen05 kernel (h1 and gelu(h1) both kept)
+            gl, h1 = linear_tc(a, w1.contiguous(), b1, "gelu" if act == 0 else "relu", want_pre=True)
+        else:
+            h1 = torch.addmm(b1, a, w1.t())                                            # :666
+            gl = torch.empty_like(h1)
+            with _prof("act_fwd", h1):
+                _lib.check(_L().pr_act_fwd_f32(_p(h1), h1.numel(), act, _p(gl), _stream(h1)), "pr_act_fwd_f32")
+            _count()
         h2 = torch.addmm(b2, gl, w2.t())                                               # :669
         y, mean2, rstd2 = _raw_add_ln_fwd(h2, a, g2, be2, eps, p_hid, seed, site + 2)  # :670-671
         ctx.save_for_backward(x, qkv, probs, ctxt, h, a, mean1, rstd1, h1, gl, h2, mean2, rstd2, wqkv, wo, w1, w2, g1, g2)
@@ -634,6 +638,23 @@ def score_topk(seq_out, item_feature, k, hist_u=None, hist_i=None, mask_col0=Tru
                                           _p(idx), _p(ws), ws_bytes, _stream(seq_out)), "pr_score_topk_f32")
     _count(4 if n_hist else 3)
     return val, idx
+
+
+def linear_tc(x, weight, bias=None, act=None, want_pre=False):
+    """y = act(x @ weight.T + bias) on the tcgen05 pipeline (pr_linear_tf32; staged alternative to cuBLAS addmm + pr_act_fwd).
+    x [..., K], weight [N, K] (nn.Linear layout).  act: None | 'gelu' | 'relu'.  want_pre: also return the pre-activation."""
+    _req(x, torch.float32, "x")
+    _req(weight, torch.float32, "weight")
+    N, K = weight.shape
+    M = x.numel() // K
+    out = torch.empty(*x.shape[:-1], N, device=x.device, dtype=torch.float32)
+    pre = torch.empty_like(out) if want_pre else None
+    act_id = -1 if act is None else ACT_IDS[act]
+    with _prof("linear_tc", x):
+        _lib.check(_L().pr_linear_tf32(_p(x), M, _p(weight), N, K, _p(bias), act_id, _p(out), _p(pre), _stream(x)),
+                   "pr_linear_tf32")
+    _count()
+    return (out, pre) if want_pre else out
 
 
 def score_prepare_f16(x, status=None):

@@ -46,6 +46,7 @@ CASES = {
     "attention_tf32": lambda o: o.attention(_f(2, 10, 3 * 64), None, 2, causal=True, tf32=True),
     "attention_long": lambda o: o.attention(_f(1, 100, 3 * 64), _i(1, 100), 2, causal=False),
     "score_topk": lambda o: o.score_topk(_f(4, 64), _f(50, 64), 5, _i(3), _i(3)),
+    "linear_tc": lambda o: o.linear_tc(_f(6, 64), _f(8, 64), _f(8), "gelu", want_pre=True),
     "score_prepare_f16": lambda o: o.score_prepare_f16(_f(50, 64)),
     "score_topk_f16": lambda o: o.score_topk_f16(_f(4, 64), torch.zeros(50, 64, dtype=torch.float16), 5, _i(3), _i(3)),
     "score_ce": lambda o: o.score_ce(_f(4, 64), _f(50, 64), _i(4)),

@@ -31,6 +31,7 @@ if [ "$stage" = stage1 ]; then
   # 2. score_topk variants: v2 epilogue (tune 16), then + cluster multicast (tune 48); each variant in its own process
   run 300 r2_score_v2    $PYT tests/test_gpu_score.py -k "v2 and not mcast"
   run 300 r2_score_mcast $PYT tests/test_gpu_score.py -k "v2_mcast"
+  run 300 r2_linear      $PYT tests/test_gpu_linear.py
   run 300 r2_score_ce    $PYT tests/test_gpu_score.py -k "score_ce and v1"
   run 300 r2_score_f16   $PYT tests/test_gpu_score.py -k "f16 and v1"
   run 300 r2_score_f16mc $PYT tests/test_gpu_score.py -k "f16 and v2_mcast"
@@ -43,6 +44,8 @@ if [ "$stage" = stage1 ]; then
   # 4. the whole default suite + bench, as the driver runs them
   run 900 r2_pytest_default env -u PR_EXPERIMENTAL python -m pytest tests -x -q -m gpu
   run 600 r2_bench_n1 python bench.py --steps 20 --warmup 5
+  run 600 r2_bench_n1_linear_tc env PR_LINEAR_TC=1 python bench.py --steps 20 --warmup 5 --no-cpu      # FFN dense_1 + GELU on pr_linear_tf32
+  run 600 r2_bench_n1_linear_tc_mc env PR_LINEAR_TC=1 PR_TUNE=$((9 | 32)) python bench.py --steps 20 --warmup 5 --no-cpu
   tail -1 gpurun_out/r2_bench_n1.log > gpurun_out/r2_bench_n1.json
 elif [ "$stage" = ncu ]; then
   # one full capture per staged kernel that passed stage1 (never a bench number: ncu replays every kernel ~40 times)
