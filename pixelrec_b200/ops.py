@@ -446,9 +446,23 @@ def bpr_loss(out, E, masked_index, slab=None):
 
 
 # ------------------------------------------------------------------------------------------- table gather w/ sparse grad
+PLAN_AHEAD = os.environ.get("PR_PLAN_AHEAD", "0") == "1"     # staged: build the scatter plan during the forward, on a side stream
+_plan_streams = {}
+
+
+def _plan_stream(device):
+    s = _plan_streams.get(device)
+    if s is None:
+        s = _plan_streams[device] = torch.cuda.Stream(device=device)
+    return s
+
+
 class GatherFn(torch.autograd.Function):
     """E = W[idx].  backward: dense mode returns a zero-filled [N,D] grad (reference semantics);
-    sparse mode deposits (plan, reduced rows) on `sink` and leaves W.grad untouched."""
+    sparse mode deposits (plan, reduced rows) on `sink` and leaves W.grad untouched.
+    PR_PLAN_AHEAD=1: the index plan of the backward (14 small sort / scan launches that depend only on idx) is enqueued on a
+    side stream at forward time, ordered after everything already on the current stream (the previous step's AdamW hands the
+    row2slot entries back), and overlaps the encoder; the backward only waits for its event."""
 
     @staticmethod
     def forward(ctx, W, idx, padding_idx, sink, impl):
@@ -457,6 +471,15 @@ class GatherFn(torch.autograd.Function):
         ctx.N = W.shape[0]
         ctx.padding_idx = padding_idx
         ctx.sink = sink
+        ctx.plan = None
+        if PLAN_AHEAD and sink is not None and sink.sparse and ctx.needs_input_grad[0]:
+            cur = torch.cuda.current_stream(idx.device)
+            side = _plan_stream(idx.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                ctx.plan = ScatterPlan(idx, ctx.N, padding_idx, row2slot=sink.row2slot)
+                ctx.plan_ready = torch.cuda.Event()
+                ctx.plan_ready.record(side)
         return out
 
     @staticmethod
@@ -465,7 +488,14 @@ class GatherFn(torch.autograd.Function):
         dE = dE.contiguous()
         sink = ctx.sink
         if sink is not None and sink.sparse:
-            plan = ScatterPlan(idx, ctx.N, ctx.padding_idx, row2slot=sink.row2slot)
+            plan = ctx.plan
+            if plan is None:
+                plan = ScatterPlan(idx, ctx.N, ctx.padding_idx, row2slot=sink.row2slot)
+            else:
+                cur = torch.cuda.current_stream(idx.device)
+                cur.wait_event(ctx.plan_ready)
+                for tns in (plan.perm, plan.uniq_ids, plan.seg_start, plan.n_uniq, plan._ws):   # allocated on the side stream
+                    tns.record_stream(cur)
             rows = scatter_add_rows(dE, plan)
             sink.deposit(plan, rows)
             return None, None, None, None, None

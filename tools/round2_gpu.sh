@@ -44,6 +44,8 @@ if [ "$stage" = stage1 ]; then
   # 4. the whole default suite + bench, as the driver runs them
   run 900 r2_pytest_default env -u PR_EXPERIMENTAL python -m pytest tests -x -q -m gpu
   run 600 r2_bench_n1 python bench.py --steps 20 --warmup 5
+  run 600 r2_plan_ahead_parity env PR_PLAN_AHEAD=1 python -m pytest tests/test_gpu_sasrec.py tests/test_gpu_e2e.py -x -q -m gpu
+  run 600 r2_bench_n1_plan_ahead env PR_PLAN_AHEAD=1 python bench.py --steps 20 --warmup 5 --no-cpu   # scatter plan overlapped with the forward
   run 600 r2_bench_n1_linear_tc env PR_LINEAR_TC=1 python bench.py --steps 20 --warmup 5 --no-cpu      # FFN dense_1 + GELU on pr_linear_tf32
   run 600 r2_bench_n1_linear_tc_mc env PR_LINEAR_TC=1 PR_TUNE=$((9 | 32)) python bench.py --steps 20 --warmup 5 --no-cpu
   tail -1 gpurun_out/r2_bench_n1.log > gpurun_out/r2_bench_n1.json
