@@ -31,6 +31,7 @@
 
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -361,8 +362,12 @@ static int launch_v2(const CUtensorMap& tmA, const void* W, long long N, long lo
     cfg.attrs = at;
     cfg.numAttrs = 1;
     if (mcast) {
+        // largest power of two <= 8 (or PR_SCORE_CLUSTER, for A/B: clusters of 8 leave SMs idle when a GPC's SM count is not a
+        // multiple of 8) that divides the number of m-tiles
+        int cl_max = 8;
+        if (const char* e = getenv("PR_SCORE_CLUSTER")) cl_max = std::max(1, std::min(8, atoi(e)));
         for (int c = 8; c > 1; c >>= 1)
-            if (p.m_tiles % c == 0) { CL = c; break; }
+            if (c <= cl_max && p.m_tiles % c == 0) { CL = c; break; }
         if (CL > 1) {
             // all clusters co-resident in one wave: the multicast couples the CTAs of a cluster, a second wave would idle SMs
             at[0].val.clusterDim.x = CL;

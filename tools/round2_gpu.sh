@@ -39,6 +39,7 @@ if [ "$stage" = stage1 ]; then
   run 300 r2_bench_attn_long python tools/bench_attn_long.py
   run 300 r2_bench_score env SCORE_TUNES=0,16,48 SCORE_F16=1 python tools/bench_score.py
   run 300 r2_bench_score_f16mc env PR_TUNE=$((9 | 32)) SCORE_F16=1 python tools/bench_score.py
+  run 300 r2_bench_score_mc_cl4 env PR_SCORE_CLUSTER=4 SCORE_TUNES=48 SCORE_F16=1 PR_TUNE=$((9 | 32)) python tools/bench_score.py
   run 300 r2_bench_score_f16mc_ares env PR_TUNE=$((9 | 32 | 128)) SCORE_F16=1 python tools/bench_score.py
   cp gpurun_out/bench_score.json gpurun_out/r2_bench_score.json 2>/dev/null
   # 4. the whole default suite + bench, as the driver runs them
