@@ -186,3 +186,33 @@ def test_mosasrec_plugin_constructs_from_reference_yaml_keys():
     trainable_vit = [n for n, p in m.named_parameters() if p.requires_grad and "visual_encoder" in n]
     assert any("layers.10." in n for n in trainable_vit) and not any("layers.9." in n for n in trainable_vit)
     assert "visual_encoder.rec_fc.0.weight" in dict(m.named_parameters())
+
+
+def test_tcgen05_ptx_forms_match_the_vendored_cutlass_headers():
+    """The PTX strings of csrc/score.cu that only a GPU can exercise (tcgen05 / TMA multicast / cluster commit) are compared
+    with the forms NVIDIA's CUTLASS headers use (vendored with flashinfer in this image; skipped where they are absent), and the
+    instruction-descriptor field values with CUTLASS's enums."""
+    import importlib.util
+    spec = importlib.util.find_spec("flashinfer")              # located, not imported
+    if spec is None or not spec.submodule_search_locations:
+        pytest.skip("flashinfer (vendored CUTLASS headers) not installed")
+    inc = os.path.join(list(spec.submodule_search_locations)[0], "data", "cutlass", "include")
+    if not os.path.isdir(inc):
+        pytest.skip("vendored CUTLASS headers not found")
+    def text(*rel):
+        return re.sub(r'"\s*\n\s*"', "", open(os.path.join(inc, *rel)).read())          # join adjacent string literals
+    umma = text("cute", "arch", "mma_sm100_umma.hpp")
+    bar = text("cutlass", "arch", "barrier.h")
+    tma90 = text("cute", "arch", "copy_sm90_tma.hpp")
+    desc = text("cute", "arch", "mma_sm100_desc.hpp")
+    ours = re.sub(r'"\s*\n\s*"', "", open(os.path.join(ROOT, "pixelrec_b200", "csrc", "score.cu")).read())
+    for form, ref in [("tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3,", umma),
+                      ("tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3,", umma),
+                      ("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;", bar),
+                      ("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster", tma90)]:
+        assert form in ref, form
+        assert form.split(" [")[0] in ours, form
+    # descriptor fields used by tf32_idesc / f16_idesc (csrc/score_kernels.cuh)
+    assert re.search(r"F16\s*=\s*0,\s*BF16\s*=\s*1,\s*TF32\s*=\s*2", desc)
+    assert "c_format_      : 2,  // bit [ 4, 6)" in desc and "a_format_      : 3,  // bit [ 7,10)" in desc
+    assert "n_dim_         : 6,  // bit [17,23)" in desc and "m_dim_         : 5,  // bit [24,29)" in desc
