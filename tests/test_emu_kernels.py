@@ -194,7 +194,8 @@ def test_push_rows_peers_emulated(emu, G, N, D, U, cap):
             assert len(got) == n and (n == len(mine) or overflow)
 
 
-@pytest.mark.parametrize("B_e,N,D,k,splits,cluster", [(100, 300, 64, 10, 1, 1),       # one CTA, 2 tiles
+@pytest.mark.parametrize("B_e,N,D,k,splits,cluster", [(7, 40, 32, 32, 1, 1),          # fewer items than list slots, one k-block
+                                                     (100, 300, 64, 10, 1, 1),       # one CTA, 2 tiles
                                                      (200, 1700, 160, 10, 2, 2),     # ring wraps 2.5x, TMEM buffers reused, cluster of 2
                                                      (130, 1000, 96, 20, 3, 2),      # K = 32 lists, ragged last tile / split
                                                      (500, 600, 64, 10, 2, 4)])      # cluster of 4 (B_e = 500: 4 m-tiles)
