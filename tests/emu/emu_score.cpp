@@ -150,3 +150,9 @@ extern "C" int emu_linear_v2(const float* x, long long M, const float* W, long l
     emu::after_launch_hook() = nullptr;
     return 0;
 }
+
+extern "C" int emu_f32_to_f16(const float* src, long long n, uint16_t* dst) {
+    bool sat = false;
+    for (long long i = 0; i < n; ++i) dst[i] = f32_to_f16_rn(src[i], &sat);
+    return sat ? 1 : 0;
+}

@@ -42,6 +42,7 @@ def emu_score():
     lib = C.CDLL(out)
     lib.emu_score_topk_v2.argtypes = [_P, _LL, _P, _LL, _LL, _P, _P, _LL, _I, _I, _I, _I, _P, _P]
     lib.emu_score_topk_f16.argtypes = [_P, _LL, _P, _LL, _LL, _P, _P, _LL, _I, _I, _I, _I, _P, _P, _P, _I]
+    lib.emu_f32_to_f16.argtypes = [_P, _LL, _P]
     lib.emu_linear_v2.argtypes = [_P, _LL, _P, _LL, _LL, _P, _I, _I, _P, _P]
     lib.emu_score_ce_v2.argtypes = [_P, _LL, _P, _LL, _LL, _P, _I, _I, _I, _P, _P, _P]
     return lib
@@ -285,3 +286,23 @@ def test_linear_pipeline_emulated(emu_score, M, N, K, act, cluster, bias):
     pre = np.full((M, N), np.nan, np.float32)
     assert emu_score.emu_linear_v2(_ptr(x), M, _ptr(W), N, K, _ptr(b) if bias else None, act, cluster, _ptr(out), _ptr(pre)) == 0
     assert np.allclose(pre, pre_ref, rtol=1e-5, atol=1e-5) and np.allclose(out, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_f32_to_f16_routine_matches_numpy(emu_score):
+    """the integer-only fp32 -> fp16 conversion used by pr_score_prepare_f16 (round to nearest even, subnormals, saturation
+    instead of overflow to inf) against numpy's float16 cast on random bit patterns, scaled normals and edge values"""
+    g = np.random.default_rng(0)
+    parts = [g.standard_normal(200_000).astype(np.float32) * s for s in (1, 1e-3, 1e-5, 1e-7, 1e3, 3e4)]
+    parts.append(g.integers(0, 2 ** 32, size=500_000, dtype=np.uint64).astype(np.uint32).view(np.float32))
+    parts.append(np.array([0.0, -0.0, 65504, 65519.99, 65520, -65520, 1e10, 6.1035e-5, 6.0e-5, 5.96e-8, 2.98e-8, 2.9802322e-8,
+                           2.99e-8, 1.0, 1.0009765625, 1.00048828125, 1.0014648, np.inf, -np.inf], np.float32))
+    x = np.concatenate(parts)
+    x = x[~np.isnan(x)]
+    out = np.zeros(x.size, np.uint16)
+    sat = emu_score.emu_f32_to_f16(_ptr(x), x.size, _ptr(out))
+    with np.errstate(over="ignore"):
+        ref = x.astype(np.float16).view(np.uint16).copy()
+    over = np.isfinite(x) & np.isinf(x.astype(np.float16, copy=True).astype(np.float32))
+    ref[over] = (ref[over] & 0x8000) | 0x7BFF                      # saturate instead of inf
+    assert sat == 1 and over.any()
+    assert np.array_equal(out, ref)
