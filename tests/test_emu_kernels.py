@@ -301,8 +301,9 @@ def test_f32_to_f16_routine_matches_numpy(emu_score):
     out = np.zeros(x.size, np.uint16)
     sat = emu_score.emu_f32_to_f16(_ptr(x), x.size, _ptr(out))
     with np.errstate(over="ignore"):
-        ref = x.astype(np.float16).view(np.uint16).copy()
-    over = np.isfinite(x) & np.isinf(x.astype(np.float16, copy=True).astype(np.float32))
+        h = x.astype(np.float16)
+    ref = h.view(np.uint16).copy()
+    over = np.isfinite(x) & np.isinf(h)
     ref[over] = (ref[over] & 0x8000) | 0x7BFF                      # saturate instead of inf
     assert sat == 1 and over.any()
     assert np.array_equal(out, ref)
