@@ -5,6 +5,7 @@
 #   gpurun --timeout 1500 -- 'bash tools/round2_gpu.sh stage1'            # 1 GPU: staged kernels, parity + A/B timing
 #   gpurun --gpus 2 --timeout 1200 -- 'bash tools/round2_gpu.sh stage2'   # 2 GPUs: peer-memory exchange vs NCCL
 #   gpurun --timeout 1500 -- 'bash tools/round2_gpu.sh configs'           # 1 GPU: BASELINE configs 3, 4, 5
+#   gpurun --gpus 8 --timeout 1200 -- 'bash tools/round2_gpu.sh stage8'  # 8 GPUs: N=8 bench, both exchanges; config 3 sharded 8-way
 #   gpurun --timeout 1800 -- 'bash tools/round2_gpu.sh ncu'               # 1 GPU: ncu --set full of the staged kernels
 #
 # Order matters: parity first (cheap, tells which variant may become a default), timing after.
@@ -73,5 +74,14 @@ elif [ "$stage" = stage2 ]; then
         bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu --exchange $ex
     tail -1 gpurun_out/r2_bench_n2_$ex.log > gpurun_out/r2_bench_n2_$ex.json
   done
+elif [ "$stage" = stage8 ]; then
+  # 8 GPUs (charged 8x): only after stage2 has confirmed the peer exchange at N=2
+  for ex in p2p nccl; do
+    run 420 r2_bench_n8_$ex python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 \
+        bench.py --gpus 8 --steps 20 --warmup 5 --exchange $ex
+    tail -1 gpurun_out/r2_bench_n8_$ex.log > gpurun_out/r2_bench_n8_$ex.json
+  done
+  run 420 r2_cfg_c3_n8 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 \
+      tools/bench_configs.py --config c3 --exchange p2p
 fi
 exit 0
