@@ -255,6 +255,16 @@ def run_ours(args, out):
 
     for i in range(max(args.warmup, 3)):
         step(resident[i % POOL])
+    graphed = None
+    if args.graph and world == 1:
+        from pixelrec_b200.trainer.graph import GraphedTrainStep
+        graphed = GraphedTrainStep(model, opt, resident[0])
+        eager_step = step
+
+        def step(batch, nxt=None):       # noqa: F811 -- timed region 1 replays the captured step; inputs are copied into its static buffers
+            return graphed(batch)
+        for i in range(3):
+            step(resident[i % POOL])
     # ---- timed region 1: inputs resident in HBM; the gather kernel is event-timed live inside it
     clocks = ClockSampler(local)
     ops.PROFILE.update(on=True, names={"gather_rows"}, events={})
@@ -268,6 +278,9 @@ def run_ours(args, out):
     ops.PROFILE.update(on=False, events={})
     value = B * world * args.steps / (ms / 1e3)
 
+    if graphed is not None:
+        graphed.close()
+        step = eager_step
     # ---- timed region 2 (e2e): pinned-host batches copied in each step, loss read back each step
     e2e_next = {}
 
@@ -356,7 +369,8 @@ def run_ours(args, out):
         "metric": METRIC, "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (tf32 tensor-core linear layers, fp32 everywhere else)", "data": "synthetic",
-        "config": workload_config(B, world, exchange=getattr(model.item_embedding, "exchange", None)),
+        "config": workload_config(B, world, exchange=getattr(model.item_embedding, "exchange", None),
+                                  note="value: the step replayed as one CUDA graph; e2e and per-kernel passes eager" if args.graph else None),
         "e2e": {"value": e2e, "unit": "sequences/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
@@ -417,6 +431,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="sequences per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--graph", action="store_true",
+                    help="N=1: replay the step as one CUDA graph (staged; dropout needs a -DPR_SEED_DEV build); `value` only")
     ap.add_argument("--exchange", default=None, choices=["nccl", "p2p"],
                     help="N>1 row exchange of the sharded table: NCCL all_to_all (default) or peer-memory kernels (staged)")
     args = ap.parse_args()

@@ -66,6 +66,12 @@ PR_API int pr_set_device(int device);
  *        fp32 kernels within TF32 tolerance).
  * mask < 0 only queries.  Returns the mask in effect.  Results are identical under every mask except where noted. */
 PR_API int pr_set_tuning(int mask);
+/* CUDA-graph replay of a training step (staged): every dropout kernel adds *seed_offset_dev (a uint64 in device memory, bumped
+ * by a kernel captured in the same graph) to the host-side seed frozen into the graph, so that replay j draws the masks the
+ * eager step j would have drawn.  NULL switches back to host seeds.  Only builds compiled with -DPR_SEED_DEV implement it
+ * (PR_BUILD_DEFS=-DPR_SEED_DEV python -m pixelrec_b200.build --force); the default build returns PR_ERR_UNSUPPORTED for a
+ * non-NULL pointer and its kernels are byte-identical to a build without this entry point. */
+PR_API int pr_set_seed_device(const uint64_t* seed_offset_dev);
 
 /* ------------------------------------------------------------------------------------------
  * K1  embedding row gather.     replaces nn.Embedding.forward: REC/model/IDNet/sasrec.py:31,68

@@ -41,6 +41,10 @@ int tune() {
 }
 void set_tune(int mask) { g_tune = mask; }
 
+static const unsigned long long* g_seed_dev = nullptr;
+const unsigned long long* seed_device() { return g_seed_dev; }
+void set_seed_device(const unsigned long long* p) { g_seed_dev = p; }
+
 }  // namespace pr
 
 extern "C" int pr_version(void) { return PR_ABI_VERSION; }
@@ -56,6 +60,16 @@ extern "C" int pr_sm_count(void) {
 extern "C" int pr_set_tuning(int mask) {
     if (mask >= 0) pr::set_tune(mask);
     return pr::tune();
+}
+extern "C" int pr_set_seed_device(const uint64_t* seed_offset_dev) {
+#ifdef PR_SEED_DEV
+    pr::set_seed_device((const unsigned long long*)seed_offset_dev);
+    return PR_OK;
+#else
+    if (seed_offset_dev == nullptr) return PR_OK;
+    pr::set_last_error("pr_set_seed_device: this build has no device-side seeds (rebuild with -DPR_SEED_DEV)");
+    return PR_ERR_UNSUPPORTED;
+#endif
 }
 extern "C" int pr_set_device(int device) {
     cudaError_t e = cudaSetDevice(device);

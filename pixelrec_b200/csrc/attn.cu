@@ -32,6 +32,9 @@ struct AttnArgs {
     float* ctx; float* probs;                     // forward outputs
     const float* dctx; float* dq; float* dk; float* dv; long long ld_grad;   // backward
     int stages;
+#ifdef PR_SEED_DEV
+    const unsigned long long* seed_dev;   // device-side seed offset (pr_set_seed_device)
+#endif
 };
 
 template <int LMAX>
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__((AttnCfg<LMAX>::NCW + 1) * 32, 1) attn_fwd_ker
     // ---------------------------------------------------------------------- consumer warps
     float* Pt = reinterpret_cast<float*>(priv) + (size_t)warp * LMAX * LP;  // Pt[j][i] = dropped P[i][j]
     const int a = lane >> 3, b8 = lane & 7;
-    const Philox ph(A.seed);
+    const Philox ph(PR_SEED(A));
     const unsigned thr = drop_threshold(A.p_drop);
     const float inv_keep = 1.0f / (1.0f - A.p_drop);
     long long n = 0;
@@ -336,7 +339,7 @@ __global__ void __launch_bounds__((AttnCfg<LMAX>::NCW_BWD + 1) * 32, 1) attn_bwd
     float* dS_s = Pd_s + LMAX * LP;                                                 // dS_s[i][j]
     float* dS_t = dS_s + LMAX * LP;                                                 // dS_t[j][i]
     const int a = lane >> 3, b8 = lane & 7;
-    const Philox ph(A.seed);
+    const Philox ph(PR_SEED(A));
     const unsigned thr = drop_threshold(A.p_drop);
     const float inv_keep = 1.0f / (1.0f - A.p_drop);
     long long n = 0;
@@ -482,6 +485,7 @@ extern "C" int pr_sasrec_attn_fwd_f32(const float* q, const float* k, const floa
     A.q = q; A.k = k; A.v = v; A.ld = ld; A.key_ids = (const long long*)key_ids;
     A.B = B; A.L = L; A.h = h; A.dh = dh; A.nc = (dh + 127) / 128; A.causal = causal;
     A.p_drop = p_drop; A.seed = seed; A.rng_stream = rng_stream;
+    PR_SET_SEED_DEV(A);
     A.inv_sqrt = (float)(1.0 / sqrt((double)dh));
     A.ctx = ctx; A.probs = probs;
     return dispatch_attn<false>(A, (cudaStream_t)stream_);
@@ -500,6 +504,7 @@ extern "C" int pr_sasrec_attn_bwd_f32(const float* q, const float* k, const floa
     A.q = q; A.k = k; A.v = v; A.ld = ld;
     A.B = B; A.L = L; A.h = h; A.dh = dh; A.nc = (dh + 127) / 128; A.causal = causal;
     A.p_drop = p_drop; A.seed = seed; A.rng_stream = rng_stream;
+    PR_SET_SEED_DEV(A);
     A.inv_sqrt = (float)(1.0 / sqrt((double)dh));
     A.probs = const_cast<float*>(probs); A.dctx = dctx; A.dq = dq; A.dk = dk; A.dv = dv; A.ld_grad = ld_grad;
     return dispatch_attn<true>(A, (cudaStream_t)stream_);

@@ -34,6 +34,9 @@ struct TcArgs {
     float inv_sqrt;
     float* ctx; float* probs;
     const float* dctx; float* dq; float* dk; float* dv; long long ld_grad;
+#ifdef PR_SEED_DEV
+    const unsigned long long* seed_dev;   // device-side seed offset (pr_set_seed_device)
+#endif
 };
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(NW * (PAIR ? 64 : 32), 1) attn_tc_fwd_kernel(c
     const long long item_hi = min(n_items, item_lo + per_warp);
     if (item_lo >= item_hi) return;
     const int g = lane >> 2, t = lane & 3;
-    const Philox ph(A.seed);
+    const Philox ph(PR_SEED(A));
     const unsigned thr = drop_threshold(A.p_drop);
     const float inv_keep = 1.0f / (1.0f - A.p_drop);
     auto coords = [&](long long item, int& row0, int& col0) {
@@ -389,7 +392,7 @@ __global__ void __launch_bounds__(NW * (PAIR ? 64 : 32), 1) attn_tc_bwd_kernel(c
     float* Pd_s = reinterpret_cast<float*>(priv);             // Pd_s[i][j]   (i < 8NT rows, j < 16MT cols)
     float* dS_s = Pd_s + PR * LS;
     const int g = lane >> 2, t = lane & 3;
-    const Philox ph(A.seed);
+    const Philox ph(PR_SEED(A));
     const unsigned thr = drop_threshold(A.p_drop);
     const float inv_keep = 1.0f / (1.0f - A.p_drop);
     auto coords = [&](long long item, int& row0, int& col0) {
@@ -617,6 +620,7 @@ extern "C" int pr_sasrec_attn_fwd_tf32(const float* q, const float* k, const flo
     A.q = q; A.k = k; A.v = v; A.ld = ld; A.key_ids = (const long long*)key_ids;
     A.B = B; A.L = L; A.h = h; A.dh = dh; A.nc = (dh + 127) / 128; A.causal = causal;
     A.p_drop = p_drop; A.seed = seed; A.rng_stream = rng_stream;
+    PR_SET_SEED_DEV(A);
     A.inv_sqrt = (float)(1.0 / sqrt((double)dh));
     A.ctx = ctx; A.probs = probs;
     return dispatch_tc<false>(A, (cudaStream_t)stream_);
@@ -635,6 +639,7 @@ extern "C" int pr_sasrec_attn_bwd_tf32(const float* q, const float* k, const flo
     A.q = q; A.k = k; A.v = v; A.ld = ld;
     A.B = B; A.L = L; A.h = h; A.dh = dh; A.nc = (dh + 127) / 128; A.causal = causal;
     A.p_drop = p_drop; A.seed = seed; A.rng_stream = rng_stream;
+    PR_SET_SEED_DEV(A);
     A.inv_sqrt = (float)(1.0 / sqrt((double)dh));
     A.probs = const_cast<float*>(probs); A.dctx = dctx; A.dq = dq; A.dk = dk; A.dv = dv; A.ld_grad = ld_grad;
     return dispatch_tc<true>(A, (cudaStream_t)stream_);

@@ -12,6 +12,16 @@ namespace pr {
 void set_last_error(const char* fmt, ...);
 int sm_count();
 int tune();                      // PR_TUNE bit mask (api.cu)
+// Device-resident dropout seed offset (pr_set_seed_device; CUDA-graph replay: the host seed is frozen into the graph, the
+// offset is bumped by a captured kernel).  Only builds with -DPR_SEED_DEV read it; the default build's kernels are unchanged.
+const unsigned long long* seed_device();
+#ifdef PR_SEED_DEV
+#define PR_SEED(a) ((a).seed_dev ? (a).seed + *(a).seed_dev : (a).seed)
+#define PR_SET_SEED_DEV(a) (a).seed_dev = pr::seed_device()
+#else
+#define PR_SEED(a) ((a).seed)
+#define PR_SET_SEED_DEV(a) (void)0
+#endif
 #define PR_TUNE_LN_BWD_PIPE 1
 #define PR_TUNE_LN_L2_PREFETCH 2
 #define PR_TUNE_LN_FWD_PIPE 4

@@ -17,6 +17,9 @@ struct LnArgs {
     long long rows; int D4;
     float p_pre, p_post; unsigned long long seed; unsigned stream_pre, stream_post;
     int l2_prefetch;   // PR_TUNE_LN_L2_PREFETCH: pull the warp's next row into L2 while this one is processed
+#ifdef PR_SEED_DEV
+    const unsigned long long* seed_dev;   // device-side seed offset (pr_set_seed_device)
+#endif
 };
 
 // keep bits of one row for this lane: chunk j (= float4 column lane + 32*j) uses bits [4*(j&1), +4) of
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 4 : 1) add_ln_fwd_kernel(LnA
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    const Philox ph(a.seed);
+    const Philox ph(PR_SEED(a));
     const unsigned thr_pre = drop_threshold(a.p_pre), thr_post = drop_threshold(a.p_post);
     const float ik_pre = 1.0f / (1.0f - a.p_pre), ik_post = 1.0f / (1.0f - a.p_post);
     const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 2 : 1) add_ln_fwd_pipe_kerne
     const long long mine = warp < a.rows ? (a.rows - warp + nwarps - 1) / nwarps : 0;
     if (lane == 0)
         for (int s = 0; s < STAGES && s < mine; ++s) issue(s, warp + s * nwarps);
-    const Philox ph(a.seed);
+    const Philox ph(PR_SEED(a));
     const unsigned thr_pre = drop_threshold(a.p_pre), thr_post = drop_threshold(a.p_post);
     const float ik_pre = 1.0f / (1.0f - a.p_pre), ik_post = 1.0f / (1.0f - a.p_post);
     const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 2 : 1) add_ln_bwd_kernel(LnA
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const long long warp = (long long)blockIdx.x * nw + wid;
     const long long nwarps = (long long)gridDim.x * nw;
-    const Philox ph(a.seed);
+    const Philox ph(PR_SEED(a));
     const unsigned thr_pre = drop_threshold(a.p_pre), thr_post = drop_threshold(a.p_post);
     const float ik_pre = 1.0f / (1.0f - a.p_pre), ik_post = 1.0f / (1.0f - a.p_post);
     const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
@@ -394,7 +397,7 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 2 : 1) add_ln_bwd_pipe_kerne
     if (lane == 0)
         for (int s = 0; s < STAGES && s < mine; ++s) issue(s, warp + s * nwarps);
 
-    const Philox ph(a.seed);
+    const Philox ph(PR_SEED(a));
     const unsigned thr_pre = drop_threshold(a.p_pre), thr_post = drop_threshold(a.p_post);
     const float ik_pre = 1.0f / (1.0f - a.p_pre), ik_post = 1.0f / (1.0f - a.p_post);
     const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
@@ -725,6 +728,7 @@ extern "C" int pr_add_ln_fwd_f32(const float* h, int64_t h_seq_stride, int64_t r
                  "pr_add_ln_fwd_f32: pointers must be 16-byte aligned");
     LnArgs a{h, h_seq_stride, rows_per_seq, res, res_period, gamma, beta, eps, rows, (int)(D / 4),
              p_pre, p_post, seed, stream_pre, stream_post, (tune() & PR_TUNE_LN_L2_PREFETCH) ? 1 : 0};
+    PR_SET_SEED_DEV(a);
     if ((tune() & PR_TUNE_LN_FWD_PIPE) && (D == 128 || D == 256 || D == 512 || D == 1024)) {
         const int pgrid = (int)std::max<long long>(1, std::min<long long>((rows + 7) / 8, (long long)sm_count() * (D <= 512 ? 2 : 1)));
 #define FPIPE(V, S)                                                                                            \
@@ -778,6 +782,7 @@ static int add_ln_bwd_impl(bool want_dbias, const float* dy, const float* h, int
                  "pr_add_ln_bwd_f32: pointers must be 16-byte aligned");
     LnArgs a{h, h_seq_stride, rows_per_seq, res, res_period, gamma, nullptr, 0.f, rows, (int)(D / 4),
              p_pre, p_post, seed, stream_pre, stream_post, 0};
+    PR_SET_SEED_DEV(a);
     a.l2_prefetch = (tune() & PR_TUNE_LN_L2_PREFETCH) ? 1 : 0;
     if (ln_bwd_pipe_ok(D)) {
 #define PIPE(V, S)                                                                                                   \

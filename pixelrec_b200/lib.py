@@ -23,6 +23,7 @@ SIGNATURES = {
     "pr_sm_count": (_I, []),
     "pr_set_device": (_I, [_I]),
     "pr_set_tuning": (_I, [_I]),
+    "pr_set_seed_device": (_I, [_P]),
     "pr_gather_rows_f32": (_I, [_P, _I64, _I64, _P, _I64, _P, _P, _I, _P]),
     "pr_scatter_plan_workspace_bytes": (C.c_size_t, [_I64, _I64]),
     "pr_scatter_plan": (_I, [_P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P]),

@@ -176,6 +176,14 @@ class DropoutRng:
         return (self.base * 1000003 + self.calls) & 0xFFFFFFFFFFFFFFFF
 
 
+def set_seed_device(offset):
+    """offset: uint64-sized CUDA tensor (int64 [1]) added to every dropout seed by the kernels, or None for host seeds only.
+    Raises PixelRecB200Error in builds without -DPR_SEED_DEV (include/pixelrec_b200.h)."""
+    if offset is not None:
+        _req(offset, torch.int64, "offset")
+    _lib.check(_L().pr_set_seed_device(_p(offset)), "pr_set_seed_device")
+
+
 # ------------------------------------------------------------------------------------------- K3/K7 add+LN
 class GradSlab:
     """Shared [B,2,L+1,D] table-gradient buffer: the loss backward creates it, the embedding LayerNorm

@@ -26,6 +26,7 @@ class FusedAdamW(torch.optim.Optimizer):
         # sharded table) and scaled by 1/world inside the kernels == DDP's gradient mean (run.py:40)
         self.grad_scale = float(grad_scale) / self.world
         self._step = 0
+        self._step_dev = None
         self._tables = {}
         for tb in tables:
             if not isinstance(tb, (TableEmbedding, ShardedTableEmbedding)):
@@ -88,6 +89,17 @@ class FusedAdamW(torch.optim.Optimizer):
             p.grad = f["g"][off:off + p.numel()].view_as(p)
             off += (p.numel() + 3) // 4 * 4
 
+    def use_device_step(self, on=True):
+        """CUDA-graph mode: keep the step count that the bias correction uses in device memory and bump it with a kernel that
+        is part of the captured step (pr_adamw_*'s step_dev argument), instead of freezing a host integer into the graph.
+        Call right before capturing; the device count starts at the steps taken so far."""
+        if not on:
+            self._step_dev = None
+            return None
+        dev = next(p for g in self.param_groups for p in g["params"]).device
+        self._step_dev = torch.full((1,), self._step, dtype=torch.int64, device=dev)
+        return self._step_dev
+
     def flat_grads(self):
         """Flat dense-gradient buffers (one per group) -- the data-parallel all-reduce works on these."""
         return [f["g"] for f in self._flat if f is not None]
@@ -99,6 +111,9 @@ class FusedAdamW(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         self._step += 1
+        sd = self._step_dev                      # CUDA-graph mode (use_device_step): the kernels read the count from device memory
+        if sd is not None:
+            sd.add_(1)
         if self.world > 1:
             for f in self._flat:
                 if f is not None:
@@ -109,7 +124,7 @@ class FusedAdamW(torch.optim.Optimizer):
             f = self._flat[gi]
             if f is not None:
                 ops.adamw_dense(f["w"], f["g"], f["m"], f["v"], group["lr"], b1, b2, group["eps"],
-                                group["weight_decay"], self._step, self.grad_scale)
+                                group["weight_decay"], self._step, self.grad_scale, step_dev=sd)
         for pid, (M, V, gi) in self._table_state.items():
             tb = self._tables[pid]
             group = self.param_groups[gi]
@@ -119,10 +134,10 @@ class FusedAdamW(torch.optim.Optimizer):
             if len(pend) == 1:
                 plan, rows = pend[0]
                 ops.adamw_rows(W, M, V, rows, tb.sink.row2slot, group["lr"], b1, b2, group["eps"],
-                               group["weight_decay"], self._step, self.grad_scale)
+                               group["weight_decay"], self._step, self.grad_scale, step_dev=sd)
             elif len(pend) == 0:
                 ops.adamw_rows(W, M, V, None, None, group["lr"], b1, b2, group["eps"], group["weight_decay"],
-                               self._step, self.grad_scale)
+                               self._step, self.grad_scale, step_dev=sd)
             else:   # several lookups of one table in a step: merge through a dense buffer (rare path)
                 tb.sink.row2slot.fill_(-1)
                 G = torch.zeros_like(W)

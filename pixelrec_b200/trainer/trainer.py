@@ -125,10 +125,23 @@ class Trainer:
         it = iter(train_data)
         nxt = next(it, None)
         staged = look.stage(nxt) if nxt is not None else None
+        graphed, n_eager = None, 0
+        want_graph = bool(self.config["cuda_graph"]) and get_world_size() == 1 and not self.clip_grad_norm   # staged, opt-in
         while staged is not None:
             data = look.acquire(staged)
             nxt = next(it, None)
             staged = look.stage(nxt) if nxt is not None else None     # overlaps with this step's kernels
+            if want_graph and graphed is None and n_eager >= 3:       # a few eager steps first (lazy initialisations)
+                from .graph import GraphedTrainStep
+                try:
+                    graphed = GraphedTrainStep(unwrap(self.model), self.optimizer, data)
+                except ops._lib.PixelRecB200Error as e:          # e.g. dropout > 0 on a build without -DPR_SEED_DEV
+                    self.logger.warning("cuda_graph: staying eager (%s)" % e)
+                    want_graph = False
+            if graphed is not None and graphed.matches(data):
+                total += graphed(data).detach()
+                continue
+            n_eager += 1
             self.optimizer.zero_grad()
             losses = self.model(data)
             total += losses.detach()
@@ -136,6 +149,8 @@ class Trainer:
             if self.clip_grad_norm:
                 clip_grad_norm_(self.model.parameters(), **self.clip_grad_norm)
             self.optimizer.step()
+        if graphed is not None:
+            graphed.close()
         total_loss = float(total.item())        # ONE device->host sync per epoch
         self._check_nan(total_loss)
         for m in unwrap(self.model).modules():  # peer-memory exchange (exchange: p2p): device flags, read once per epoch

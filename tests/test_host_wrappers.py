@@ -53,6 +53,7 @@ CASES = {
     "gather_rows_peers": lambda o: o.gather_rows_peers(_i(2), 2, 10, 8, _i(5)),
     "push_rows_peers": lambda o: o.push_rows_peers(_f(5, 8), _i(5), 2, 0, 4, 0, _i(2), _i(2), torch.zeros(2, dtype=torch.int32)),
     "seq_batch_build": lambda o: o.seq_batch_build(_i(7, 11), _i(3), 50, 1),
+    "set_seed_device": lambda o: o.set_seed_device(_i(1)),
     "shared_buffer": lambda o: o.SharedBuffer(1024, "cuda:0"),
     "shared_open": lambda o: o.shared_open(b"\\0" * 64, "cuda:0"),
 }

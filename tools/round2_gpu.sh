@@ -48,6 +48,15 @@ if [ "$stage" = stage1 ]; then
   run 600 r2_bench_n1 python bench.py --steps 20 --warmup 5
   run 600 r2_plan_ahead_parity env PR_PLAN_AHEAD=1 python -m pytest tests/test_gpu_sasrec.py tests/test_gpu_e2e.py -x -q -m gpu
   run 600 r2_bench_n1_plan_ahead env PR_PLAN_AHEAD=1 python bench.py --steps 20 --warmup 5 --no-cpu   # scatter plan overlapped with the forward
+  # CUDA-graph replay of the step: dropout-free parity on the default build, then a -DPR_SEED_DEV build for the shipped dropout
+  run 300 r2_graph_p0 $PYT tests/test_gpu_graph.py
+  run 300 r2_bench_b64_eager python bench.py --batch 64 --steps 200 --warmup 20 --no-cpu
+  cp pixelrec_b200/libpixelrec_b200.so /tmp/libpixelrec_b200.default.so
+  run 600 r2_build_seeddev env PR_BUILD_DEFS=-DPR_SEED_DEV python -m pixelrec_b200.build --force
+  run 300 r2_graph_p01 $PYT tests/test_gpu_graph.py
+  run 300 r2_bench_b64_graph python bench.py --batch 64 --steps 200 --warmup 20 --no-cpu --graph
+  run 300 r2_bench_b4096_graph python bench.py --steps 20 --warmup 5 --no-cpu --graph
+  cp /tmp/libpixelrec_b200.default.so pixelrec_b200/libpixelrec_b200.so      # back to the default binary for the stages below
   run 600 r2_bench_n1_linear_tc env PR_LINEAR_TC=1 python bench.py --steps 20 --warmup 5 --no-cpu      # FFN dense_1 + GELU on pr_linear_tf32
   run 600 r2_bench_n1_linear_tc_mc env PR_LINEAR_TC=1 PR_TUNE=$((9 | 32)) python bench.py --steps 20 --warmup 5 --no-cpu
   tail -1 gpurun_out/r2_bench_n1.log > gpurun_out/r2_bench_n1.json
