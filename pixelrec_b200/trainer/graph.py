@@ -33,6 +33,7 @@ class GraphedTrainStep:
         optimizer.use_device_step(True)
         self.graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize(dev)
+        launches0 = ops.LAUNCHES["count"]
         try:
             with torch.cuda.graph(self.graph):
                 optimizer.zero_grad()
@@ -44,6 +45,8 @@ class GraphedTrainStep:
         except Exception:
             self.close()
             raise
+        self.launches_per_replay = ops.LAUNCHES["count"] - launches0     # kernels of ours inside the graph
+        ops.LAUNCHES["count"] = launches0                                 # capture itself launched nothing
         # capturing ran the step's Python once (seed counter, optimizer._step) without executing a kernel: the first replay IS that step
         self._first = True
 
@@ -59,6 +62,7 @@ class GraphedTrainStep:
             if rng is not None:
                 rng.calls += 1                   # host mirror of the device-side seed offset
         self._first = False
+        ops.LAUNCHES["count"] += self.launches_per_replay
         self.graph.replay()
         return self.loss
 
