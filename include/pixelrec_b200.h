@@ -17,7 +17,7 @@
  *   - fp32 tensors are row-major and contiguous unless a stride is part of the signature;
  *     feature dims must be multiples of 4 floats (16-byte rows) -- true for every reference config;
  *   - re-entrant across streams and devices (no global mutable state besides cached
- *     per-device attributes).
+ *     per-device attributes and the process-wide switches pr_set_tuning / pr_set_seed_device).
  */
 #ifndef PIXELREC_B200_H_
 #define PIXELREC_B200_H_
