@@ -167,12 +167,12 @@ inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
     std::unique_lock<std::mutex> lk(emu::g_m());
-    const bool ok = emu::g_cv().wait_for(lk, std::chrono::seconds(30), [&]() {
+    const bool ok = emu::g_cv().wait_for(lk, std::chrono::seconds(180), [&]() {
         auto it = emu::bars().find(bar);
         if (it == emu::bars().end()) emu::fail("wait on an uninitialised mbarrier");
         return it->second.phase != (int)parity;
     });
-    if (!ok) emu::fail("DEADLOCK: an mbarrier wait was not satisfied within 30 s");
+    if (!ok) emu::fail("DEADLOCK: an mbarrier wait was not satisfied within 180 s");
 }
 inline void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
     const CUtensorMap m = *tm;
