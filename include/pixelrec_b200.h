@@ -245,6 +245,34 @@ PR_API int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float* W, 
 PR_API int pr_linear_tf32(const float* x, int64_t M, const float* W, int64_t N, int64_t K, const float* bias, int act, float* out,
                           float* pre, pr_stream_t stream);
 
+/* K5: the encoder's linear layers AND their backward on tcgen05 (csrc/gemm.cu): one persistent CTA-pair kernel
+ *   (tcgen05.mma.cta_group::2, UMMA 256x256x8 TF32, TMEM double-buffered accumulators, TMA-fed 5-stage ring, TMA-store epilogue).
+ *   replaces nn.Linear forward, REC/model/layers.py:586-588, :613, :666, :669, and autograd's two GEMMs per Linear.
+ *     out[m, n] = epilogue( sum_k A(m, k) * B(n, k) ),   m < M, n < N, k < K;  fp32 in memory, TF32 operands, fp32 accumulate.
+ *   A: a_mn == 0 -> K-major, memory [M][K] with row stride lda;  a_mn != 0 -> MN-major, memory [K][M] with row stride lda.
+ *   B: b_mn == 0 -> K-major, memory [N][K] (nn.Linear weight layout), row stride ldb;  b_mn != 0 -> memory [K][N].
+ *       forward      y  = x W^T + b :  A = x  (K-major),  B = W  (K-major)
+ *       input grad   dx = dy W      :  A = dy (K-major),  B = W  (MN-major: memory [out_features][in_features] = [K][N])
+ *       weight grad  dW = dy^T x    :  A = dy (MN-major: memory [rows][out] = [K][M]),  B = x (MN-major), splits > 1
+ *   epi: PR_GEMM_STORE    out = acc + bias
+ *        PR_GEMM_ADD      out = acc + bias + aux                      (aux [M, N]: residual / gradient accumulation)
+ *        PR_GEMM_ACT      out = act(acc + bias); out2 (optional) = acc + bias    (dense_1 + gelu, layers.py:666-667)
+ *        PR_GEMM_ACT_BWD  out = acc * act'(aux)                       (aux = the pre-activation: input grad through the activation)
+ *   bias [N] may be NULL.  colsum_partials (optional, [pr_gemm_colsum_rows(M), N], no bias): per-32-row column sums of `out`
+ *   (bias gradient; reduce with pr_colsum_f32).  splits > 1 (PR_GEMM_STORE without bias only): `out` is [splits, M, N], slab s holding
+ *   the partial sum over k-blocks [s*ceil(K/32/splits), ...); pr_gemm_splitk_reduce_f32 adds the slabs in ascending order.
+ *   K % 32 == 0, N % 4 == 0, M % 4 == 0 for an MN-major A, all pointers 16-byte aligned, out / out2 / aux dense [M, N].
+ */
+#define PR_GEMM_STORE 0
+#define PR_GEMM_ADD 1
+#define PR_GEMM_ACT 2
+#define PR_GEMM_ACT_BWD 3
+PR_API int pr_gemm_colsum_rows(int64_t M);
+PR_API int pr_gemm_tf32(const float* A, int a_mn, int64_t lda, const float* B, int b_mn, int64_t ldb, int64_t M, int64_t N,
+                        int64_t K, const float* bias, const float* aux, int epi, int act, float* out, float* out2, int splits,
+                        float* colsum_partials, pr_stream_t stream);
+PR_API int pr_gemm_splitk_reduce_f32(const float* partials, int splits, int64_t n, float* out, pr_stream_t stream);
+
 /* K9 with fp16 operands (staged): fp16 has the 10 explicit mantissa bits of TF32 (and is rounded to nearest, where the TF32
  *   datapath reads truncated fp32 words) but kind::f16 MMAs run at twice the TF32 rate on half the operand bytes.  The
  *   exponent range is narrower: |x| > 65504 saturates and raises status bit 2; |x| < 6e-5 loses precision (absolute error

@@ -9,7 +9,7 @@ seed), feeds seeded synthetic (items, masked_index), and stores inputs, every pa
 reference loss, the encoder output, every gradient produced by loss.backward(), the result of
 one torch.optim.AdamW step (trainer.py:100-103,125), predict() scores, and the masked top-k of
 trainer.py:334-336 + collector.py:133.  tests/test_oracle_golden.py pins oracle/sasrec_np.py,
-oracle/torch_port.py and oracle/rowops.c to these files; the GPU parity tests compare the CUDA
+and oracle/torch_port.py to these files; the GPU parity tests compare the CUDA
 path with the same files.
 """
 import os
@@ -206,3 +206,136 @@ if __name__ == "__main__" and (len(sys.argv) == 1 or "vit_small" in sys.argv[1:]
     make_vit_case()
 if __name__ == "__main__" and (len(sys.argv) == 1 or "vit_long197" in sys.argv[1:]):
     make_vit_case("vit_long197", image_size=112, patch_size=8, n_img=3)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Bench-shape golden (BASELINE.json configs[1] / bench.py: D=512, L=20, h=4, 2 layers).  The parameters of that shape are
+# 4.2 M encoder floats + the table -- too large for a fixture -- so they are a pure function of a seed
+# (`bench_shape_params`, numpy's frozen legacy RandomState stream) that the tests re-create; the file holds inputs, the
+# reference's loss / encoder output / predict scores and a FIXED SUBSET of every gradient (all 1-D tensors and the position
+# table in full, the touched table rows, rows [::16] of every weight matrix).
+BENCH_SHAPE = dict(N=3001, D=512, L=20, B=24, h=4, layers=2, seed=512)
+
+
+def bench_shape_params(shapes, seed):
+    """{name: fp32 array} for the given {name: shape}; N(0, 0.02^2) weights (sasrec.py:51-61), LayerNorm weights 1 + N(0, 0.05^2),
+    biases N(0, 0.05^2).  Order-independent: every tensor has its own stream keyed by a stable hash of its name."""
+    import zlib
+    out = {}
+    for name in sorted(shapes):
+        rs = np.random.RandomState((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 32))
+        x = rs.standard_normal(size=tuple(shapes[name])).astype(np.float32)
+        if len(shapes[name]) == 1:
+            x = (0.05 * x + (1.0 if name.endswith("LayerNorm.weight") else 0.0)).astype(np.float32)
+        else:
+            x = (0.02 * x).astype(np.float32)
+        out[name] = x
+    return out
+
+
+def grad_subset(name, g, touched_rows):
+    """the slice of a gradient the bench-shape golden keeps (see above)"""
+    if name == "item_embedding.weight":
+        return g[touched_rows]
+    if g.ndim == 1 or name == "position_embedding.weight":
+        return g
+    return g[::16]
+
+
+def make_bench_shape_case(name="sasrec_bench_shape"):
+    c = BENCH_SHAPE
+    torch.manual_seed(c["seed"])
+    g = np.random.default_rng(c["seed"])
+    cfg = dict(n_layers=c["layers"], n_heads=c["h"], embedding_size=c["D"], inner_size=2,
+               hidden_dropout_prob=0.0, attn_dropout_prob=0.0, hidden_act="gelu", layer_norm_eps=1e-12,
+               initializer_range=0.02, MAX_ITEM_LIST_LENGTH=c["L"])
+    model = ref_sasrec(cfg, c["N"])
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    params = bench_shape_params(shapes, c["seed"])
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()}, strict=True)
+    model.train()
+    items, mask = synth_batch(g, c["N"], c["L"], c["B"])
+    out = {"cfg_" + k: np.array(v) for k, v in c.items()}
+    for k, s in shapes.items():
+        out["shape/" + k] = np.array(s, dtype=np.int64)
+    out["items"], out["masked_index"] = items, mask
+    cap = {}
+    hk = model.trm_encoder.register_forward_hook(lambda m, i, o: cap.__setitem__("enc_out", o[-1].detach().clone()))
+    loss = model((torch.from_numpy(items), torch.from_numpy(mask)))
+    loss.backward()
+    hk.remove()
+    out["loss"] = loss.detach().numpy()
+    out["enc_out"] = cap["enc_out"].numpy()
+    touched = np.unique(items)
+    out["touched_rows"] = touched
+    for k, p in model.named_parameters():
+        out["grad/" + k] = grad_subset(k, p.grad.detach().numpy(), touched).copy()
+    untouched = np.setdiff1d(np.arange(c["N"]), touched)
+    assert not model.item_embedding.weight.grad[untouched].any()
+    # eval: predict + mask + top-k at the same shape (trainer.py:327-337, collector.py:133)
+    model.eval()
+    Be = 48
+    seqs = np.zeros((Be, c["L"]), dtype=np.int64)
+    hist_u, hist_i = [], []
+    for u in range(Be):
+        n = int(g.integers(1, c["L"] + 6))
+        full = g.integers(1, c["N"], size=n)
+        seq = full[-c["L"]:]
+        seqs[u, c["L"] - len(seq):] = seq
+        hist_u += [u] * n
+        hist_i += full.tolist()
+    hist_u, hist_i = np.array(hist_u, dtype=np.int64), np.array(hist_i, dtype=np.int64)
+    with torch.no_grad():
+        scores = model.predict(torch.from_numpy(seqs), model.compute_item_all())
+        out["eval_scores_raw"] = scores.numpy().copy()
+        scores[:, 0] = -np.inf
+        scores[(torch.from_numpy(hist_u), torch.from_numpy(hist_i))] = -np.inf
+        tv, ti = torch.topk(scores, 10, dim=-1)
+    out.update(eval_item_seq=seqs, eval_hist_u=hist_u, eval_hist_i=hist_i, eval_topk_val=tv.numpy(), eval_topk_idx=ti.numpy())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "loss", float(loss.detach()), "size", os.path.getsize(os.path.join(OUT, name + ".npz")) // 1024, "KiB")
+
+
+def make_seqtrain_case(name="seqtrain_ref"):
+    """A1 pin: the reference's own SEQTrainDataset (data/dataset/trainset.py:22-75) under a seeded `random` -- the stream its
+    _neg_sample draws from (trainset.py:40-44) -- on ragged sequences incl. ones longer than L+1 and a small catalog (so that
+    rejections happen).  tests/test_oracle_sampler.py replays oracle.seq_train_sample with random.Random(seed)."""
+    import random
+    from oracle.refload import load_reference
+    load_reference()
+    from REC.data.dataset.trainset import SEQTrainDataset
+    g = np.random.default_rng(99)
+    out = {}
+    for ci, (item_num, L, n_seq) in enumerate([(40, 10, 64), (5000, 20, 64), (12, 5, 32)]):
+        seqs = []
+        for _ in range(n_seq):
+            # dataload.py:125-132 caps windows at L+1; case 0 also feeds longer ones (_padding_sequence keeps the tail)
+            ln = int(g.integers(2, min(L + (6 if ci == 0 else 2), item_num - 1)))
+            seqs.append(g.choice(np.arange(1, item_num), size=ln, replace=False).astype(np.int64))
+
+        class Dl:
+            pass
+        dl = Dl()
+        dl.item_num = item_num
+        dl.train_feat = {"item_seq": seqs}
+        ds = SEQTrainDataset({"MAX_ITEM_LIST_LENGTH": L, "device": "cpu"}, dl)
+        seed = 1234 + ci
+        random.seed(seed)
+        items, masks = [], []
+        for i in range(len(ds)):
+            it, m = ds[i]
+            items.append(it.numpy())
+            masks.append(m.numpy())
+        out[f"c{ci}_meta"] = np.array([item_num, L, n_seq, seed], dtype=np.int64)
+        out[f"c{ci}_flat"] = np.concatenate(seqs)
+        out[f"c{ci}_offs"] = np.cumsum([0] + [len(s) for s in seqs]).astype(np.int64)
+        out[f"c{ci}_items"] = np.stack(items)
+        out[f"c{ci}_mask"] = np.stack(masks)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, {k: v.shape for k, v in out.items() if k.endswith("items")})
+
+
+if __name__ == "__main__" and (len(sys.argv) == 1 or "sasrec_bench_shape" in sys.argv[1:]):
+    make_bench_shape_case()
+if __name__ == "__main__" and (len(sys.argv) == 1 or "seqtrain_ref" in sys.argv[1:]):
+    make_seqtrain_case()

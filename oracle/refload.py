@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE -- not product code.
 
 Imports the *unmodified* reference modules from /root/reference/code so that the
-oracle restatement (oracle/sasrec_np.py, oracle/torch_port.py, oracle/rowops.c)
+oracle restatement (oracle/sasrec_np.py, oracle/torch_port.py)
 can be pinned against the reference itself, and golden vectors can be generated
 (oracle/make_golden.py -> tests/golden/*.npz).
 

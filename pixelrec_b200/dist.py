@@ -290,11 +290,29 @@ class ShardedTableEmbedding(nn.Module):
         if padding_idx is not None and padding_idx % self.world == self.rank:
             self.local_padding_idx = padding_idx // self.world
         self.weight = nn.Parameter(torch.empty(self.n_local, embedding_dim))
-        nn.init.normal_(self.weight)
+        self.init_normal_(0.0, 1.0)
         self.sink = TableGradSink(self)
         self.sink.sparse = True          # a sharded table has no dense-gradient mode
         self._register_state_dict_hook(self._full_on_save)
         self._register_load_state_dict_pre_hook(self._shard_on_load)
+
+    @torch.no_grad()
+    def init_normal_(self, mean=0.0, std=1.0, chunk_rows=65536):
+        """Initialise the shard as rows rank::world of the LOGICAL [N, D] table drawn from the global generator
+        (sasrec.py:56 draws the whole table): every rank consumes the same random stream -- the generators stay in
+        lockstep and the logical table is iid and independent of the world size -- and keeps only its own rows.
+        (Drawing `weight.normal_()` per rank under the common seed gave up to `world` items one embedding.)"""
+        N, D, G, r = self.num_embeddings, self.embedding_dim, self.world, self.rank
+        w = self.weight.data
+        for r0 in range(0, N, chunk_rows):
+            n = min(chunk_rows, N - r0)
+            block = torch.empty(n, D, dtype=torch.float32).normal_(mean, std)       # host draw, like the reference's CPU init
+            first = (r - r0) % G                                                     # first row of the block owned by this rank
+            mine = block[first::G]
+            if mine.shape[0]:
+                lo = (r0 + first) // G
+                w[lo:lo + mine.shape[0]].copy_(mine)
+        return self
 
     def forward(self, idx):
         if self.sink.row2slot is None:
@@ -365,6 +383,22 @@ class ShardedTableEmbedding(nn.Module):
         dist.all_gather(chunks, pad, group=self.group)
         allw = torch.stack(chunks)                                   # [world, n_max, D]; row i = shard i%world, i//world
         return allw.permute(1, 0, 2).reshape(-1, self.embedding_dim)[:self.num_embeddings].contiguous()
+
+    @torch.no_grad()
+    def gather_rows_full(self, local):
+        """[n_local, D] per-rank tensor aligned with the shard (e.g. an Adam moment) -> the full [N, D] layout.  Collective."""
+        if self.world == 1:
+            return local.detach().clone()
+        keep, self_w = self.weight.data, None
+        try:
+            self.weight.data = local
+            return self.full_weight()
+        finally:
+            self.weight.data = keep
+
+    def shard_of_full(self, full):
+        """rows rank::world of a full [N, D] tensor (inverse of gather_rows_full)"""
+        return full[self.rank::self.world].contiguous()
 
     @staticmethod
     def _full_on_save(module, state_dict, prefix, local_metadata):

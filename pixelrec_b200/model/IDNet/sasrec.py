@@ -50,7 +50,9 @@ class SASRec(BaseModel):
 
     def _init_weights(self, module):
         """sasrec.py:51-61.  NB: like the reference this re-initialises the pad row (id 0) to N(0, std)."""
-        if isinstance(module, (nn.Linear, nn.Embedding, TableEmbedding, ShardedTableEmbedding)):
+        if isinstance(module, ShardedTableEmbedding):
+            module.init_normal_(0.0, self.initializer_range)       # rows rank::world of the logical table (iid across ranks)
+        elif isinstance(module, (nn.Linear, nn.Embedding, TableEmbedding)):
             module.weight.data.normal_(mean=0.0, std=self.initializer_range)
         elif isinstance(module, nn.LayerNorm):
             module.bias.data.zero_()
@@ -86,15 +88,21 @@ class SASRec(BaseModel):
     @torch.no_grad()
     def predict(self, item_seq, item_feature):
         """sasrec.py:94-113: scores [B_e, N] = encoder(item_seq)[:, -1] @ item_feature.T"""
-        seq_output = self.encode_last(item_seq)
+        seq_output = self.encode_last(item_seq, item_feature)
         return torch.matmul(seq_output, item_feature.t())
 
     @torch.no_grad()
-    def encode_last(self, item_seq):
+    def encode_last(self, item_seq, item_feature=None):
+        """Encoder output at the last position.  With a row-sharded table pass the all-gathered `item_feature`
+        (compute_item_all()): the rows are then read locally -- the sharded lookup issues collectives, and ranks may hold
+        different numbers of eval batches (data/utils.py strided sampler), which would deadlock."""
         item_seq = item_seq.contiguous()
         B, L = item_seq.shape
         D = self.hidden_size
-        E = self.item_embedding(item_seq)                         # [B,L,D]
+        if item_feature is not None and isinstance(self.item_embedding, ShardedTableEmbedding):
+            E = ops.gather_rows(item_feature.contiguous(), item_seq)
+        else:
+            E = self.item_embedding(item_seq)                     # [B,L,D]
         x = self._embed(E, L, L * D, B, 0, None)
         out = self.trm_encoder(x, item_seq, output_all_encoded_layers=False, causal=True, seed=0)[-1]
         return out[:, -1].contiguous()

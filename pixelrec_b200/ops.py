@@ -566,7 +566,38 @@ def _raw_act_bwd_bias(x, dy, act):
 
 
 WGRAD_SPLIT = int(os.environ.get("PR_WGRAD_SPLIT", "8"))
-LINEAR_TC = os.environ.get("PR_LINEAR_TC", "0") == "1"      # staged: FFN dense_1 + GELU through pr_linear_tf32
+# Linear layers of the encoder: "tc" = our CTA-pair tcgen05 GEMM (pr_gemm_tf32) for forward, input-gradient and weight-gradient
+# GEMMs whenever TF32 matmuls are allowed (torch.backends.cuda.matmul.allow_tf32, the reference's torch-1.10 default);
+# "cublas" = torch.addmm / mm (kept for A/B runs and for strict-fp32 parity runs, where allow_tf32 is off).
+LINEAR_IMPL = os.environ.get("PR_LINEAR", "tc").lower()
+
+
+def _use_tc(*dims):
+    return LINEAR_IMPL == "tc" and bool(torch.backends.cuda.matmul.allow_tf32) and all(d % 4 == 0 for d in dims)
+
+
+def _linear_fwd(x2, w, b):
+    """x2 [M, K] @ w[N, K]^T + b   (nn.Linear, layers.py:586-588, 613, 669)"""
+    if _use_tc(x2.shape[1], w.shape[0]):
+        return gemm(x2, w, bias=b)
+    return torch.addmm(b, x2, w.t())
+
+
+def _linear_dgrad(dy2, w, add=None):
+    """dy2 [M, N] @ w[N, K] (+ add): the input gradient of nn.Linear; `add` folds a residual gradient in"""
+    if _use_tc(w.shape[0], w.shape[1]):
+        if add is None:
+            return gemm(dy2, w, b_mn=True)
+        return gemm(dy2, w, b_mn=True, aux=add, epi=GEMM_ADD)
+    return dy2.mm(w) if add is None else torch.addmm(add, dy2, w)
+
+
+def _wgrad_splits(n_out, n_in, rows):
+    tiles = ((n_out + 255) // 256) * ((n_in + 255) // 256)
+    kb = (rows + 31) // 32
+    s = max(1, min(74 // max(tiles, 1), kb // 8))           # ~one work item per CTA pair, >= 8 k-blocks each
+    per = (kb + s - 1) // s
+    return (kb + per - 1) // per                              # no empty split
 
 
 def _wgrad(dy2, x2):
@@ -575,6 +606,8 @@ def _wgrad(dy2, x2):
     WGRAD_SPLIT slabs of M + one fixed-order sum) measured 1.3-2.0x faster at M = 81920 (profiles/r01h_rowkernels_ab.md)
     and stays deterministic."""
     M = dy2.shape[0]
+    if _use_tc(dy2.shape[1], x2.shape[1]):
+        return gemm(dy2, x2, a_mn=True, b_mn=True, splits=_wgrad_splits(dy2.shape[1], x2.shape[1], M))
     S = WGRAD_SPLIT
     if S > 1 and M % S == 0 and M // S >= 2048:
         return torch.bmm(dy2.view(S, M // S, -1).transpose(1, 2), x2.view(S, M // S, -1)).sum(0)
@@ -592,7 +625,7 @@ class TransformerLayerFn(torch.autograd.Function):
         x2 = x.view(B * L, D)
         wqkv = torch.cat([wq, wk, wv], 0)
         bqkv = torch.cat([bq, bk, bv], 0)
-        qkv = torch.addmm(bqkv, x2, wqkv.t()).view(B, L, 3 * D)                      # layers.py:586-588
+        qkv = _linear_fwd(x2, wqkv, bqkv).view(B, L, 3 * D)                          # layers.py:586-588
         tf32 = bool(torch.backends.cuda.matmul.allow_tf32) and L <= 32 and (D // n_heads) % 32 == 0 and \
             ((D // n_heads) <= 128 or (D // n_heads) % 128 == 0)
         ctxt = torch.empty(B, L, D, device=x.device, dtype=torch.float32)
@@ -603,17 +636,17 @@ class TransformerLayerFn(torch.autograd.Function):
             _lib.check(fwd(base, base + 4 * D, base + 8 * D, 3 * D, _p(key_ids), B, L, n_heads, D // n_heads, int(causal), p_attn,
                            seed, site, _p(ctxt), _p(probs), _stream(qkv)), "pr_sasrec_attn_fwd")
         _count()
-        h = torch.addmm(bo, ctxt.view(B * L, D), wo.t())                               # :613
+        h = _linear_fwd(ctxt.view(B * L, D), wo, bo)                                   # :613
         a, mean1, rstd1 = _raw_add_ln_fwd(h, x2, g1, be1, eps, p_hid, seed, site + 1)  # :614-615
-        if LINEAR_TC and torch.backends.cuda.matmul.allow_tf32 and act in (0, 1):     # staged: dense_1 + activation in one tcgen05 kernel (h1 and gelu(h1) both kept)
-            gl, h1 = linear_tc(a, w1.contiguous(), b1, "gelu" if act == 0 else "relu", want_pre=True)
+        if _use_tc(a.shape[1], w1.shape[0]):                                          # dense_1 + activation in ONE kernel (h1 and act(h1) both kept)
+            gl, h1 = gemm(a, w1, bias=b1, epi=GEMM_ACT, act=act, want_pre=True)        # :666-667
         else:
             h1 = torch.addmm(b1, a, w1.t())                                            # :666
             gl = torch.empty_like(h1)
             with _prof("act_fwd", h1):
                 _lib.check(_L().pr_act_fwd_f32(_p(h1), h1.numel(), act, _p(gl), _stream(h1)), "pr_act_fwd_f32")
             _count()
-        h2 = torch.addmm(b2, gl, w2.t())                                               # :669
+        h2 = _linear_fwd(gl, w2, b2)                                                   # :669
         y, mean2, rstd2 = _raw_add_ln_fwd(h2, a, g2, be2, eps, p_hid, seed, site + 2)  # :670-671
         ctx.save_for_backward(x, qkv, probs, ctxt, h, a, mean1, rstd1, h1, gl, h2, mean2, rstd2, wqkv, wo, w1, w2, g1, g2)
         ctx.cfg = (B, L, D, n_heads, int(causal), eps, p_attn, p_hid, act, seed, site, tf32)
@@ -629,14 +662,14 @@ class TransformerLayerFn(torch.autograd.Function):
         # ---- feed-forward block
         dh2, da_res, dg2, dbe2, db2 = _raw_add_ln_bwd_bias(dy, h2, a, g2, mean2, rstd2, p_hid, seed, site + 2)
         dw2 = _wgrad(dh2, gl)
-        dgl = dh2.mm(w2)
+        dgl = _linear_dgrad(dh2, w2)
         dh1, db1 = _raw_act_bwd_bias(h1, dgl, act)
         dw1 = _wgrad(dh1, a)
-        da = torch.addmm(da_res, dh1, w1)                                  # residual grad folded into the GEMM (beta = 1)
+        da = _linear_dgrad(dh1, w1, add=da_res)                            # residual grad folded into the GEMM epilogue
         # ---- attention block
         dh, dx_res, dg1, dbe1, dbo = _raw_add_ln_bwd_bias(da, h, x2, g1, mean1, rstd1, p_hid, seed, site + 1)
         dwo = _wgrad(dh, ctxt.view(M, D))
-        dctx = dh.mm(wo)
+        dctx = _linear_dgrad(dh, wo)
         dqkv = torch.empty_like(qkv)
         base, gbase = qkv.data_ptr(), dqkv.data_ptr()
         bwd = _L().pr_sasrec_attn_bwd_tf32 if tf32 else _L().pr_sasrec_attn_bwd_f32
@@ -647,7 +680,7 @@ class TransformerLayerFn(torch.autograd.Function):
         dqkv2 = dqkv.view(M, 3 * D)
         dwqkv = _wgrad(dqkv2, x2)                                           # one GEMM for the three projections
         dbqkv = dqkv2.sum(0)
-        dx = torch.addmm(dx_res, dqkv2, wqkv).view(B, L, D)                # residual grad folded into the GEMM
+        dx = _linear_dgrad(dqkv2, wqkv, add=dx_res).view(B, L, D)          # residual grad folded into the GEMM epilogue
         return (dx, None, dwqkv[:D], dbqkv[:D], dwqkv[D:2 * D], dbqkv[D:2 * D], dwqkv[2 * D:], dbqkv[2 * D:], dwo, dbo, dg1, dbe1,
                 dw1, db1, dw2, db2, dg2, dbe2, None, None, None, None, None, None, None, None)
 
@@ -692,6 +725,59 @@ def linear_tc(x, weight, bias=None, act=None, want_pre=False):
         _lib.check(_L().pr_linear_tf32(_p(x), M, _p(weight), N, K, _p(bias), act_id, _p(out), _p(pre), _stream(x)),
                    "pr_linear_tf32")
     _count()
+    return (out, pre) if want_pre else out
+
+
+GEMM_STORE, GEMM_ADD, GEMM_ACT, GEMM_ACT_BWD = 0, 1, 2, 3
+
+
+def gemm(A, B, a_mn=False, b_mn=False, bias=None, aux=None, epi=GEMM_STORE, act=None, out=None, want_pre=False, splits=1,
+         want_colsum=False):
+    """out[M, N] = epilogue(A . B^T) on the CTA-pair tcgen05 GEMM (pr_gemm_tf32, csrc/gemm.cu) -- forward, input-gradient
+    and weight-gradient GEMMs of nn.Linear (REC/model/layers.py:586-588, 613, 666, 669) without a transposed copy:
+      A: [M, K] (a_mn=False) or [K, M] (a_mn=True);  B: [N, K] (b_mn=False, nn.Linear weight layout) or [K, N] (b_mn=True).
+    epi / act / aux / want_pre / want_colsum: see include/pixelrec_b200.h.  splits > 1: split-K, reduced here in fixed order.
+    Returns out, or (out, pre) with want_pre, or (out, colsum [N]) with want_colsum."""
+    _req(A, torch.float32, "A")
+    _req(B, torch.float32, "B")
+    if A.dim() != 2 or B.dim() != 2:
+        raise ValueError("gemm: A and B must be 2-D")
+    K, M = (A.shape if a_mn else (A.shape[1], A.shape[0]))
+    Kb, N = (B.shape if b_mn else (B.shape[1], B.shape[0]))
+    if K != Kb:
+        raise ValueError(f"gemm: contraction lengths differ (A {tuple(A.shape)}, B {tuple(B.shape)})")
+    dev = A.device
+    if out is None:
+        out = torch.empty(M, N, device=dev, dtype=torch.float32)
+    else:
+        _req(out, torch.float32, "out")
+    pre = torch.empty(M, N, device=dev, dtype=torch.float32) if want_pre else None
+    if aux is not None:
+        _req(aux, torch.float32, "aux")
+    act_id = -1 if act is None else (act if isinstance(act, int) else ACT_IDS[act])
+    L_ = _L()
+    partials = None
+    if want_colsum:
+        n_part = L_.pr_gemm_colsum_rows(M)
+        partials = torch.empty(n_part, N, device=dev, dtype=torch.float32)
+    dst = out
+    if splits > 1:
+        dst = torch.empty(splits, M, N, device=dev, dtype=torch.float32)
+    with _prof("gemm", A):
+        _lib.check(L_.pr_gemm_tf32(_p(A), int(a_mn), A.stride(0), _p(B), int(b_mn), B.stride(0), M, N, K, _p(bias), _p(aux),
+                                   int(epi), act_id, _p(dst), _p(pre), int(splits), _p(partials), _stream(A)), "pr_gemm_tf32")
+    _count()
+    if splits > 1:
+        with _prof("gemm_splitk_reduce", A):
+            _lib.check(L_.pr_gemm_splitk_reduce_f32(_p(dst), int(splits), M * N, _p(out), _stream(A)),
+                       "pr_gemm_splitk_reduce_f32")
+        _count()
+    if want_colsum:
+        cs = torch.empty(1, N, device=dev, dtype=torch.float32)
+        with _prof("colsum", A):
+            _lib.check(L_.pr_colsum_f32(_p(partials), 1, partials.shape[0], N, _p(cs), _stream(A)), "pr_colsum_f32")
+        _count()
+        return out, cs[0]
     return (out, pre) if want_pre else out
 
 

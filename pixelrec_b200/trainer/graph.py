@@ -9,6 +9,10 @@ it can be captured once and replayed with one launch.  Two host-side scalars wou
     `add_(1)` bumps at the end of every replay, so replay j uses exactly the seed eager step j would have used;
   * AdamW's step count (bias correction) -> FusedAdamW.use_device_step(): read from device memory, bumped inside the graph.
 
+The caller must not hold the loss tensor (or anything else with a grad_fn) of an earlier EAGER step when the capture starts:
+a live autograd graph keeps its AccumulateGrad nodes, which stay bound to the stream they were created on (the default one),
+and the engine would then make that stream wait on the capturing one -- cudaErrorStreamCaptureImplicit.
+
 Single GPU only (the row exchange of a sharded table needs host-side split sizes), fixed batch shape (a ragged last batch runs
 eagerly), dropout > 0 needs a library built with -DPR_SEED_DEV.
 """
@@ -42,8 +46,11 @@ class GraphedTrainStep:
                 optimizer.step()
                 if self._seeded:
                     self.seed_offset.add_(1)
-        except Exception:
+        except Exception as e:
             self.close()
+            if "legacy stream depend on a capturing" in str(e):
+                raise RuntimeError("CUDA-graph capture of the training step failed because an autograd graph of an earlier eager "
+                                   "step is still alive (drop the previous loss tensor before capturing)") from e
             raise
         self.launches_per_replay = ops.LAUNCHES["count"] - launches0     # kernels of ours inside the graph
         ops.LAUNCHES["count"] = launches0                                 # capture itself launched nothing

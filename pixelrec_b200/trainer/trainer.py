@@ -42,6 +42,15 @@ class Lookahead:
         """host batch -> (device batch, ready event)"""
         if self.stream is None:
             return batch, None
+        tensors = batch if isinstance(batch, (tuple, list)) else (batch,)
+        if any(isinstance(t, torch.Tensor) and t.is_cuda for t in tensors):
+            # a batch built ON the device (device_sampler: pr_seq_batch_build on the current stream) is only complete once
+            # that stream reaches this point: the side stream must not read it (prefetch builds the exchange plan from
+            # the ids) before then.  `.to()` is a no-op for such tensors, so nothing else orders the two streams.
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            for t in tensors:
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(self.stream)
         with torch.cuda.stream(self.stream):
             dev = tuple(t.to(self.device, non_blocking=True) for t in batch) if isinstance(batch, (tuple, list)) \
                 else batch.to(self.device, non_blocking=True)
@@ -146,6 +155,7 @@ class Trainer:
             losses = self.model(data)
             total += losses.detach()
             losses.backward()
+            del losses     # keeps no autograd graph (and its AccumulateGrad nodes, bound to THIS stream) alive into a later capture
             if self.clip_grad_norm:
                 clip_grad_norm_(self.model.parameters(), **self.clip_grad_norm)
             self.optimizer.step()
@@ -259,7 +269,7 @@ class Trainer:
         The [B_e, N] score matrix (397 MB at C2) is never written."""
         user, history_index, positive_u, positive_i = batched_data
         model = unwrap(self.model)
-        seq_out = model.encode_last(self.to_device(user))
+        seq_out = model.encode_last(self.to_device(user), self.item_feature)
         hu = hi = None
         if history_index is not None:
             hu, hi = (x.to(self.device).contiguous() for x in history_index)

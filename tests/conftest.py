@@ -29,3 +29,17 @@ def load_golden(name):
 @pytest.fixture(params=GOLDEN_CASES)
 def golden(request):
     return load_golden(request.param)
+
+
+def load_bench_shape_golden():
+    """tests/golden/sasrec_bench_shape.npz (D=512, L=20, h=4, 2 layers -- the shape bench.py times): parameters are
+    regenerated from the seed (oracle.make_golden.bench_shape_params), gradients are the stored subset (grad_subset)."""
+    import numpy as np
+    from oracle.make_golden import bench_shape_params
+    z = np.load(os.path.join(GOLDEN_DIR, "sasrec_bench_shape.npz"))
+    g = {k: z[k] for k in z.files}
+    g["cfg"] = {k[len("cfg_"):]: int(v) for k, v in g.items() if k.startswith("cfg_")}
+    shapes = {k[len("shape/"):]: tuple(int(x) for x in v) for k, v in g.items() if k.startswith("shape/")}
+    g["params"] = bench_shape_params(shapes, g["cfg"]["seed"])
+    g["grads"] = {k[len("grad/"):]: v for k, v in g.items() if k.startswith("grad/")}
+    return g

@@ -12,7 +12,7 @@ from oracle import sasrec_np as O
 from tests.gpu_util import rel, t
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PR_EXPERIMENTAL") != "1", reason="staged kernels: set PR_EXPERIMENTAL=1")]
+]
 
 
 @pytest.fixture(params=[0, 64], ids=["fp32_fwd", "tf32_mma_fwd"])

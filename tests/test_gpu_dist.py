@@ -101,7 +101,7 @@ def _worker(rank, world, port, state, q, exchange="nccl"):
 
 
 # "p2p" (peer-memory kernels + CUDA IPC, csrc/peer.cu) was written without multi-GPU access: opt-in until confirmed
-_EXCHANGES = ["nccl"] + (["p2p"] if os.environ.get("PR_EXPERIMENTAL") == "1" else [])
+_EXCHANGES = ["nccl", "p2p"]
 
 
 @pytest.mark.parametrize("exchange", _EXCHANGES)

@@ -12,7 +12,7 @@ import torch
 from tests.gpu_util import t
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PR_EXPERIMENTAL") != "1", reason="staged kernels: set PR_EXPERIMENTAL=1")]
+]
 
 
 @pytest.fixture(params=[0, 32], ids=["unicast", "w_multicast"])

@@ -12,7 +12,7 @@ from oracle import sasrec_np as O
 from tests.gpu_util import dev, t
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PR_EXPERIMENTAL") != "1", reason="staged kernels: set PR_EXPERIMENTAL=1")]
+]
 
 
 @pytest.mark.parametrize("G,N,D,R", [(1, 50, 8, 33), (2, 101, 64, 500), (4, 1003, 512, 4097), (8, 97001, 512, 20000), (3, 77, 36, 10)])

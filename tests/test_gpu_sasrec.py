@@ -144,3 +144,33 @@ def test_gru4rec_plugin_matches_reference_golden():
     assert rel(sc.cpu().numpy(), z["eval_scores_raw"]) < 1e-4
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
+
+
+@pytest.mark.parametrize("tf32,tol", [(False, 1e-4), (True, 1e-3)])
+def test_bench_shape_forward_backward_matches_reference(tf32, tol):
+    """The shape bench.py times (D=512, L=20, h=4, 2 layers; K up to 1024 in dense_2) against the reference's golden:
+    TF32 linear layers + tensor-core attention must hold north_star's 1e-3 there, not only on the small fixtures."""
+    from oracle.make_golden import grad_subset
+    from tests.conftest import load_bench_shape_golden
+    g = load_bench_shape_golden()
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    torch.backends.cudnn.allow_tf32 = tf32
+    m = build(g)
+    m.train()
+    loss = m((t(g["items"]), t(g["masked_index"])))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - float(g["loss"])) / float(g["loss"]) < tol
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    for k, ref in g["grads"].items():
+        got = grad_subset(k, grads[k].cpu().numpy(), g["touched_rows"])
+        if k.endswith("key.bias"):
+            assert np.abs(got).max() < 1e-6
+            continue
+        assert rel(got, ref) < tol * 3, (k, rel(got, ref))
+    m.eval()
+    with torch.no_grad():
+        sc = m.predict(t(g["eval_item_seq"]), m.compute_item_all())
+    assert rel(sc.cpu().numpy(), g["eval_scores_raw"]) < tol
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True

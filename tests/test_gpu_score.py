@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 # Kernel variants of pr_score_topk_f32 (pr_set_tuning bits 16 / 32, csrc/score.cu "v2").  The default kernel always runs;
 # the staged variants were written without GPU access and stay opt-in (PR_EXPERIMENTAL=1, run under a timeout: see
 # tools/round2_gpu.sh) until a B200 run has confirmed them.
-_VARIANTS = [0] + ([16, 48] if os.environ.get("PR_EXPERIMENTAL") == "1" else [])
+_VARIANTS = [0, 16, 48]
 
 
 @pytest.fixture(params=_VARIANTS, ids=lambda v: {0: "v1", 16: "v2", 48: "v2_mcast"}[v], autouse=True)
@@ -114,7 +114,6 @@ def test_score_topk_fewer_valid_items_than_k_and_bad_args():
         ops.score_topk(seq, W, 33)
 
 
-@pytest.mark.skipif(os.environ.get("PR_EXPERIMENTAL") != "1", reason="staged kernels: set PR_EXPERIMENTAL=1")
 @pytest.mark.parametrize("B_e,N,D", [(64, 3000, 128), (1024, 97001, 512), (5, 300, 32)])
 def test_score_ce_matches_oracle(B_e, N, D):
     """full-catalog softmax CE on the v2 scoring pipeline (extension; oracle restates F.cross_entropy): TF32 operands, fp32
@@ -131,7 +130,6 @@ def test_score_ce_matches_oracle(B_e, N, D):
     assert np.abs(lse - lse_r).max() < tol and np.abs(tl - tl_r).max() < tol and np.abs(nll - nll_r).max() < 2 * tol
 
 
-@pytest.mark.skipif(os.environ.get("PR_EXPERIMENTAL") != "1", reason="staged kernels: set PR_EXPERIMENTAL=1")
 @pytest.mark.parametrize("B_e,N,D,k", [(5, 300, 64, 10), (300, 5003, 512, 10), (1024, 20011, 512, 10), (33, 777, 128, 20)])
 @pytest.mark.parametrize("ares", [0, 128], ids=["ring", "resident_seq"])
 def test_score_topk_f16_exact_on_small_integers(B_e, N, D, k, ares):
@@ -154,7 +152,6 @@ def test_score_topk_f16_exact_on_small_integers(B_e, N, D, k, ares):
     assert int(status.item()) == 0
 
 
-@pytest.mark.skipif(os.environ.get("PR_EXPERIMENTAL") != "1", reason="staged kernels: set PR_EXPERIMENTAL=1")
 def test_score_topk_f16_gaussian_matches_tf32_quality_and_flags_overflow():
     from pixelrec_b200 import ops
     B_e, N, D, k = 1024, 97001, 512, 10

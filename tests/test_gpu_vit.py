@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # vit_long197 (197 tokens = ViT-B/16's sequence length) runs on the long-sequence attention kernels (csrc/attn_long.cuh), whose
 # logic is checked on CPU by tests/test_emu_kernels.py but which have not run on a GPU yet: opt-in until confirmed
-_LONG = pytest.mark.skipif(os.environ.get("PR_EXPERIMENTAL") != "1", reason="staged kernels: set PR_EXPERIMENTAL=1")
+_LONG = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("case,image_size,patch_size", [("vit_small", 96, 32),

@@ -205,7 +205,21 @@ def test_tcgen05_ptx_forms_match_the_vendored_cutlass_headers():
     bar = text("cutlass", "arch", "barrier.h")
     tma90 = text("cute", "arch", "copy_sm90_tma.hpp")
     desc = text("cute", "arch", "mma_sm100_desc.hpp")
-    ours = re.sub(r'"\s*\n\s*"', "", open(os.path.join(ROOT, "pixelrec_b200", "csrc", "score.cu")).read())
+    ours = "".join(re.sub(r'"\s*\n\s*"', "", open(os.path.join(ROOT, "pixelrec_b200", "csrc", f)).read())
+                   for f in ("tc_ptx.cuh", "score.cu", "gemm.cu"))
+    tma100 = text("cute", "arch", "copy_sm100_tma.hpp")
+    alloc = text("cute", "arch", "tmem_allocator_sm100.hpp")
+    # CTA-pair forms of csrc/gemm.cu
+    for form, ref in [("tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5,", umma),
+                      ("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;", bar),
+                      ("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes", tma100),
+                      ("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;", alloc),
+                      ("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;", alloc),
+                      ("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group", tma90)]:
+        assert form in ref, form
+        assert form.split(" [")[0] in ours, form
+    assert "SWIZZLE_128B_BASE32B = 1" in desc and "SWIZZLE_128B = 2" in desc          # gm_desc layout types
+    assert "a_major_       : 1;  // bit [15,16)" in desc and "b_major_       : 1,  // bit [16,17)" in desc
     for form, ref in [("tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3,", umma),
                       ("tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3,", umma),
                       ("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;", bar),

@@ -47,6 +47,10 @@ CASES = {
     "attention_long": lambda o: o.attention(_f(1, 100, 3 * 64), _i(1, 100), 2, causal=False),
     "score_topk": lambda o: o.score_topk(_f(4, 64), _f(50, 64), 5, _i(3), _i(3)),
     "linear_tc": lambda o: o.linear_tc(_f(6, 64), _f(8, 64), _f(8), "gelu", want_pre=True),
+    "gemm": lambda o: o.gemm(_f(6, 64), _f(8, 64), bias=_f(8), epi=o.GEMM_ACT, act="gelu", want_pre=True),
+    "gemm_wgrad_splitk": lambda o: o.gemm(_f(64, 8), _f(64, 12), a_mn=True, b_mn=True, splits=2),
+    "gemm_act_bwd_colsum": lambda o: o.gemm(_f(6, 64), _f(64, 8), b_mn=True, aux=_f(6, 8), epi=o.GEMM_ACT_BWD, act="gelu",
+                                            want_colsum=True),
     "score_prepare_f16": lambda o: o.score_prepare_f16(_f(50, 64)),
     "score_topk_f16": lambda o: o.score_topk_f16(_f(4, 64), torch.zeros(50, 64, dtype=torch.float16), 5, _i(3), _i(3)),
     "score_ce": lambda o: o.score_ce(_f(4, 64), _f(50, 64), _i(4)),
@@ -66,6 +70,9 @@ def test_wrapper_argument_lists_match_the_abi(cpu_calls, name):
     from pixelrec_b200.lib import PixelRecB200Error
     try:
         CASES[name](cpu_calls)
+        if name == "set_seed_device":            # -DPR_SEED_DEV builds (the default) only record the pointer: nothing to refuse
+            cpu_calls.set_seed_device(None)
+            return
     except PixelRecB200Error:
         return                                   # reached the library, which refused (no device): the expected outcome
     except (ctypes.ArgumentError, TypeError) as e:      # pragma: no cover

@@ -166,3 +166,37 @@ def test_full_catalog_ce_oracle_restates_torch_cross_entropy():
     lse0, _, nll0 = O.full_catalog_ce(scores, target, mask_col0=True)
     ref0 = F.cross_entropy(torch.from_numpy(scores[:, 1:]), torch.from_numpy(target - 1), reduction="none").numpy()
     assert np.allclose(nll0, ref0, rtol=1e-12, atol=1e-12) and (lse0 <= lse + 1e-12).all()
+
+
+def test_bench_shape_golden_pins_the_oracle_at_d512_l20():
+    """D=512 / L=20 / h=4 / 2 layers (the shape the headline is quoted on): fp64 oracle and the torch port (the CPU baseline)
+    vs the reference's loss, encoder output, the stored gradient subset and the masked top-k ids."""
+    import torch
+    from oracle import torch_port as TP
+    from oracle.make_golden import grad_subset
+    from tests.conftest import load_bench_shape_golden
+    g = load_bench_shape_golden()
+    c = g["cfg"]
+    loss, cache = O.sasrec_forward(g["params"], g["items"], g["masked_index"], c["layers"], c["h"], EPS, dtype=np.float64)
+    assert rel(loss, g["loss"]) < 2e-6
+    valid = g["masked_index"].astype(bool)
+    assert rel(cache["out"][valid], g["enc_out"][valid]) < 1e-4
+    grads = O.sasrec_backward(cache)
+    for k, ref in g["grads"].items():
+        got = grad_subset(k, grads[k], g["touched_rows"])
+        assert got.shape == ref.shape, k
+        if k.endswith("key.bias"):
+            assert np.abs(got).max() < 1e-9
+            continue
+        assert rel(got, ref) < 5e-5, (k, rel(got, ref))
+    P = {k: torch.from_numpy(v.copy()).requires_grad_() for k, v in g["params"].items()}
+    tl, _ = TP.forward_loss(P, torch.from_numpy(g["items"]), torch.from_numpy(g["masked_index"]), c["layers"], c["h"])
+    tl.backward()
+    assert abs(tl.item() - float(g["loss"])) < 1e-5 * float(g["loss"])
+    for k, ref in g["grads"].items():
+        if not k.endswith("key.bias"):
+            assert rel(grad_subset(k, P[k].grad.numpy(), g["touched_rows"]), ref) < 1e-4, k
+    scores, _ = O.sasrec_predict(g["params"], g["eval_item_seq"], c["layers"], c["h"], EPS)
+    assert rel(scores, g["eval_scores_raw"]) < 1e-4
+    _, idx = O.full_sort_topk(g["eval_scores_raw"], g["eval_hist_u"], g["eval_hist_i"], 10)
+    assert np.array_equal(idx, g["eval_topk_idx"])

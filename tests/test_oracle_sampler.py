@@ -69,3 +69,25 @@ def test_batch_builder_oracle_is_a_pure_function_of_seed_and_position():
     neg = np.concatenate([O.seq_batch_build(padded, sel, 1000, seed=s)[0][:, 1].ravel() for s in range(40)])
     neg = neg[neg != 0]
     assert abs(neg.mean() - 500) < 25          # uniform on [1, item_num - 1]
+
+
+def test_seq_train_sample_equals_the_reference_dataset_under_a_seeded_random():
+    """A1 pin: tests/golden/seqtrain_ref.npz holds what the UNMODIFIED SEQTrainDataset.__getitem__
+    (trainset.py:65-75) returned under random.seed(s) (oracle/make_golden.py::make_seqtrain_case); the oracle must
+    reproduce items AND negatives bit for bit from the same stream."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "seqtrain_ref.npz"))
+    n_cases = len([k for k in z.files if k.endswith("_meta")])
+    assert n_cases == 3
+    long_seen = False
+    for ci in range(n_cases):
+        item_num, L, n_seq, seed = (int(x) for x in z[f"c{ci}_meta"])
+        flat, offs = z[f"c{ci}_flat"], z[f"c{ci}_offs"]
+        rnd = random.Random(seed)                       # same Mersenne stream as random.seed(seed) + module functions
+        for i in range(n_seq):
+            seq = flat[offs[i]:offs[i + 1]]
+            long_seen |= len(seq) > L + 1
+            items, mask = O.seq_train_sample(seq, item_num, L, rnd)
+            assert np.array_equal(items, z[f"c{ci}_items"][i]), (ci, i)
+            assert np.array_equal(mask, z[f"c{ci}_mask"][i]), (ci, i)
+    assert long_seen                                    # windows longer than L+1 keep their tail (trainset.py:46-50)
