@@ -11,7 +11,9 @@ the reference's REC/trainer/trainer.py:116-125 on BASELINE.json configs[1] (IDNe
 L=20, 4 heads, 2 layers).  Batch per GPU is fixed (weak scaling); the table is row-sharded for N > 1.
 
 Prints ONE JSON line (rank 0).  `value` = whole-job sequences/s with inputs resident in HBM; `e2e` = the same
-through the public plugin API with pinned-HOST batches copied in every step and the loss read back every step;
+through the public plugin API with pinned-HOST batches copied in every step and the loss read back every step
+(at N = 1 both replay the captured step as one CUDA graph, which is what `cuda_graph: True` makes the Trainer do);
+`reference_batch` = the same step at the yaml's own train_batch_size (64);
 `roofline` = the embedding-gather kernel (BASELINE.json's named kernel) timed live with CUDA events inside the
 timed region; `roofline_kernels` = every kernel of ours, timed the same way in an extra pass; `roofline_score_topk` =
 the eval scoring call (tcgen05 GEMM + mask + top-k, the path's one tensor-bound kernel) timed alone; `cpu_baseline` =
@@ -99,6 +101,16 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
+def gather_traffic(B, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the gather kernel from the committed `ncu --set full` capture of
+    this very workload (profiles/gather_traffic.json, written by tools/ncu_traffic.py); None for other shapes."""
+    path = os.path.join(ROOT, "profiles", "gather_traffic.json")
+    if world != 1 or not os.path.exists(path):
+        return None
+    d = json.load(open(path))
+    return d.get("dram_bytes_per_launch") if d.get("batch") == B else None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -135,13 +147,18 @@ def run_reference(args, out):
     if rank != 0:
         return
     import torch
-    # bounded sample: calibrate the per-step batch so (steps + warmup) finishes in ~2 minutes
-    rate, ms, cores, _ = cpu_step_rate(128, 1, 1)
-    budget_s = 120.0
+    # all host cores at every N (torch.distributed.run exports OMP_NUM_THREADS=1 to its workers)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    # the GPU arm's own per-GPU batch, unless (steps + warmup) of it would not finish in ~4 minutes on this host: then the
+    # largest multiple of 64 that does (the bounded sample the contract allows; stated in `sample`)
+    rate, ms, cores, _ = cpu_step_rate(256, 1, 1, threads=threads)
+    budget_s = 240.0
     per_step = budget_s / max(args.steps + args.warmup, 1)
-    B_cpu = int(min(1024, max(64, (per_step * rate) // 64 * 64)))
-    rate, ms, cores, loss = cpu_step_rate(B_cpu, args.steps, args.warmup)
-    sample = f"{args.steps} steps x {B_cpu} sequences per step on {cores} host threads (torch {torch.__version__} CPU fp32)"
+    B_cpu = int(min(args.batch, max(64, (per_step * rate) // 64 * 64)))
+    rate, ms, cores, loss = cpu_step_rate(B_cpu, args.steps, args.warmup, threads=threads)
+    sample = (f"{args.steps} steps x {B_cpu} sequences per step (GPU arm: {args.batch}/GPU) on {cores} host threads "
+              f"(torch {torch.__version__} CPU fp32)")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "sequences/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -193,7 +210,7 @@ def run_ours(args, out):
     from pixelrec_b200.model.IDNet.sasrec import SASRec
     from pixelrec_b200.trainer.optim import FusedAdamW
 
-    torch.backends.cuda.matmul.allow_tf32 = True       # linear layers: cuBLAS TF32 (torch 1.10's default on Ampere)
+    torch.backends.cuda.matmul.allow_tf32 = True       # linear layers on TF32 tensor cores (torch 1.10's default on Ampere): pr_gemm_tf32
     c = C2
     B = args.batch
     torch.manual_seed(2020)
@@ -278,9 +295,6 @@ def run_ours(args, out):
     ops.PROFILE.update(on=False, events={})
     value = B * world * args.steps / (ms / 1e3)
 
-    if graphed is not None:
-        graphed.close()
-        step = eager_step
     # ---- timed region 2 (e2e): pinned-host batches copied in each step, loss read back each step
     e2e_next = {}
 
@@ -291,6 +305,8 @@ def run_ours(args, out):
         staged = e2e_next.pop(i, None) or look.stage(host[i % POOL])
         cur = look.acquire(staged)
         e2e_next[i + 1] = look.stage(host[(i + 1) % POOL])
+        if graphed is not None:              # what Trainer._train_epoch does with `cuda_graph: True`
+            return graphed(cur).item()
         opt.zero_grad()
         loss = model(cur)
         loss.backward()
@@ -301,13 +317,40 @@ def run_ours(args, out):
     ms_e2e = timed(e2e_step, args.steps)
     e2e = B * world * args.steps / (ms_e2e / 1e3)
 
-    # ---- extra pass: every kernel of ours, event-timed (roofline_kernels)
+    if graphed is not None:
+        graphed.close()
+        step = eager_step
+    # ---- extra pass: every kernel of ours, event-timed (roofline_kernels); always eager
     ops.PROFILE.update(on=True, names=None, events={})
     for i in range(min(args.steps, 5)):
         step(resident[i % POOL])
     torch.cuda.synchronize()
     prof = ops.profile_summary()
     ops.PROFILE.update(on=False, events={})
+
+    # ---- the reference's own batch size (train_batch_size: 64, overall/ID.yaml:19): launch-bound, so the graph replay matters
+    ref_batch = None
+    if world == 1 and args.batch != 64:
+        try:
+            small = []
+            for _ in range(POOL):
+                it_, mk_ = synth_batch(g, 64, c["N"], c["L"], perm, p)
+                small.append((torch.from_numpy(it_).to(dev), torch.from_numpy(mk_).to(dev)))
+            for i in range(10):
+                eager_loss = step(small[i % POOL])
+            del eager_loss
+            ms_eager = timed(lambda i: step(small[i % POOL]), 100) / 100
+            from pixelrec_b200.trainer.graph import GraphedTrainStep
+            g64 = GraphedTrainStep(model, opt, small[0])
+            for i in range(10):
+                g64(small[i % POOL])
+            ms_graph = timed(lambda i: g64(small[i % POOL]), 200) / 200
+            g64.close()
+            ref_batch = {"batch_per_gpu": 64, "value": 64 / (ms_graph / 1e3), "unit": "sequences/s", "ms_per_step": ms_graph,
+                         "eager_ms_per_step": ms_eager, "eager_value": 64 / (ms_eager / 1e3),
+                         "note": "same model and step at the yaml's train_batch_size; value = CUDA-graph replay, inputs resident"}
+        except Exception as ex:  # pragma: no cover
+            ref_batch = {"error": f"{type(ex).__name__}: {ex}"}
 
     xs = getattr(model.item_embedding, "exchange_status", lambda: 0)()
     if xs:
@@ -321,22 +364,30 @@ def run_ours(args, out):
             seq_e = torch.randn(B_e, c["D"], device=dev)
             hu = torch.arange(B_e, device=dev).repeat_interleave(c["L"])
             hi = torch.randint(1, c["N"], (B_e * c["L"],), device=dev)
-            for _ in range(3):
-                ops.score_topk(seq_e, W_full, k_top, hu, hi)
-            torch.cuda.synchronize()
-            evs = []
-            for _ in range(10):                      # the 199 MB table exceeds the 126 MB L2: every call streams it from HBM
-                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s_.record(); ops.score_topk(seq_e, W_full, k_top, hu, hi); e_.record()
-                evs.append((s_, e_))
-            torch.cuda.synchronize()
-            sc_ms = float(np.median([a.elapsed_time(b) for a, b in evs]))
+            wmax = ops.table_norm_max(W_full)
+
+            def med_ms(fn):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                evs = []
+                for _ in range(10):                  # the 199 MB table exceeds the 126 MB L2: every call streams it from HBM
+                    s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s_.record(); fn(); e_.record()
+                    evs.append((s_, e_))
+                torch.cuda.synchronize()
+                return float(np.median([a.elapsed_time(b) for a, b in evs]))
+            sc_ms = med_ms(lambda: ops.score_topk(seq_e, W_full, k_top, hu, hi))
+            ex_ms = med_ms(lambda: ops.score_topk_exact(seq_e, W_full, k_top, hu, hi, w_norm_max=wmax))
             pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1400.0) \
                 if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
             tf = 2.0 * B_e * c["N"] * c["D"] / sc_ms / 1e9
             score_line = {"kernel": "score_topk_kernel (pr_score_topk_f32, K9): mask kernels + tcgen05 GEMM/top-k + merge",
                           "bound": "tensor", "achieved": tf, "peak": pk, "unit": "TFLOP/s", "frac": tf / pk,
-                          "ms": sc_ms, "workload": f"B_e={B_e} users x N={c['N']} items x D={c['D']}, k={k_top}, {c['L']} history items masked per user",
+                          "ms": sc_ms, "ms_id_exact": ex_ms,
+                          "id_exact": "pr_score_topk_exact_f32 (Trainer.evaluate's default): 32 TF32 candidates per row re-scored "
+                                      "and ranked in fp32, proven complete or re-ranked over the catalog",
+                          "workload": f"B_e={B_e} users x N={c['N']} items x D={c['D']}, k={k_top}, {c['L']} history items masked per user",
                           "note": "kind::tf32 MMAs run at half the dense bf16 rate the peak was measured with; burst peak (kernel timed alone)"}
         except Exception as ex:  # pragma: no cover -- never lose the training line over the secondary measurement
             score_line = {"error": f"{type(ex).__name__}: {ex}"}
@@ -354,12 +405,26 @@ def run_ours(args, out):
         "bpr_fwd": 3 * B * L * D * 4, "bpr_bwd": 6 * B * L * D * 4,
         "act_fwd": 2 * B * L * 2 * D * 4, "act_bwd": 3 * B * L * 2 * D * 4,
     }
+    # loss kernels never read the rows of masked positions: count the valid ones of the batches that were timed
+    n_prof = max(min(args.steps, 5), 1)
+    valid = float(np.mean([int(resident[i % POOL][1].sum().item()) for i in range(n_prof)]))
+    alg["bpr_fwd"] = 3 * valid * D * 4
+    alg["bpr_bwd"] = 6 * valid * D * 4
+    if world > 1:                         # sharded lookup: three gathers of different sizes per step, no single per-launch figure
+        alg["gather_rows"] = None
+    gemm_flop = 96.0 * B * L * D * D      # forward + input-gradient + weight-gradient GEMMs of the 2 layers
+    _, tf_sustained, _ = peaks()
     kernels = {}
     for name, (n, mean_ms) in sorted(prof.items()):
-        entry = {"launches_per_step": n / max(min(args.steps, 5), 1), "ms": mean_ms}
+        entry = {"launches_per_step": n / n_prof, "ms": mean_ms}
         if alg.get(name):
             entry["GBps"] = alg[name] / mean_ms / 1e6
             entry["frac_of_hbm_peak"] = entry["GBps"] / hbm
+        if name == "gemm":
+            entry["TFLOPs"] = gemm_flop / (entry["launches_per_step"] * mean_ms) / 1e9
+            entry["frac_of_tf32_peak"] = entry["TFLOPs"] / (tf_sustained / 2.0)
+            entry["note"] = ("all linear-layer GEMMs of the step (pr_gemm_tf32); peak = half the measured sustained bf16 rate "
+                             "(kind::tf32 issues at half the bf16 rate)")
         kernels[name] = entry
     gather_gbps = alg["gather_rows"] / gather_ms / 1e6 if gather_n else None
     if world > 1:
@@ -370,7 +435,8 @@ def run_ours(args, out):
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (tf32 tensor-core linear layers, fp32 everywhere else)", "data": "synthetic",
         "config": workload_config(B, world, exchange=getattr(model.item_embedding, "exchange", None),
-                                  note="value: the step replayed as one CUDA graph; e2e and per-kernel passes eager" if args.graph else None),
+                                  note=("both timed regions replay the captured step as one CUDA graph (yaml `cuda_graph: True`); "
+                                        "the per-kernel pass is eager") if (args.graph and world == 1) else None),
         "e2e": {"value": e2e, "unit": "sequences/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
@@ -379,10 +445,7 @@ def run_ours(args, out):
         "roofline": {"kernel": "gather_rows_bulk_kernel (pr_gather_rows_f32, K1)", "bound": "hbm",
                      "achieved": gather_gbps, "peak": hbm, "unit": "GB/s",
                      "frac": (gather_gbps / hbm) if gather_gbps else None,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload (B=4096/GPU, N=1), one
-                     # `ncu --set full` capture: profiles/r01a_ncu_full_summary.md (146.17 MB read + 297.61 MB written; below
-                     # the algorithmic bytes because repeated ids hit L2 and part of the output is still in L2 at kernel end)
-                     "traffic": 443776512 if (B == 4096 and world == 1) else None,
+                     "traffic": gather_traffic(B, world),
                      "algorithmic_bytes_per_launch": alg["gather_rows"], "launch_ms": gather_ms if gather_n else None,
                      "launches_timed": gather_n, "peak_source": peak_src,
                      "note": "long-tail ids repeat inside a step, so part of the table reads hit L2: achieved can exceed the DRAM copy peak"},
@@ -390,6 +453,8 @@ def run_ours(args, out):
     }
     if score_line is not None:
         line["roofline_score_topk"] = score_line
+    if ref_batch is not None:
+        line["reference_batch"] = ref_batch
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             rate, cms, cores, _ = cpu_step_rate(1024, 3, 1)
@@ -431,8 +496,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="sequences per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--graph", action="store_true",
-                    help="N=1: replay the step as one CUDA graph (staged; dropout needs a -DPR_SEED_DEV build); `value` only")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="N=1 replays the captured step as one CUDA graph (trainer/graph.py, yaml `cuda_graph: True`) in both "
+                         "timed regions; this flag runs it eagerly instead")
+    ap.set_defaults(graph=True)
     ap.add_argument("--exchange", default=None, choices=["nccl", "p2p"],
                     help="N>1 row exchange of the sharded table: NCCL all_to_all (default) or peer-memory kernels (staged)")
     args = ap.parse_args()

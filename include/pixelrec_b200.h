@@ -245,6 +245,20 @@ PR_API int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float* W, 
 PR_API int pr_linear_tf32(const float* x, int64_t M, const float* W, int64_t N, int64_t K, const float* bias, int act, float* out,
                           float* pre, pr_stream_t stream);
 
+/* K9, id-exact: the ranking the reference computes on fp32 scores (collector.py:133).  Same fused TF32 pass as above as a
+ *   candidate generator (top-32 per row), then every candidate is re-scored in fp32 and ranked (ties: lower item id); a row whose
+ *   k-th fp32 score is not provably above everything outside its candidate list -- bound: last TF32 candidate value
+ *   + 1.25 * 2^-9 * |seq_out[row]| * max_j |W[j]| -- is re-ranked over the whole catalog in fp32 (rare; *n_fallback_rows, a device
+ *   int32, counts them; may be NULL).  k <= 16, N >= 32.  w_norm_max: device float holding max_j |W[j]| (pr_table_norm_max_f32;
+ *   compute it once per evaluation), or NULL to have it computed here.  topk_val are fp32 scores.
+ */
+PR_API size_t pr_score_topk_exact_workspace_bytes(int64_t B_e, int64_t N, int k);
+PR_API int pr_table_norm_max_f32(const float* W, int64_t N, int64_t D, float* out_max, pr_stream_t stream);
+PR_API int pr_score_topk_exact_f32(const float* seq_out, int64_t B_e, const float* W, int64_t N, int64_t D,
+                                   const int64_t* hist_u, const int64_t* hist_i, int64_t n_hist, int mask_col0, int k,
+                                   const float* w_norm_max, float* topk_val, int64_t* topk_idx, int32_t* n_fallback_rows,
+                                   void* workspace, size_t workspace_bytes, pr_stream_t stream);
+
 /* K5: the encoder's linear layers AND their backward on tcgen05 (csrc/gemm.cu): one persistent CTA-pair kernel
  *   (tcgen05.mma.cta_group::2, UMMA 256x256x8 TF32, TMEM double-buffered accumulators, TMA-fed 5-stage ring, TMA-store epilogue).
  *   replaces nn.Linear forward, REC/model/layers.py:586-588, :613, :666, :669, and autograd's two GEMMs per Linear.
@@ -261,8 +275,16 @@ PR_API int pr_linear_tf32(const float* x, int64_t M, const float* W, int64_t N, 
  *   bias [N] may be NULL.  colsum_partials (optional, [pr_gemm_colsum_rows(M), N], no bias): per-32-row column sums of `out`
  *   (bias gradient; reduce with pr_colsum_f32).  splits > 1 (PR_GEMM_STORE without bias only): `out` is [splits, M, N], slab s holding
  *   the partial sum over k-blocks [s*ceil(K/32/splits), ...); pr_gemm_splitk_reduce_f32 adds the slabs in ascending order.
- *   K % 32 == 0, N % 4 == 0, M % 4 == 0 for an MN-major A, all pointers 16-byte aligned, out / out2 / aux dense [M, N].
+ *   flags bit 0 (PR_GEMM_DEBIAS): the tensor core reads fp32 operands as TF32 by TRUNCATING the low 13 mantissa bits: an operand
+ *   with mantissa m in [1, 2) loses on average 2^-11 / m of its value, i.e. 0.72 * 2^-11 = 3.5e-4 for log-uniform mantissas, so
+ *   every product is ~7.1e-4 too small (measured on Gaussian operands: -7.16e-4) -- a systematic shrink per GEMM that compounds
+ *   through a chain of layers (measured: -0.29 % on a weight gradient) where round-to-nearest errors would average out.  With
+ *   the flag the accumulator is multiplied by 1.00071 before the epilogue: the error becomes zero-mean with the variance of
+ *   round-to-nearest TF32.  Leave it off for operands that are exactly representable in TF32 (nothing is truncated then).
+ *   N % 4 == 0, K % 4 == 0 for a K-major operand (a K tail is zero-filled by TMA), M % 4 == 0 for an MN-major A, all pointers
+ *   16-byte aligned, out / out2 / aux dense [M, N].
  */
+#define PR_GEMM_DEBIAS 1
 #define PR_GEMM_STORE 0
 #define PR_GEMM_ADD 1
 #define PR_GEMM_ACT 2
@@ -270,7 +292,7 @@ PR_API int pr_linear_tf32(const float* x, int64_t M, const float* W, int64_t N, 
 PR_API int pr_gemm_colsum_rows(int64_t M);
 PR_API int pr_gemm_tf32(const float* A, int a_mn, int64_t lda, const float* B, int b_mn, int64_t ldb, int64_t M, int64_t N,
                         int64_t K, const float* bias, const float* aux, int epi, int act, float* out, float* out2, int splits,
-                        float* colsum_partials, pr_stream_t stream);
+                        float* colsum_partials, int flags, pr_stream_t stream);
 PR_API int pr_gemm_splitk_reduce_f32(const float* partials, int splits, int64_t n, float* out, pr_stream_t stream);
 
 /* K9 with fp16 operands (staged): fp16 has the 10 explicit mantissa bits of TF32 (and is rounded to nearest, where the TF32

@@ -66,6 +66,9 @@ struct GemmArgs {
     float* colsum;                         // [n_part_rows, N] or null: per-warp column sums of the stored output
     int has_out2;
     int stages, obuf;                      // ring depth; out-staging buffers per epilogue warp (1 or 2)
+    int debias;                            // scale the accumulator by 1.00071 (TF32 truncation shrink): see pr_gemm_tf32 in the header
+    int debug;                             // PR_GEMM_DEBUG (timing experiments only, results are garbage): 1 = no output stores,
+                                           // 2 = no operand loads (MMAs on whatever the ring holds)
 };
 
 // ---- PTX forms of the CTA-pair pipeline (cute/arch/copy_sm100_tma.hpp, mma_sm100_umma.hpp, cutlass/arch/barrier.h)
@@ -199,16 +202,21 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tf32_kernel(const __grid_c
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (one thread in every CTA)
         if (lane == 0) {
-            long long it = 0;
+            // ring position as (stage, phase) counters: no division on the per-k-block path of any role
+            int s = 0;
+            uint32_t ph = 0;
             for (long long w = group; w < n_items; w += n_groups) {
                 const GmItem wi = gm_item(a, w);
-                const int m0 = wi.m_tile * (GM_BM * CG) + rank * GM_BM;             // this CTA's rows of A
+                const int m0 = (a.debug & 8) ? rank * GM_BM : wi.m_tile * (GM_BM * CG) + rank * GM_BM;   // this CTA's rows of A
                 const int n0 = wi.n_tile * GM_BN + rank * C::B_ROWS;                // this CTA's rows of B
-                for (int kb = 0; kb < wi.nkb; ++kb, ++it) {
-                    const int s = (int)(it % NST);
-                    const int k0 = (wi.kb0 + kb) * GM_BK;
-                    mbar_wait(&empty_bar[s], (uint32_t)(((it / NST) & 1) ^ 1));
+                for (int kb = 0; kb < wi.nkb; ++kb, s = (s + 1 == NST) ? 0 : s + 1, ph ^= (s == 0) ? 1u : 0u) {
+                    const int k0 = (a.debug & 8) ? 0 : (wi.kb0 + kb) * GM_BK;      // 8 = always the same (L2-hot) k-block
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
                     unsigned char* st = ring + (size_t)s * C::STAGE_BYTES;
+                    if (a.debug & 2) {
+                        if (rank == 0) mbar_arrive(&full_bar[s]);
+                        continue;
+                    }
                     if (CG == 2) {
                         // the pair leader's barrier collects the bytes of both CTAs
                         const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
@@ -249,19 +257,23 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tf32_kernel(const __grid_c
             const uint32_t idesc = gm_idesc(GM_BM * CG, GM_BN, a.a_mn, a.b_mn);
             const uint32_t a_step = a.a_mn ? (1024u >> 4) : (32u >> 4);            // 8 k-rows: two 512-B groups / 32 bytes along the row
             const uint32_t b_step = a.b_mn ? (1024u >> 4) : (32u >> 4);
-            long long it = 0, tc = 0;
+            // descriptors differ between stages only in their 14-bit address field: add the stage offset to stage 0's
+            const uint32_t ring0 = smem_u32(ring);
+            const uint64_t adesc0 = gm_desc(ring0, a.a_mn), bdesc0 = gm_desc(ring0 + GM_A_BYTES, a.b_mn);
+            constexpr uint32_t stage_step = (uint32_t)C::STAGE_BYTES >> 4;
+            int s = 0;
+            uint32_t ph = 0, tc = 0;
             for (long long w = group; w < n_items; w += n_groups, ++tc) {
                 const GmItem wi = gm_item(a, w);
-                const int buf = (int)(tc & 1);
-                mbar_wait(&tempty_bar[buf], (uint32_t)(((tc >> 1) & 1) ^ 1));       // both epilogues drained this TMEM buffer
+                const int buf = (int)(tc & 1u);
+                mbar_wait(&tempty_bar[buf], ((tc >> 1) & 1u) ^ 1u);                 // both epilogues drained this TMEM buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * GM_BN;
-                for (int kb = 0; kb < wi.nkb; ++kb, ++it) {
-                    const int s = (int)(it % NST);
-                    mbar_wait(&full_bar[s], (uint32_t)((it / NST) & 1));
+                for (int kb = 0; kb < wi.nkb; ++kb, s = (s + 1 == NST) ? 0 : s + 1, ph ^= (s == 0) ? 1u : 0u) {
+                    mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(ring + (size_t)s * C::STAGE_BYTES);
-                    const uint64_t adesc = gm_desc(sa, a.a_mn), bdesc = gm_desc(sa + GM_A_BYTES, a.b_mn);
+                    const uint64_t adesc = adesc0 + (uint64_t)(stage_step * (uint32_t)s);
+                    const uint64_t bdesc = bdesc0 + (uint64_t)(stage_step * (uint32_t)s);
 #pragma unroll
                     for (int k4 = 0; k4 < GM_BK / 8; ++k4) {
                         if (CG == 2) umma_tf32_cg2(d_tmem, adesc + a_step * k4, bdesc + b_step * k4, idesc, (kb | k4) ? 1u : 0u);
@@ -352,6 +364,10 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tf32_kernel(const __grid_c
                         else mbar_arrive(&tempty_bar[buf]);
                     }
                 }
+                if (a.debias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= 1.00071f;
+                }
                 if (a.bias) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -368,7 +384,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tf32_kernel(const __grid_c
                 } else if (a.epi == GM_EPI_ACT_BWD) {
                     if (a.act == PR_ACT_GELU) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] *= act_df(x[j], PR_ACT_GELU);
+                        for (int j = 0; j < 32; ++j) v[j] *= dgelu_fast(x[j]);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] *= act_df(x[j], a.act);
@@ -391,7 +407,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tf32_kernel(const __grid_c
                 if (a.epi == GM_EPI_ACT) {
                     if (a.act == PR_ACT_GELU) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = act_f(v[j], PR_ACT_GELU);
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = act_f(v[j], a.act);
@@ -399,6 +415,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tf32_kernel(const __grid_c
                 }
                 // staging buffer free again once the TMA store that last read it has done so (two buffers: the store before last)
                 float* ost = ost0 + ob * obuf_stride;
+                if (a.debug & 4) continue;                                          // 4 = no staging at all (TMEM drain only)
                 if (lane == 0) {
                     if (a.obuf > 1 && !a.has_out2) bulk_wait_read<1>();
                     else bulk_wait_read<0>();
@@ -411,7 +428,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tf32_kernel(const __grid_c
                         make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) {
+                if (lane == 0 && !(a.debug & 1)) {
                     if (a.splits > 1) tma_store_3d(&tmOut, ost, col0, row0, wi.split);
                     else tma_store_2d(&tmOut, ost, col0, row0);
                     bulk_commit();
@@ -552,7 +569,7 @@ extern "C" int pr_gemm_colsum_rows(int64_t M) {
 
 extern "C" int pr_gemm_tf32(const float* A, int a_mn, int64_t lda, const float* B, int b_mn, int64_t ldb, int64_t M, int64_t N,
                             int64_t K, const float* bias, const float* aux, int epi, int act, float* out, float* out2,
-                            int splits, float* colsum_partials, pr_stream_t stream_) {
+                            int splits, float* colsum_partials, int flags, pr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PR_CHECK_ARG(M > 0 && N > 0 && K > 0, "pr_gemm_tf32: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
     // a K tail needs no code: the tensor maps carry the true K and TMA zero-fills what lies beyond it
@@ -582,6 +599,7 @@ extern "C" int pr_gemm_tf32(const float* A, int a_mn, int64_t lda, const float* 
     PR_CHECK_ARG(a.splits == splits, "pr_gemm_tf32: splits=%d does not divide %d k-blocks into non-empty parts", splits, a.kb_total);
     a.a_mn = a_mn ? 1 : 0; a.b_mn = b_mn ? 1 : 0;
     a.epi = epi; a.act = act; a.M = M; a.N = N; a.bias = bias; a.colsum = colsum_partials; a.has_out2 = out2 ? 1 : 0;
+    a.debias = (flags & 1) ? 1 : 0;
     {
         // deepest ring that fits beside the staging buffers (PR_GEMM_STAGES / PR_GEMM_OBUF override, for A/B runs)
         const int stage_bytes = (cg == 2) ? GemmCfg<2>::STAGE_BYTES : GemmCfg<1>::STAGE_BYTES;
@@ -593,6 +611,12 @@ extern "C" int pr_gemm_tf32(const float* A, int a_mn, int64_t lda, const float* 
             const char* f = getenv("PR_GEMM_STAGES");
             env_stages = f ? std::max(2, std::min(GM_MAX_STAGES, atoi(f))) : 0;
         }
+        static int env_debug = -1;
+        if (env_debug < 0) {
+            const char* d = getenv("PR_GEMM_DEBUG");
+            env_debug = d ? atoi(d) : 0;
+        }
+        a.debug = env_debug;
         a.obuf = env_obuf ? env_obuf : 1;
         int st = GM_MAX_STAGES;
         while (st > 2 && gm_smem_bytes(stage_bytes, st, a.obuf, aux_st) > (size_t)GM_SMEM_LIMIT) --st;

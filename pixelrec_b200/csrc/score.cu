@@ -386,6 +386,217 @@ extern "C" int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float*
     return PR_OK;
 }
 
+// ---- id-exact ranking (collector.py:133 ranks fp32 scores): TF32 candidates re-scored in fp32 ---------------------------------
+// The tensor core reads TF32 (operands truncated to 10 mantissa bits), so two items whose fp32 scores differ by less than the
+// TF32 error can come out in the wrong order (0.7 % of the top-10 ids at C2, profiles/r01f).  Exact mode keeps that pipeline as a
+// candidate generator: (1) top-32 per row by TF32 score; (2) one warp per row recomputes the 32 scores in fp32 and ranks them;
+// (3) proof of completeness: an item outside the list has TF32 score <= v32 (the list's last TF32 value) and hence fp32 score
+// <= v32 + eps, eps = 1.25 * 2^-9 * |seq_row| * max_j |W_j| (truncation of both operands, Cauchy-Schwarz) -- if the k-th fp32
+// score is above that, the fp32 top-k is certain; (4) rows that fail the test (near-ties deeper than 32, rare) are flagged and
+// re-ranked over the whole catalog in fp32 by score_exact_rows_kernel.
+namespace pr {
+
+constexpr int SCX_C = 32;                 // candidates per row
+
+// out_max (zero-initialised) <- max_j |W_j|   (non-negative floats order like their bit patterns)
+__global__ void __launch_bounds__(256) rownorm_max_kernel(const float* __restrict__ W, long long N, int D4, float* __restrict__ out_max) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+    float best = 0.f;
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < N; r += warps) {
+        const float4* p = reinterpret_cast<const float4*>(W) + r * D4;
+        float s = 0.f;
+        for (int c = lane; c < D4; c += 32) {
+            const float4 v = __ldg(p + c);
+            s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+        best = fmaxf(best, warp_sum(s));
+    }
+    if (lane == 0) atomicMax(reinterpret_cast<int*>(out_max), __float_as_int(sqrtf(best)));
+}
+
+// fp32 dot of two rows, the summation order exact mode defines: lane-strided float4 partial sums, xor-shuffle reduction
+__device__ __forceinline__ float warp_dot(const float4* __restrict__ a, const float4* __restrict__ b, int D4, int lane) {
+    float s = 0.f;
+    for (int c = lane; c < D4; c += 32) {
+        const float4 x = a[c], y = __ldg(b + c);
+        s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+    }
+    return warp_sum(s);
+}
+
+__global__ void __launch_bounds__(128) score_rescore_kernel(const float* __restrict__ seq, const float* __restrict__ W, int D4,
+                                                            long long B_e, int k, const float* __restrict__ cand_val,
+                                                            const long long* __restrict__ cand_idx,
+                                                            const float* __restrict__ w_norm_max, float* __restrict__ out_val,
+                                                            long long* __restrict__ out_idx, int* __restrict__ flagged) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= B_e) return;
+    const float4* a = reinterpret_cast<const float4*>(seq) + row * D4;
+    const long long my_id = cand_idx[row * SCX_C + lane];
+    const float v_last = cand_val[row * SCX_C + SCX_C - 1];
+    const bool list_full = cand_idx[row * SCX_C + SCX_C - 1] >= 0;
+    float my = -INFINITY;
+    for (int c = 0; c < SCX_C; ++c) {
+        const long long id = __shfl_sync(0xffffffffu, my_id, c);
+        if (id < 0) break;                                            // the list is sorted: the rest is empty too
+        const float d = warp_dot(a, reinterpret_cast<const float4*>(W) + id * D4, D4, lane);
+        if (lane == c) my = d;
+    }
+    const float an = sqrtf(warp_dot(a, a, D4, lane));
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < SCX_C; ++j) {
+        const float sj = __shfl_sync(0xffffffffu, my, j);
+        const long long ij = __shfl_sync(0xffffffffu, my_id, j);
+        if (ij >= 0 && my_id >= 0 && (sj > my || (sj == my && ij < my_id))) ++rank;
+    }
+    if (my_id < 0) rank = SCX_C;                                      // empty slots sort last
+    if (rank < k) {
+        out_val[row * k + rank] = my;
+        out_idx[row * k + rank] = my_id;
+    }
+    const unsigned valid = __ballot_sync(0xffffffffu, my_id >= 0);
+    const int n_valid = __popc(valid);
+    if (lane >= n_valid && lane < k) {                                // fewer unmasked items than k
+        out_val[row * k + lane] = -INFINITY;
+        out_idx[row * k + lane] = -1;
+    }
+    // completeness test against everything that is NOT in the list
+    const unsigned kth_lane = __ballot_sync(0xffffffffu, rank == k - 1);
+    const float s_k = kth_lane ? __shfl_sync(0xffffffffu, my, __ffs((int)kth_lane) - 1) : -INFINITY;
+    const float eps = 1.25f * 0.001953125f * an * w_norm_max[0];
+    if (lane == 0 && list_full && !(s_k > v_last + eps)) {
+        const int pos = atomicAdd(flagged, 1);
+        flagged[1 + pos] = (int)row;
+    }
+}
+
+// exact fp32 ranking of one flagged row over the whole catalog (one CTA per row; rare path)
+template <int K>
+__global__ void __launch_bounds__(256) score_exact_rows_kernel(const float* __restrict__ seq, const float* __restrict__ W, int D4,
+                                                               long long N, int k, const uint32_t* __restrict__ mask, int n_words,
+                                                               const int* __restrict__ flagged, float* __restrict__ out_val,
+                                                               long long* __restrict__ out_idx) {
+    extern __shared__ __align__(16) unsigned char sx_smem[];
+    float4* a_s = reinterpret_cast<float4*>(sx_smem);                                  // [D4]
+    float* lv = reinterpret_cast<float*>(a_s + D4);                                     // [8 warps][K]
+    int* li = reinterpret_cast<int*>(lv + 8 * K);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_flag = flagged[0];
+    for (int f = blockIdx.x; f < n_flag; f += gridDim.x) {
+        const long long row = flagged[1 + f];
+        __syncthreads();
+        for (int c = threadIdx.x; c < D4; c += blockDim.x) a_s[c] = reinterpret_cast<const float4*>(seq)[row * D4 + c];
+        __syncthreads();
+        float val[K];
+        int idx[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) { val[i] = -INFINITY; idx[i] = -1; }
+        const uint32_t* mrow = mask + (size_t)row * n_words;
+        for (long long i = warp; i < N; i += 8) {                                       // ascending ids: ties keep the lower id
+            if ((mrow[i >> 5] >> (i & 31)) & 1u) continue;
+            const float d = warp_dot(a_s, reinterpret_cast<const float4*>(W) + i * D4, D4, lane);
+            if (d > val[K - 1]) topk_insert<K>(val, idx, d, (int)i);                   // every lane keeps the same list
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < K; ++i) { lv[warp * K + i] = val[i]; li[warp * K + i] = idx[i]; }
+        }
+        __syncthreads();
+        if (warp == 0) {                                                               // merge 8 x K candidates: k rounds of arg-max
+            for (int r = 0; r < k; ++r) {
+                float bv = -INFINITY;
+                int bi = 0x7fffffff, bs = -1;
+                for (int c = lane; c < 8 * K; c += 32) {
+                    const float v = lv[c];
+                    const int id = li[c];
+                    if (id >= 0 && (v > bv || (v == bv && id < bi))) { bv = v; bi = id; bs = c; }
+                }
+                float wv = bv;
+                int wi = bi;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+                    if (ov > wv || (ov == wv && oi < wi)) { wv = ov; wi = oi; }
+                }
+                if (bs >= 0 && wi == bi) li[bs] = -1;                                  // consumed (ids are unique)
+                __syncwarp();
+                if (lane == 0) {
+                    const bool none = (wi == 0x7fffffff);
+                    out_val[row * k + r] = none ? -INFINITY : wv;
+                    out_idx[row * k + r] = none ? -1 : (long long)wi;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace pr
+
+static size_t scx_extra_bytes(int64_t B_e) {      // top-32 (val, idx) per row + [count | flagged rows] + max norm
+    return ((size_t)B_e * SCX_C * 12 + ((size_t)B_e + 2) * 4 + 16 + 255) / 256 * 256;
+}
+
+extern "C" size_t pr_score_topk_exact_workspace_bytes(int64_t B_e, int64_t N, int k) {
+    if (B_e <= 0 || N <= 0 || k <= 0 || k > 16) return 0;
+    return score_plan(B_e, N, SCX_C).total + scx_extra_bytes(B_e);
+}
+
+extern "C" int pr_table_norm_max_f32(const float* W, int64_t N, int64_t D, float* out_max, pr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PR_CHECK_ARG(W && out_max && N > 0 && D > 0 && D % 4 == 0 && aligned16(W), "pr_table_norm_max_f32: bad arguments");
+    PR_CUDA_CALL(cudaMemsetAsync(out_max, 0, 4, stream));
+    const int grid = (int)std::min<long long>((N + 7) / 8, (long long)sm_count() * 8);
+    rownorm_max_kernel<<<grid, 256, 0, stream>>>(W, N, (int)(D / 4), out_max);
+    PR_CUDA_LAUNCH_CHECK("rownorm_max_kernel");
+    return PR_OK;
+}
+
+extern "C" int pr_score_topk_exact_f32(const float* seq_out, int64_t B_e, const float* W, int64_t N, int64_t D,
+                                       const int64_t* hist_u, const int64_t* hist_i, int64_t n_hist, int mask_col0, int k,
+                                       const float* w_norm_max, float* topk_val, int64_t* topk_idx, int32_t* n_fallback_rows,
+                                       void* workspace, size_t workspace_bytes, pr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PR_CHECK_ARG(k >= 1 && k <= 16 && k <= N, "pr_score_topk_exact_f32: k=%d outside [1, min(16, N)]", k);
+    PR_CHECK_ARG(B_e > 0 && N > 0 && D > 0 && D % SC_BK == 0, "pr_score_topk_exact_f32: bad shape B_e=%lld N=%lld D=%lld",
+                 (long long)B_e, (long long)N, (long long)D);
+    PR_CHECK_ARG(seq_out && W && topk_val && topk_idx && workspace, "pr_score_topk_exact_f32: null pointer");
+    const size_t need = pr_score_topk_exact_workspace_bytes(B_e, N, k);
+    PR_CHECK_ARG(workspace_bytes >= need, "pr_score_topk_exact_f32: workspace %zu < required %zu", workspace_bytes, need);
+    const ScorePlan p = score_plan(B_e, N, SCX_C);
+    char* extra = (char*)workspace + p.total;
+    float* c_val = (float*)extra;
+    long long* c_idx = (long long*)(extra + (size_t)B_e * SCX_C * 4);
+    int* flagged = (int*)(extra + (size_t)B_e * SCX_C * 12);
+    float* own_max = (float*)(flagged + B_e + 2);
+    // (1) TF32 candidates: the ordinary fused pass with 32-deep lists
+    PR_CHECK_ARG(N >= SCX_C, "pr_score_topk_exact_f32: N=%lld < %d candidates (use pr_score_topk_f32)", (long long)N, SCX_C);
+    int rc = pr_score_topk_f32(seq_out, B_e, W, N, D, hist_u, hist_i, n_hist, mask_col0, SCX_C, c_val, (int64_t*)c_idx,
+                               workspace, p.total, stream_);
+    if (rc) return rc;
+    if (!w_norm_max) {
+        rc = pr_table_norm_max_f32(W, N, D, own_max, stream_);
+        if (rc) return rc;
+        w_norm_max = own_max;
+    }
+    PR_CUDA_CALL(cudaMemsetAsync(flagged, 0, 4, stream));
+    score_rescore_kernel<<<(int)((B_e + 3) / 4), 128, 0, stream>>>(seq_out, W, (int)(D / 4), B_e, k, c_val, c_idx, w_norm_max,
+                                                                   topk_val, (long long*)topk_idx, flagged);
+    PR_CUDA_LAUNCH_CHECK("score_rescore_kernel");
+    // (4) flagged rows: whole-catalog fp32 ranking (grid sized for the worst case; CTAs without a row exit at once)
+    const size_t smem = (size_t)D * 4 + 8 * 16 * 8;
+    const int grid = (int)std::min<long long>(B_e, (long long)sm_count() * 4);
+    PR_CUDA_CALL(cudaFuncSetAttribute(score_exact_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    score_exact_rows_kernel<16><<<grid, 256, smem, stream>>>(seq_out, W, (int)(D / 4), N, k, (const uint32_t*)workspace, p.n_words,
+                                                             flagged, topk_val, (long long*)topk_idx);
+    PR_CUDA_LAUNCH_CHECK("score_exact_rows_kernel");
+    if (n_fallback_rows) PR_CUDA_CALL(cudaMemcpyAsync(n_fallback_rows, flagged, 4, cudaMemcpyDeviceToDevice, stream));
+    return PR_OK;
+}
+
 // ---- full-catalog softmax cross-entropy (extension: the reference trains with sampled negatives, sasrec.py:88-92) ---------
 extern "C" size_t pr_score_ce_workspace_bytes(int64_t B_e, int64_t N) {
     if (B_e <= 0 || N <= 0) return 0;

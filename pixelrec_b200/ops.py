@@ -572,6 +572,9 @@ WGRAD_SPLIT = int(os.environ.get("PR_WGRAD_SPLIT", "8"))
 LINEAR_IMPL = os.environ.get("PR_LINEAR", "tc").lower()
 
 
+FUSE_ACT_BWD = os.environ.get("PR_FUSE_ACT_BWD", "1") == "1"
+
+
 def _use_tc(*dims):
     return LINEAR_IMPL == "tc" and bool(torch.backends.cuda.matmul.allow_tf32) and all(d % 4 == 0 for d in dims)
 
@@ -579,7 +582,7 @@ def _use_tc(*dims):
 def _linear_fwd(x2, w, b):
     """x2 [M, K] @ w[N, K]^T + b   (nn.Linear, layers.py:586-588, 613, 669)"""
     if _use_tc(x2.shape[1], w.shape[0]):
-        return gemm(x2, w, bias=b)
+        return gemm(x2, w, bias=b, debias=True)
     return torch.addmm(b, x2, w.t())
 
 
@@ -587,8 +590,8 @@ def _linear_dgrad(dy2, w, add=None):
     """dy2 [M, N] @ w[N, K] (+ add): the input gradient of nn.Linear; `add` folds a residual gradient in"""
     if _use_tc(w.shape[0], w.shape[1]):
         if add is None:
-            return gemm(dy2, w, b_mn=True)
-        return gemm(dy2, w, b_mn=True, aux=add, epi=GEMM_ADD)
+            return gemm(dy2, w, b_mn=True, debias=True)
+        return gemm(dy2, w, b_mn=True, aux=add, epi=GEMM_ADD, debias=True)
     return dy2.mm(w) if add is None else torch.addmm(add, dy2, w)
 
 
@@ -607,7 +610,7 @@ def _wgrad(dy2, x2):
     and stays deterministic."""
     M = dy2.shape[0]
     if _use_tc(dy2.shape[1], x2.shape[1]):
-        return gemm(dy2, x2, a_mn=True, b_mn=True, splits=_wgrad_splits(dy2.shape[1], x2.shape[1], M))
+        return gemm(dy2, x2, a_mn=True, b_mn=True, splits=_wgrad_splits(dy2.shape[1], x2.shape[1], M), debias=True)
     S = WGRAD_SPLIT
     if S > 1 and M % S == 0 and M // S >= 2048:
         return torch.bmm(dy2.view(S, M // S, -1).transpose(1, 2), x2.view(S, M // S, -1)).sum(0)
@@ -639,7 +642,7 @@ class TransformerLayerFn(torch.autograd.Function):
         h = _linear_fwd(ctxt.view(B * L, D), wo, bo)                                   # :613
         a, mean1, rstd1 = _raw_add_ln_fwd(h, x2, g1, be1, eps, p_hid, seed, site + 1)  # :614-615
         if _use_tc(a.shape[1], w1.shape[0]):                                          # dense_1 + activation in ONE kernel (h1 and act(h1) both kept)
-            gl, h1 = gemm(a, w1, bias=b1, epi=GEMM_ACT, act=act, want_pre=True)        # :666-667
+            gl, h1 = gemm(a, w1, bias=b1, epi=GEMM_ACT, act=act, want_pre=True, debias=True)   # :666-667
         else:
             h1 = torch.addmm(b1, a, w1.t())                                            # :666
             gl = torch.empty_like(h1)
@@ -662,8 +665,12 @@ class TransformerLayerFn(torch.autograd.Function):
         # ---- feed-forward block
         dh2, da_res, dg2, dbe2, db2 = _raw_add_ln_bwd_bias(dy, h2, a, g2, mean2, rstd2, p_hid, seed, site + 2)
         dw2 = _wgrad(dh2, gl)
-        dgl = _linear_dgrad(dh2, w2)
-        dh1, db1 = _raw_act_bwd_bias(h1, dgl, act)
+        if _use_tc(w2.shape[0], w2.shape[1]) and FUSE_ACT_BWD:
+            # input gradient of dense_2, the activation's backward and the bias gradient of dense_1 in one kernel
+            dh1, db1 = gemm(dh2, w2, b_mn=True, aux=h1, epi=GEMM_ACT_BWD, act=act, want_colsum=True, debias=True)
+        else:
+            dgl = _linear_dgrad(dh2, w2)
+            dh1, db1 = _raw_act_bwd_bias(h1, dgl, act)
         dw1 = _wgrad(dh1, a)
         da = _linear_dgrad(dh1, w1, add=da_res)                            # residual grad folded into the GEMM epilogue
         # ---- attention block
@@ -711,6 +718,45 @@ def score_topk(seq_out, item_feature, k, hist_u=None, hist_i=None, mask_col0=Tru
     return val, idx
 
 
+def table_norm_max(item_feature):
+    """device scalar max_j |item_feature[j]| -- the bound score_topk_exact needs; compute once per evaluation"""
+    _req(item_feature, torch.float32, "item_feature")
+    out = torch.empty(1, device=item_feature.device, dtype=torch.float32)
+    with _prof("table_norm_max", item_feature):
+        _lib.check(_L().pr_table_norm_max_f32(_p(item_feature), item_feature.shape[0], item_feature.shape[1], _p(out),
+                                              _stream(item_feature)), "pr_table_norm_max_f32")
+    _count()
+    return out
+
+
+def score_topk_exact(seq_out, item_feature, k, hist_u=None, hist_i=None, mask_col0=True, w_norm_max=None):
+    """score_topk whose ids are those of an fp32 ranking (collector.py:133): TF32 tensor-core pass for 32 candidates per row,
+    fp32 re-score + rank, whole-catalog fp32 fallback for rows that cannot be proven complete.  k <= 16, N >= 32.
+    Returns (values, indices, n_fallback_rows [1] int32 on the device)."""
+    _req(seq_out, torch.float32, "seq_out")
+    _req(item_feature, torch.float32, "item_feature")
+    B_e, D = seq_out.shape
+    N = item_feature.shape[0]
+    n_hist = 0
+    if hist_u is not None and hist_u.numel():
+        _req(hist_u, torch.int64, "hist_u"); _req(hist_i, torch.int64, "hist_i")
+        n_hist = hist_u.numel()
+    ws_bytes = _L().pr_score_topk_exact_workspace_bytes(B_e, N, k)
+    if ws_bytes == 0 or N < 32:
+        raise _lib.PixelRecB200Error(f"score_topk_exact: unsupported shape B_e={B_e} N={N} k={k} (k <= 16, N >= 32)")
+    ws = torch.empty(ws_bytes, device=seq_out.device, dtype=torch.uint8)
+    val = torch.empty(B_e, k, device=seq_out.device, dtype=torch.float32)
+    idx = torch.empty(B_e, k, device=seq_out.device, dtype=torch.int64)
+    nfb = torch.zeros(1, device=seq_out.device, dtype=torch.int32)
+    with _prof("score_topk_exact", seq_out):
+        _lib.check(_L().pr_score_topk_exact_f32(_p(seq_out), B_e, _p(item_feature), N, D, _p(hist_u) if n_hist else None,
+                                                _p(hist_i) if n_hist else None, n_hist, int(bool(mask_col0)), int(k),
+                                                _p(w_norm_max), _p(val), _p(idx), _p(nfb), _p(ws), ws_bytes, _stream(seq_out)),
+                   "pr_score_topk_exact_f32")
+    _count((4 if n_hist else 3) + 2 + (0 if w_norm_max is not None else 1))
+    return val, idx, nfb
+
+
 def linear_tc(x, weight, bias=None, act=None, want_pre=False):
     """y = act(x @ weight.T + bias) on the tcgen05 pipeline (pr_linear_tf32; staged alternative to cuBLAS addmm + pr_act_fwd).
     x [..., K], weight [N, K] (nn.Linear layout).  act: None | 'gelu' | 'relu'.  want_pre: also return the pre-activation."""
@@ -732,11 +778,12 @@ GEMM_STORE, GEMM_ADD, GEMM_ACT, GEMM_ACT_BWD = 0, 1, 2, 3
 
 
 def gemm(A, B, a_mn=False, b_mn=False, bias=None, aux=None, epi=GEMM_STORE, act=None, out=None, want_pre=False, splits=1,
-         want_colsum=False):
+         want_colsum=False, debias=False):
     """out[M, N] = epilogue(A . B^T) on the CTA-pair tcgen05 GEMM (pr_gemm_tf32, csrc/gemm.cu) -- forward, input-gradient
     and weight-gradient GEMMs of nn.Linear (REC/model/layers.py:586-588, 613, 666, 669) without a transposed copy:
       A: [M, K] (a_mn=False) or [K, M] (a_mn=True);  B: [N, K] (b_mn=False, nn.Linear weight layout) or [K, N] (b_mn=True).
     epi / act / aux / want_pre / want_colsum: see include/pixelrec_b200.h.  splits > 1: split-K, reduced here in fixed order.
+    debias: compensate the systematic shrink of TF32 operand truncation (PR_GEMM_DEBIAS; the layer path turns it on).
     Returns out, or (out, pre) with want_pre, or (out, colsum [N]) with want_colsum."""
     _req(A, torch.float32, "A")
     _req(B, torch.float32, "B")
@@ -765,7 +812,8 @@ def gemm(A, B, a_mn=False, b_mn=False, bias=None, aux=None, epi=GEMM_STORE, act=
         dst = torch.empty(splits, M, N, device=dev, dtype=torch.float32)
     with _prof("gemm", A):
         _lib.check(L_.pr_gemm_tf32(_p(A), int(a_mn), A.stride(0), _p(B), int(b_mn), B.stride(0), M, N, K, _p(bias), _p(aux),
-                                   int(epi), act_id, _p(dst), _p(pre), int(splits), _p(partials), _stream(A)), "pr_gemm_tf32")
+                                   int(epi), act_id, _p(dst), _p(pre), int(splits), _p(partials), int(bool(debias)), _stream(A)),
+                   "pr_gemm_tf32")
     _count()
     if splits > 1:
         with _prof("gemm_splitk_reduce", A):

@@ -100,6 +100,7 @@ class Trainer:
         self.evaluator = Evaluator(config)
         self.item_feature = None
         self.item_feature_f16 = None
+        self.item_norm_max = None
         self.tot_item_num = None
 
     # ------------------------------------------------------------------ optimizer (trainer.py:66-103)
@@ -277,7 +278,13 @@ class Trainer:
             if self.item_feature_f16 is None:
                 self.item_feature_f16 = ops.score_prepare_f16(self.item_feature.contiguous())   # once per evaluate()
             _, topk_idx = ops.score_topk_f16(seq_out, self.item_feature_f16, max(self.config["topk"]), hu, hi, mask_col0=True)
-        else:
+        elif self._scoring_mode() == "tcgen05" and max(self.config["topk"]) <= 16 and self.item_feature.shape[0] >= 32:
+            # default: ids of the reference's fp32 ranking (TF32 candidates, fp32 re-score, proven complete or re-ranked)
+            if self.item_norm_max is None:
+                self.item_norm_max = ops.table_norm_max(self.item_feature.contiguous())          # once per evaluate()
+            _, topk_idx, _ = ops.score_topk_exact(seq_out, self.item_feature.contiguous(), max(self.config["topk"]), hu, hi,
+                                                  mask_col0=True, w_norm_max=self.item_norm_max)
+        else:                                            # "tcgen05_tf32": ranks the TF32 scores directly (near-ties may swap)
             _, topk_idx = ops.score_topk(seq_out, self.item_feature.contiguous(), max(self.config["topk"]), hu, hi,
                                          mask_col0=True)
         return topk_idx, positive_u, positive_i
@@ -289,13 +296,14 @@ class Trainer:
         mode = self._scoring_mode()
         model = unwrap(self.model)
         D = self.item_feature.shape[1]
-        return (mode in ("tcgen05", "tcgen05_f16") and hasattr(model, "encode_last") and D % 32 == 0
+        return (mode in ("tcgen05", "tcgen05_tf32", "tcgen05_f16") and hasattr(model, "encode_last") and D % 32 == 0
                 and max(self.config["topk"]) <= 32 and self.item_feature.is_cuda)
 
     @torch.no_grad()
     def compute_item_feature(self, config, data):
         self.item_feature = unwrap(self.model).compute_item_all()
         self.item_feature_f16 = None
+        self.item_norm_max = None
 
     def distributed_concat(self, tensor, num_total_examples):
         if dist_ready():

@@ -73,7 +73,7 @@ def test_input_gradient_form(M, N, K):
     assert _rel(got, dy @ W + res) < TOL
 
 
-@pytest.mark.parametrize("R,O,I,splits", [(512, 256, 256, 1), (4096, 512, 512, 8), (81920, 1536, 512, 6), (3000, 100, 260, 3),
+@pytest.mark.parametrize("R,O,I,splits", [(512, 256, 256, 1), (4096, 512, 512, 8), (81920, 1536, 512, 6), (3000, 100, 260, 3), (1000, 128, 64, 2),
                                           (2080, 512, 1024, 5)])
 def test_weight_gradient_form(R, O, I, splits):
     """dW[O, I] = dy^T x: A = dy [R, O] and B = x [R, I], both MN-major (contraction over the R rows), split-K"""
@@ -134,8 +134,28 @@ def test_full_step_shape_against_cublas():
 def test_rejects_bad_arguments():
     from pixelrec_b200 import ops
     from pixelrec_b200.lib import PixelRecB200Error
-    x, W = torch.randn(64, 48, device="cuda"), torch.randn(32, 48, device="cuda")
+    x, W = torch.randn(64, 50, device="cuda"), torch.randn(32, 50, device="cuda")
     with pytest.raises(PixelRecB200Error):
-        ops.gemm(x, W)                                    # K % 32 != 0
+        ops.gemm(x, W)                                    # K-major operands need K % 4 == 0 (16-byte row pitch for TMA)
+    x, W = torch.randn(64, 48, device="cuda"), torch.randn(32, 48, device="cuda")     # a K tail (48 = 32 + 16) is fine
+    ref = x.double() @ W.double().t()
+    assert float((ops.gemm(x, W).double() - ref).abs().max() / ref.abs().max()) < TOL
     with pytest.raises(PixelRecB200Error):
         ops.gemm(torch.randn(64, 64), torch.randn(32, 64))   # CPU tensors: no fallback
+
+
+def test_truncation_debias_removes_the_systematic_shrink():
+    """The tensor core truncates fp32 operands to TF32: without compensation every output is ~0.07 % too small (a bias that
+    compounds through a chain of GEMMs); PR_GEMM_DEBIAS makes the error zero-mean."""
+    from pixelrec_b200 import ops
+    g = np.random.default_rng(3)
+    M, N, K = 512, 256, 1024
+    x = np.abs(g.standard_normal((M, K))).astype(np.float32) + 0.5        # same-sign terms: the shrink shows directly
+    W = np.abs(g.standard_normal((N, K))).astype(np.float32) + 0.5
+    ref = x.astype(np.float64) @ W.astype(np.float64).T
+    raw = ops.gemm(t(x), t(W)).double().cpu().numpy()
+    fix = ops.gemm(t(x), t(W), debias=True).double().cpu().numpy()
+    shrink = float((raw / ref - 1).mean())
+    assert -0.9e-3 < shrink < -0.55e-3, shrink                       # ~2 * 0.72 * 2^-11 = -7.0e-4 (mantissa-averaged truncation)
+    assert abs(float((fix / ref - 1).mean())) < 5e-5
+    assert np.abs(fix / ref - 1).max() < 2e-4

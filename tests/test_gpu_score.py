@@ -78,6 +78,66 @@ def test_score_topk_gaussian_within_tf32_tolerance(B_e, N, D):
     assert (idx == i_ref).mean() > 0.97                                          # only near-ties may swap
 
 
+@pytest.mark.parametrize("B_e,N,D", [(64, 3000, 128), (1024, 97001, 512), (300, 5003, 512)])
+def test_score_topk_exact_ids_equal_the_fp32_ranking(B_e, N, D):
+    """pr_score_topk_exact_f32: the ids (and their order) are those of ranking the fp32 scores -- what the reference's
+    torch.topk on an fp32 matmul returns (collector.py:133) -- not of ranking TF32 scores."""
+    from pixelrec_b200 import ops
+    g = np.random.default_rng(N + 1)
+    seq = g.standard_normal((B_e, D)).astype(np.float32)
+    W = (0.02 * g.standard_normal((N, D))).astype(np.float32)
+    hu, hi = _hist(g, B_e, N, 12)
+    k = 10
+    scores = seq.astype(np.float64) @ W.astype(np.float64).T
+    v_ref, i_ref = O.full_sort_topk(scores, hu, hi, k)
+    val, idx, nfb = ops.score_topk_exact(t(seq), t(W), k, t(hu), t(hi))
+    val, idx = val.cpu().numpy(), idx.cpu().numpy()
+    # fp32 dot products differ from the fp64 oracle by ~1e-6 relative: only pairs closer than that may swap
+    diff = idx != i_ref
+    if diff.any():
+        r, c = np.nonzero(diff)
+        gap = np.abs(v_ref[r, c] - scores[r, idx[r, c]])
+        assert gap.max() < 1e-5 * np.abs(scores).max(), gap.max()
+    assert diff.mean() < 1e-3
+    assert np.abs(val - v_ref).max() < 1e-5 * np.abs(scores).max()                 # fp32 values, not TF32 ones
+    assert int(nfb.item()) <= B_e // 20                                           # the whole-catalog fallback is the rare path
+
+
+def test_score_topk_exact_fallback_path_on_crowded_scores():
+    """integer operands put hundreds of items on the same score: the candidate list cannot be proven complete, every such row
+    goes through the whole-catalog fp32 fallback, and the result must still be the oracle's (ties: lower id first)"""
+    from pixelrec_b200 import ops
+    g = np.random.default_rng(5)
+    B_e, N, D, k = 40, 3000, 64, 10
+    W = g.integers(-2, 3, size=(N, D)).astype(np.float32)
+    W[500:560] = W[7]                                   # 61 identical items ...
+    seq = (2 * W[7][None, :] + g.integers(-1, 2, size=(B_e, D))).astype(np.float32)      # ... that every user scores highest
+    hu, hi = _hist(g, B_e, N, 6)
+    scores = seq.astype(np.float64) @ W.astype(np.float64).T
+    v_ref, i_ref = O.full_sort_topk(scores, hu, hi, k)
+    assert (v_ref[:, 0] == v_ref[:, -1]).all()          # the whole top-k is one 61-way tie: 32 candidates cannot settle it
+    val, idx, nfb = ops.score_topk_exact(t(seq), t(W), k, t(hu), t(hi))
+    assert np.array_equal(idx.cpu().numpy(), i_ref)
+    assert np.array_equal(val.cpu().numpy().astype(np.float64), v_ref)
+    assert int(nfb.item()) == B_e
+
+
+def test_score_topk_exact_matches_reference_golden(golden):
+    """ids identical to the reference's own masked top-k (goldens: torch.topk on the reference's fp32 predict scores)"""
+    from pixelrec_b200 import ops
+    from tests.test_gpu_sasrec import build
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m = build(golden).eval()
+    seq = m.encode_last(t(golden["eval_item_seq"]))
+    W = m.compute_item_all()
+    torch.backends.cuda.matmul.allow_tf32 = True
+    if W.shape[1] % 32:
+        pytest.skip("D % 32 != 0")
+    val, idx, _ = ops.score_topk_exact(seq, W.contiguous(), 10, t(golden["eval_hist_u"]), t(golden["eval_hist_i"]))
+    assert np.array_equal(idx.cpu().numpy(), golden["eval_topk_idx"])
+    assert np.abs(val.cpu().numpy() - golden["eval_topk_val"]).max() < 1e-5 * np.abs(golden["eval_scores_raw"]).max()
+
+
 def test_score_topk_matches_reference_golden(golden):
     from pixelrec_b200 import ops
     from tests.test_gpu_sasrec import build

@@ -29,6 +29,46 @@ SHAPES = {
 }
 
 
+def cpu_port(sh, N, D, L, g, perm, p, B_cpu=64):
+    """The same step on the host cores: oracle/torch_port.py (SASRec) or a torch-CPU restatement of gru4rec.py:47-67 +
+    trainer.py:116-125 (GRU4Rec); ONE timed step of B_cpu sequences after one warm-up (the dense AdamW over the table alone
+    moves 7*N*D*4 bytes: 23 GB at C3)."""
+    import time
+    torch.set_num_threads(os.cpu_count() or 1)
+    items, mask = bench.synth_batch(g, B_cpu, N, L, perm, p)
+    items, mask = torch.from_numpy(items), torch.from_numpy(mask)
+    if sh["model"] == "SASRec":
+        from oracle import torch_port as TP
+        P = TP.init_params(N, D, L, 2, 2, seed=2020)
+        step = TP.TrainStep(P, 2, 4, lr=1e-4, weight_decay=0.1, p_drop=0.1)
+    elif sh["model"] == "GRU4Rec":
+        import torch.nn as nn
+        import torch.nn.functional as F
+        emb = nn.Embedding(N, D, padding_idx=0)
+        gru = nn.GRU(D, D, 1, bias=False, batch_first=True)
+        dense = nn.Linear(D, D)
+        params = list(emb.parameters()) + list(gru.parameters()) + list(dense.parameters())
+        opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01)
+
+        def step(it, mk):
+            opt.zero_grad(set_to_none=False)
+            E = emb(it)
+            out = dense(gru(E[:, 0, :-1])[0])
+            ps, ns = (out * E[:, 0, 1:]).sum(-1), (out * E[:, 1, 1:]).sum(-1)
+            loss = -(torch.log((ps - ns).sigmoid() + 1e-8) * mk).sum(-1).mean(-1)
+            loss.backward()
+            opt.step()
+            return loss.detach()
+    else:
+        return None                      # PixelNet: the ViT forward of 352 images per sample is minutes on CPU; not timed
+    step(items, mask)
+    t0 = time.perf_counter()
+    step(items, mask)
+    dt = time.perf_counter() - t0
+    return {"value": B_cpu / dt, "unit": "sequences/s", "cores": torch.get_num_threads(), "kind": "port", "ms_per_step": dt * 1e3,
+            "sample": f"1 timed step x {B_cpu} sequences (1 warm-up), torch CPU fp32 on {torch.get_num_threads()} threads"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", required=True, choices=sorted(SHAPES))
@@ -37,6 +77,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--patch", type=int, default=32, choices=[16, 32], help="c4: ViT-B/<patch>")
     ap.add_argument("--exchange", default=None, choices=["nccl", "p2p"])
+    ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -121,6 +162,34 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = ms.item()
+    # per-kernel pass (CUDA events around every launch of ours) -> achieved GB/s against the measured HBM peak
+    from pixelrec_b200 import ops
+    ops.PROFILE.update(on=True, names=None, events={})
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    prof = ops.profile_summary()
+    ops.PROFILE.update(on=False, events={})
+    hbm, _, peak_src = bench.peaks()
+    R_u = B * (2 * L + 1)
+    n_local = (N + world - 1) // world
+    alg = {"gather_rows": R_u * (8 * D + 8) if world == 1 else None, "adamw_rows": 6 * n_local * D * 4,
+           "bpr_fwd": None, "add_ln_fwd": 3 * B * L * D * 4, "add_ln_bwd": 5 * B * L * D * 4,
+           "attn_fwd": 16 * B * L * D, "attn_bwd": 32 * B * L * D}
+    kernels = {}
+    for name, (n, mean_ms) in sorted(prof.items()):
+        ent = {"launches_per_step": n / 3.0, "ms": mean_ms}
+        if alg.get(name) and sh["model"] != "MOSASRec":
+            ent["GBps"] = alg[name] / mean_ms / 1e6
+            ent["frac_of_hbm_peak"] = ent["GBps"] / hbm
+        kernels[name] = ent
+    # CPU port of the same step on the host cores (bounded sample), rank 0 at N = 1 only
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        try:
+            cpu = cpu_port(sh, N, D, L, g, perm, p)
+        except Exception as ex:  # noqa: BLE001
+            cpu = {"error": f"{type(ex).__name__}: {ex}"}
     xs = getattr(getattr(model, "item_embedding", None), "exchange_status", lambda: 0)()
     if rank == 0:
         print(json.dumps({
@@ -130,6 +199,7 @@ def main():
             "config": {"workload": what, "batch_per_gpu": B, "global_batch": B * world,
                        "parallelism": ("single GPU" if world == 1 else
                                        f"dp{world}" + ("" if sh["model"] == "MOSASRec" else f" + item table row-sharded {world}-way"))},
+            "roofline_kernels": kernels, "hbm_peak_GBps": hbm, "peak_source": peak_src, "cpu_baseline": cpu,
             "loss": float(loss), "exchange_status": xs,
             "max_memory_GB": torch.cuda.max_memory_allocated(dev) / 2 ** 30}))
     if world > 1:
