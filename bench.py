@@ -426,9 +426,12 @@ def run_ours(args, out):
             entry["note"] = ("all linear-layer GEMMs of the step (pr_gemm_tf32); peak = half the measured sustained bf16 rate "
                              "(kind::tf32 issues at half the bf16 rate)")
         kernels[name] = entry
-    gather_gbps = alg["gather_rows"] / gather_ms / 1e6 if gather_n else None
-    if world > 1:
-        gather_gbps = None   # sharded path: several gathers of different sizes per step; see roofline_kernels
+    gather_alg = R_u * (8 * D + 8)
+    gather_src = "CUDA events around the launch inside timed region 1"
+    if not gather_n and "gather_rows" in prof:      # region 1 replayed a CUDA graph: its kernels cannot be bracketed one by one,
+        gather_n, gather_ms = prof["gather_rows"]   # so the figure comes from the eager per-kernel pass of the same process
+        gather_src = "CUDA events around the launch in the eager per-kernel pass (timed region 1 is one CUDA-graph launch per step)"
+    gather_gbps = gather_alg / gather_ms / 1e6 if (gather_n and world == 1) else None   # sharded path: see roofline_kernels
 
     line = {
         "metric": METRIC, "value": value, "unit": "sequences/s", "n_gpus": world, "steps": args.steps,
@@ -446,8 +449,8 @@ def run_ours(args, out):
                      "achieved": gather_gbps, "peak": hbm, "unit": "GB/s",
                      "frac": (gather_gbps / hbm) if gather_gbps else None,
                      "traffic": gather_traffic(B, world),
-                     "algorithmic_bytes_per_launch": alg["gather_rows"], "launch_ms": gather_ms if gather_n else None,
-                     "launches_timed": gather_n, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": gather_alg, "launch_ms": gather_ms if gather_n else None,
+                     "launches_timed": gather_n, "timing": gather_src, "peak_source": peak_src,
                      "note": "long-tail ids repeat inside a step, so part of the table reads hit L2: achieved can exceed the DRAM copy peak"},
         "roofline_kernels": kernels,
     }

@@ -235,21 +235,11 @@ PR_API int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float* W, 
                              float* topk_val, int64_t* topk_idx, void* workspace, size_t workspace_bytes,
                              pr_stream_t stream);
 
-/* K5 (staged): linear layer on the tcgen05 pipeline of K9.   replaces nn.Linear [+ erf-GELU] of the encoder layers,
- *   REC/model/layers.py:586-588 (query/key/value), :613 (dense), :666 + :651-660 (dense_1 + gelu), :669 (dense_2)
- *   out[m, n] = act(sum_k x[m, k] * W[n, k] + bias[n]);  x [M, K], W [N, K] (nn.Linear layout), out [M, N], all fp32
- *   row-major; TF32 operands, fp32 accumulation.  K % 32 == 0, N % 4 == 0.  bias may be NULL.  act: -1 none, PR_ACT_GELU,
- *   PR_ACT_RELU.  pre (optional, [M, N]): the pre-activation values, which the backward of the activation needs.
- *   pr_set_tuning bit 32 multicasts the W tiles across the m-tiles of a cluster.
- */
-PR_API int pr_linear_tf32(const float* x, int64_t M, const float* W, int64_t N, int64_t K, const float* bias, int act, float* out,
-                          float* pre, pr_stream_t stream);
-
 /* K9, id-exact: the ranking the reference computes on fp32 scores (collector.py:133).  Same fused TF32 pass as above as a
- *   candidate generator (top-32 per row), then every candidate is re-scored in fp32 and ranked (ties: lower item id); a row whose
- *   k-th fp32 score is not provably above everything outside its candidate list -- bound: last TF32 candidate value
- *   + 1.25 * 2^-9 * |seq_out[row]| * max_j |W[j]| -- is re-ranked over the whole catalog in fp32 (rare; *n_fallback_rows, a device
- *   int32, counts them; may be NULL).  k <= 16, N >= 32.  w_norm_max: device float holding max_j |W[j]| (pr_table_norm_max_f32;
+ *   candidate generator (the 32 best of the row's per-thread lists), then every candidate is re-scored in fp32 and ranked (ties:
+ *   lower item id); a row whose k-th fp32 score is not provably above everything outside its candidates -- bound: the largest
+ *   TF32 value any list dropped or the 32nd candidate, + 1.25 * 2^-9 * |seq_out[row]| * max_j |W[j]| -- is re-ranked over the
+ *   whole catalog in fp32 (rare; *n_fallback_rows, a device int32, counts them; may be NULL).  k <= 16, N >= 32.  w_norm_max: device float holding max_j |W[j]| (pr_table_norm_max_f32;
  *   compute it once per evaluation), or NULL to have it computed here.  topk_val are fp32 scores.
  */
 PR_API size_t pr_score_topk_exact_workspace_bytes(int64_t B_e, int64_t N, int k);

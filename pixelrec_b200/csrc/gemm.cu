@@ -408,6 +408,12 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tf32_kernel(const __grid_c
                     if (a.act == PR_ACT_GELU) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+                    } else if (a.act == PR_ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                    } else if (a.act == PR_ACT_QUICK_GELU) {                       // x * sigmoid(1.702 x), CLIP ViT (fc1)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-1.702f * v[j]));
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = act_f(v[j], a.act);
@@ -640,10 +646,16 @@ extern "C" int pr_gemm_tf32(const float* A, int a_mn, int64_t lda, const float* 
         }
         if (rc) return rc;
         const long long dims[2] = {N, M}, strides[2] = {1, N};
-        rc = gm_map(&tmOut2, out2 ? out2 : out, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "out2");
-        if (rc) return rc;
-        rc = gm_map(&tmAux, aux ? aux : out, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "aux");
-        if (rc) return rc;
+        tmOut2 = tmOut;                                    // unused maps are never dereferenced: skip their (host-side) encoding
+        tmAux = tmOut;
+        if (out2) {
+            rc = gm_map(&tmOut2, out2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "out2");
+            if (rc) return rc;
+        }
+        if (aux) {
+            rc = gm_map(&tmAux, aux, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, "aux");
+            if (rc) return rc;
+        }
     }
     return (cg == 2) ? gm_launch<2>(tmA, tmB, tmOut, tmOut2, tmAux, a, stream) : gm_launch<1>(tmA, tmB, tmOut, tmOut2, tmAux, a, stream);
 }

@@ -290,12 +290,12 @@ static int launch_v2(const CUtensorMap& tmA, const void* W, long long N, long lo
             cfg.gridDim = dim3(p.m_tiles * splits);
             int max_clusters = 0;
             const bool ok = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) == cudaSuccess;
-            if (!ok || max_clusters < 1 || (MODE != 2 && max_clusters < p.m_tiles / CL)) {
+            if (!ok || max_clusters < 1 || max_clusters < p.m_tiles / CL) {
                 (void)cudaGetLastError();
                 CL = 1;                                                     // cluster shape not schedulable here: plain v2
-            } else if (MODE != 2) {
+            } else {
                 splits = std::max(1, std::min(splits, max_clusters / (p.m_tiles / CL)));
-            }                                                               // linear mode: one split, as many waves as it takes
+            }
         }
     }
     a.cluster = CL;
@@ -322,10 +322,10 @@ extern "C" size_t pr_score_topk_workspace_bytes(int64_t B_e, int64_t N, int k) {
     return score_plan(B_e, N, k).total;
 }
 
-extern "C" int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float* W, int64_t N, int64_t D,
-                                 const int64_t* hist_u, const int64_t* hist_i, int64_t n_hist, int mask_col0, int k,
-                                 float* topk_val, int64_t* topk_idx, void* workspace, size_t workspace_bytes,
-                                 pr_stream_t stream_) {
+// k_lists: depth of the per-thread lists (16 or 32; >= k unless bound_out certifies what the lists cannot hold)
+static int score_topk_impl(const float* seq_out, int64_t B_e, const float* W, int64_t N, int64_t D, const int64_t* hist_u,
+                           const int64_t* hist_i, int64_t n_hist, int mask_col0, int k, int k_lists, float* bound_out,
+                           float* topk_val, int64_t* topk_idx, void* workspace, size_t workspace_bytes, pr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PR_CHECK_ARG(B_e > 0 && N > 0 && D > 0, "pr_score_topk_f32: bad shape B_e=%lld N=%lld D=%lld", (long long)B_e,
                  (long long)N, (long long)D);
@@ -335,7 +335,7 @@ extern "C" int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float*
     PR_CHECK_ARG(seq_out && W && topk_val && topk_idx && workspace, "pr_score_topk_f32: null pointer");
     PR_CHECK_ARG(aligned16(seq_out) && aligned16(W), "pr_score_topk_f32: seq_out / W must be 16-byte aligned");
     PR_CHECK_ARG(n_hist >= 0 && (n_hist == 0 || (hist_u && hist_i)), "pr_score_topk_f32: bad history arguments");
-    const ScorePlan p = score_plan(B_e, N, k);
+    const ScorePlan p = score_plan(B_e, N, k_lists);
     PR_CHECK_ARG(workspace_bytes >= p.total, "pr_score_topk_f32: workspace %zu < required %zu", workspace_bytes, p.total);
     PR_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "pr_score_topk_f32: workspace must be 256-byte aligned");
 
@@ -359,7 +359,7 @@ extern "C" int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float*
     a.kblocks = (int)(D / SC_BK);
     a.m_tiles = p.m_tiles; a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.n_splits = p.n_splits;
     a.n_words = p.n_words; a.mask = mask; a.cand_val = cand_val; a.cand_idx = cand_idx; a.cluster = 1;
-    a.target = nullptr; a.n_rows = B_e; a.ce_part = nullptr; a.lin_out = nullptr; a.lin_pre = nullptr; a.lin_bias = nullptr;
+    a.target = nullptr; a.n_rows = B_e; a.ce_part = nullptr;
     int n_lists = p.n_splits;
     if (tune() & PR_TUNE_SCORE_V2) {
         const bool mcast = (tune() & PR_TUNE_SCORE_MCAST) != 0;
@@ -381,19 +381,29 @@ extern "C" int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float*
         PR_CUDA_LAUNCH_CHECK("score_topk_kernel");
     }
     score_merge_kernel<<<(int)((B_e + 3) / 4), 128, 0, stream>>>(cand_val, cand_idx, n_lists * p.K, B_e, k, topk_val,
-                                                                 (long long*)topk_idx);
+                                                                 (long long*)topk_idx, p.K, bound_out);
     PR_CUDA_LAUNCH_CHECK("score_merge_kernel");
     return PR_OK;
+}
+
+extern "C" int pr_score_topk_f32(const float* seq_out, int64_t B_e, const float* W, int64_t N, int64_t D,
+                                 const int64_t* hist_u, const int64_t* hist_i, int64_t n_hist, int mask_col0, int k,
+                                 float* topk_val, int64_t* topk_idx, void* workspace, size_t workspace_bytes,
+                                 pr_stream_t stream_) {
+    return score_topk_impl(seq_out, B_e, W, N, D, hist_u, hist_i, n_hist, mask_col0, k, k, nullptr, topk_val, topk_idx, workspace,
+                           workspace_bytes, stream_);
 }
 
 // ---- id-exact ranking (collector.py:133 ranks fp32 scores): TF32 candidates re-scored in fp32 ---------------------------------
 // The tensor core reads TF32 (operands truncated to 10 mantissa bits), so two items whose fp32 scores differ by less than the
 // TF32 error can come out in the wrong order (0.7 % of the top-10 ids at C2, profiles/r01f).  Exact mode keeps that pipeline as a
-// candidate generator: (1) top-32 per row by TF32 score; (2) one warp per row recomputes the 32 scores in fp32 and ranks them;
-// (3) proof of completeness: an item outside the list has TF32 score <= v32 (the list's last TF32 value) and hence fp32 score
-// <= v32 + eps, eps = 1.25 * 2^-9 * |seq_row| * max_j |W_j| (truncation of both operands, Cauchy-Schwarz) -- if the k-th fp32
-// score is above that, the fp32 top-k is certain; (4) rows that fail the test (near-ties deeper than 32, rare) are flagged and
-// re-ranked over the whole catalog in fp32 by score_exact_rows_kernel.
+// candidate generator: (1) the usual pass with 16-deep per-thread lists, whose merge returns the best 32 candidates of the row
+// AND v_bound = the largest "last kept value" of any full list: an item that is in no list has TF32 score <= v_bound; (2) one
+// warp per row recomputes the 32 candidates' scores in fp32 and ranks them; (3) proof of completeness: everything outside the
+// 32 has TF32 score <= max(v_bound, 32nd candidate value) =: v_out and hence fp32 score <= v_out + eps,
+// eps = 1.25 * 2^-9 * |seq_row| * max_j |W_j| (truncation of both operands, Cauchy-Schwarz) -- if the k-th fp32 score is above
+// that, the fp32 top-k is certain; (4) rows that fail the test (near-ties, rare) are flagged and re-ranked over the whole
+// catalog in fp32 by score_exact_rows_kernel.
 namespace pr {
 
 constexpr int SCX_C = 32;                 // candidates per row
@@ -428,6 +438,7 @@ __device__ __forceinline__ float warp_dot(const float4* __restrict__ a, const fl
 __global__ void __launch_bounds__(128) score_rescore_kernel(const float* __restrict__ seq, const float* __restrict__ W, int D4,
                                                             long long B_e, int k, const float* __restrict__ cand_val,
                                                             const long long* __restrict__ cand_idx,
+                                                            const float* __restrict__ list_bound,
                                                             const float* __restrict__ w_norm_max, float* __restrict__ out_val,
                                                             long long* __restrict__ out_idx, int* __restrict__ flagged) {
     const int lane = threadIdx.x & 31;
@@ -435,8 +446,10 @@ __global__ void __launch_bounds__(128) score_rescore_kernel(const float* __restr
     if (row >= B_e) return;
     const float4* a = reinterpret_cast<const float4*>(seq) + row * D4;
     const long long my_id = cand_idx[row * SCX_C + lane];
-    const float v_last = cand_val[row * SCX_C + SCX_C - 1];
+    // best TF32 score anything OUTSIDE the 32 candidates can have: the 32nd candidate (if the merged list is full) or an item
+    // that fell off one of the per-thread lists
     const bool list_full = cand_idx[row * SCX_C + SCX_C - 1] >= 0;
+    const float v_last = fmaxf(list_full ? cand_val[row * SCX_C + SCX_C - 1] : -INFINITY, list_bound[row]);
     float my = -INFINITY;
     for (int c = 0; c < SCX_C; ++c) {
         const long long id = __shfl_sync(0xffffffffu, my_id, c);
@@ -467,7 +480,7 @@ __global__ void __launch_bounds__(128) score_rescore_kernel(const float* __restr
     const unsigned kth_lane = __ballot_sync(0xffffffffu, rank == k - 1);
     const float s_k = kth_lane ? __shfl_sync(0xffffffffu, my, __ffs((int)kth_lane) - 1) : -INFINITY;
     const float eps = 1.25f * 0.001953125f * an * w_norm_max[0];
-    if (lane == 0 && list_full && !(s_k > v_last + eps)) {
+    if (lane == 0 && v_last > -INFINITY && !(s_k > v_last + eps)) {
         const int pos = atomicAdd(flagged, 1);
         flagged[1 + pos] = (int)row;
     }
@@ -536,13 +549,13 @@ __global__ void __launch_bounds__(256) score_exact_rows_kernel(const float* __re
 
 }  // namespace pr
 
-static size_t scx_extra_bytes(int64_t B_e) {      // top-32 (val, idx) per row + [count | flagged rows] + max norm
-    return ((size_t)B_e * SCX_C * 12 + ((size_t)B_e + 2) * 4 + 16 + 255) / 256 * 256;
+static size_t scx_extra_bytes(int64_t B_e) {      // top-32 (val, idx) per row + list bound + [count | flagged rows] + max norm
+    return ((size_t)B_e * SCX_C * 12 + (size_t)B_e * 4 + ((size_t)B_e + 2) * 4 + 16 + 255) / 256 * 256;
 }
 
 extern "C" size_t pr_score_topk_exact_workspace_bytes(int64_t B_e, int64_t N, int k) {
     if (B_e <= 0 || N <= 0 || k <= 0 || k > 16) return 0;
-    return score_plan(B_e, N, SCX_C).total + scx_extra_bytes(B_e);
+    return score_plan(B_e, N, 16).total + scx_extra_bytes(B_e);
 }
 
 extern "C" int pr_table_norm_max_f32(const float* W, int64_t N, int64_t D, float* out_max, pr_stream_t stream_) {
@@ -566,16 +579,17 @@ extern "C" int pr_score_topk_exact_f32(const float* seq_out, int64_t B_e, const 
     PR_CHECK_ARG(seq_out && W && topk_val && topk_idx && workspace, "pr_score_topk_exact_f32: null pointer");
     const size_t need = pr_score_topk_exact_workspace_bytes(B_e, N, k);
     PR_CHECK_ARG(workspace_bytes >= need, "pr_score_topk_exact_f32: workspace %zu < required %zu", workspace_bytes, need);
-    const ScorePlan p = score_plan(B_e, N, SCX_C);
+    const ScorePlan p = score_plan(B_e, N, 16);
     char* extra = (char*)workspace + p.total;
     float* c_val = (float*)extra;
     long long* c_idx = (long long*)(extra + (size_t)B_e * SCX_C * 4);
-    int* flagged = (int*)(extra + (size_t)B_e * SCX_C * 12);
+    float* bound = (float*)(extra + (size_t)B_e * SCX_C * 12);
+    int* flagged = (int*)(bound + B_e);
     float* own_max = (float*)(flagged + B_e + 2);
     // (1) TF32 candidates: the ordinary fused pass with 32-deep lists
     PR_CHECK_ARG(N >= SCX_C, "pr_score_topk_exact_f32: N=%lld < %d candidates (use pr_score_topk_f32)", (long long)N, SCX_C);
-    int rc = pr_score_topk_f32(seq_out, B_e, W, N, D, hist_u, hist_i, n_hist, mask_col0, SCX_C, c_val, (int64_t*)c_idx,
-                               workspace, p.total, stream_);
+    int rc = score_topk_impl(seq_out, B_e, W, N, D, hist_u, hist_i, n_hist, mask_col0, SCX_C, 16, bound, c_val, (int64_t*)c_idx,
+                             workspace, p.total, stream_);
     if (rc) return rc;
     if (!w_norm_max) {
         rc = pr_table_norm_max_f32(W, N, D, own_max, stream_);
@@ -583,7 +597,7 @@ extern "C" int pr_score_topk_exact_f32(const float* seq_out, int64_t B_e, const 
         w_norm_max = own_max;
     }
     PR_CUDA_CALL(cudaMemsetAsync(flagged, 0, 4, stream));
-    score_rescore_kernel<<<(int)((B_e + 3) / 4), 128, 0, stream>>>(seq_out, W, (int)(D / 4), B_e, k, c_val, c_idx, w_norm_max,
+    score_rescore_kernel<<<(int)((B_e + 3) / 4), 128, 0, stream>>>(seq_out, W, (int)(D / 4), B_e, k, c_val, c_idx, bound, w_norm_max,
                                                                    topk_val, (long long*)topk_idx, flagged);
     PR_CUDA_LAUNCH_CHECK("score_rescore_kernel");
     // (4) flagged rows: whole-catalog fp32 ranking (grid sized for the worst case; CTAs without a row exit at once)
@@ -714,35 +728,4 @@ extern "C" int pr_score_topk_f16(const float* seq_out, int64_t B_e, const void* 
                                                                  (long long*)topk_idx);
     PR_CUDA_LAUNCH_CHECK("score_merge_kernel");
     return PR_OK;
-}
-
-// ---- linear layers on the same pipeline (K5): y = act(x W^T + b) -----------------------------------------------------------
-extern "C" int pr_linear_tf32(const float* x, int64_t M, const float* W, int64_t N, int64_t Kd, const float* bias, int act,
-                              float* out, float* pre, pr_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    PR_CHECK_ARG(M > 0 && N > 0 && Kd > 0, "pr_linear_tf32: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)Kd);
-    PR_CHECK_ARG(Kd % SC_BK == 0 && N % 4 == 0, "pr_linear_tf32: K=%lld must be a multiple of %d and N=%lld of 4", (long long)Kd,
-                 SC_BK, (long long)N);
-    PR_CHECK_ARG(act == -1 || act == PR_ACT_GELU || act == PR_ACT_RELU, "pr_linear_tf32: act must be -1 (none), gelu or relu");
-    PR_CHECK_ARG(x && W && out, "pr_linear_tf32: null pointer");
-    PR_CHECK_ARG(aligned16(x) && aligned16(W) && aligned16(out) && aligned16(pre) && aligned16(bias), "pr_linear_tf32: alignment");
-    PR_CHECK_ARG(M < (1LL << 31) - 256 && N < (1LL << 31) - 512, "pr_linear_tf32: shape too large");
-    CUtensorMap tmA;
-    int rc = make_map(&tmA, x, M, Kd, SC_BM);
-    if (rc) return rc;
-    ScorePlan p;                                           // one split: every CTA owns an m-tile and walks all n-tiles
-    p.K = 16;
-    p.m_tiles = (int)((M + SC_BM - 1) / SC_BM);
-    p.n_tiles = (int)((N + SC_BN - 1) / SC_BN);
-    p.n_splits = 1;
-    p.tiles_per_split = p.n_tiles;
-    p.n_words = 0; p.mask_bytes = p.cand_bytes = p.total = 0;
-    ScoreArgs a;
-    a.kblocks = (int)(Kd / SC_BK);
-    a.m_tiles = p.m_tiles; a.n_tiles = p.n_tiles; a.tiles_per_split = p.tiles_per_split; a.n_splits = 1;
-    a.n_words = 0; a.mask = nullptr; a.cand_val = nullptr; a.cand_idx = nullptr; a.cluster = 1;
-    a.target = nullptr; a.n_rows = M; a.ce_part = nullptr;
-    a.lin_out = out; a.lin_pre = pre; a.lin_bias = bias; a.lin_act = act; a.lin_M = M; a.lin_N = N;
-    int n_lists = 0;
-    return launch_v2<16, 2>(tmA, W, N, Kd, a, p, (tune() & PR_TUNE_SCORE_MCAST) != 0, stream, &n_lists);
 }

@@ -27,8 +27,6 @@ struct ScoreArgs {
     int* cand_idx;
     int cluster;          // v2: CTAs per cluster sharing each table tile by TMA multicast (1 = none)
     const long long* target;   // CE mode: [B_e] target item per row
-    // linear mode (MODE 2): out = act(A . B^T + bias) written as a dense [lin_M, lin_N] fp32 matrix, optional pre-activation copy
-    float* lin_out; float* lin_pre; const float* lin_bias; int lin_act; long long lin_M, lin_N;
     long long n_rows;          // CE mode: B_e
     float* ce_part;            // CE mode: [m_tiles*128][n_splits*2][4] = (running max, sum of exp, target logit or -inf, unused)
 };
@@ -126,9 +124,8 @@ __device__ __forceinline__ float pick32(const float (&v)[32], int j) {
     return (j & 16) ? d1 : d0;
 }
 
-// MODE 2: plain linear layer y = act(x W^T + b) (REC/model/layers.py:586-588,613,666,669 nn.Linear [+ erf-GELU :651-660]) on the
-// same pipeline: "users" = rows of x, "items" = rows of W (output features); the epilogue adds the bias, applies the
-// activation and stores the tile (each thread owns one row: 32 consecutive floats = one 128-byte line per tcgen05.ld).
+// (The linear layers of the encoder ran on this pipeline as a MODE 2 in round 1 -- 155-405 TFLOP/s, bound by its uncoalesced
+// row-per-thread stores; they now have their own CTA-pair kernel with a TMA-store epilogue, csrc/gemm.cu.)
 // MODE 0: masked per-row top-k (eval ranking).  MODE 1: online log-sum-exp over the unmasked catalog + the target item's
 // logit = full-catalog softmax cross-entropy (K unused).
 // F16: operands are fp16 copies of seq_out / the table (pr_score_prepare_f16): same 10 explicit mantissa bits as TF32 -- and
@@ -247,49 +244,7 @@ __global__ void __launch_bounds__(SC2_THREADS, 1) score_topk2_kernel(const __gri
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         const int row = m_tile * SC_BM + q * 32 + lane;
-        if constexpr (MODE == 2) {
-        for (int t = 0; t < n_my; ++t) {
-            const int buf = t & 1;
-            const int tile = t_begin + t;
-            mbar_wait(&tfull_bar[buf], (uint32_t)((t >> 1) & 1));
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * SC_BN + half * 128);
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                float v[32];
-                __syncwarp();
-                tmem_ld32(taddr + c * 32, v);
-                const long long c0 = (long long)tile * SC_BN + half * 128 + c * 32;
-                if (row < a.lin_M && c0 < a.lin_N) {                  // lin_N % 4 == 0: float4 groups are all-in or all-out
-                    float* po = a.lin_out + (long long)row * a.lin_N + c0;
-                    float* pp = a.lin_pre ? a.lin_pre + (long long)row * a.lin_N + c0 : nullptr;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (c0 + j < a.lin_N) {
-                            float4 x = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                            if (a.lin_bias) {
-                                const float4 bb = PR_LDG4(reinterpret_cast<const float4*>(a.lin_bias + c0 + j));
-                                x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
-                            }
-                            if (pp) *reinterpret_cast<float4*>(pp + j) = x;
-                            if (a.lin_act == 0) {                     // PR_ACT_GELU, erf form (csrc/ln.cu act_apply)
-                                x.x = x.x * 0.5f * (1.0f + erff(x.x * 0.70710678118654752440f));
-                                x.y = x.y * 0.5f * (1.0f + erff(x.y * 0.70710678118654752440f));
-                                x.z = x.z * 0.5f * (1.0f + erff(x.z * 0.70710678118654752440f));
-                                x.w = x.w * 0.5f * (1.0f + erff(x.w * 0.70710678118654752440f));
-                            } else if (a.lin_act == 1) {              // PR_ACT_RELU
-                                x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
-                            }
-                            *reinterpret_cast<float4*>(po + j) = x;
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-        }
-        } else {
+        {
         const uint32_t* mrow = a.mask + (size_t)row * a.n_words + half * 4;
         if constexpr (MODE == 0) {
         float val[K];
@@ -385,15 +340,19 @@ __global__ void __launch_bounds__(SC2_THREADS, 1) score_topk2_kernel(const __gri
 }
 
 // merge the n_splits sorted candidate lists of a row: k rounds of warp arg-max (value desc, then item id asc)
+// out_bound (optional): max over the row's lists of the LAST value a full list kept (list_len entries each) -- every item that is
+// in no list scores at most that (the id-exact mode's completeness bound); -inf when no list is full.
 __global__ void __launch_bounds__(128) score_merge_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
                                                           int n_cand, long long B_e, int k, float* __restrict__ out_val,
-                                                          long long* __restrict__ out_idx) {
+                                                          long long* __restrict__ out_idx, int list_len = 0,
+                                                          float* __restrict__ out_bound = nullptr) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= B_e) return;
     constexpr int MAXC = 32;                      // up to 1024 candidates per row
     float v[MAXC];
     int id[MAXC];
+    float bound = -INFINITY;
 #pragma unroll
     for (int i = 0; i < MAXC; ++i) {
         const int c = lane + 32 * i;
@@ -401,6 +360,12 @@ __global__ void __launch_bounds__(128) score_merge_kernel(const float* __restric
         v[i] = ok ? cand_val[row * n_cand + c] : -INFINITY;
         id[i] = ok ? cand_idx[row * n_cand + c] : -1;
         if (id[i] < 0) v[i] = -INFINITY;
+        if (out_bound && ok && list_len > 0 && (c % list_len) == list_len - 1 && id[i] >= 0) bound = fmaxf(bound, v[i]);
+    }
+    if (out_bound) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+        if (lane == 0) out_bound[row] = bound;
     }
     for (int r = 0; r < k; ++r) {
         float bv = -INFINITY;

@@ -12,7 +12,7 @@ NVLink/NVSwitch) ONLY at the shard boundary.
     dense-semantics AdamW.  There is no dense [N,D] gradient and no dense all-reduce of the table anywhere
     (the reference all-reduces N*D*4 bytes every step).
 
-  * `exchange="p2p"` (PR_EXCHANGE=p2p; staged, opt-in until confirmed on a multi-GPU box): the two row all_to_alls,
+  * `exchange="p2p"` (the default; PR_EXCHANGE=nccl selects the all_to_all path above): the two row all_to_alls,
     the owner-side gather into a send buffer, the index all_to_all and its host sync are replaced by peer-memory
     kernels (csrc/peer.cu).  Every rank maps its peers' shards and receive buffers (CUDA IPC); the lookup reads each
     distinct row straight out of its owner's shard over NVLink (pr_gather_rows_peers_f32), the backward writes the
@@ -276,7 +276,8 @@ class ShardedTableEmbedding(nn.Module):
         super().__init__()
         from .model.layers import TableGradSink
         self.group = group
-        self.exchange = (exchange or os.environ.get("PR_EXCHANGE", "nccl")).lower()    # "nccl" (all_to_all) | "p2p" (peer memory)
+        # "p2p" (peer-memory kernels over NVLink; default: r02 measured 1.03 M vs 0.84 M seq/s at N=2) | "nccl" (all_to_all)
+        self.exchange = (exchange or os.environ.get("PR_EXCHANGE", "p2p")).lower()
         if self.exchange not in ("nccl", "p2p"):
             raise ValueError(f"exchange must be 'nccl' or 'p2p', got {self.exchange!r}")
         self._px = None
@@ -374,27 +375,21 @@ class ShardedTableEmbedding(nn.Module):
     @torch.no_grad()
     def full_weight(self):
         """All-gather the shards into the reference layout [N, D] (compute_item_all / checkpoints)."""
+        return self.gather_rows_full(self.weight.detach(), clone=False)
+
+    @torch.no_grad()
+    def gather_rows_full(self, local, clone=True):
+        """[n_local, D] per-rank tensor aligned with the shard (the weights, an Adam moment) -> the full [N, D] layout the
+        reference's checkpoints use.  Collective: every rank calls it."""
         if self.world == 1:
-            return self.weight.detach()
+            return local.clone() if clone else local
         n_max = shard_rows(self.num_embeddings, self.world, 0)
-        pad = torch.zeros(n_max, self.embedding_dim, dtype=self.weight.dtype, device=self.weight.device)
-        pad[:self.n_local] = self.weight
+        pad = torch.zeros(n_max, self.embedding_dim, dtype=local.dtype, device=local.device)
+        pad[:self.n_local] = local
         chunks = [torch.empty_like(pad) for _ in range(self.world)]
         dist.all_gather(chunks, pad, group=self.group)
         allw = torch.stack(chunks)                                   # [world, n_max, D]; row i = shard i%world, i//world
         return allw.permute(1, 0, 2).reshape(-1, self.embedding_dim)[:self.num_embeddings].contiguous()
-
-    @torch.no_grad()
-    def gather_rows_full(self, local):
-        """[n_local, D] per-rank tensor aligned with the shard (e.g. an Adam moment) -> the full [N, D] layout.  Collective."""
-        if self.world == 1:
-            return local.detach().clone()
-        keep, self_w = self.weight.data, None
-        try:
-            self.weight.data = local
-            return self.full_weight()
-        finally:
-            self.weight.data = keep
 
     def shard_of_full(self, full):
         """rows rank::world of a full [N, D] tensor (inverse of gather_rows_full)"""

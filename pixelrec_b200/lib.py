@@ -50,7 +50,6 @@ SIGNATURES = {
     "pr_seq_batch_build": (_I, [_P, _I64, _I, _P, _I64, _I64, _U64, _P, _P, _P, _P]),
     "pr_score_topk_workspace_bytes": (C.c_size_t, [_I64, _I64, _I]),
     "pr_score_topk_f32": (_I, [_P, _I64, _P, _I64, _I64, _P, _P, _I64, _I, _I, _P, _P, _P, C.c_size_t, _P]),
-    "pr_linear_tf32": (_I, [_P, _I64, _P, _I64, _I64, _P, _I, _P, _P, _P]),
     "pr_score_topk_exact_workspace_bytes": (C.c_size_t, [_I64, _I64, _I]),
     "pr_table_norm_max_f32": (_I, [_P, _I64, _I64, _P, _P]),
     "pr_score_topk_exact_f32": (_I, [_P, _I64, _P, _I64, _I64, _P, _P, _I64, _I, _I, _P, _P, _P, _P, _P, C.c_size_t, _P]),

@@ -5,7 +5,9 @@ Same module tree / parameter names / parameter ORDER as HF's CLIPVisionModel, so
 load with load_state_dict, (b) the reference's index-based freezing (`tune_scale: 165` = embeddings + pre-LN + the
 first 10 of 12 layers, load.py:97-99) selects the same tensors.  The forward runs on our kernels: LayerNorm via
 pr_add_ln_*, attention core via pr_sasrec_attn_* (bidirectional, no key padding, L = 50 tokens, dh = 64),
-quick-GELU via pr_act_*; Linear / patch conv are cuBLAS / cuDNN library calls.  Frozen leading layers run under
+quick-GELU via pr_act_* or the GEMM epilogue; every Linear (q/k/v, out_proj, fc1 + quick-GELU, fc2, rec_fc + ReLU) runs forward,
+input-gradient and weight-gradient on pr_gemm_tf32 (ops.linear) when TF32 matmuls are allowed; only the patch-embedding
+convolution (frozen, forward only) stays a cuDNN call.  Frozen leading layers run under
 no_grad (nothing is saved for a backward that never happens).
 """
 import torch
@@ -52,9 +54,9 @@ class CLIPAttention(nn.Module):
     def forward(self, x):
         w = torch.cat([self.q_proj.weight, self.k_proj.weight, self.v_proj.weight], 0)
         b = torch.cat([self.q_proj.bias, self.k_proj.bias, self.v_proj.bias], 0)
-        qkv = F.linear(x, w, b)
+        qkv = ops.linear(x, w, b)
         ctx = ops.attention(qkv, None, self.num_heads, causal=False)     # softmax(q k^T / sqrt(dh)) v, no mask
-        return self.out_proj(ctx)
+        return ops.linear(ctx, self.out_proj.weight, self.out_proj.bias)
 
 
 class CLIPMLP(nn.Module):
@@ -65,7 +67,8 @@ class CLIPMLP(nn.Module):
         self.act = c.hidden_act
 
     def forward(self, x):
-        return self.fc2(ops.activation(self.fc1(x), self.act))
+        h = ops.linear(x, self.fc1.weight, self.fc1.bias, act=self.act)   # bias + quick-GELU in the GEMM epilogue
+        return ops.linear(h, self.fc2.weight, self.fc2.bias)
 
 
 def _ln(x, ln):
@@ -149,7 +152,6 @@ class MeanItemEncoder(nn.Module):
 
     def forward(self, x):
         h = self.item_encoder(x)[0]                                      # [n, T, H]
-        y = self.rec_fc[0](h)
-        if self.act_name in ops.ACT_IDS:
-            y = ops.activation(y.contiguous(), self.act_name)
+        fc = self.rec_fc[0]
+        y = ops.linear(h, fc.weight, fc.bias, act=self.act_name if self.act_name in ops.ACT_IDS else None)
         return y.mean(dim=1)

@@ -399,6 +399,13 @@ def attention(qkv, key_ids, n_heads, causal=True, p_drop=0.0, seed=0, rng_stream
         if p_drop:
             raise _lib.PixelRecB200Error(f"attention: dropout is not supported for L={qkv.shape[1]} > 64")
         return LongAttnFn.apply(qkv, key_ids, int(n_heads), bool(causal))
+    want_tf32 = bool(torch.backends.cuda.matmul.allow_tf32) if tf32 is None else bool(tf32)
+    if qkv.dim() == 3 and 32 < qkv.shape[1] <= 64 and not p_drop and want_tf32:
+        # CLIP ViT-B/32's 50 tokens: beyond the tensor-core kernel for short sequences (L <= 32), which left them to the FFMA
+        # kernel (0.36 ms per layer at 352 images); the long-sequence kernels have an mma.sync forward and no lower bound on L
+        dh = qkv.shape[2] // 3 // int(n_heads)
+        if dh in (4, 8, 16, 32, 64, 128):
+            return LongAttnFn.apply(qkv, key_ids, int(n_heads), bool(causal))
     return AttnFn.apply(qkv, key_ids, int(n_heads), bool(causal), float(p_drop), int(seed), int(rng_stream), tf32)
 
 
@@ -617,6 +624,54 @@ def _wgrad(dy2, x2):
     return dy2.t().mm(x2)
 
 
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) for a stand-alone nn.Linear (the CLIP ViT item encoder's projections, REC/model/load.py:90-117): forward,
+    input gradient and weight gradient on pr_gemm_tf32; bias + activation fused into the forward epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        K = w.shape[1]
+        x2 = x.reshape(-1, K)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        pre = None
+        if act is None:
+            y = gemm(x2, w, bias=b, debias=True)
+        elif need:
+            y, pre = gemm(x2, w, bias=b, epi=GEMM_ACT, act=act, want_pre=True, debias=True)
+        else:
+            y = gemm(x2, w, bias=b, epi=GEMM_ACT, act=act, debias=True)
+        ctx.save_for_backward(x2, w, pre)
+        ctx.act, ctx.xshape, ctx.has_bias = act, x.shape, b is not None
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, pre = ctx.saved_tensors
+        dy2 = dy.reshape(-1, w.shape[0]).contiguous()
+        if ctx.act is not None:
+            d = torch.empty_like(dy2)
+            with _prof("act_bwd", dy2):
+                _lib.check(_L().pr_act_bwd_f32(_p(pre), _p(dy2), dy2.numel(), ctx.act, _p(d), _stream(dy2)), "pr_act_bwd_f32")
+            _count()
+            dy2 = d
+        dx = gemm(dy2, w, b_mn=True, debias=True).view(ctx.xshape) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = gemm(dy2, x2, a_mn=True, b_mn=True, splits=_wgrad_splits(w.shape[0], w.shape[1], x2.shape[0]), debias=True)
+        db = dy2.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db, None
+
+
+def linear(x, weight, bias=None, act=None):
+    """nn.Linear [+ activation] on our tcgen05 GEMM when TF32 matmuls are allowed (torch.backends.cuda.matmul.allow_tf32), else
+    the strict-fp32 library path (torch F.linear + our activation kernel) used by the 1e-4 parity runs."""
+    act_id = None if act is None else ACT_IDS[act]
+    if _use_tc(weight.shape[0], weight.shape[1]) and x.is_cuda:
+        return LinearFn.apply(x.contiguous(), weight, bias, act_id)
+    y = torch.nn.functional.linear(x, weight, bias)
+    return y if act is None else activation(y.contiguous(), act)
+
+
 class TransformerLayerFn(torch.autograd.Function):
     """x [B,L,D] -> FeedForward(MultiHeadAttention(x))  (layers.py:700-703), one autograd node."""
 
@@ -755,23 +810,6 @@ def score_topk_exact(seq_out, item_feature, k, hist_u=None, hist_i=None, mask_co
                    "pr_score_topk_exact_f32")
     _count((4 if n_hist else 3) + 2 + (0 if w_norm_max is not None else 1))
     return val, idx, nfb
-
-
-def linear_tc(x, weight, bias=None, act=None, want_pre=False):
-    """y = act(x @ weight.T + bias) on the tcgen05 pipeline (pr_linear_tf32; staged alternative to cuBLAS addmm + pr_act_fwd).
-    x [..., K], weight [N, K] (nn.Linear layout).  act: None | 'gelu' | 'relu'.  want_pre: also return the pre-activation."""
-    _req(x, torch.float32, "x")
-    _req(weight, torch.float32, "weight")
-    N, K = weight.shape
-    M = x.numel() // K
-    out = torch.empty(*x.shape[:-1], N, device=x.device, dtype=torch.float32)
-    pre = torch.empty_like(out) if want_pre else None
-    act_id = -1 if act is None else ACT_IDS[act]
-    with _prof("linear_tc", x):
-        _lib.check(_L().pr_linear_tf32(_p(x), M, _p(weight), N, K, _p(bias), act_id, _p(out), _p(pre), _stream(x)),
-                   "pr_linear_tf32")
-    _count()
-    return (out, pre) if want_pre else out
 
 
 GEMM_STORE, GEMM_ADD, GEMM_ACT, GEMM_ACT_BWD = 0, 1, 2, 3

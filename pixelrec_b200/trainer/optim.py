@@ -151,10 +151,19 @@ class FusedAdamW(torch.optim.Optimizer):
 
     # ---- checkpoint interchange (trainer.py:153 stores optimizer.state_dict()) ----
     def state_dict(self):
+        """Collective when a table is row-sharded (every rank must call it, like model.state_dict()): the table's Adam moments are
+        gathered into the reference's full [N, D] layout, so a checkpoint written by rank 0 restores every rank's shard."""
         sd = super().state_dict()
+        tables = []
+        for pid, (M, V, _) in self._table_state.items():
+            tb = self._tables[pid]
+            if isinstance(tb, ShardedTableEmbedding):
+                tables.append((tb.gather_rows_full(M), tb.gather_rows_full(V)))
+            else:
+                tables.append((M.clone(), V.clone()))
         sd["fused"] = dict(step=self._step,
                            flat=[None if f is None else dict(m=f["m"].clone(), v=f["v"].clone()) for f in self._flat],
-                           tables=[(M.clone(), V.clone()) for (M, V, _) in self._table_state.values()])
+                           tables=tables)
         return sd
 
     def load_state_dict(self, sd):
@@ -165,5 +174,8 @@ class FusedAdamW(torch.optim.Optimizer):
             for f, s in zip(self._flat, fused["flat"]):
                 if f is not None and s is not None:
                     f["m"].copy_(s["m"]); f["v"].copy_(s["v"])
-            for (M, V, _), (m2, v2) in zip(self._table_state.values(), fused["tables"]):
+            for (pid, (M, V, _)), (m2, v2) in zip(self._table_state.items(), fused["tables"]):
+                tb = self._tables[pid]
+                if isinstance(tb, ShardedTableEmbedding) and m2.shape[0] == tb.num_embeddings and tb.world > 1:
+                    m2, v2 = tb.shard_of_full(m2), tb.shard_of_full(v2)          # full [N, D] moments -> rows rank::world
                 M.copy_(m2); V.copy_(v2)

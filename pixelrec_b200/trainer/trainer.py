@@ -186,11 +186,12 @@ class Trainer:
     # ------------------------------------------------------------------ checkpoint (trainer.py:138-190)
     def _save_checkpoint(self, epoch, verbose=True):
         model_state = unwrap(self.model).state_dict()      # collective when the table is sharded: every rank calls it
+        optim_state = self.optimizer.state_dict()          # likewise (the table's Adam moments are gathered to [N, D])
         if self.rank == 0:
             state = {
                 "config": self.config, "epoch": epoch, "cur_step": self.cur_step,
                 "best_valid_score": self.best_valid_score, "state_dict": model_state,
-                "optimizer": self.optimizer.state_dict(), "rng_state": torch.get_rng_state(),
+                "optimizer": optim_state, "rng_state": torch.get_rng_state(),
                 "cuda_rng_state": torch.cuda.get_rng_state() if torch.cuda.is_available() else None,
             }
             torch.save(state, self.saved_model_file)

@@ -131,26 +131,6 @@ extern "C" int emu_score_topk_f16(const float* seq, long long B_e, const float* 
     return a.n_splits;
 }
 
-// linear mode: y = act(x W^T + b)
-extern "C" int emu_linear_v2(const float* x, long long M, const float* W, long long N, long long Kd, const float* bias, int act,
-                             int cluster, float* out, float* pre) {
-    ScoreArgs a{};
-    a.kblocks = (int)(Kd / SC_BK);
-    a.m_tiles = (int)((M + SC_BM - 1) / SC_BM);
-    a.n_tiles = (int)((N + SC_BN - 1) / SC_BN);
-    if (a.m_tiles % cluster) return -1;
-    a.tiles_per_split = a.n_tiles;
-    a.n_splits = 1;
-    a.cluster = cluster;
-    a.lin_out = out; a.lin_pre = pre; a.lin_bias = bias; a.lin_act = act; a.lin_M = M; a.lin_N = N;
-    const CUtensorMap tmA{x, M, Kd, SC_BM, 4}, tmB{W, N, Kd, SC_BN / cluster, 4};
-    const size_t smem = (size_t)SC_STAGES * SC_STAGE_BYTES + SC2_BAR_BYTES + 1024;
-    emu::after_launch_hook() = emu::join_async;
-    emu::launch_cluster(a.m_tiles, cluster, SC2_THREADS, smem, [&]() { score_topk2_kernel<16, 2>(tmA, tmB, a); });
-    emu::after_launch_hook() = nullptr;
-    return 0;
-}
-
 extern "C" int emu_f32_to_f16(const float* src, long long n, uint16_t* dst) {
     bool sat = false;
     for (long long i = 0; i < n; ++i) dst[i] = f32_to_f16_rn(src[i], &sat);

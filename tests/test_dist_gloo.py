@@ -106,7 +106,7 @@ def _worker(rank, world, port, N, D, out_q):
         idx_all[:, :, 1, 0] = 0
         idx_all[0, 0, 0, :] = [0, 1, 2, 3, N - 1]
         dE_all = g.standard_normal((world, 6, 2, 5, D)).astype(np.float32)
-        table = pd.ShardedTableEmbedding(N, D, padding_idx=0)
+        table = pd.ShardedTableEmbedding(N, D, padding_idx=0, exchange="nccl")
         table.sink.row2slot = torch.zeros(1)            # oracle backend ignores it
         assert table.n_local == len(range(rank, N, world))
         table.load_state_dict({"weight": torch.from_numpy(W)})
@@ -272,3 +272,55 @@ def test_shard_rows_partition():
     for N in (1, 7, 97001, 408375):
         for world in (1, 2, 4, 8):
             assert sum(shard_rows(N, world, r) for r in range(world)) == N
+
+
+def _init_worker(rank, world, port, N, D, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pixelrec_b200 import dist as pd
+        torch.manual_seed(2020)                      # run.py seeds every rank identically (init_seed)
+        table = pd.ShardedTableEmbedding(N, D, padding_idx=0)
+        table.init_normal_(0.0, 0.02, chunk_rows=7)  # small chunks: the block / shard arithmetic is exercised
+        full = table.full_weight()                   # collective
+        moment = torch.arange(table.n_local * D, dtype=torch.float32).view(table.n_local, D) + 1000 * rank
+        m_full = table.gather_rows_full(moment)      # Adam-moment layout used by FusedAdamW.state_dict()
+        back = table.shard_of_full(m_full)
+        after = torch.rand(1)                        # generators of all ranks stay in lockstep
+        if rank == 0:
+            out_q.put(("ok", full.numpy(), torch.equal(back, moment), float(after)))
+        else:
+            out_q.put(("ok1", None, torch.equal(back, moment), float(after)))
+    except Exception:  # pragma: no cover
+        import traceback
+        out_q.put(("err", traceback.format_exc(), None, None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_table_init_is_the_logical_table_world2_gloo():
+    """with one seed on every rank, `weight.normal_()` per shard gave up to `world` items the same embedding.  The shard
+    must be rows rank::world of the logical [N, D] table: all rows distinct, iid, independent of the world size; and the
+    optimizer-state gather / re-shard round trip is exact."""
+    N, D, world = 45, 8, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_init_worker, args=(r, world, port, N, D, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+    assert all(r[0].startswith("ok") for r in res), res
+    full = next(r[1] for r in res if r[0] == "ok")
+    assert all(r[2] for r in res)                                   # gather_rows_full -> shard_of_full is the identity
+    assert res[0][3] == res[1][3]                                   # same random stream position on both ranks
+    assert full.shape == (N, D) and len(np.unique(full.round(7), axis=0)) == N      # no two items share an embedding
+    # the same seed in ONE process (world 1) draws the same logical table
+    from pixelrec_b200 import dist as pd
+    torch.manual_seed(2020)
+    single = pd.ShardedTableEmbedding(N, D, padding_idx=0)
+    single.init_normal_(0.0, 0.02, chunk_rows=7)
+    assert np.array_equal(single.weight.detach().numpy(), full)

@@ -43,7 +43,6 @@ def emu_score():
     lib.emu_score_topk_v2.argtypes = [_P, _LL, _P, _LL, _LL, _P, _P, _LL, _I, _I, _I, _I, _P, _P]
     lib.emu_score_topk_f16.argtypes = [_P, _LL, _P, _LL, _LL, _P, _P, _LL, _I, _I, _I, _I, _P, _P, _P, _I]
     lib.emu_f32_to_f16.argtypes = [_P, _LL, _P]
-    lib.emu_linear_v2.argtypes = [_P, _LL, _P, _LL, _LL, _P, _I, _I, _P, _P]
     lib.emu_score_ce_v2.argtypes = [_P, _LL, _P, _LL, _LL, _P, _I, _I, _I, _P, _P, _P]
     return lib
 
@@ -264,28 +263,6 @@ def test_score_topk_f16_pipeline_emulated(emu_score, B_e, N, D, k, splits, clust
         emu_score.emu_score_topk_f16(_ptr(seq), B_e, _ptr(W2), N, D, _ptr(hu), _ptr(hi), len(hu), 1, k, splits, cluster,
                                      _ptr(val), _ptr(idx), _ptr(status), ares)
         assert status[0] == 4
-
-
-@pytest.mark.parametrize("M,N,K,act,cluster,bias", [(200, 300, 64, 0, 1, True), (256, 520, 96, -1, 2, True), (130, 256, 32, 1, 1, False)])
-def test_linear_pipeline_emulated(emu_score, M, N, K, act, cluster, bias):
-    """linear-layer mode of the v2 pipeline: y = act(x W^T + b) with the bias / erf-GELU / store epilogue, ragged M and N,
-    optional pre-activation copy, W tiles multicast across the m-tiles of a cluster -- vs numpy (fp32 MMAs in the emulation)."""
-    import math
-    g = np.random.default_rng(M + N)
-    x = g.standard_normal((M, K)).astype(np.float32)
-    W = (0.2 * g.standard_normal((N, K))).astype(np.float32)
-    b = g.standard_normal(N).astype(np.float32) if bias else None
-    pre_ref = x.astype(np.float64) @ W.astype(np.float64).T + (b.astype(np.float64) if bias else 0.0)
-    if act == 0:
-        ref = 0.5 * pre_ref * (1.0 + np.vectorize(math.erf)(pre_ref / math.sqrt(2.0)))
-    elif act == 1:
-        ref = np.maximum(pre_ref, 0.0)
-    else:
-        ref = pre_ref
-    out = np.full((M, N), np.nan, np.float32)
-    pre = np.full((M, N), np.nan, np.float32)
-    assert emu_score.emu_linear_v2(_ptr(x), M, _ptr(W), N, K, _ptr(b) if bias else None, act, cluster, _ptr(out), _ptr(pre)) == 0
-    assert np.allclose(pre, pre_ref, rtol=1e-5, atol=1e-5) and np.allclose(out, ref, rtol=1e-5, atol=1e-5)
 
 
 def test_f32_to_f16_routine_matches_numpy(emu_score):

@@ -34,7 +34,8 @@ def _mask(key_ids, causal, B, L):
 
 @pytest.mark.parametrize("B,L,h,dh,causal,padded", [(3, 197, 12, 64, False, False), (2, 65, 2, 16, False, False),
                                                   (4, 100, 4, 32, True, True), (2, 256, 1, 64, False, True),
-                                                  (1, 130, 2, 128, True, False), (5, 77, 3, 8, False, False)])
+                                                  (1, 130, 2, 128, True, False), (5, 77, 3, 8, False, False),
+                                                  (6, 50, 12, 64, False, False), (3, 33, 2, 32, True, True), (2, 64, 4, 64, False, True)])
 def test_attn_long_fwd_bwd(B, L, h, dh, causal, padded, long_variant):
     from pixelrec_b200 import ops
     tc = bool(long_variant) and dh in (32, 64, 128)

@@ -46,7 +46,6 @@ CASES = {
     "attention_tf32": lambda o: o.attention(_f(2, 10, 3 * 64), None, 2, causal=True, tf32=True),
     "attention_long": lambda o: o.attention(_f(1, 100, 3 * 64), _i(1, 100), 2, causal=False),
     "score_topk": lambda o: o.score_topk(_f(4, 64), _f(50, 64), 5, _i(3), _i(3)),
-    "linear_tc": lambda o: o.linear_tc(_f(6, 64), _f(8, 64), _f(8), "gelu", want_pre=True),
     "score_topk_exact": lambda o: o.score_topk_exact(_f(4, 64), _f(50, 64), 5, _i(3), _i(3)),
     "table_norm_max": lambda o: o.table_norm_max(_f(50, 64)),
     "gemm": lambda o: o.gemm(_f(6, 64), _f(8, 64), bias=_f(8), epi=o.GEMM_ACT, act="gelu", want_pre=True),

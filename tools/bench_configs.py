@@ -78,6 +78,7 @@ def main():
     ap.add_argument("--patch", type=int, default=32, choices=[16, 32], help="c4: ViT-B/<patch>")
     ap.add_argument("--exchange", default=None, choices=["nccl", "p2p"])
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -150,7 +151,23 @@ def main():
             torch.cuda.synchronize()
 
     for i in range(max(args.warmup, 3)):
-        step(i)
+        loss = step(i)
+    del loss
+    eager_step, graphed = step, None
+    if world == 1 and not args.no_graph:
+        # one CUDA-graph launch per step (trainer/graph.py; yaml `cuda_graph: True`): these configurations are launch-bound in eager
+        # mode (C4: ~400 kernels of 20-100 us per step)
+        from pixelrec_b200.trainer.graph import GraphedTrainStep
+        try:
+            graphed = GraphedTrainStep(model, opt, batches[0])
+
+            def step(i):  # noqa: F811
+                return graphed(batches[i % POOL])
+            for i in range(3):
+                step(i)
+        except Exception as ex:  # noqa: BLE001
+            print(f"graph capture failed, staying eager: {type(ex).__name__}: {ex}", file=sys.stderr)
+            graphed, step = None, eager_step
     sync_all()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
@@ -162,6 +179,10 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = ms.item()
+    loss = float(loss)
+    if graphed is not None:
+        graphed.close()
+        step = eager_step
     # per-kernel pass (CUDA events around every launch of ours) -> achieved GB/s against the measured HBM peak
     from pixelrec_b200 import ops
     ops.PROFILE.update(on=True, names=None, events={})
@@ -200,7 +221,7 @@ def main():
                        "parallelism": ("single GPU" if world == 1 else
                                        f"dp{world}" + ("" if sh["model"] == "MOSASRec" else f" + item table row-sharded {world}-way"))},
             "roofline_kernels": kernels, "hbm_peak_GBps": hbm, "peak_source": peak_src, "cpu_baseline": cpu,
-            "loss": float(loss), "exchange_status": xs,
+            "loss": loss, "cuda_graph": graphed is not None, "exchange_status": xs,
             "max_memory_GB": torch.cuda.max_memory_allocated(dev) / 2 ** 30}))
     if world > 1:
         dist.destroy_process_group()

@@ -1,4 +1,4 @@
-"""Linear layers of the SASRec step (M = B*L = 81920 rows) on our tcgen05 GEMM vs cuBLAS TF32 (torch.addmm), CUDA events,
+"""Linear layers of the SASRec step (M = B*L = 81920 rows) on our CTA-pair tcgen05 GEMM vs cuBLAS TF32 (torch.addmm / mm / bmm), CUDA events,
 L2 flushed between iterations.  python tools/bench_linear.py [--M 81920] [--only fwd]"""
 import argparse
 import json
@@ -37,24 +37,6 @@ def timeit(fn, iters=args.iters):
 
 M = args.M
 out = {"M": M}
-for name, K, N, act in [("qkv", 512, 1536, None), ("dense", 512, 512, None), ("dense_1+gelu", 512, 1024, "gelu"),
-                        ("dense_2", 1024, 512, None)]:
-    x = torch.randn(M, K, device=dev)
-    W = torch.randn(N, K, device=dev) * 0.02
-    b = torch.randn(N, device=dev) * 0.05
-    fl = 2.0 * M * N * K
-
-    def ref():
-        y = torch.addmm(b, x, W.t())
-        return torch.nn.functional.gelu(y) if act else y
-    t_ref = timeit(ref)
-    t_mm = timeit(lambda: torch.addmm(b, x, W.t()))
-    t_tc = timeit(lambda: ops.linear_tc(x, W, b, act, want_pre=act is not None))
-    got = ops.linear_tc(x, W, b, act)
-    err = float((got - ref()).abs().max() / ref().abs().max())
-    out[name] = dict(K=K, N=N, cublas_ms=t_mm, cublas_TFLOPs=fl / t_mm / 1e9, cublas_plus_act_ms=t_ref, ours_ms=t_tc,
-                     ours_TFLOPs=fl / t_tc / 1e9, rel_err_vs_cublas_tf32=err)
-    print(name, out[name], flush=True)
 # ---- the CTA-pair GEMM (pr_gemm_tf32): forward, input-gradient and weight-gradient forms of every layer shape
 g2 = {}
 for name, K, N in [("qkv", 512, 1536), ("dense", 512, 512), ("dense_1", 512, 1024), ("dense_2", 1024, 512)]:

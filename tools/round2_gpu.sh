@@ -57,8 +57,6 @@ if [ "$stage" = stage1 ]; then
   run 300 r2_bench_b64_graph python bench.py --batch 64 --steps 200 --warmup 20 --no-cpu --graph
   run 300 r2_bench_b4096_graph python bench.py --steps 20 --warmup 5 --no-cpu --graph
   cp /tmp/libpixelrec_b200.default.so pixelrec_b200/libpixelrec_b200.so      # back to the default binary for the stages below
-  run 600 r2_bench_n1_linear_tc env PR_LINEAR_TC=1 python bench.py --steps 20 --warmup 5 --no-cpu      # FFN dense_1 + GELU on pr_linear_tf32
-  run 600 r2_bench_n1_linear_tc_mc env PR_LINEAR_TC=1 PR_TUNE=$((9 | 32)) python bench.py --steps 20 --warmup 5 --no-cpu
   tail -1 gpurun_out/r2_bench_n1.log > gpurun_out/r2_bench_n1.json
 elif [ "$stage" = ncu ]; then
   # one full capture per staged kernel that passed stage1 (never a bench number: ncu replays every kernel ~40 times)
