@@ -273,15 +273,26 @@ def run_ours(args, out):
     for i in range(max(args.warmup, 3)):
         step(resident[i % POOL])
     graphed = None
-    if args.graph and world == 1:
+    eager_step = step
+    if args.graph:
+        # N = 1, or N > 1 with the peer-memory exchange (device-side index plan + flag barriers: no host sync in the step)
         from pixelrec_b200.trainer.graph import GraphedTrainStep
-        graphed = GraphedTrainStep(model, opt, resident[0])
-        eager_step = step
-
-        def step(batch, nxt=None):       # noqa: F811 -- timed region 1 replays the captured step; inputs are copied into its static buffers
-            return graphed(batch)
-        for i in range(3):
-            step(resident[i % POOL])
+        ok = torch.ones(1, device=dev)
+        try:
+            graphed = GraphedTrainStep(model, opt, resident[0])
+        except Exception as ex:  # noqa: BLE001
+            print(f"[bench] rank {rank}: CUDA-graph capture not possible, staying eager: {type(ex).__name__}: {ex}", file=sys.stderr)
+            ok.zero_()
+        if world > 1:                    # all ranks replay or none does (the captured step contains collectives)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() < 1 and graphed is not None:
+            graphed.close()
+            graphed = None
+        if graphed is not None:
+            def step(batch, nxt=None):   # noqa: F811 -- timed region 1 replays the captured step; inputs are copied into its static buffers
+                return graphed(batch)
+            for i in range(3):
+                step(resident[i % POOL])
     # ---- timed region 1: inputs resident in HBM; the gather kernel is event-timed live inside it
     clocks = ClockSampler(local)
     ops.PROFILE.update(on=True, names={"gather_rows"}, events={})
@@ -302,6 +313,7 @@ def run_ours(args, out):
     look = Lookahead(model, dev)             # the public Trainer's own lookahead (H2D + plan of the next batch on a side stream)
 
     def e2e_step(i):
+        look.prefetch_plans = graphed is None
         staged = e2e_next.pop(i, None) or look.stage(host[i % POOL])
         cur = look.acquire(staged)
         e2e_next[i + 1] = look.stage(host[(i + 1) % POOL])
@@ -317,6 +329,7 @@ def run_ours(args, out):
     ms_e2e = timed(e2e_step, args.steps)
     e2e = B * world * args.steps / (ms_e2e / 1e3)
 
+    graphed_used = graphed is not None
     if graphed is not None:
         graphed.close()
         step = eager_step
@@ -439,7 +452,7 @@ def run_ours(args, out):
         "vs_baseline": None, "dtype": "f32 (tf32 tensor-core linear layers, fp32 everywhere else)", "data": "synthetic",
         "config": workload_config(B, world, exchange=getattr(model.item_embedding, "exchange", None),
                                   note=("both timed regions replay the captured step as one CUDA graph (yaml `cuda_graph: True`); "
-                                        "the per-kernel pass is eager") if (args.graph and world == 1) else None),
+                                        "the per-kernel pass is eager") if graphed_used else None),
         "e2e": {"value": e2e, "unit": "sequences/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
@@ -468,7 +481,14 @@ def run_ours(args, out):
     if rank == 0:
         out.emit(json.dumps(line))
     if world > 1:
+        # the line is out: tear down without any chance of hanging the launcher (captured graphs / IPC mappings / NCCL)
+        import gc
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        graphed = None  # noqa: F841
+        gc.collect()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 class StdoutGuard:

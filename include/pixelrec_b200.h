@@ -165,6 +165,11 @@ PR_API int pr_add_ln_bwd_bias_f32(const float* dy, const float* h, int64_t h_seq
 /* out[m, c] = sum_p partials[m, p, c]   (m < n_mats, p < n_partials), fixed order */
 PR_API int pr_colsum_f32(const float* partials, int n_mats, int n_partials, int64_t D, float* out, pr_stream_t stream);
 
+/* out[c] = sum_r x[r, c] for a dense row-major [M, C] matrix (C % 4 == 0): the bias gradient of the fused q|k|v projection
+ * (layers.py:586-588), whose output gradient comes from the attention backward.  partials: [pr_colsum_rows_partials(M, C), C]. */
+PR_API int pr_colsum_rows_partials(int64_t M, int64_t C);
+PR_API int pr_colsum_rows_f32(const float* x, int64_t M, int64_t C, float* partials, int n_partials, float* out, pr_stream_t stream);
+
 /* activation of the feed-forward layer: layers.py:640-660,667   y = act(x) ; dx = act'(x) * dy */
 PR_API int pr_act_fwd_f32(const float* x, int64_t n, int act, float* y, pr_stream_t stream);
 PR_API int pr_act_bwd_f32(const float* x, const float* dy, int64_t n, int act, float* dx, pr_stream_t stream);
@@ -364,6 +369,30 @@ PR_API int pr_gather_rows_peers_f32(const float* const* shards, int G, int64_t N
 PR_API int pr_push_rows_peers_f32(const float* rows, const int64_t* ids, int64_t U, int64_t D, int G, int rank, int64_t cap,
                                   int64_t skip_id, float* const* recv_rows, int64_t* const* recv_ids, int32_t* counters,
                                   int32_t* status, pr_stream_t stream);
+/* Barrier over peer-mapped flags: flag_tables[r] = device address (mapped here) of rank r's uint64 flag array [G], all zero at
+ * start; `epoch` = 1, 2, 3, ... the same sequence on every rank.  Returns (on the stream) once every rank has called it with this
+ * epoch; everything rank r wrote into peer memory before its call is visible to kernels launched after it.  status bit 4 = a
+ * peer did not arrive within ~2 s. */
+PR_API int pr_peer_barrier(uint64_t* const* flag_tables, int G, int rank, uint64_t epoch, uint64_t* epoch_dev, int32_t* status,
+                           pr_stream_t stream);
+/* epoch_dev != NULL: the call's epoch is ++(*epoch_dev) taken on the device (`epoch` ignored), so a captured CUDA graph can be
+ * replayed.
+ *
+ * Device-side exchange plan: the peer kernels driven by ONE pr_scatter_plan of the step's ids (padding id dropped), the number
+ * of distinct ids staying in device memory -- no host synchronisation, the multi-GPU step is CUDA-graph capturable.
+ *   pr_plan_inverse                 inverse[r] = slot u of request position r in uniq_ids, pad_slot for dropped positions
+ *   pr_gather_rows_peers_plan_f32   out[u] = owner's row of uniq_ids[u], u < *n_uniq; out[pad_slot] = row of pad_id (pad_slot >= 0);
+ *                                   out has max_uniq + 1 rows; expand to request order with pr_gather_rows_f32(out, inverse)
+ *   pr_push_rows_peers_plan_f32     pr_push_rows_peers_f32 over ids[0 .. *n_dev) (int32 global ids) */
+PR_API int pr_plan_inverse(const int32_t* perm, const int32_t* seg_start, const int32_t* n_uniq, int64_t R, int64_t pad_slot,
+                           int64_t* inverse, pr_stream_t stream);
+PR_API int pr_gather_rows_peers_plan_f32(const float* const* shards, int G, int64_t N, int64_t D, const int32_t* uniq_ids,
+                                         const int32_t* n_uniq, int64_t max_uniq, int64_t pad_id, int64_t pad_slot, float* out,
+                                         int32_t* status, pr_stream_t stream);
+PR_API int pr_push_rows_peers_plan_f32(const float* rows, const int32_t* ids, const int32_t* n_dev, int64_t max_n, int64_t D, int G,
+                                       int rank, int64_t cap, float* const* recv_rows, int64_t* const* recv_ids, int32_t* counters,
+                                       int32_t* status, pr_stream_t stream);
+
 
 #ifdef __cplusplus
 }

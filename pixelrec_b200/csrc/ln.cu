@@ -804,6 +804,62 @@ extern "C" int pr_colsum_f32(const float* partials, int n_mats, int n_partials, 
     return PR_OK;
 }
 
+// ---- column sums of a row-major matrix (bias gradient of a Linear whose output gradient no kernel of ours produced with
+// partials attached: the fused q|k|v projection, REC/model/layers.py:586-588).  Stage 1: CTA (row block, 128-column block), lane =
+// float4 column group, 8 warps stride the rows with 4 loads in flight, fixed-order reduction over the warps -> partials
+// [row_blocks, C]; stage 2: colsum_kernel.  Deterministic; reads the matrix once at HBM speed.
+__global__ void __launch_bounds__(256) colsum_rows_kernel(const float* __restrict__ x, long long M, long long C, int rows_per_cta,
+                                                          float* __restrict__ partials) {
+    __shared__ float4 sm[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long c0 = ((long long)blockIdx.x * 32 + lane) * 4;
+    const long long r0 = (long long)blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c0 < C) {
+        long long r = r0 + warp;
+        for (; r + 24 < r1; r += 32) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = ldg_stream(reinterpret_cast<const float4*>(x + (r + 8 * u) * C + c0));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+        }
+        for (; r < r1; r += 8) {
+            const float4 v = ldg_stream(reinterpret_cast<const float4*>(x + r * C + c0));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    sm[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && c0 < C) {
+        float4 t = sm[0][lane];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { t.x += sm[w][lane].x; t.y += sm[w][lane].y; t.z += sm[w][lane].z; t.w += sm[w][lane].w; }
+        *reinterpret_cast<float4*>(partials + (long long)blockIdx.y * C + c0) = t;
+    }
+}
+
+extern "C" int pr_colsum_rows_partials(int64_t M, int64_t C) {
+    if (M <= 0 || C <= 0) return 0;
+    const long long col_blocks = (C + 127) / 128;
+    long long row_blocks = std::max<long long>(1, (long long)sm_count() * 4 / col_blocks);
+    row_blocks = std::min<long long>(row_blocks, (M + 63) / 64);
+    return (int)row_blocks;
+}
+
+extern "C" int pr_colsum_rows_f32(const float* x, int64_t M, int64_t C, float* partials, int n_partials, float* out,
+                                  pr_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PR_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "pr_colsum_rows_f32: bad shape M=%lld C=%lld (C %% 4)", (long long)M, (long long)C);
+    PR_CHECK_ARG(x && partials && out && aligned16(x) && aligned16(partials), "pr_colsum_rows_f32: null/unaligned pointer");
+    PR_CHECK_ARG(n_partials == pr_colsum_rows_partials(M, C), "pr_colsum_rows_f32: n_partials=%d, expected %d", n_partials,
+                 pr_colsum_rows_partials(M, C));
+    const int rows_per_cta = (int)((M + n_partials - 1) / n_partials);
+    colsum_rows_kernel<<<dim3((unsigned)((C + 127) / 128), (unsigned)n_partials), 256, 0, stream>>>(x, M, C, rows_per_cta, partials);
+    PR_CUDA_LAUNCH_CHECK("colsum_rows_kernel");
+    return pr_colsum_f32(partials, 1, n_partials, C, out, stream_);
+}
+
 extern "C" int pr_act_fwd_f32(const float* x, int64_t n, int act, float* y, pr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PR_CHECK_ARG(n >= 0 && act >= 0 && act <= PR_ACT_QUICK_GELU, "pr_act_fwd_f32: bad n/act");

@@ -87,6 +87,12 @@ class CudaPeer:
     def push(rows, ids, G, rank, cap, skip_id, rows_table, ids_table, counters, status):
         ops.push_rows_peers(rows, ids, G, rank, cap, skip_id, rows_table, ids_table, counters, status)
 
+    @staticmethod
+    def barrier(flag_table, G, rank, epoch, status, epoch_dev=None):
+        ops.peer_barrier(flag_table, G, rank, epoch, status, epoch_dev)
+
+    device_plan = True          # the plan variants below exist (CPU stand-ins in tests/ keep the host-side PeerPlan)
+
 
 PEER = CudaPeer
 
@@ -190,6 +196,25 @@ class PeerPlan:
         return (self.uniq, self.inverse)
 
 
+class PeerPlanDev:
+    """Device-side index plan of one lookup for the peer-memory exchange: ONE pr_scatter_plan of the step's ids (padding id
+    dropped) gives the distinct ids, the runs that the backward reduces, and -- through pr_plan_inverse -- the map back to request
+    order.  The number of distinct ids never leaves the device: no host synchronisation, so the whole step (lookup, exchange,
+    backward, optimizer) can be captured into a CUDA graph and costs one launch per replay."""
+
+    def __init__(self, idx, N, padding_idx=None):
+        flat = idx.reshape(-1)
+        self.R = flat.numel()
+        self.splan = ops.ScatterPlan(flat, N, padding_idx)
+        self.pad_id = padding_idx
+        self.pad_slot = self.splan.max_uniq if padding_idx is not None else -1      # the pull's extra row holds W[pad]
+        self.inverse = ops.plan_inverse(self.splan, self.pad_slot)
+
+    def tensors(self):
+        p = self.splan
+        return (p.perm, p.uniq_ids, p.seg_start, p.n_uniq, p._ws, self.inverse)
+
+
 class PeerExchange:
     """Peer-mapped state of one ShardedTableEmbedding: the shard itself (moved into shareable memory), this rank's
     receive buffers, and device tables of every rank's addresses."""
@@ -215,14 +240,21 @@ class PeerExchange:
         self.recv_rows = self._rows.tensor((G * self.cap, D), torch.float32)
         self.recv_ids = self._ids.tensor((G * self.cap,), torch.int64)
         self.recv_ids.fill_(-1)                                                # -1 = unused slot (dropped by the plan)
-        mine = (self._w.handle, self._rows.handle, self._ids.handle, self.cap)
+        # barrier flags: one uint64 per peer, written remotely by that peer (pr_peer_barrier); PR_P2P_BARRIER=nccl keeps the
+        # 4-byte all_reduce instead
+        self.flag_barrier = os.environ.get("PR_P2P_BARRIER", "flags").lower() == "flags" and hasattr(PEER, "barrier")
+        self._flags = PEER.alloc(max(G, 1) * 8, dev)
+        self._flags.tensor((G,), torch.int64).zero_()
+        self.epoch = 0
+        self.epoch_dev = None
+        mine = (self._w.handle, self._rows.handle, self._ids.handle, self.cap, self._flags.handle)
         everyone = [None] * G
         dist.all_gather_object(everyone, mine, group=table.group)
         if any(e[3] != self.cap for e in everyone):
             raise ops._lib.PixelRecB200Error("peer exchange: ranks disagree on the receive capacity (unequal batch sizes?)")
-        own = (self._w.ref, self._rows.ref, self._ids.ref)
-        refs = [[own[k] if r == rank else PEER.open(everyone[r][k], dev) for r in range(G)] for k in range(3)]
-        self.w_table, self.rows_table, self.ids_table = (PEER.table(x, dev) for x in refs)
+        own = (self._w.ref, self._rows.ref, self._ids.ref, None, self._flags.ref)
+        refs = [[own[k] if r == rank else PEER.open(everyone[r][k], dev) for r in range(G)] for k in (0, 1, 2, 4)]
+        self.w_table, self.rows_table, self.ids_table, self.flag_table = (PEER.table(x, dev) for x in refs)
         self.counters = torch.zeros(G, dtype=torch.int32, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         self._sync = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -231,8 +263,25 @@ class PeerExchange:
             torch.cuda.synchronize(dev)
         dist.barrier(group=table.group)          # every shard copied and every id buffer initialised before the first pull
 
+    def use_device_epoch(self, on=True):
+        """CUDA-graph mode: the barrier's epoch is counted in device memory (a captured kernel cannot take a new host value per
+        replay).  Call right before capturing / after the last replay; the count carries over in both directions."""
+        if on and self.epoch_dev is None:
+            self.epoch_dev = torch.full((1,), self.epoch, dtype=torch.int64, device=self.status.device)
+        elif not on and self.epoch_dev is not None:
+            self.epoch = int(self.epoch_dev.item())
+            self.epoch_dev = None
+
     def barrier(self):
-        """Orders the peer kernels of all ranks on their streams (4-byte all_reduce; asynchronous w.r.t. the host)."""
+        """Orders the peer kernels of all ranks on their streams (asynchronous w.r.t. the host): one small kernel over peer-mapped
+        flags (pr_peer_barrier), or a 4-byte NCCL all_reduce with PR_P2P_BARRIER=nccl."""
+        if self.flag_barrier:
+            self.epoch += 1
+            if self.epoch_dev is not None:
+                PEER.barrier(self.flag_table, self.G, self.rank, self.epoch, self.status, self.epoch_dev)
+            else:
+                PEER.barrier(self.flag_table, self.G, self.rank, self.epoch, self.status)
+            return
         with ops._prof("exchange_barrier", self._sync):
             dist.all_reduce(self._sync, group=self.group)
 
@@ -244,7 +293,11 @@ class PeerGatherFn(torch.autograd.Function):
         px = table.peer_exchange(plan.R)
         D = table.embedding_dim
         px.barrier()                          # S1: every owner has finished the optimizer step of the previous batch
-        rows_u = PEER.gather(px.w_table, table.world, table.num_embeddings, D, plan.uniq)   # lookup + exchange, one kernel
+        if isinstance(plan, PeerPlanDev):
+            rows_u = ops.gather_rows_peers_plan(px.w_table, table.world, table.num_embeddings, D, plan.splan, plan.pad_id,
+                                                plan.pad_slot, px.status)                   # lookup + exchange, one kernel
+        else:
+            rows_u = PEER.gather(px.w_table, table.world, table.num_embeddings, D, plan.uniq)
         out = ROWS.gather(rows_u, plan.inverse)                                             # distinct rows -> request order
         ctx.plan, ctx.table, ctx.px = plan, table, px
         return out.view(*idx.shape, D)
@@ -256,10 +309,15 @@ class PeerGatherFn(torch.autograd.Function):
         if plan.R > px.R:
             raise ops._lib.PixelRecB200Error(f"peer exchange sized for {px.R} lookups per step, got {plan.R}")
         dE = dE.contiguous().view(plan.R, D)
-        d_u = ROWS.scatter_slots(dE, plan.inverse, plan.U, plan.pad_slot)       # local duplicates reduced first
         px.counters.zero_()
-        PEER.push(d_u, plan.uniq, table.world, table.rank, px.cap, table.padding_idx, px.rows_table, px.ids_table,
-                  px.counters, px.status)
+        if isinstance(plan, PeerPlanDev):
+            d_u = ROWS.scatter(dE, plan.splan)                                   # local duplicates reduced first (pad dropped)
+            ops.push_rows_peers_plan(d_u, plan.splan, table.world, table.rank, px.cap, px.rows_table, px.ids_table,
+                                     px.counters, px.status)
+        else:
+            d_u = ROWS.scatter_slots(dE, plan.inverse, plan.U, plan.pad_slot)
+            PEER.push(d_u, plan.uniq, table.world, table.rank, px.cap, table.padding_idx, px.rows_table, px.ids_table,
+                      px.counters, px.status)
         px.barrier()                          # S2: every rank's rows have landed in the owners' receive buffers
         splan = ROWS.plan(px.recv_ids, table.n_local, None, row2slot=table.sink.row2slot)
         rows = ROWS.scatter(px.recv_rows, splan)            # duplicates ACROSS ranks reduced here, in ascending source rank
@@ -323,6 +381,8 @@ class ShardedTableEmbedding(nn.Module):
 
     def _make_plan(self, idx):
         if self.exchange == "p2p":
+            if getattr(PEER, "device_plan", False) and os.environ.get("PR_P2P_PLAN", "device") == "device":
+                return PeerPlanDev(idx, self.num_embeddings, self.padding_idx)
             return PeerPlan(idx, self.padding_idx)
         return ExchangePlan(idx, self.world, self.group, self.padding_idx)
 
@@ -331,6 +391,12 @@ class ShardedTableEmbedding(nn.Module):
         if self._px is None:
             self._px = PeerExchange(self, R)
         return self._px
+
+    def graph_capturable(self):
+        """True when a training step through this table contains no host synchronisation (peer exchange with the device plan
+        and flag barriers): trainer/graph.py may capture it."""
+        return (self.exchange == "p2p" and getattr(PEER, "device_plan", False)
+                and os.environ.get("PR_P2P_PLAN", "device") == "device" and self._px is not None and self._px.flag_barrier)
 
     def exchange_status(self):
         """Host-synchronising check of the peer exchange's device flags (bit 0: bad id, bit 1: a receive region

@@ -39,6 +39,8 @@ SIGNATURES = {
     "pr_act_bwd_bias_partials": (_I, [_I64, _I64]),
     "pr_act_bwd_bias_f32": (_I, [_P, _P, _I64, _I64, _I, _P, _P, _I, _P]),
     "pr_colsum_f32": (_I, [_P, _I, _I, _I64, _P, _P]),
+    "pr_colsum_rows_partials": (_I, [_I64, _I64]),
+    "pr_colsum_rows_f32": (_I, [_P, _I64, _I64, _P, _I, _P, _P]),
     "pr_act_fwd_f32": (_I, [_P, _I64, _I, _P, _P]),
     "pr_act_bwd_f32": (_I, [_P, _P, _I64, _I, _P, _P]),
     "pr_sasrec_attn_fwd_f32": (_I, [_P, _P, _P, _I64, _P, _I, _I, _I, _I, _I, _F, _U64, _U32, _P, _P, _P]),
@@ -68,6 +70,10 @@ SIGNATURES = {
     "pr_shared_open": (_I, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "pr_shared_close": (_I, [_P]),
     "pr_gather_rows_peers_f32": (_I, [_P, _I, _I64, _I64, _P, _I64, _P, _P, _P]),
+    "pr_peer_barrier": (_I, [_P, _I, _I, _U64, _P, _P, _P]),
+    "pr_plan_inverse": (_I, [_P, _P, _P, _I64, _I64, _P, _P]),
+    "pr_gather_rows_peers_plan_f32": (_I, [_P, _I, _I64, _I64, _P, _P, _I64, _I64, _I64, _P, _P, _P]),
+    "pr_push_rows_peers_plan_f32": (_I, [_P, _P, _P, _I64, _I64, _I, _I, _I64, _P, _P, _P, _P, _P]),
     "pr_push_rows_peers_f32": (_I, [_P, _P, _I64, _I64, _I, _I, _I64, _I64, _P, _P, _P, _P, _P]),
 }
 

@@ -572,6 +572,19 @@ def _raw_act_bwd_bias(x, dy, act):
     return dx, db[0]
 
 
+def colsum_rows(x2):
+    """[M, C] -> [C] column sums (bias gradient), one pass over x2 at HBM speed, deterministic (pr_colsum_rows_f32)"""
+    _req(x2, torch.float32, "x2")
+    M, C = x2.shape
+    n_part = _L().pr_colsum_rows_partials(M, C)
+    partials = torch.empty(max(n_part, 1), C, device=x2.device, dtype=torch.float32)
+    out = torch.empty(C, device=x2.device, dtype=torch.float32)
+    with _prof("colsum_rows", x2):
+        _lib.check(_L().pr_colsum_rows_f32(_p(x2), M, C, _p(partials), n_part, _p(out), _stream(x2)), "pr_colsum_rows_f32")
+    _count(2)
+    return out
+
+
 WGRAD_SPLIT = int(os.environ.get("PR_WGRAD_SPLIT", "8"))
 # Linear layers of the encoder: "tc" = our CTA-pair tcgen05 GEMM (pr_gemm_tf32) for forward, input-gradient and weight-gradient
 # GEMMs whenever TF32 matmuls are allowed (torch.backends.cuda.matmul.allow_tf32, the reference's torch-1.10 default);
@@ -658,7 +671,7 @@ class LinearFn(torch.autograd.Function):
         dw = None
         if ctx.needs_input_grad[1]:
             dw = gemm(dy2, x2, a_mn=True, b_mn=True, splits=_wgrad_splits(w.shape[0], w.shape[1], x2.shape[0]), debias=True)
-        db = dy2.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        db = (colsum_rows(dy2) if dy2.shape[1] % 4 == 0 else dy2.sum(0)) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db, None
 
 
@@ -741,7 +754,7 @@ class TransformerLayerFn(torch.autograd.Function):
         _count()
         dqkv2 = dqkv.view(M, 3 * D)
         dwqkv = _wgrad(dqkv2, x2)                                           # one GEMM for the three projections
-        dbqkv = dqkv2.sum(0)
+        dbqkv = colsum_rows(dqkv2) if dqkv2.shape[1] % 4 == 0 else dqkv2.sum(0)
         dx = _linear_dgrad(dqkv2, wqkv, add=dx_res).view(B, L, D)          # residual grad folded into the GEMM epilogue
         return (dx, None, dwqkv[:D], dbqkv[:D], dwqkv[D:2 * D], dbqkv[D:2 * D], dwqkv[2 * D:], dbqkv[2 * D:], dwo, dbo, dg1, dbe1,
                 dw1, db1, dw2, db2, dg2, dbe2, None, None, None, None, None, None, None, None)
@@ -993,6 +1006,48 @@ def gather_rows_peers(shard_table, G, N, D, idx, status=None):
                                                  _stream(idx)), "pr_gather_rows_peers_f32")
     _count()
     return out
+
+
+def peer_barrier(flag_table, G, rank, epoch, status=None, epoch_dev=None):
+    """flag_table: int64 CUDA tensor [G] of device addresses of every rank's uint64 flag array (pr_peer_barrier);
+    epoch_dev: int64 [1] device counter used instead of `epoch` (CUDA-graph replay)"""
+    _req(flag_table, torch.int64, "flag_table")
+    with _prof("exchange_barrier", flag_table):
+        _lib.check(_L().pr_peer_barrier(_p(flag_table), int(G), int(rank), int(epoch), _p(epoch_dev), _p(status),
+                                        _stream(flag_table)), "pr_peer_barrier")
+    _count()
+
+
+def plan_inverse(plan, pad_slot):
+    """request position -> slot in plan.uniq_ids (pad_slot for the positions the plan dropped); int64 [R]"""
+    inv = torch.empty(max(plan.R, 1), device=plan.perm.device, dtype=torch.int64)
+    with _prof("plan_inverse", plan.perm):
+        _lib.check(_L().pr_plan_inverse(_p(plan.perm), _p(plan.seg_start), _p(plan.n_uniq), plan.R, int(pad_slot), _p(inv),
+                                        _stream(plan.perm)), "pr_plan_inverse")
+    _count()
+    return inv
+
+
+def gather_rows_peers_plan(shard_table, G, N, D, plan, pad_id, pad_slot, status=None):
+    """[plan.max_uniq + 1, D]: row u = the owner's row of plan.uniq_ids[u] (u < n_uniq, read over NVLink), row pad_slot = pad row"""
+    _req(shard_table, torch.int64, "shard_table")
+    out = torch.empty(plan.max_uniq + 1, D, device=plan.perm.device, dtype=torch.float32)
+    with _prof("gather_rows_peers", plan.perm):
+        _lib.check(_L().pr_gather_rows_peers_plan_f32(_p(shard_table), int(G), int(N), int(D), _p(plan.uniq_ids), _p(plan.n_uniq),
+                                                      plan.max_uniq, -1 if pad_id is None else int(pad_id), int(pad_slot), _p(out),
+                                                      _p(status), _stream(plan.perm)), "pr_gather_rows_peers_plan_f32")
+    _count()
+    return out
+
+
+def push_rows_peers_plan(rows, plan, G, rank, cap, recv_rows_table, recv_ids_table, counters, status=None):
+    _req(rows, torch.float32, "rows")
+    _req(counters, torch.int32, "counters")
+    with _prof("push_rows_peers", rows):
+        _lib.check(_L().pr_push_rows_peers_plan_f32(_p(rows), _p(plan.uniq_ids), _p(plan.n_uniq), plan.max_uniq, rows.shape[1],
+                                                    int(G), int(rank), int(cap), _p(recv_rows_table), _p(recv_ids_table),
+                                                    _p(counters), _p(status), _stream(rows)), "pr_push_rows_peers_plan_f32")
+    _count()
 
 
 def push_rows_peers(rows, ids, G, rank, cap, skip_id, recv_rows_table, recv_ids_table, counters, status=None):

@@ -13,8 +13,9 @@ The caller must not hold the loss tensor (or anything else with a grad_fn) of an
 a live autograd graph keeps its AccumulateGrad nodes, which stay bound to the stream they were created on (the default one),
 and the engine would then make that stream wait on the capturing one -- cudaErrorStreamCaptureImplicit.
 
-Single GPU only (the row exchange of a sharded table needs host-side split sizes), fixed batch shape (a ragged last batch runs
-eagerly), dropout > 0 needs a library built with -DPR_SEED_DEV.
+Multi-GPU: capturable with the peer-memory exchange (`exchange: p2p`, the default) whose index plan and barrier epochs stay on
+the device (dist.PeerPlanDev, pr_peer_barrier); the NCCL all_to_all exchange needs host-side split sizes and stays eager.
+Fixed batch shape (a ragged last batch runs eagerly); dropout > 0 needs device-side seeds (-DPR_SEED_DEV, the default build).
 """
 import torch
 
@@ -35,6 +36,17 @@ class GraphedTrainStep:
         if self._seeded:
             ops.set_seed_device(self.seed_offset)            # raises in builds without -DPR_SEED_DEV
         optimizer.use_device_step(True)
+        # row-sharded table (N > 1): only the peer-memory exchange with the device-side plan is free of host syncs; its barrier
+        # epochs move to device memory for the replays
+        self._px = []
+        for m in model.modules():
+            if hasattr(m, "graph_capturable"):
+                if not m.graph_capturable():
+                    optimizer.use_device_step(False)
+                    raise ops._lib.PixelRecB200Error("cuda_graph: this table's row exchange synchronises with the host "
+                                                     "(needs exchange='p2p' with the device plan, after one eager step)")
+                m._px.use_device_epoch(True)
+                self._px.append(m._px)
         self.graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize(dev)
         launches0 = ops.LAUNCHES["count"]
@@ -78,3 +90,10 @@ class GraphedTrainStep:
         if self._seeded:
             ops.set_seed_device(None)
         self.optimizer.use_device_step(False)
+        for px in getattr(self, "_px", []):
+            px.use_device_epoch(False)
+        self._px = []
+        # release the captured graph now: it holds references to NCCL work (N > 1) and to the private memory pool, and a process
+        # group cannot be destroyed cleanly while such a graph is alive
+        self.graph = None
+        self.loss = None

@@ -37,6 +37,7 @@ class Lookahead:
         self.model = model
         self.device = device
         self.stream = torch.cuda.Stream(device=device) if torch.cuda.is_available() else None
+        self.prefetch_plans = True
 
     def stage(self, batch):
         """host batch -> (device batch, ready event)"""
@@ -54,7 +55,7 @@ class Lookahead:
         with torch.cuda.stream(self.stream):
             dev = tuple(t.to(self.device, non_blocking=True) for t in batch) if isinstance(batch, (tuple, list)) \
                 else batch.to(self.device, non_blocking=True)
-            if hasattr(self.model, "prefetch"):
+            if self.prefetch_plans and hasattr(self.model, "prefetch"):
                 self.model.prefetch(dev)
             ev = torch.cuda.Event()
             ev.record(self.stream)
@@ -136,7 +137,9 @@ class Trainer:
         nxt = next(it, None)
         staged = look.stage(nxt) if nxt is not None else None
         graphed, n_eager = None, 0
-        want_graph = bool(self.config["cuda_graph"]) and get_world_size() == 1 and not self.clip_grad_norm   # staged, opt-in
+        # yaml `cuda_graph: True`: one launch per step.  N > 1 needs the peer-memory exchange (GraphedTrainStep checks and the
+        # loop stays eager otherwise)
+        want_graph = bool(self.config["cuda_graph"]) and not self.clip_grad_norm
         while staged is not None:
             data = look.acquire(staged)
             nxt = next(it, None)
@@ -149,6 +152,7 @@ class Trainer:
                     self.logger.warning("cuda_graph: staying eager (%s)" % e)
                     want_graph = False
             if graphed is not None and graphed.matches(data):
+                look.prefetch_plans = False       # the index plan is built inside the captured step
                 total += graphed(data).detach()
                 continue
             n_eager += 1

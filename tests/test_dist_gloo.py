@@ -70,6 +70,20 @@ class ShmPeer:
         return out.view(*idx.shape, D)
 
     @staticmethod
+    def barrier(flag_table, G, rank, epoch, status):
+        """same flag protocol as peer_barrier_kernel: publish `epoch` in every peer's array, wait for every peer's flag"""
+        import time
+        for r in range(G):
+            flag_table[r].view(torch.int64)[rank] = epoch
+        t0 = time.time()
+        mine = flag_table[rank].view(torch.int64)
+        while any(int(mine[r]) < epoch for r in range(G)):
+            if time.time() - t0 > 60:
+                status[0] |= 4
+                return
+            time.sleep(0.001)
+
+    @staticmethod
     def push(rows, ids, G, rank, cap, skip_id, rows_table, ids_table, counters, status):
         for u, i in enumerate(ids.tolist()):
             if i == skip_id:

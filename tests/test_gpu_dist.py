@@ -116,15 +116,105 @@ def test_sharded_dp_step_equals_single_gpu(world, exchange):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, state, q, exchange)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, state, q, exchange), daemon=True) for r in range(world)]
     for p in procs:
         p.start()
     status, loss, sd = q.get(timeout=300)
     for p in procs:
         p.join(60)
+        if p.is_alive():
+            p.kill()
     assert status == "ok", loss
     assert abs(loss - ref_loss) / abs(ref_loss) < 1e-5
     for k in ref_sd:
         assert sd[k].shape == ref_sd[k].shape, k
         err = (sd[k] - ref_sd[k]).abs().max().item()
         assert err < 2e-5, (k, err)            # lr 1e-3: one AdamW step moves weights by <= 1e-3
+
+
+def _graph_worker(rank, world, port, state, q):
+    """4 steps eager vs 2 eager + 2 CUDA-graph replays of the SAME sharded step (peer-memory exchange, device-side plan)"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), PR_EXCHANGE="p2p", PR_P2P_CAP_FACTOR=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from pixelrec_b200.model.IDNet.sasrec import SASRec
+        from pixelrec_b200.trainer.graph import GraphedTrainStep
+        from pixelrec_b200.trainer.optim import FusedAdamW
+        torch.backends.cuda.matmul.allow_tf32 = False
+        cfg = dict(CFG, hidden_dropout_prob=0.1, attn_dropout_prob=0.1)
+        g = np.random.default_rng(100 + rank)
+        batches = []
+        for _ in range(4):
+            items = g.integers(1, N, size=(B, 2, L + 1)).astype(np.int64)
+            items[:, 1, 0] = 0
+            items[::3, 0, :3] = 0
+            items[::3, 1, :4] = 0
+            mask = (items[:, 1, 1:] != 0).astype(np.int64)
+            batches.append((torch.from_numpy(items).to(dev), torch.from_numpy(mask).to(dev)))
+        results = []
+        for use_graph in (False, True):
+            m = SASRec(cfg, _Dl())
+            m.load_state_dict(state)
+            m = m.to(dev).train()
+            opt = FusedAdamW(m.parameters(), lr=1e-3, weight_decay=0.1, tables=[m.item_embedding])
+            graphed, losses = None, []
+            for i, b in enumerate(batches):
+                if use_graph and i == 2:
+                    graphed = GraphedTrainStep(m, opt, b)
+                if graphed is not None:
+                    losses.append(float(graphed(b)))
+                else:
+                    opt.zero_grad()
+                    loss = m(b)
+                    loss.backward()
+                    opt.step()
+                    losses.append(float(loss))
+                    del loss
+            if graphed is not None:
+                graphed.close()
+            assert m.item_embedding.exchange_status() == 0
+            sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+            results.append((losses, sd))
+            del graphed, m, opt                  # no captured NCCL work / IPC mappings alive at process-group teardown
+            import gc
+            gc.collect()
+            torch.cuda.synchronize()
+            dist.barrier()
+        (l_e, sd_e), (l_g, sd_g) = results
+        same = l_e == l_g and all(torch.equal(sd_e[k], sd_g[k]) for k in sd_e)
+        worst = max(float((sd_e[k] - sd_g[k]).abs().max()) for k in sd_e)
+        q.put(("ok", rank, same, worst, l_e, l_g))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put(("err", rank, traceback.format_exc(), None, None, None))
+    finally:
+        import threading
+        threading.Timer(20.0, lambda: os._exit(0)).start()     # never leave a worker behind (it would keep pytest alive)
+        dist.destroy_process_group()
+
+
+def test_sharded_step_graph_replay_equals_eager_world2():
+    """N > 1 CUDA-graph replay: the peer-memory exchange with the device-side index plan and flag barriers has no host
+    synchronisation, so the whole sharded step is captured; replays must be bit-identical to eager steps (dropout included)."""
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from pixelrec_b200.model.IDNet.sasrec import SASRec
+    torch.manual_seed(1)
+    state = {k: v.clone() for k, v in SASRec(CFG, _Dl()).state_dict().items()}
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_graph_worker, args=(r, world, port, state, q), daemon=True) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+        if p.is_alive():
+            p.kill()
+    for r in res:
+        assert r[0] == "ok", r[2]
+        assert r[2], f"rank {r[1]}: graph replay differs from eager (max |dw| {r[3]}, losses {r[4]} vs {r[5]})"

@@ -252,3 +252,16 @@ def test_weight_grad_split_k_matches_single_gemm():
         torch.backends.cuda.matmul.allow_tf32 = old
     assert got.shape == (o, i) and rel(got.cpu().numpy(), ref) < TOL
     assert rel(small.cpu().numpy(), dy[:1000].astype(np.float64).T @ x[:1000].astype(np.float64)) < TOL
+
+
+@pytest.mark.parametrize("M,C", [(1, 4), (70, 16), (1000, 132), (81920, 1536), (4097, 512)])
+def test_colsum_rows(M, C):
+    """bias gradient of the fused q|k|v projection: column sums of its output gradient (layers.py:586-588)"""
+    from pixelrec_b200 import ops
+    g = np.random.default_rng(M + C)
+    x = g.standard_normal((M, C)).astype(np.float32)
+    got = ops.colsum_rows(t(x))
+    ref = x.astype(np.float64).sum(0)
+    assert got.shape == (C,)
+    assert np.abs(got.cpu().numpy() - ref).max() <= 1e-5 * np.abs(x).sum(0).max()
+    assert torch.equal(got, ops.colsum_rows(t(x)))          # deterministic

@@ -48,6 +48,7 @@ CASES = {
     "score_topk": lambda o: o.score_topk(_f(4, 64), _f(50, 64), 5, _i(3), _i(3)),
     "score_topk_exact": lambda o: o.score_topk_exact(_f(4, 64), _f(50, 64), 5, _i(3), _i(3)),
     "table_norm_max": lambda o: o.table_norm_max(_f(50, 64)),
+    "colsum_rows": lambda o: o.colsum_rows(_f(70, 16)),
     "gemm": lambda o: o.gemm(_f(6, 64), _f(8, 64), bias=_f(8), epi=o.GEMM_ACT, act="gelu", want_pre=True),
     "gemm_wgrad_splitk": lambda o: o.gemm(_f(64, 8), _f(64, 12), a_mn=True, b_mn=True, splits=2),
     "gemm_act_bwd_colsum": lambda o: o.gemm(_f(6, 64), _f(64, 8), b_mn=True, aux=_f(6, 8), epi=o.GEMM_ACT_BWD, act="gelu",

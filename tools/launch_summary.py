@@ -16,7 +16,7 @@ def short(name):
 
 
 def owner(name):
-    if "pixelrec_b200" in name or re.search(r"\b(gather_rows|scatter_add|adamw_|add_ln|act_|attn_|bpr_|colsum|plan_|rs_|scan_|seg_|seq_batch|score_topk|mask_)", name):
+    if "pixelrec_b200" in name or re.search(r"\b(gather_rows|scatter_add|adamw_|add_ln|act_|attn_|bpr_|colsum|plan_|rs_|scan_|seg_|seq_batch|score_|mask_|gemm_tf32|gemm_splitk|rownorm)", name):
         return "ours"
     if "cutlass" in name or "gemm" in name.lower() or "cublas" in name.lower() or "splitK" in name:
         return "cuBLAS"
