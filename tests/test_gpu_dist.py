@@ -97,6 +97,8 @@ def _worker(rank, world, port, state, q, exchange="nccl"):
         import traceback
         q.put(("err", traceback.format_exc(), None))
     finally:
+        import threading
+        threading.Timer(20.0, lambda: os._exit(0)).start()     # never leave a worker behind (it would keep pytest alive)
         dist.destroy_process_group()
 
 
