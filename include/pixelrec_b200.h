@@ -162,6 +162,14 @@ PR_API int pr_add_ln_bwd_bias_f32(const float* dy, const float* h, int64_t h_seq
                       int64_t D, float p_pre, float p_post, uint64_t seed, uint32_t stream_pre, uint32_t stream_post,
                       float* dh, int64_t dh_seq_stride, int dh_accumulate, float* dres, float* partials,
                       int n_partials, pr_stream_t stream);
+/* Backward of LayerNorm(z) where z = drop_pre(h) + res was WRITTEN by the producing Linear (pr_gemm_tf32_drop: bias + dropout +
+ * residual in the GEMM epilogue, layers.py:613-615 / 669-671), so the forward is pr_add_ln_fwd_f32(z, res = NULL, p_pre = 0) and
+ * the backward reads two tensors instead of three:  dz = LN'(dy) (gradient of the residual branch; NULL when p_pre == 0, where
+ * dh == dz),  dh = drop_pre mask applied to dz (same Philox draws as the epilogue),  partials [3, n_partials, D] = (dgamma,
+ * dbeta, column sums of dh = bias gradient of the Linear).  Contiguous [rows, D] tensors. */
+PR_API int pr_add_ln_bwd_bias_z_f32(const float* dy, const float* z, const float* gamma, const float* mean, const float* rstd,
+                      int64_t rows, int64_t D, float p_pre, uint64_t seed, uint32_t stream_pre, float* dh, float* dz,
+                      float* partials, int n_partials, pr_stream_t stream);
 /* out[m, c] = sum_p partials[m, p, c]   (m < n_mats, p < n_partials), fixed order */
 PR_API int pr_colsum_f32(const float* partials, int n_mats, int n_partials, int64_t D, float* out, pr_stream_t stream);
 
@@ -288,6 +296,12 @@ PR_API int pr_gemm_colsum_rows(int64_t M);
 PR_API int pr_gemm_tf32(const float* A, int a_mn, int64_t lda, const float* B, int b_mn, int64_t ldb, int64_t M, int64_t N,
                         int64_t K, const float* bias, const float* aux, int epi, int act, float* out, float* out2, int splits,
                         float* colsum_partials, int flags, pr_stream_t stream);
+/* PR_GEMM_ADD with the hidden dropout of layers.py:614 / :670 in the epilogue:  out = drop(acc + bias) + aux, the keep bits being
+ *   exactly those pr_add_ln_fwd_f32 would draw for (seed, rng_stream) on a [M, N] tensor (Philox4x32-10, layout in ln.cu), so that
+ *   pr_add_ln_bwd_bias_z_f32 and the oracle (oracle/philox_np.py) regenerate the same mask.  One draw serves 8 outputs.  p_drop in [0, 1). */
+PR_API int pr_gemm_tf32_drop(const float* A, int a_mn, int64_t lda, const float* B, int b_mn, int64_t ldb, int64_t M, int64_t N,
+                             int64_t K, const float* bias, const float* aux, float* out, int flags, float p_drop, uint64_t seed,
+                             uint32_t rng_stream, pr_stream_t stream);
 PR_API int pr_gemm_splitk_reduce_f32(const float* partials, int splits, int64_t n, float* out, pr_stream_t stream);
 
 /* K9 with fp16 operands (staged): fp16 has the 10 explicit mantissa bits of TF32 (and is rounded to nearest, where the TF32

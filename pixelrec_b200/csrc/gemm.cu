@@ -67,6 +67,12 @@ struct GemmArgs {
     int has_out2;
     int stages, obuf;                      // ring depth; out-staging buffers per epilogue warp (1 or 2)
     int debias;                            // scale the accumulator by 1.00071 (TF32 truncation shrink): see pr_gemm_tf32 in the header
+    float p_drop;                          // PR_GEMM_ADD only: out = drop(acc + bias) + aux with ln.cu's keep-bit layout (pr_gemm_tf32_drop)
+    unsigned long long seed;
+    unsigned rng_stream;
+#ifdef PR_SEED_DEV
+    const unsigned long long* seed_dev;
+#endif
     int debug;                             // PR_GEMM_DEBUG (timing experiments only, results are garbage): 1 = no output stores,
                                            // 2 = no operand loads (MMAs on whatever the ring holds)
 };
@@ -291,7 +297,9 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tf32_kernel(const __grid_c
         // ------------------------------------------------------------------ epilogue warps 2..9: thread == output row
         const int ew = warp - 2;
         const int q = warp & 3;                                                     // TMEM lane quadrant of this warp
-        const int half = ew >> 2;                                                   // which 128 of the tile's 256 columns
+        // chunk c of this warp = columns [64c + 32*half, +32) of the tile's 256: float4 columns f and f + 32 of a 512-byte
+        // group then belong to the SAME thread (chunks c and c + 2), which is what lets one Philox draw serve both (dropout)
+        const int half = ew >> 2;
         float* ost0 = reinterpret_cast<float*>(out_stage + ew * GM_CHUNK_BYTES);
         float* ast = reinterpret_cast<float*>(aux_stage + ew * GM_CHUNK_BYTES);
         const int obuf_stride = (a.obuf > 1) ? GM_EPI_WARPS * GM_CHUNK_BYTES / 4 : 0;   // floats between this warp's two buffers
@@ -305,21 +313,30 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tf32_kernel(const __grid_c
         if (has_aux && lane == 0 && group < n_items) {                              // aux chunk of the first item
             const GmItem wi = gm_item(a, group);
             mbar_arrive_expect_tx(abar, GM_CHUNK_BYTES);
-            tma_load_2d(ast, &tmAux, wi.n_tile * GM_BN + half * 128, wi.m_tile * (GM_BM * CG) + rank * GM_BM + q * 32, abar);
+            tma_load_2d(ast, &tmAux, wi.n_tile * GM_BN + half * 32, wi.m_tile * (GM_BM * CG) + rank * GM_BM + q * 32, abar);
         }
+        const bool drop = a.p_drop > 0.f;
+        const Philox ph(drop ? PR_SEED(a) : 0ull);
+        const unsigned drop_thr = drop_threshold(a.p_drop);
+        const float drop_ik = 1.0f / (1.0f - a.p_drop);
+        const unsigned long long D4 = (unsigned long long)(a.N >> 2);
         for (long long w = group; w < n_items; w += n_groups, ++tc) {
             const GmItem wi = gm_item(a, w);
             const int buf = (int)(tc & 1);
             const int row0 = wi.m_tile * (GM_BM * CG) + rank * GM_BM + q * 32;
-            const int colb = wi.n_tile * GM_BN + half * 128;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * GM_BN + half * 128);
-            // this warp's 128 bias values: lane l holds columns [colb + 4l, +4); broadcast by shuffles below (one global load
-            // per lane and tile, issued before the wait for the accumulator)
+            const int colb = wi.n_tile * GM_BN + half * 32;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * GM_BN + half * 32);
+            // this warp's 128 bias values: lane l holds the 4 columns at (chunk l / 8, float4 l % 8); broadcast by shuffles below
+            // (one global load per lane and tile, issued before the wait for the accumulator)
             float4 bl = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.bias && colb + lane * 4 < a.N) bl = __ldg(reinterpret_cast<const float4*>(a.bias + colb + lane * 4));
+            {
+                const int bc = colb + (lane >> 3) * 64 + (lane & 7) * 4;
+                if (a.bias && bc < a.N) bl = __ldg(reinterpret_cast<const float4*>(a.bias + bc));
+            }
+            unsigned keep_hi0 = 0, keep_hi1 = 0;                                   // high nibbles of chunks 0 / 1, used by chunks 2 / 3
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
-                const int col0 = colb + c * 32;
+                const int col0 = colb + c * 64;
                 float x[32];
                 if (has_aux) {
                     mbar_wait(abar, aux_par);
@@ -332,7 +349,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tf32_kernel(const __grid_c
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {                                               // next chunk's aux (this item or the next one)
-                        int nr = row0, nc = col0 + 32;
+                        int nr = row0, nc = col0 + 64;
                         bool more = true;
                         if (c == 3) {
                             const long long wn = w + n_groups;
@@ -340,7 +357,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tf32_kernel(const __grid_c
                             if (more) {
                                 const GmItem nx = gm_item(a, wn);
                                 nr = nx.m_tile * (GM_BM * CG) + rank * GM_BM + q * 32;
-                                nc = nx.n_tile * GM_BN + half * 128;
+                                nc = nx.n_tile * GM_BN + half * 32;
                             }
                         }
                         if (more) {
@@ -355,7 +372,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tf32_kernel(const __grid_c
                 }
                 float v[32];
                 __syncwarp();                                                      // tcgen05.ld is warp-collective
-                tmem_ld32(taddr + c * 32, v);
+                tmem_ld32(taddr + c * 64, v);
                 if (c == 3) {                                                      // last TMEM read of this item: hand the buffer back
                     tc_fence_before();
                     __syncwarp();
@@ -379,6 +396,25 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tf32_kernel(const __grid_c
                     }
                 }
                 if (a.epi == GM_EPI_ADD) {
+                    if (drop) {
+                        // ln.cu's layout: float4 column f of row r takes nibble (f / 32) & 1 of keep_bits8(Philox(r * D4 + f % 32 + 64 * (f / 64)));
+                        // here f = 64 * n_tile + 16 * c + 8 * half + j, so chunks c and c + 2 share their eight draws
+                        unsigned kb = (c & 1) ? keep_hi1 : keep_hi0;
+                        if (c < 2) {
+                            const unsigned long long ctr = (unsigned long long)(row0 + lane) * D4 + (unsigned)(64 * wi.n_tile + 16 * c + 8 * half);
+                            unsigned lo = 0, hi = 0;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const unsigned m = keep_bits8(ph(ctr + j, a.rng_stream), drop_thr);
+                                lo |= (m & 15u) << (4 * j);
+                                hi |= (m >> 4) << (4 * j);
+                            }
+                            kb = lo;
+                            if (c == 0) keep_hi0 = hi; else keep_hi1 = hi;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = ((kb >> j) & 1u) ? v[j] * drop_ik : 0.f;
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] += x[j];
                 } else if (a.epi == GM_EPI_ACT_BWD) {
@@ -573,10 +609,13 @@ extern "C" int pr_gemm_colsum_rows(int64_t M) {
     return (int)(mt * (GM_BM * cg) / 32);
 }
 
-extern "C" int pr_gemm_tf32(const float* A, int a_mn, int64_t lda, const float* B, int b_mn, int64_t ldb, int64_t M, int64_t N,
-                            int64_t K, const float* bias, const float* aux, int epi, int act, float* out, float* out2,
-                            int splits, float* colsum_partials, int flags, pr_stream_t stream_) {
+static int gemm_impl(const float* A, int a_mn, int64_t lda, const float* B, int b_mn, int64_t ldb, int64_t M, int64_t N,
+                     int64_t K, const float* bias, const float* aux, int epi, int act, float* out, float* out2,
+                     int splits, float* colsum_partials, int flags, float p_drop, uint64_t seed, uint32_t rng_stream,
+                     pr_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    PR_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "pr_gemm_tf32_drop: p_drop=%f outside [0, 1)", (double)p_drop);
+    PR_CHECK_ARG(p_drop == 0.f || epi == GM_EPI_ADD, "pr_gemm_tf32_drop: dropout belongs to the PR_GEMM_ADD epilogue");
     PR_CHECK_ARG(M > 0 && N > 0 && K > 0, "pr_gemm_tf32: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
     // a K tail needs no code: the tensor maps carry the true K and TMA zero-fills what lies beyond it
     PR_CHECK_ARG((a_mn || K % 4 == 0) && (b_mn || K % 4 == 0), "pr_gemm_tf32: a K-major operand needs K %% 4 == 0 (K=%lld)", (long long)K);
@@ -606,6 +645,8 @@ extern "C" int pr_gemm_tf32(const float* A, int a_mn, int64_t lda, const float* 
     a.a_mn = a_mn ? 1 : 0; a.b_mn = b_mn ? 1 : 0;
     a.epi = epi; a.act = act; a.M = M; a.N = N; a.bias = bias; a.colsum = colsum_partials; a.has_out2 = out2 ? 1 : 0;
     a.debias = (flags & 1) ? 1 : 0;
+    a.p_drop = p_drop; a.seed = seed; a.rng_stream = rng_stream;
+    PR_SET_SEED_DEV(a);
     {
         // deepest ring that fits beside the staging buffers (PR_GEMM_STAGES / PR_GEMM_OBUF override, for A/B runs)
         const int stage_bytes = (cg == 2) ? GemmCfg<2>::STAGE_BYTES : GemmCfg<1>::STAGE_BYTES;
@@ -658,6 +699,20 @@ extern "C" int pr_gemm_tf32(const float* A, int a_mn, int64_t lda, const float* 
         }
     }
     return (cg == 2) ? gm_launch<2>(tmA, tmB, tmOut, tmOut2, tmAux, a, stream) : gm_launch<1>(tmA, tmB, tmOut, tmOut2, tmAux, a, stream);
+}
+
+extern "C" int pr_gemm_tf32(const float* A, int a_mn, int64_t lda, const float* B, int b_mn, int64_t ldb, int64_t M, int64_t N,
+                            int64_t K, const float* bias, const float* aux, int epi, int act, float* out, float* out2,
+                            int splits, float* colsum_partials, int flags, pr_stream_t stream) {
+    return gemm_impl(A, a_mn, lda, B, b_mn, ldb, M, N, K, bias, aux, epi, act, out, out2, splits, colsum_partials, flags, 0.f, 0, 0,
+                     stream);
+}
+
+extern "C" int pr_gemm_tf32_drop(const float* A, int a_mn, int64_t lda, const float* B, int b_mn, int64_t ldb, int64_t M, int64_t N,
+                                 int64_t K, const float* bias, const float* aux, float* out, int flags, float p_drop,
+                                 uint64_t seed, uint32_t rng_stream, pr_stream_t stream) {
+    return gemm_impl(A, a_mn, lda, B, b_mn, ldb, M, N, K, bias, aux, PR_GEMM_ADD, -1, out, nullptr, 1, nullptr, flags, p_drop, seed,
+                     rng_stream, stream);
 }
 
 extern "C" int pr_gemm_splitk_reduce_f32(const float* partials, int splits, int64_t n, float* out, pr_stream_t stream_) {

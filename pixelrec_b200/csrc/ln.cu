@@ -18,6 +18,8 @@ struct LnArgs {
     long long rows; int D4;
     float p_pre, p_post; unsigned long long seed; unsigned stream_pre, stream_post;
     int l2_prefetch;   // PR_TUNE_LN_L2_PREFETCH: pull the warp's next row into L2 while this one is processed
+    int h_is_z;        // backward only: `h` already holds z = drop_pre(h) + res (written by pr_gemm_tf32_drop's epilogue), res is null;
+                       // the pre-dropout mask is then applied to the outgoing gradient only
 #ifdef PR_SEED_DEV
     const unsigned long long* seed_dev;   // device-side seed offset (pr_set_seed_device)
 #endif
@@ -58,7 +60,7 @@ __device__ __forceinline__ void load_z(const LnArgs& a, long long row, int lane,
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
         float4 v = hv[j];
-        if (a.p_pre > 0.f) v = apply_keep(v, mk_pre[j >> 1] >> (4 * (j & 1)), inv_keep_pre);
+        if (a.p_pre > 0.f && !a.h_is_z) v = apply_keep(v, mk_pre[j >> 1] >> (4 * (j & 1)), inv_keep_pre);
         v.x += rv[j].x; v.y += rv[j].y; v.z += rv[j].z; v.w += rv[j].w;
         z[j] = v;
     }
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 2 : 1) add_ln_bwd_kernel(LnA
 // flight (cp.async.bulk + mbarrier complete_tx) while the warp works on the oldest one, so the bytes in flight per SM
 // no longer depend on how many rows fit in registers.  Row -> warp mapping, arithmetic and summation order are those
 // of add_ln_bwd_kernel.
-template <int VPL, bool DBIAS, int STAGES>
+template <int VPL, bool DBIAS, int STAGES, int NSRC>   // NSRC rows per stage: [dy | h | res], or [dy | z] (no residual / z mode)
 __global__ void __launch_bounds__(256, (VPL <= 4) ? 2 : 1) add_ln_bwd_pipe_kernel(
     LnArgs a, const float* __restrict__ dy, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
     float* __restrict__ dh, long long dh_seq_stride, int dh_accumulate, float* __restrict__ dres,
@@ -371,12 +373,12 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 2 : 1) add_ln_bwd_pipe_kerne
     constexpr int RF4 = VPL * 32;                       // float4 per row
     constexpr unsigned ROW_BYTES = RF4 * 16u;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    float4* ring = sm_dyn + (size_t)wid * STAGES * 3 * RF4;
-    float4* sm_acc = sm_dyn + (size_t)nw * STAGES * 3 * RF4;
+    float4* ring = sm_dyn + (size_t)wid * STAGES * NSRC * RF4;
+    float4* sm_acc = sm_dyn + (size_t)nw * STAGES * NSRC * RF4;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm_acc + 3 * RF4) + wid * STAGES;
     const long long warp = (long long)blockIdx.x * nw + wid;
     const long long nwarps = (long long)gridDim.x * nw;
-    const bool has_res = a.res != nullptr;
+    const bool has_res = NSRC == 3 && a.res != nullptr;
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 2 : 1) add_ln_bwd_pipe_kerne
     __syncwarp();
     auto issue = [&](int s, long long row) {            // lane 0 only
         const long long sq = row / a.rows_per_seq, tt = row - sq * a.rows_per_seq;
-        float4* st = ring + (size_t)s * 3 * RF4;
+        float4* st = ring + (size_t)s * NSRC * RF4;
         mbar_arrive_expect_tx(&bars[s], (has_res ? 3u : 2u) * ROW_BYTES);
         bulk_g2s(st, dy + row * (long long)(RF4 * 4), ROW_BYTES, &bars[s]);
         bulk_g2s(st + RF4, a.h + sq * a.h_seq_stride + tt * (long long)(RF4 * 4), ROW_BYTES, &bars[s]);
@@ -418,14 +420,14 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 2 : 1) add_ln_bwd_pipe_kerne
         if (a.p_post > 0.f) row_keep_bits<VPL>(ph, a.stream_post, thr_post, row, RF4, lane, mk_post);
         const float mean = mean_in[row], rstd = rstd_in[row];
         mbar_wait(&bars[s], parity);
-        const float4* st = ring + (size_t)s * 3 * RF4;
+        const float4* st = ring + (size_t)s * NSRC * RF4;
         float4 d[VPL], z[VPL];
 #pragma unroll
         for (int j = 0; j < VPL; ++j) {
             const int c = lane + 32 * j;
             d[j] = st[c];
             float4 v = st[RF4 + c];
-            if (a.p_pre > 0.f) v = apply_keep(v, mk_pre[j >> 1] >> (4 * (j & 1)), ik_pre);
+            if (a.p_pre > 0.f && !a.h_is_z) v = apply_keep(v, mk_pre[j >> 1] >> (4 * (j & 1)), ik_pre);
             if (has_res) {
                 const float4 r = st[2 * RF4 + c];
                 v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
@@ -721,7 +723,7 @@ extern "C" int pr_add_ln_bwd_partials(int64_t rows, int64_t D) {
     return ln_bwd_grid(rows, D);
 }
 
-static int add_ln_bwd_impl(bool want_dbias, const float* dy, const float* h, int64_t h_seq_stride, int64_t rows_per_seq,
+static int add_ln_bwd_impl(bool want_dbias, bool h_is_z, const float* dy, const float* h, int64_t h_seq_stride, int64_t rows_per_seq,
                                  const float* res, int64_t res_period, const float* gamma, const float* mean,
                                  const float* rstd, int64_t rows, int64_t D, float p_pre, float p_post, uint64_t seed,
                                  uint32_t stream_pre, uint32_t stream_post, float* dh, int64_t dh_seq_stride,
@@ -747,19 +749,28 @@ static int add_ln_bwd_impl(bool want_dbias, const float* dy, const float* h, int
              p_pre, p_post, seed, stream_pre, stream_post, 0};
     PR_SET_SEED_DEV(a);
     a.l2_prefetch = (tune() & PR_TUNE_LN_L2_PREFETCH) ? 1 : 0;
+    a.h_is_z = h_is_z ? 1 : 0;
+    PR_CHECK_ARG(!h_is_z || !res, "pr_add_ln_bwd_bias_z_f32: z already contains the residual");
     if (ln_bwd_pipe_ok(D)) {
-#define PIPE(V, S)                                                                                                   \
+#define PIPE(V, S, NS)                                                                                               \
     do {                                                                                                             \
-        const size_t sm = (size_t)8 * S * 3 * D * 4 + (size_t)3 * D * 4 + 8 * S * sizeof(uint64_t);                   \
-        auto kt = add_ln_bwd_pipe_kernel<V, true, S>;                                                                \
-        auto kf = add_ln_bwd_pipe_kernel<V, false, S>;                                                               \
+        const size_t sm = (size_t)8 * S * NS * D * 4 + (size_t)3 * D * 4 + 8 * S * sizeof(uint64_t);                  \
+        auto kt = add_ln_bwd_pipe_kernel<V, true, S, NS>;                                                            \
+        auto kf = add_ln_bwd_pipe_kernel<V, false, S, NS>;                                                           \
         PR_CUDA_CALL(cudaFuncSetAttribute(want_dbias ? kt : kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
         (want_dbias ? kt : kf)<<<grid, 256, sm, stream>>>(a, dy, mean, rstd, dh, dh_seq_stride, dh_accumulate, dres, partials); \
     } while (0)
-        if (D == 128) PIPE(1, 8);
-        else if (D == 256) PIPE(2, 4);
-        else if (D == 512) PIPE(4, 2);
-        else PIPE(8, 2);
+        if (res) {                      // three source rows per stage
+            if (D == 128) PIPE(1, 8, 3);
+            else if (D == 256) PIPE(2, 4, 3);
+            else if (D == 512) PIPE(4, 2, 3);
+            else PIPE(8, 2, 3);
+        } else {                        // two source rows per stage: the same shared memory holds 1.5x the stages
+            if (D == 128) PIPE(1, 12, 2);
+            else if (D == 256) PIPE(2, 6, 2);
+            else if (D == 512) PIPE(4, 3, 2);
+            else PIPE(8, 3, 2);
+        }
 #undef PIPE
         PR_CUDA_LAUNCH_CHECK("add_ln_bwd_pipe_kernel");
         return PR_OK;
@@ -781,7 +792,7 @@ extern "C" int pr_add_ln_bwd_f32(const float* dy, const float* h, int64_t h_seq_
                                  const float* rstd, int64_t rows, int64_t D, float p_pre, float p_post, uint64_t seed,
                                  uint32_t stream_pre, uint32_t stream_post, float* dh, int64_t dh_seq_stride,
                                  int dh_accumulate, float* dres, float* partials, int n_partials, pr_stream_t stream_) {
-    return add_ln_bwd_impl(false, dy, h, h_seq_stride, rows_per_seq, res, res_period, gamma, mean, rstd, rows, D, p_pre, p_post,
+    return add_ln_bwd_impl(false, false, dy, h, h_seq_stride, rows_per_seq, res, res_period, gamma, mean, rstd, rows, D, p_pre, p_post,
                            seed, stream_pre, stream_post, dh, dh_seq_stride, dh_accumulate, dres, partials, n_partials, stream_);
 }
 
@@ -790,8 +801,15 @@ extern "C" int pr_add_ln_bwd_bias_f32(const float* dy, const float* h, int64_t h
                                       const float* rstd, int64_t rows, int64_t D, float p_pre, float p_post, uint64_t seed,
                                       uint32_t stream_pre, uint32_t stream_post, float* dh, int64_t dh_seq_stride,
                                       int dh_accumulate, float* dres, float* partials, int n_partials, pr_stream_t stream_) {
-    return add_ln_bwd_impl(true, dy, h, h_seq_stride, rows_per_seq, res, res_period, gamma, mean, rstd, rows, D, p_pre, p_post,
+    return add_ln_bwd_impl(true, false, dy, h, h_seq_stride, rows_per_seq, res, res_period, gamma, mean, rstd, rows, D, p_pre, p_post,
                            seed, stream_pre, stream_post, dh, dh_seq_stride, dh_accumulate, dres, partials, n_partials, stream_);
+}
+
+extern "C" int pr_add_ln_bwd_bias_z_f32(const float* dy, const float* z, const float* gamma, const float* mean, const float* rstd,
+                                        int64_t rows, int64_t D, float p_pre, uint64_t seed, uint32_t stream_pre, float* dh,
+                                        float* dz, float* partials, int n_partials, pr_stream_t stream_) {
+    return add_ln_bwd_impl(true, true, dy, z, 0, rows > 0 ? rows : 1, nullptr, 0, gamma, mean, rstd, rows, D, p_pre, 0.f, seed,
+                           stream_pre, 0, dh, 0, 0, dz, partials, n_partials, stream_);
 }
 
 extern "C" int pr_colsum_f32(const float* partials, int n_mats, int n_partials, int64_t D, float* out,

@@ -8,6 +8,9 @@
 
 #include "common.cuh"
 
+#define PR_DYN_SMEM_BYTES(name) extern __shared__ __align__(128) unsigned char name[]
+#include "rows_ring.cuh"
+
 namespace pr {
 
 // =====================================================================================
@@ -343,8 +346,9 @@ __global__ void plan_empty_kernel(int* seg_start, int* n_uniq) {
 }
 
 // =====================================================================================
-// K2 segment reduce: one warp per (unique id, 32*VPL-float4 column block); rows of a run are
-// added sequentially in ascending position -> deterministic, matches the oracle bit for bit
+// K2 segment reduce, LDG form (rows outside the ring kernel's range, A/B under PR_TUNE without bit 256): one warp per
+// (unique id, 32*VPL-float4 column block); rows of a run are added sequentially in ascending position -> deterministic,
+// matches the oracle bit for bit.  The default path is scatter_add_rows_ring_kernel (rows_ring.cuh).
 // =====================================================================================
 template <int VPL>
 __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float4* __restrict__ dOut, int D4, int ncb,
@@ -645,6 +649,38 @@ extern "C" int pr_scatter_add_rows_f32(const float* dOut, int64_t R, int64_t D, 
     const int D4 = (int)(D / 4);
     const int sms = sm_count();
     const long long work_hint = std::min<long long>(max_uniq, R);
+    if ((tune() & PR_TUNE_SCATTER_RING) && D >= 64 && D <= 2048) {
+        // TMA-staged ring (rows_ring.cuh): VPL float4 per lane cover a row, 8 KiB stages.  Measured (profiles/r02j_scatter_ab.json):
+        // 1.1-2.5x the LDG kernel up to D = 2048; at D = 4096 a row is 32 float4 per lane and the LDG kernel's 4 warps per row win.
+        int vpl = 1;
+        while (32 * vpl < D4) vpl *= 2;
+        const int rps = std::max(1, 16 / vpl);
+        const size_t smem = (size_t)SR_STAGES * rps * D * 4 + SR_BAR_BYTES;
+        int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
+        ctas_per_sm = std::max(1, std::min(16, ctas_per_sm));
+        const long long max_ctas = (long long)sms * ctas_per_sm;
+        int gr = 32;   // runs per group: fewer when the step is small, so that every CTA still gets work
+        while (gr > 2 && work_hint / gr < 2 * max_ctas) gr >>= 1;
+        const int grid = (int)std::max<long long>(1, std::min<long long>((work_hint + gr - 1) / gr, max_ctas));
+#define PR_LAUNCH_RING(VPL, RPS)                                                                                    \
+    do {                                                                                                            \
+        if (smem > 48 * 1024)                                                                                       \
+            PR_CUDA_CALL(cudaFuncSetAttribute(scatter_add_rows_ring_kernel<VPL, RPS>,                               \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+        scatter_add_rows_ring_kernel<VPL, RPS><<<grid, 32, smem, stream>>>(dOut, (int)D, gr, perm, uniq_ids, seg_start, \
+                                                                          n_uniq, max_uniq, scale, out_rows, dense_G); \
+    } while (0)
+        switch (vpl) {
+            case 1: PR_LAUNCH_RING(1, 16); break;
+            case 2: PR_LAUNCH_RING(2, 8); break;
+            case 4: PR_LAUNCH_RING(4, 4); break;
+            case 8: PR_LAUNCH_RING(8, 2); break;
+            default: PR_LAUNCH_RING(16, 1); break;
+        }
+#undef PR_LAUNCH_RING
+        PR_CUDA_LAUNCH_CHECK("scatter_add_rows_ring_kernel");
+        return PR_OK;
+    }
 #define PR_LAUNCH_SCATTER(VPL)                                                                                      \
     do {                                                                                                            \
         const int ncb = (D4 + 32 * VPL - 1) / (32 * VPL);                                                           \

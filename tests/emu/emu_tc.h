@@ -174,6 +174,14 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity) {
     });
     if (!ok) emu::fail("DEADLOCK: an mbarrier wait was not satisfied within 180 s");
 }
+// 1-D bulk copy global -> shared (cp.async.bulk): asynchronous, completes `bytes` on the barrier
+inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    if (bytes % 16 || ((uintptr_t)dst & 15) || ((uintptr_t)src & 15)) emu::fail("bulk copy needs 16-byte aligned addresses and size");
+    emu::run_async([=]() {
+        memcpy(dst, src, bytes);
+        emu::complete_tx_at(bar, (long long)bytes);
+    });
+}
 inline void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
     const CUtensorMap m = *tm;
     unsigned char* d = (unsigned char*)dst;

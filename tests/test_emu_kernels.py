@@ -284,3 +284,59 @@ def test_f32_to_f16_routine_matches_numpy(emu_score):
     ref[over] = (ref[over] & 0x8000) | 0x7BFF                      # saturate instead of inf
     assert sat == 1 and over.any()
     assert np.array_equal(out, ref)
+
+
+@pytest.fixture(scope="module")
+def emu_rows():
+    """csrc/rows_ring.cuh on the emulated mbarrier / bulk-copy layer (tests/emu/emu_tc.h)"""
+    out = os.path.join(tempfile.mkdtemp(prefix="pr_emu_"), "libemu_rows.so")
+    src = os.path.join(ROOT, "tests", "emu", "emu_rows.cpp")
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", out, src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lib = C.CDLL(out)
+    lib.emu_scatter_add_rows_ring.argtypes = [_P, _I, _I, _P, _P, _P, _P, _LL, C.c_float, _P, _P, _I]
+    return lib
+
+
+def _np_plan(idx, N, pad):
+    """what pr_scatter_plan emits: stable sort of (id, position) with padding / nothing dropped to the end"""
+    key = np.where(idx == pad, N, idx)
+    perm = np.argsort(key, kind="stable").astype(np.int32)
+    sk = key[perm]
+    nreal = int((sk < N).sum())
+    starts = np.flatnonzero(np.r_[True, sk[1:nreal] != sk[:nreal - 1]]) if nreal else np.zeros(0, np.int64)
+    uniq = sk[starts].astype(np.int32)
+    seg = np.r_[starts, nreal].astype(np.int32)
+    return perm, uniq, seg
+
+
+@pytest.mark.parametrize("N,D,R,gr,grid,hot", [(50, 64, 300, 4, 3, 0), (200, 512, 260, 32, 2, 0), (40, 384, 200, 8, 1, 0),
+                                               (30, 128, 500, 2, 7, 0.6), (300, 1024, 90, 32, 5, 0), (64, 2048, 70, 16, 2, 0.3),
+                                               (20, 1536, 40, 32, 3, 0), (10, 512, 0, 32, 2, 0), (10, 512, 40, 32, 2, 1.0)])
+def test_scatter_add_rows_ring_emulated(emu_rows, N, D, R, gr, grid, hot):
+    """TMA-staged segment reduce (rows_ring.cuh): ring protocol, group / run bookkeeping and the summation order, bit for bit
+    against oracle.scatter_add_rows -- including one hot id that owns most rows, all-padding input and R = 0."""
+    g = np.random.default_rng(N * 131 + D + R)
+    idx = g.integers(0, N, size=R).astype(np.int64)
+    if hot:
+        idx[g.random(R) < hot] = 0 if hot == 1.0 else 7
+    dO = g.standard_normal((max(R, 1), D)).astype(np.float32)[:R]
+    perm, uniq, seg = _np_plan(idx, N, 0)
+    U = len(uniq)
+    max_uniq = max(1, min(R, N))
+    uniq_b = np.full(max_uniq, -1, np.int32); uniq_b[:U] = uniq
+    seg_b = np.full(max_uniq + 1, -1, np.int32); seg_b[:U + 1] = seg
+    n_uniq = np.array([U], np.int32)
+    rows = np.full((max_uniq, D), np.nan, np.float32)
+    G = np.zeros((N, D), np.float32)
+    dOc = np.ascontiguousarray(dO) if R else np.zeros((1, D), np.float32)
+    assert emu_rows.emu_scatter_add_rows_ring(_ptr(dOc), D, gr, _ptr(perm), _ptr(uniq_b), _ptr(seg_b), _ptr(n_uniq), max_uniq, 1.0,
+                                              _ptr(rows), _ptr(G), grid) > 0
+    G_ref = O.scatter_add_rows(dO, idx, N, 0) if R else np.zeros((N, D), np.float32)
+    np.testing.assert_array_equal(G, G_ref)
+    np.testing.assert_array_equal(rows[:U], G_ref[uniq])
+    assert np.isnan(rows[U:]).all()                    # rows beyond n_uniq are never written
+    rows2 = np.full((max_uniq, D), np.nan, np.float32)
+    emu_rows.emu_scatter_add_rows_ring(_ptr(dOc), D, gr, _ptr(perm), _ptr(uniq_b), _ptr(seg_b), _ptr(n_uniq), max_uniq, 0.25,
+                                       _ptr(rows2), None, grid)
+    np.testing.assert_array_equal(rows2[:U], G_ref[uniq] * np.float32(0.25))
