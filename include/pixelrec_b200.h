@@ -324,12 +324,19 @@ PR_API int pr_score_topk_f16(const float* seq_out, int64_t B_e, const void* W16,
  *   For every row: lse = log sum_c exp(<seq_out[row], W[c]>) over the catalog (column 0 excluded when mask_col0 != 0),
  *   tgt_logit = <seq_out[row], W[target[row]]>, nll = lse - tgt_logit.  Any of lse / tgt_logit / nll may be NULL (not all);
  *   target may be NULL when only lse is wanted.  The logits are never written (online max / sum in the GEMM epilogue).
- *   Forward only.
+ *   Forward; pr_ce_grad_chunk_f32 below is the backward's building block.
  */
 PR_API size_t pr_score_ce_workspace_bytes(int64_t B_e, int64_t N);
 PR_API int pr_score_ce_f32(const float* seq_out, int64_t B_e, const float* W, int64_t N, int64_t D, const int64_t* target,
                            int mask_col0, float* lse, float* tgt_logit, float* nll, void* workspace, size_t workspace_bytes,
                            pr_stream_t stream);
+
+/* Backward building block of the same extension (pixelrec_b200/ops.py ScoreCEFn walks the catalog in column chunks: recompute a
+ *   chunk of logits with pr_gemm_tf32, turn it into dS with this kernel, then dX += dS W_c and dW_c = dS^T X on pr_gemm_tf32, so the
+ *   [B_e, N] probabilities are never held either).  In place on S [rows, C] (row stride ld), columns = items c0 .. c0 + C - 1:
+ *   S[r, j] <- dnll[r] * (exp(S[r, j] - lse[r]) - [c0 + j == target[r]]);  the padding column (item 0) <- 0 when mask_col0 != 0. */
+PR_API int pr_ce_grad_chunk_f32(float* S, int64_t ld, int64_t rows, int64_t C, int64_t c0, const float* lse, const int64_t* target,
+                                const float* dnll, int mask_col0, pr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * A1  on-device batch construction.   replaces SEQTrainDataset.__getitem__ + default collate,

@@ -439,6 +439,19 @@ class ShardedTableEmbedding(nn.Module):
         return plan
 
     @torch.no_grad()
+    def lookup_static(self, idx, r_hint=0):
+        """Evaluation-time lookup while NO rank is updating the table (call a barrier after the last optimizer step first): one
+        pull kernel over peer memory, straight from the owners' shards -- no index plan, no barrier, no collective, so ranks may
+        run different numbers of eval batches.  p2p exchange only.  r_hint: lookups per TRAINING step, used when this call is the
+        one that creates the peer buffers (evaluation before the first training step)."""
+        if self.exchange != "p2p":
+            raise ops._lib.PixelRecB200Error("lookup_static needs the peer-memory exchange (PR_EXCHANGE=p2p)")
+        idx = idx.contiguous()
+        px = self.peer_exchange(max(int(r_hint), idx.numel()))
+        out = PEER.gather(px.w_table, self.world, self.num_embeddings, self.embedding_dim, idx.reshape(-1))
+        return out.view(*idx.shape, self.embedding_dim)
+
+    @torch.no_grad()
     def full_weight(self):
         """All-gather the shards into the reference layout [N, D] (compute_item_all / checkpoints)."""
         return self.gather_rows_full(self.weight.detach(), clone=False)
@@ -492,3 +505,83 @@ def broadcast_dense_params(model, src=0):
     for p in model.parameters():
         if id(p) not in sharded:
             dist.broadcast(p.data, src)
+
+
+# ----------------------------------------------------------------------------------------------- sharded evaluation
+def merge_topk_candidates(val, idx, k):
+    """[B, C] candidate scores / global item ids -> the k best per row, ordered by (score descending, id ascending): the order
+    torch.topk over the full score row produces for distinct scores, with the exact kernels' tie rule (lower id first)."""
+    by_id = torch.argsort(idx, dim=1, stable=True)
+    v1, i1 = torch.gather(val, 1, by_id), torch.gather(idx, 1, by_id)
+    by_val = torch.argsort(v1, dim=1, descending=True, stable=True)[:, :k]
+    return torch.gather(v1, 1, by_val), torch.gather(i1, 1, by_val)
+
+
+class ShardedTopK:
+    """Full-catalog ranking with the item table LEFT row-sharded ('preferred for C3'; replaces
+    REC/trainer/trainer.py:339-358 compute_item_feature + :327-337 + evaluator/collector.py:133 at N > 1): instead of
+    all-gathering the [N, D] table on every rank (3.35 GB per rank at C3), every eval batch
+      1. all-gathers the ranks' encoder outputs        [G, B_e, D]   (16 MB at C2 / 8 GPUs)
+      2. all-gathers the (user, item) history pairs and keeps those whose item this rank owns (item % G == rank)
+      3. scores ALL G*B_e users against the LOCAL shard with the fused tcgen05 scoring + exact top-k   -> [G*B_e, k] candidates
+      4. all-to-alls the candidates back to the users' ranks and merges the G lists                   -> [B_e, k] global ids.
+    Per-shard candidates carry fp32 scores computed by the same kernel whatever the rank, so the merged ids equal the
+    single-GPU pr_score_topk_exact_f32 ranking bit for bit.  Collective: every rank calls it once per step with the same
+    B_e (pad the last / missing batches; `n_valid` users of this rank's batch are real)."""
+
+    def __init__(self, world, rank, group=None, score_fn=None):
+        self.world, self.rank, self.group = world, rank, group
+        self.score_fn = score_fn or self._score_cuda
+        self._norm_max = None
+
+    def reset(self):
+        self._norm_max = None                         # call when the table changed (once per evaluation)
+
+    def _score_cuda(self, seq_all, W_local, k, hu, hi, mask_col0):
+        if self._norm_max is None:
+            self._norm_max = ops.table_norm_max(W_local)
+        val, idx, _ = ops.score_topk_exact(seq_all, W_local, k, hu, hi, mask_col0=mask_col0, w_norm_max=self._norm_max)
+        return val, idx
+
+    def __call__(self, seq_out, W_local, k, hist_u=None, hist_i=None, pad_id=0):
+        G, rank = self.world, self.rank
+        B_e, D = seq_out.shape
+        dev = seq_out.device
+        # 1. encoder outputs of every rank
+        seq_all = torch.empty(G * B_e, D, device=dev, dtype=seq_out.dtype)
+        dist.all_gather_into_tensor(seq_all, seq_out.contiguous(), group=self.group)
+        # 2. history pairs of every rank (variable length: sizes first), user index shifted into the gathered batch
+        n = 0 if hist_u is None else int(hist_u.numel())
+        sizes = torch.tensor([n], dtype=torch.int64, device=dev)
+        all_sizes = torch.empty(G, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_sizes, sizes, group=self.group)
+        all_sizes = all_sizes.tolist()
+        n_max = max(all_sizes)
+        hu = hi = None
+        if n_max > 0:
+            mine = torch.zeros(2, n_max, dtype=torch.int64, device=dev)
+            if n:
+                mine[0, :n] = hist_u.to(dev)
+                mine[1, :n] = hist_i.to(dev)
+            everyone = torch.empty(G, 2, n_max, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(everyone.view(-1), mine.view(-1), group=self.group)
+            valid = torch.arange(n_max, device=dev)[None, :] < torch.tensor(all_sizes, device=dev)[:, None]     # [G, n_max]
+            gu = everyone[:, 0] + (torch.arange(G, device=dev) * B_e)[:, None]
+            gi = everyone[:, 1]
+            keep = valid & (gi % G == rank)
+            hu, hi = gu[keep].contiguous(), torch.div(gi[keep], G, rounding_mode="floor").contiguous()
+            if hu.numel() == 0:
+                hu = hi = None
+        # 3. all users against the local shard; the padding item lives on rank pad_id % G at local row pad_id // G == 0
+        mask_col0 = pad_id is not None and pad_id % G == rank
+        if mask_col0 and pad_id // G != 0:
+            raise ValueError("ShardedTopK: the padding id must be the first row of its shard")
+        val, idx_local = self.score_fn(seq_all, W_local, k, hu, hi, mask_col0)
+        idx = idx_local.to(torch.int64) * G + rank
+        # 4. candidates of rank s's users go to rank s
+        val_in, idx_in = torch.empty_like(val), torch.empty_like(idx)
+        dist.all_to_all_single(val_in, val.contiguous(), group=self.group)
+        dist.all_to_all_single(idx_in, idx.contiguous(), group=self.group)
+        cand_v = val_in.view(G, B_e, k).permute(1, 0, 2).reshape(B_e, G * k)
+        cand_i = idx_in.view(G, B_e, k).permute(1, 0, 2).reshape(B_e, G * k)
+        return merge_topk_candidates(cand_v, cand_i, k)

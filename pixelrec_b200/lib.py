@@ -36,6 +36,7 @@ SIGNATURES = {
                                _P, _P, _I, _P]),
     "pr_add_ln_bwd_bias_f32": (_I, [_P, _P, _I64, _I64, _P, _I64, _P, _P, _P, _I64, _I64, _F, _F, _U64, _U32, _U32, _P, _I64, _I,
                                     _P, _P, _I, _P]),
+    "pr_add_ln_bwd_bias_z_f32": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _F, _U64, _U32, _P, _P, _P, _I, _P]),
     "pr_act_bwd_bias_partials": (_I, [_I64, _I64]),
     "pr_act_bwd_bias_f32": (_I, [_P, _P, _I64, _I64, _I, _P, _P, _I, _P]),
     "pr_colsum_f32": (_I, [_P, _I, _I, _I64, _P, _P]),
@@ -57,6 +58,7 @@ SIGNATURES = {
     "pr_score_topk_exact_f32": (_I, [_P, _I64, _P, _I64, _I64, _P, _P, _I64, _I, _I, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "pr_gemm_colsum_rows": (_I, [_I64]),
     "pr_gemm_tf32": (_I, [_P, _I, _I64, _P, _I, _I64, _I64, _I64, _I64, _P, _P, _I, _I, _P, _P, _I, _P, _I, _P]),
+    "pr_gemm_tf32_drop": (_I, [_P, _I, _I64, _P, _I, _I64, _I64, _I64, _I64, _P, _P, _P, _I, _F, _U64, _U32, _P]),
     "pr_gemm_splitk_reduce_f32": (_I, [_P, _I, _I64, _P, _P]),
     "pr_score_prepare_f16": (_I, [_P, _I64, _P, _P, _P]),
     "pr_score_topk_f16_workspace_bytes": (C.c_size_t, [_I64, _I64, _I64, _I]),

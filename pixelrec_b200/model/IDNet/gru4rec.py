@@ -56,8 +56,13 @@ class GRU4Rec(BaseModel):
 
     @torch.no_grad()
     def encode_last(self, item_seq, item_feature=None):
-        feat = self.compute_item_all() if item_feature is None else item_feature
-        x = self.emb_dropout(ops.gather_rows(feat.contiguous(), item_seq.contiguous()))
+        tab = self.item_embedding
+        if item_feature is None and isinstance(tab, ShardedTableEmbedding) and tab.exchange == "p2p" and not self.training:
+            rows = tab.lookup_static(item_seq, getattr(self, "train_lookups_hint", 0))              # sharded evaluation: no collective
+        else:
+            feat = self.compute_item_all() if item_feature is None else item_feature
+            rows = ops.gather_rows(feat.contiguous(), item_seq.contiguous())
+        x = self.emb_dropout(rows)
         out, _ = self.gru_layers(x)
         return self.dense(out)[:, -1].contiguous()
 

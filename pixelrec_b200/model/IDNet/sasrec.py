@@ -101,6 +101,8 @@ class SASRec(BaseModel):
         D = self.hidden_size
         if item_feature is not None and isinstance(self.item_embedding, ShardedTableEmbedding):
             E = ops.gather_rows(item_feature.contiguous(), item_seq)
+        elif isinstance(self.item_embedding, ShardedTableEmbedding) and self.item_embedding.exchange == "p2p" and not self.training:
+            E = self.item_embedding.lookup_static(item_seq, getattr(self, "train_lookups_hint", 0))   # sharded evaluation: no collective
         else:
             E = self.item_embedding(item_seq)                     # [B,L,D]
         x = self._embed(E, L, L * D, B, 0, None)

@@ -557,6 +557,24 @@ def _raw_add_ln_bwd_bias(dy, h, res, gamma, mean, rstd, p_pre, seed, stream_pre)
     return dh, (dres if dres is not None else dh), out[0], out[1], out[2]
 
 
+def _raw_ln_z_bwd_bias(dy, z, gamma, mean, rstd, p_pre, seed, stream_pre):
+    """backward of LayerNorm(z), z = drop(h) + res written by gemm_drop_add -> dh (dropout applied), dz (gradient of the
+    residual branch; == dh when p_pre == 0), dgamma, dbeta, dbias (column sums of dh).  Reads dy and z only."""
+    rows, D = z.numel() // gamma.numel(), gamma.numel()
+    n_part = _L().pr_add_ln_bwd_partials(rows, D)
+    partials = torch.empty(3, n_part, D, device=dy.device, dtype=torch.float32)
+    dh = torch.empty_like(z)
+    dz = torch.empty_like(z) if p_pre > 0.0 else None
+    with _prof("add_ln_bwd", dy):
+        _lib.check(_L().pr_add_ln_bwd_bias_z_f32(_p(dy), _p(z), _p(gamma), _p(mean), _p(rstd), rows, D, p_pre, seed, stream_pre,
+                                                 _p(dh), _p(dz), _p(partials), n_part, _stream(dy)), "pr_add_ln_bwd_bias_z_f32")
+    out = torch.empty(3, D, device=dy.device, dtype=torch.float32)
+    with _prof("colsum", dy):
+        _lib.check(_L().pr_colsum_f32(_p(partials), 3, n_part, D, _p(out), _stream(dy)), "pr_colsum_f32")
+    _count(2)
+    return dh, (dz if dz is not None else dh), out[0], out[1], out[2]
+
+
 def _raw_act_bwd_bias(x, dy, act):
     rows, cols = x.numel() // x.shape[-1], x.shape[-1]
     n_part = _L().pr_act_bwd_bias_partials(rows, cols)
@@ -593,6 +611,9 @@ LINEAR_IMPL = os.environ.get("PR_LINEAR", "tc").lower()
 
 
 FUSE_ACT_BWD = os.environ.get("PR_FUSE_ACT_BWD", "1") == "1"
+# dense / dense_2 write z = dropout(x W^T + b) + residual from the GEMM epilogue (pr_gemm_tf32_drop); LayerNorm forward then reads one
+# tensor instead of two and its backward two instead of three (PR_FUSE_LN_Z=0: the separate-kernel form, for A/B runs)
+FUSE_LN_Z = os.environ.get("PR_FUSE_LN_Z", "1") == "1"
 
 
 def _use_tc(*dims):
@@ -707,8 +728,13 @@ class TransformerLayerFn(torch.autograd.Function):
             _lib.check(fwd(base, base + 4 * D, base + 8 * D, 3 * D, _p(key_ids), B, L, n_heads, D // n_heads, int(causal), p_attn,
                            seed, site, _p(ctxt), _p(probs), _stream(qkv)), "pr_sasrec_attn_fwd")
         _count()
-        h = _linear_fwd(ctxt.view(B * L, D), wo, bo)                                   # :613
-        a, mean1, rstd1 = _raw_add_ln_fwd(h, x2, g1, be1, eps, p_hid, seed, site + 1)  # :614-615
+        zmode = FUSE_LN_Z and _use_tc(D, D, w1.shape[0])     # dense / dense_2 write z = dropout(linear) + residual themselves
+        if zmode:
+            h = gemm_drop_add(ctxt.view(B * L, D), wo, bo, x2, p_hid, seed, site + 1)      # :613-614 and the residual add of :615
+            a, mean1, rstd1 = _raw_add_ln_fwd(h, None, g1, be1, eps, 0.0, seed, site + 1)  # :615
+        else:
+            h = _linear_fwd(ctxt.view(B * L, D), wo, bo)                                   # :613
+            a, mean1, rstd1 = _raw_add_ln_fwd(h, x2, g1, be1, eps, p_hid, seed, site + 1)  # :614-615
         if _use_tc(a.shape[1], w1.shape[0]):                                          # dense_1 + activation in ONE kernel (h1 and act(h1) both kept)
             gl, h1 = gemm(a, w1, bias=b1, epi=GEMM_ACT, act=act, want_pre=True, debias=True)   # :666-667
         else:
@@ -717,21 +743,28 @@ class TransformerLayerFn(torch.autograd.Function):
             with _prof("act_fwd", h1):
                 _lib.check(_L().pr_act_fwd_f32(_p(h1), h1.numel(), act, _p(gl), _stream(h1)), "pr_act_fwd_f32")
             _count()
-        h2 = _linear_fwd(gl, w2, b2)                                                   # :669
-        y, mean2, rstd2 = _raw_add_ln_fwd(h2, a, g2, be2, eps, p_hid, seed, site + 2)  # :670-671
+        if zmode:
+            h2 = gemm_drop_add(gl, w2, b2, a, p_hid, seed, site + 2)                       # :669-670 and the residual add of :671
+            y, mean2, rstd2 = _raw_add_ln_fwd(h2, None, g2, be2, eps, 0.0, seed, site + 2)
+        else:
+            h2 = _linear_fwd(gl, w2, b2)                                                   # :669
+            y, mean2, rstd2 = _raw_add_ln_fwd(h2, a, g2, be2, eps, p_hid, seed, site + 2)  # :670-671
         ctx.save_for_backward(x, qkv, probs, ctxt, h, a, mean1, rstd1, h1, gl, h2, mean2, rstd2, wqkv, wo, w1, w2, g1, g2)
-        ctx.cfg = (B, L, D, n_heads, int(causal), eps, p_attn, p_hid, act, seed, site, tf32)
+        ctx.cfg = (B, L, D, n_heads, int(causal), eps, p_attn, p_hid, act, seed, site, tf32, zmode)
         return y.view(B, L, D)
 
     @staticmethod
     def backward(ctx, dy):
         x, qkv, probs, ctxt, h, a, mean1, rstd1, h1, gl, h2, mean2, rstd2, wqkv, wo, w1, w2, g1, g2 = ctx.saved_tensors
-        B, L, D, n_heads, causal, eps, p_attn, p_hid, act, seed, site, tf32 = ctx.cfg
+        B, L, D, n_heads, causal, eps, p_attn, p_hid, act, seed, site, tf32, zmode = ctx.cfg
         M = B * L
         dy = dy.contiguous().view(M, D)
         x2 = x.view(M, D)
         # ---- feed-forward block
-        dh2, da_res, dg2, dbe2, db2 = _raw_add_ln_bwd_bias(dy, h2, a, g2, mean2, rstd2, p_hid, seed, site + 2)
+        if zmode:                                                          # h2 / h hold z: two tensors read instead of three
+            dh2, da_res, dg2, dbe2, db2 = _raw_ln_z_bwd_bias(dy, h2, g2, mean2, rstd2, p_hid, seed, site + 2)
+        else:
+            dh2, da_res, dg2, dbe2, db2 = _raw_add_ln_bwd_bias(dy, h2, a, g2, mean2, rstd2, p_hid, seed, site + 2)
         dw2 = _wgrad(dh2, gl)
         if _use_tc(w2.shape[0], w2.shape[1]) and FUSE_ACT_BWD:
             # input gradient of dense_2, the activation's backward and the bias gradient of dense_1 in one kernel
@@ -742,7 +775,10 @@ class TransformerLayerFn(torch.autograd.Function):
         dw1 = _wgrad(dh1, a)
         da = _linear_dgrad(dh1, w1, add=da_res)                            # residual grad folded into the GEMM epilogue
         # ---- attention block
-        dh, dx_res, dg1, dbe1, dbo = _raw_add_ln_bwd_bias(da, h, x2, g1, mean1, rstd1, p_hid, seed, site + 1)
+        if zmode:
+            dh, dx_res, dg1, dbe1, dbo = _raw_ln_z_bwd_bias(da, h, g1, mean1, rstd1, p_hid, seed, site + 1)
+        else:
+            dh, dx_res, dg1, dbe1, dbo = _raw_add_ln_bwd_bias(da, h, x2, g1, mean1, rstd1, p_hid, seed, site + 1)
         dwo = _wgrad(dh, ctxt.view(M, D))
         dctx = _linear_dgrad(dh, wo)
         dqkv = torch.empty_like(qkv)
@@ -878,6 +914,24 @@ def gemm(A, B, a_mn=False, b_mn=False, bias=None, aux=None, epi=GEMM_STORE, act=
         _count()
         return out, cs[0]
     return (out, pre) if want_pre else out
+
+
+def gemm_drop_add(x2, w, bias, res, p_drop, seed, rng_stream, debias=True):
+    """z = dropout(x2 @ w^T + bias) + res in ONE kernel (pr_gemm_tf32_drop: REC/model/layers.py:613-614 / 669-670 up to the
+    LayerNorm): the keep bits are those pr_add_ln_fwd_f32 would draw for (seed, rng_stream), so the LayerNorm that follows
+    reads one tensor instead of two and its backward (pr_add_ln_bwd_bias_z_f32) regenerates the same mask."""
+    _req(x2, torch.float32, "x2"); _req(w, torch.float32, "w"); _req(res, torch.float32, "res")
+    M, K = x2.shape
+    N = w.shape[0]
+    if w.shape[1] != K or res.shape != (M, N):
+        raise ValueError("gemm_drop_add: shapes do not match")
+    out = torch.empty(M, N, device=x2.device, dtype=torch.float32)
+    with _prof("gemm", x2):
+        _lib.check(_L().pr_gemm_tf32_drop(_p(x2), 0, x2.stride(0), _p(w), 0, w.stride(0), M, N, K, _p(bias), _p(res), _p(out),
+                                          int(bool(debias)), float(p_drop), int(seed), int(rng_stream), _stream(x2)),
+                   "pr_gemm_tf32_drop")
+    _count()
+    return out
 
 
 def score_prepare_f16(x, status=None):

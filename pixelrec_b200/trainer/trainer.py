@@ -17,7 +17,7 @@ from torch.nn.utils.clip_grad import clip_grad_norm_
 
 from .. import ops
 from ..evaluator import Collector, Evaluator
-from ..dist import ShardedTableEmbedding
+from ..dist import ShardedTableEmbedding, ShardedTopK, shard_rows
 from ..model.layers import TableEmbedding
 from ..utils.utils import (barrier, calculate_valid_score, dict2str, dist_ready, early_stopping, ensure_dir,
                            get_local_time, get_rank, get_world_size)
@@ -102,6 +102,7 @@ class Trainer:
         self.item_feature = None
         self.item_feature_f16 = None
         self.item_norm_max = None
+        self._sharded_topk = None
         self.tot_item_num = None
 
     # ------------------------------------------------------------------ optimizer (trainer.py:66-103)
@@ -304,6 +305,57 @@ class Trainer:
         return (mode in ("tcgen05", "tcgen05_tf32", "tcgen05_f16") and hasattr(model, "encode_last") and D % 32 == 0
                 and max(self.config["topk"]) <= 32 and self.item_feature.is_cuda)
 
+    def _use_sharded_eval(self):
+        """yaml `eval_table`: auto (default) | sharded | gathered.  Sharded: the table stays row-sharded during evaluation and
+        every batch is ranked shard by shard with a candidate merge (dist.ShardedTopK) instead of all-gathering [N, D] per rank."""
+        mode = (self.config["eval_table"] or "auto").lower()
+        model = unwrap(self.model)
+        tab = getattr(model, "item_embedding", None)
+        if mode == "gathered" or not isinstance(tab, ShardedTableEmbedding) or tab.world == 1:
+            return False
+        ok = (tab.exchange == "p2p" and self._scoring_mode() == "tcgen05" and hasattr(model, "encode_last")
+              and max(self.config["topk"]) <= 16 and tab.embedding_dim % 32 == 0 and tab.weight.is_cuda
+              and shard_rows(tab.num_embeddings, tab.world, tab.world - 1) >= 32 and (tab.padding_idx in (None, 0)))
+        if mode == "sharded" and not ok:
+            raise ValueError("eval_table: sharded needs the p2p exchange, eval_scoring: tcgen05, topk <= 16 and >= 32 rows per shard")
+        return ok
+
+    @torch.no_grad()
+    def _evaluate_sharded(self, eval_data):
+        """The evaluation loop of evaluate() with the table left sharded.  Collectives per batch: every rank runs the same number of
+        steps (ranks that hold fewer eval batches -- data/utils.py strided sampler -- contribute empty, padded ones)."""
+        import torch.distributed as dist
+        model = unwrap(self.model)
+        tab = model.item_embedding
+        k = max(self.config["topk"])
+        B_e = int(self.config["eval_batch_size"])
+        L = int(self.config["MAX_ITEM_LIST_LENGTH"])
+        model.train_lookups_hint = int(self.config["train_batch_size"]) * 2 * (L + 1)
+        torch.cuda.synchronize(self.device)
+        dist.barrier()                                   # every rank's last optimizer step has landed: the shards are static now
+        nb = torch.tensor([len(eval_data)], dtype=torch.int64, device=self.device)
+        dist.all_reduce(nb, op=dist.ReduceOp.MAX)
+        if self._sharded_topk is None:
+            self._sharded_topk = ShardedTopK(tab.world, tab.rank)
+        self._sharded_topk.reset()
+        W_local = tab.weight.detach()
+        it = iter(eval_data)
+        for _ in range(int(nb.item())):
+            batch = next(it, None)
+            seqs = torch.zeros(B_e, L, dtype=torch.int64, device=self.device)
+            b, hu, hi = 0, None, None
+            if batch is not None:
+                user, history_index, positive_u, positive_i = batch
+                b = user.shape[0]
+                seqs[:b] = self.to_device(user)
+                if history_index is not None:
+                    hu, hi = history_index
+            seq_out = model.encode_last(seqs, None)
+            _, topk_idx = self._sharded_topk(seq_out, W_local, k, hu, hi, pad_id=0)
+            if b:
+                self.eval_collector.eval_batch_collect_topk(topk_idx[:b], positive_u, positive_i)
+        dist.barrier()                                   # nobody resumes training (and updates its shard) while a peer still reads it
+
     @torch.no_grad()
     def compute_item_feature(self, config, data):
         self.item_feature = unwrap(self.model).compute_item_all()
@@ -327,15 +379,18 @@ class Trainer:
             self.logger.info("Loading model structure and parameters from {}".format(model_file or self.saved_model_file))
         self.model.eval()
         self.tot_item_num = eval_data.dataset.dataload.item_num
-        self.compute_item_feature(self.config, eval_data.dataset.dataload)
-        fused = self._use_fused_topk()
-        for batched_data in eval_data:
-            if fused:
-                topk_idx, positive_u, positive_i = self._fused_topk_batch_eval(batched_data)
-                self.eval_collector.eval_batch_collect_topk(topk_idx, positive_u, positive_i)
-            else:
-                scores, positive_u, positive_i = self._full_sort_batch_eval(batched_data)
-                self.eval_collector.eval_batch_collect(scores, positive_u, positive_i)
+        if self._use_sharded_eval():
+            self._evaluate_sharded(eval_data)
+        else:
+            self.compute_item_feature(self.config, eval_data.dataset.dataload)
+            fused = self._use_fused_topk()
+            for batched_data in eval_data:
+                if fused:
+                    topk_idx, positive_u, positive_i = self._fused_topk_batch_eval(batched_data)
+                    self.eval_collector.eval_batch_collect_topk(topk_idx, positive_u, positive_i)
+                else:
+                    scores, positive_u, positive_i = self._full_sort_batch_eval(batched_data)
+                    self.eval_collector.eval_batch_collect(scores, positive_u, positive_i)
         num_total_examples = len(eval_data.sampler.dataset)
         result = self.evaluator.evaluate(self.eval_collector.get_data_struct())
         places = 5 if self.config["metric_decimal_place"] is None else self.config["metric_decimal_place"]

@@ -338,3 +338,49 @@ def test_sharded_table_init_is_the_logical_table_world2_gloo():
     single = pd.ShardedTableEmbedding(N, D, padding_idx=0)
     single.init_normal_(0.0, 0.02, chunk_rows=7)
     assert np.array_equal(single.weight.detach().numpy(), full)
+
+
+def _cpu_score_fn(seq_all, W_local, k, hu, hi, mask_col0):
+    """stand-in for ops.score_topk_exact on the CPU: fp32 scores, pad column / history masked, (score desc, id asc) order"""
+    from pixelrec_b200.dist import merge_topk_candidates
+    s = seq_all @ W_local.t()
+    if mask_col0:
+        s[:, 0] = -float("inf")
+    if hu is not None:
+        s[hu, hi] = -float("inf")
+    ids = torch.arange(W_local.shape[0]).expand_as(s).contiguous()
+    return merge_topk_candidates(s, ids, k)
+
+
+def _worker_sharded_topk(rank, world, port, N, D, B_e, k, out_q):
+    try:
+        import torch.distributed as dist
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        from pixelrec_b200.dist import ShardedTopK, merge_topk_candidates
+        g = torch.Generator().manual_seed(5)                      # same on every rank: the logical problem
+        W = torch.randint(-3, 4, (N, D), generator=g).float()     # integers: fp32 scores are exact, ties are frequent
+        seq = torch.randint(-3, 4, (world, B_e, D), generator=g).float()
+        n_hist = [int(x) for x in torch.randint(0, 3 * B_e, (world,), generator=g)]
+        n_hist[-1] = 0                                            # one rank without history pairs
+        hist = [(torch.randint(0, B_e, (n,), generator=g), torch.randint(1, N, (n,), generator=g)) for n in n_hist]
+        scorer = ShardedTopK(world, rank, score_fn=_cpu_score_fn)
+        for _ in range(2):                                        # reusable across batches
+            val, idx = scorer(seq[rank], W[rank::world].contiguous(), k, hist[rank][0], hist[rank][1], pad_id=0)
+            full = seq[rank] @ W.t()
+            full[:, 0] = -float("inf")
+            full[hist[rank][0], hist[rank][1]] = -float("inf")
+            ref_v, ref_i = merge_topk_candidates(full, torch.arange(N).expand_as(full).contiguous(), k)
+            assert torch.equal(idx, ref_i), (idx[:2], ref_i[:2])
+            assert torch.equal(val, ref_v)
+        dist.destroy_process_group()
+        out_q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        out_q.put((rank, "fail: " + repr(e) + traceback.format_exc()))
+
+
+@pytest.mark.parametrize("world,N,D,B_e,k", [(2, 101, 8, 7, 10), (3, 64, 4, 5, 3)])
+def test_sharded_topk_merge_equals_full_catalog_ranking_gloo(world, N, D, B_e, k):
+    """ShardedTopK: all-gather of the encoder outputs and history pairs, per-shard candidates, all-to-all + merge == the ranking of
+    the whole catalog (ids AND order, ties by lower id), with uneven shards and a rank that has no history pairs."""
+    _spawn(_worker_sharded_topk, world, N, D, B_e, k)

@@ -220,3 +220,85 @@ def test_sharded_step_graph_replay_equals_eager_world2():
     for r in res:
         assert r[0] == "ok", r[2]
         assert r[2], f"rank {r[1]}: graph replay differs from eager (max |dw| {r[3]}, losses {r[4]} vs {r[5]})"
+
+
+def _eval_worker(rank, world, port, tmp, q):
+    """Trainer.evaluate with the table left sharded (candidate merge) vs all-gathered, same model, unequal batch counts per rank"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), PR_EXCHANGE="p2p", PR_P2P_CAP_FACTOR=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        os.chdir(tmp)
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        from pixelrec_b200.config import Config
+        from pixelrec_b200.data import bulid_dataloader, load_data
+        from pixelrec_b200.dist import ShardedTableEmbedding, ShardedTopK
+        from pixelrec_b200.trainer import Trainer
+        from pixelrec_b200.utils import get_model, init_seed
+        from pixelrec_b200 import ops
+        cfg = dict(dataset="synthetic", synthetic_users=513, synthetic_items=500, MAX_ITEM_LIST_LENGTH=10, embedding_size=64,
+                   train_batch_size=64, eval_batch_size=128, epochs=1, num_workers=0, checkpoint_dir=os.path.join(tmp, "saved"))
+        files = [os.path.join(root, "configs/IDNet/sasrec.yaml"), os.path.join(root, "configs/overall/ID.yaml")]
+        res, nb = {}, None
+        for mode in ("sharded", "gathered"):
+            c = Config(files, config_dict=dict(cfg, eval_table=mode))
+            c["device"] = dev
+            init_seed(7, True)
+            data = load_data(c)
+            _, valid, _ = bulid_dataloader(c, data)
+            nb = len(valid)
+            model = get_model(c["model"])(c, data).to(dev)
+            assert isinstance(model.item_embedding, ShardedTableEmbedding)
+            tr = Trainer(c, model)
+            assert tr._use_sharded_eval() == (mode == "sharded")
+            res[mode] = tr.evaluate(valid, load_best_model=False)
+        # ids of one batch, directly: sharded merge == exact ranking over the gathered table
+        model.eval()
+        g = torch.Generator().manual_seed(rank)
+        seqs = torch.randint(1, 501, (128, 10), generator=g).to(dev)
+        seq_out = model.encode_last(seqs, None)
+        full = model.compute_item_all()
+        seq_ref = model.encode_last(seqs, full)
+        same_rows = bool(torch.equal(seq_out, seq_ref))
+        hu = torch.randint(0, 128, (300,), generator=g).to(dev)
+        hi = torch.randint(1, 501, (300,), generator=g).to(dev)
+        _, idx_s = ShardedTopK(world, rank)(seq_out, model.item_embedding.weight.detach(), 10, hu, hi, pad_id=0)
+        _, idx_g, _ = ops.score_topk_exact(seq_ref, full.contiguous(), 10, hu, hi, mask_col0=True)
+        same_ids = bool(torch.equal(idx_s, idx_g))
+        nbs = [None] * world
+        dist.all_gather_object(nbs, nb)
+        q.put(("ok", rank, res, same_rows, same_ids, nbs))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put(("err", rank, traceback.format_exc(), None, None, None))
+    finally:
+        import threading
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        dist.destroy_process_group()
+
+
+def test_sharded_eval_equals_gathered_eval_world2(tmp_path):
+    """Evaluation with the item table LEFT row-sharded (dist.ShardedTopK: per-shard tcgen05 candidates + merge; history rows pulled
+    over peer memory) gives the metrics -- and the top-k ids -- of the all-gathered [N, D] path, with ranks holding different
+    numbers of eval batches (REC/trainer/trainer.py:339-358)."""
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_eval_worker, args=(r, world, port, str(tmp_path), q), daemon=True) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+        if p.is_alive():
+            p.kill()
+    for r in res:
+        assert r[0] == "ok", r[2]
+        assert r[3], "rows pulled over peer memory differ from the gathered table's"
+        assert r[4], "merged top-k ids differ from the exact ranking over the gathered table"
+        assert r[2]["sharded"] == r[2]["gathered"], r[2]
+    assert len(set(res[0][5])) == 2, f"the test wants unequal batch counts per rank, got {res[0][5]}"

@@ -159,3 +159,28 @@ def test_truncation_debias_removes_the_systematic_shrink():
     assert -0.9e-3 < shrink < -0.55e-3, shrink                       # ~2 * 0.72 * 2^-11 = -7.0e-4 (mantissa-averaged truncation)
     assert abs(float((fix / ref - 1).mean())) < 5e-5
     assert np.abs(fix / ref - 1).max() < 2e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(640, 512, 256), (300, 260, 96), (1000, 1536, 512), (81, 512, 1024), (4099, 1024, 64)])
+def test_drop_add_epilogue_exact_and_mask_is_the_layernorm_mask(M, N, K):
+    """pr_gemm_tf32_drop: out = dropout(x W^T + b) + res with the keep bits of pr_add_ln_fwd_f32 (oracle/philox_np.py
+    rowwise_keep_scale).  Integer operands and p = 0.5 (scale 2) make every value exact: a wrong Philox counter, nibble or
+    column mapping shows as a wrong integer."""
+    from oracle import philox_np as PH
+    from pixelrec_b200 import ops
+    g = np.random.default_rng(M + N)
+    x = g.integers(-3, 4, size=(M, K)).astype(np.float32)
+    W = g.integers(-3, 4, size=(N, K)).astype(np.float32)
+    b = g.integers(-5, 6, size=N).astype(np.float32)
+    res = g.integers(-9, 10, size=(M, N)).astype(np.float32)
+    keep = PH.rowwise_keep_scale(M, N, 0.5, 77, 5).astype(np.float64)          # 0 or 2
+    ref = (x.astype(np.float64) @ W.astype(np.float64).T + b) * keep + res
+    got = ops.gemm_drop_add(t(x), t(W), t(b), t(res), 0.5, 77, 5, debias=False).cpu().numpy().astype(np.float64)
+    assert 0.4 < (keep == 0).mean() < 0.6
+    assert np.array_equal(got, ref), f"{(got != ref).mean():.4f} of the outputs differ"
+    # p = 0: plain bias + residual epilogue
+    got0 = ops.gemm_drop_add(t(x), t(W), t(b), t(res), 0.0, 77, 5, debias=False).cpu().numpy().astype(np.float64)
+    assert np.array_equal(got0, x.astype(np.float64) @ W.astype(np.float64).T + b + res)
+    # another stream id draws another mask
+    other = ops.gemm_drop_add(t(x), t(W), t(b), t(res), 0.5, 77, 6, debias=False).cpu().numpy()
+    assert (other != got).mean() > 0.2
