@@ -90,6 +90,55 @@ class DeviceSeqLoader:
                                             (self.seed * 1000003 + self.sampler.epoch) * 1000003 + self._step * self.world + self.rank)
 
 
+class DeviceSeqEvalLoader:
+    """Eval loader whose batches are VIEWS of tensors resident in HBM: what SeqEvalDataset.__getitem__ + seq_eval_collate
+    (REC/data/dataset/evalset.py:24-37, collate_fn.py:6-32) rebuild per batch in Python -- the left-padded history window, the
+    target, and the (history_u, history_i) pairs that the scoring kernel masks -- is laid out ONCE for this rank's users in
+    their evaluation order (rank r: users r, r+W, ...: data/utils.py:134-159) as a CSR over batches; a step is four slices, no
+    kernel, no host loop.  Output is element-for-element the DataLoader's (`device_sampler: True`, SEQ models)."""
+
+    def __init__(self, dataset, batch_size, device, rank=0, world=1):
+        self.dataset = dataset
+        self.batch_size = B = int(batch_size)
+        self.device = device
+        self.sampler = NonConsecutiveSequentialDistributedSampler(dataset, rank=rank, num_replicas=world)
+        L = dataset.max_item_list_length
+        cut = -2 if dataset.phase == "valid" else -1
+        users = range(rank, len(dataset), world)
+        n = len(users)
+        seqs = np.zeros((n, L), dtype=np.int64)
+        tgt = np.zeros(n, dtype=np.int64)
+        lens = np.zeros(n + 1, dtype=np.int64)
+        hist = []
+        for j, u in enumerate(users):
+            s = dataset.user_seq[u]
+            h = np.asarray(s[:cut], dtype=np.int64)
+            tail = h[-L:]
+            if len(tail):
+                seqs[j, L - len(tail):] = tail
+            tgt[j] = s[cut]
+            lens[j + 1] = len(h)
+            hist.append(h)
+        offs = np.cumsum(lens)
+        hist_i = np.concatenate(hist) if hist else np.zeros(0, np.int64)
+        hist_u = np.repeat(np.arange(n, dtype=np.int64) % B, lens[1:])          # row of the user inside ITS batch
+        self.num_samples = n
+        self._batch_offs = [int(offs[min(i, n)]) for i in range(0, n + B, B)]  # pair range of batch k: [offs[k*B], offs[(k+1)*B])
+        to = lambda a: torch.from_numpy(a).to(device)
+        self.item_seq, self.target, self.hist_u, self.hist_i = to(seqs), to(tgt), to(hist_u), to(hist_i)
+        self.positive_u = torch.arange(B, device=device)
+
+    def __len__(self):
+        return math.ceil(self.num_samples / self.batch_size)
+
+    def __iter__(self):
+        B = self.batch_size
+        for k in range(len(self)):
+            lo, hi = k * B, min((k + 1) * B, self.num_samples)
+            p0, p1 = self._batch_offs[k], self._batch_offs[k + 1]
+            yield (self.item_seq[lo:hi], (self.hist_u[p0:p1], self.hist_i[p0:p1]), self.positive_u[:hi - lo], self.target[lo:hi])
+
+
 def _worker_init(worker_id, num_workers, rank, seed):
     s = (num_workers * rank + worker_id + seed) % (2 ** 32)
     np.random.seed(s)
@@ -119,6 +168,9 @@ def bulid_dataloader(config, dataload):
     else:
         train_loader = DataLoader(train_data, batch_size=config["train_batch_size"], num_workers=workers, pin_memory=pin,
                                   sampler=train_sampler, worker_init_fn=init_fn)
-    mk = lambda ds: DataLoader(ds, batch_size=config["eval_batch_size"], num_workers=workers, pin_memory=pin,
-                               sampler=NonConsecutiveSequentialDistributedSampler(ds), collate_fn=collate)
+    if config["device_sampler"] and torch.cuda.is_available() and config["device"] is not None and collate is seq_eval_collate:
+        mk = lambda ds: DeviceSeqEvalLoader(ds, config["eval_batch_size"], config["device"], rank, world)
+    else:
+        mk = lambda ds: DataLoader(ds, batch_size=config["eval_batch_size"], num_workers=workers, pin_memory=pin,
+                                   sampler=NonConsecutiveSequentialDistributedSampler(ds), collate_fn=collate)
     return train_loader, mk(valid_data), mk(test_data)

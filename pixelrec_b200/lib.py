@@ -50,6 +50,7 @@ SIGNATURES = {
     "pr_sasrec_attn_bwd_tf32": (_I, [_P, _P, _P, _I64, _P, _P, _I, _I, _I, _I, _I, _F, _U64, _U32, _P, _P, _P, _I64, _P]),
     "pr_bpr_loss_fwd_f32": (_I, [_P, _P, _P, _I64, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P]),
     "pr_bpr_loss_bwd_f32": (_I, [_P, _P, _P, _I64, _P, _P, _I64, _I64, _I64, _P, _P, _P, _I64, _P]),
+    "pr_ce_grad_chunk_f32": (_I, [_P, _I64, _I64, _I64, _I64, _P, _P, _P, _I, _P]),
     "pr_seq_batch_build": (_I, [_P, _I64, _I, _P, _I64, _I64, _U64, _P, _P, _P, _P]),
     "pr_score_topk_workspace_bytes": (C.c_size_t, [_I64, _I64, _I]),
     "pr_score_topk_f32": (_I, [_P, _I64, _P, _I64, _I64, _P, _P, _I64, _I, _I, _P, _P, _P, C.c_size_t, _P]),

@@ -992,6 +992,63 @@ def score_ce(seq_out, item_feature, target, mask_col0=True):
     return out[0], out[1], out[2]
 
 
+CE_CHUNK = int(os.environ.get("PR_CE_CHUNK", "8192"))      # catalog columns per backward chunk (multiple of 4)
+
+
+class ScoreCEFn(torch.autograd.Function):
+    """nll[r] = logsumexp_c <seq_out[r], W[c]> - <seq_out[r], W[target[r]]> over the whole catalog (padding item excluded), forward
+    AND backward without ever holding the [B_e, N] logits (extension: the reference trains with sampled negatives, sasrec.py:88-92;
+    oracle = F.cross_entropy, oracle/sasrec_np.py full_catalog_ce).
+      forward : pr_score_ce_f32 -- tcgen05 scoring GEMM with the online max / sum-of-exp in its epilogue;
+      backward: the catalog in chunks of CE_CHUNK items: logits of the chunk recomputed by pr_gemm_tf32, turned in place into
+                dS = dnll * (softmax - onehot) (pr_ce_grad_chunk_f32), then dX += dS W_c and dW_c = dS^T X on pr_gemm_tf32."""
+
+    @staticmethod
+    def forward(ctx, seq_out, item_feature, target, mask_col0):
+        lse, tgt, nll = score_ce(seq_out, item_feature, target, mask_col0)
+        ctx.save_for_backward(seq_out, item_feature, target, lse)
+        ctx.mask_col0 = bool(mask_col0)
+        return nll
+
+    @staticmethod
+    def backward(ctx, dnll):
+        X, W, target, lse = ctx.saved_tensors
+        B_e, D = X.shape
+        N = W.shape[0]
+        dnll = dnll.contiguous().float()
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dX = torch.zeros_like(X) if need_x else None
+        dW = torch.empty_like(W) if need_w else None
+        Xc, Wc = X.contiguous(), W.contiguous()
+        C = max(4, CE_CHUNK // 4 * 4)
+        for c0 in range(0, N, C):
+            n = min(C, N - c0)
+            n4 = (n + 3) // 4 * 4                       # the GEMM wants N % 4 == 0: pad columns read past the chunk
+            Wch = Wc[c0:c0 + n]
+            if n4 != n:                                 # ragged tail of the catalog: zero rows give exp(-lse) ~ 0 logits' worth of
+                Wch = torch.cat([Wch, Wch.new_zeros(n4 - n, D)], 0)   # gradient; they are cut off below
+            S = gemm(Xc, Wch)                           # [B_e, n4] logits of the chunk (TF32, like the forward)
+            with _prof("ce_grad_chunk", S):
+                _lib.check(_L().pr_ce_grad_chunk_f32(_p(S), S.stride(0), B_e, n4, c0, _p(lse), _p(target), _p(dnll),
+                                                     int(ctx.mask_col0), _stream(S)), "pr_ce_grad_chunk_f32")
+            _count()
+            if n4 != n:
+                S[:, n:] = 0.0
+            if need_x:
+                dX = gemm(S, Wch, b_mn=True, aux=dX, epi=GEMM_ADD)                  # dX += dS W_c   (contraction over the chunk)
+            if need_w:
+                if n4 == n:
+                    gemm(S, Xc, a_mn=True, b_mn=True, out=dW[c0:c0 + n])              # dW_c = dS^T X  (contraction over the rows)
+                else:
+                    dW[c0:c0 + n] = gemm(S, Xc, a_mn=True, b_mn=True)[:n]
+        return dX, dW, None, None
+
+
+def score_ce_loss(seq_out, item_feature, target, mask_col0=True):
+    """differentiable per-row full-catalog cross-entropy (see ScoreCEFn)"""
+    return ScoreCEFn.apply(seq_out, item_feature, target, mask_col0)
+
+
 # ------------------------------------------------------------------------------------------- peer-memory exchange
 _CAI_TYPESTR = {torch.float32: "<f4", torch.int64: "<i8", torch.int32: "<i4", torch.uint8: "|u1"}
 

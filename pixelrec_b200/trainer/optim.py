@@ -105,7 +105,40 @@ class FusedAdamW(torch.optim.Optimizer):
         return [f["g"] for f in self._flat if f is not None]
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def clip_grad_norm_(self, max_norm, norm_type=2.0):
+        """torch.nn.utils.clip_grad_norm_ over ALL parameters of the optimizer -- the flat dense gradients AND the tables' sparse
+        gradient rows -- with DDP's semantics (the norm of the rank-averaged gradient, trainer.py:123 after run.py:40).  Call it
+        through step(clip=...): the dense gradients must already be summed over ranks.  No host synchronisation."""
+        if float(norm_type) != 2.0:
+            raise NotImplementedError("FusedAdamW.clip_grad_norm_: only the 2-norm is implemented")
+        dev = next(p for g in self.param_groups for p in g["params"]).device
+        sq = torch.zeros((), device=dev, dtype=torch.float32)
+        for f in self._flat:
+            if f is not None:
+                sq += (f["g"] * f["g"]).sum()
+        tsq = torch.zeros((), device=dev, dtype=torch.float32)
+        sharded = False
+        for tb in self._tables.values():
+            if self.world > 1 and not isinstance(tb, ShardedTableEmbedding):
+                raise NotImplementedError("clip_grad_norm with a replicated table on several GPUs")
+            sharded = sharded or isinstance(tb, ShardedTableEmbedding)
+            for plan, rows in tb.sink.pending:                      # rows >= n_uniq are undefined memory: mask, do not multiply
+                live = torch.arange(rows.shape[0], device=dev) < plan.n_uniq
+                tsq += torch.where(live, (rows * rows).sum(1), torch.zeros((), device=dev)).sum()
+        if self.world > 1 and sharded:
+            torch.distributed.all_reduce(tsq)                       # every rank owns different rows
+        total = torch.sqrt(sq + tsq) * self.grad_scale              # grad_scale = 1 / world: the mean over ranks
+        coef = torch.clamp(float(max_norm) / (total + 1e-6), max=1.0)
+        for f in self._flat:
+            if f is not None:
+                f["g"].mul_(coef)
+        for tb in self._tables.values():
+            for plan, rows in tb.sink.pending:
+                rows.mul_(coef)
+        return total
+
+    @torch.no_grad()
+    def step(self, closure=None, clip=None):
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -119,6 +152,8 @@ class FusedAdamW(torch.optim.Optimizer):
                 if f is not None:
                     with ops._prof("dense_grad_allreduce", f["g"]):
                         torch.distributed.all_reduce(f["g"])
+        if clip:
+            self.clip_grad_norm_(**clip)
         for gi, group in enumerate(self.param_groups):
             b1, b2 = group["betas"]
             f = self._flat[gi]

@@ -13,7 +13,6 @@ from time import time
 
 import numpy as np
 import torch
-from torch.nn.utils.clip_grad import clip_grad_norm_
 
 from .. import ops
 from ..evaluator import Collector, Evaluator
@@ -162,9 +161,8 @@ class Trainer:
             total += losses.detach()
             losses.backward()
             del losses     # keeps no autograd graph (and its AccumulateGrad nodes, bound to THIS stream) alive into a later capture
-            if self.clip_grad_norm:
-                clip_grad_norm_(self.model.parameters(), **self.clip_grad_norm)
-            self.optimizer.step()
+            # clip_grad_norm (trainer.py:123): over the dense gradients AND the table's sparse rows, after the rank average
+            self.optimizer.step(clip=self.clip_grad_norm or None)
         if graphed is not None:
             graphed.close()
         total_loss = float(total.item())        # ONE device->host sync per epoch

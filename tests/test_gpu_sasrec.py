@@ -119,6 +119,46 @@ def test_training_with_dropout_is_finite_and_seeded():
     assert m((t(items), t(mask))).item() == m((t(items), t(mask))).item()
 
 
+def test_clip_grad_norm_covers_the_sparse_table_rows():
+    """trainer.py:123 clip_grad_norm_ over ALL parameters: FusedAdamW.clip_grad_norm_ counts the table's sparse gradient rows (the
+    table has no dense .grad here) -- the norm must equal torch's over a dense-gradient replica, and one clipped step must move
+    the weights exactly as torch.optim.AdamW moves the replica after torch.nn.utils.clip_grad_norm_."""
+    from pixelrec_b200.model.IDNet.sasrec import SASRec
+    from pixelrec_b200.trainer.optim import FusedAdamW
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = dict(n_layers=1, n_heads=2, embedding_size=64, inner_size=2, hidden_dropout_prob=0.0, attn_dropout_prob=0.0,
+               hidden_act="gelu", layer_norm_eps=1e-12, initializer_range=0.02, MAX_ITEM_LIST_LENGTH=10, seed=1)
+    g = np.random.default_rng(3)
+    items = g.integers(1, 300, size=(16, 2, 11)).astype(np.int64)
+    items[:, 1, 0] = 0
+    mask = np.ones((16, 10), dtype=np.int64)
+    torch.manual_seed(0)
+    m = SASRec(cfg, _Data(300)).to(dev()).train()
+    ref = SASRec(cfg, _Data(300)).to(dev()).train()
+    ref.load_state_dict(m.state_dict())
+    ref.item_embedding.sink.sparse = False                       # dense [N, D] gradient, as in the reference
+    opt = FusedAdamW(m.parameters(), lr=1e-2, weight_decay=0.1, tables=[m.item_embedding])
+    ropt = torch.optim.AdamW(ref.parameters(), lr=1e-2, weight_decay=0.1)
+    batch = (t(items), t(mask))
+    opt.zero_grad()
+    (m(batch) * 50.0).backward()
+    ropt.zero_grad()
+    (ref(batch) * 50.0).backward()
+    assert m.item_embedding.weight.grad is None and ref.item_embedding.weight.grad is not None
+    max_norm = 1.0
+    want = torch.nn.utils.clip_grad_norm_(ref.parameters(), max_norm).item()
+    assert want > 2 * max_norm                                   # the clip is active
+    ropt.step()
+    before = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    total = opt.clip_grad_norm_(max_norm)
+    assert abs(total.item() - want) < 1e-4 * want
+    opt.step()
+    for (k, a), b in zip(m.state_dict().items(), ref.state_dict().values()):
+        assert (a - b).abs().max().item() < 2e-5, k
+        assert k.endswith("LayerNorm.bias") or not torch.equal(a, before[k]), k
+    torch.backends.cuda.matmul.allow_tf32 = True
+
+
 def test_gru4rec_plugin_matches_reference_golden():
     """config 5 backbone: our table gather / scatter-add / loss around cuDNN's GRU vs the reference module."""
     import os

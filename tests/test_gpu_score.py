@@ -190,6 +190,39 @@ def test_score_ce_matches_oracle(B_e, N, D):
     assert np.abs(lse - lse_r).max() < tol and np.abs(tl - tl_r).max() < tol and np.abs(nll - nll_r).max() < 2 * tol
 
 
+@pytest.mark.parametrize("B_e,N,D,chunk", [(300, 5003, 64, 2048), (128, 1000, 128, 8192), (1024, 20011, 512, 8192), (37, 333, 32, 100)])
+def test_score_ce_backward_matches_autograd(B_e, N, D, chunk):
+    """ops.score_ce_loss (extension): forward on the fused tcgen05 scoring kernel, backward as chunked recompute on pr_gemm_tf32 +
+    pr_ce_grad_chunk_f32 -- gradients of sum_r w_r * nll_r w.r.t. seq_out and the table vs float64 autograd of
+    F.cross_entropy-style logits with the padding column excluded.  TF32 operands: 2e-3 of the largest gradient entry."""
+    from pixelrec_b200 import ops
+    g = np.random.default_rng(N + B_e)
+    seq = g.standard_normal((B_e, D)).astype(np.float32)
+    W = (0.2 * g.standard_normal((N, D))).astype(np.float32)
+    target = g.integers(1, N, size=B_e).astype(np.int64)
+    target[0] = N - 1                                               # the last (ragged) chunk holds a target
+    wts = g.random(B_e).astype(np.float32) + 0.5
+    X64 = torch.from_numpy(seq).double().requires_grad_()
+    W64 = torch.from_numpy(W).double().requires_grad_()
+    sc = X64 @ W64.t()
+    sc = torch.cat([torch.full_like(sc[:, :1], -float("inf")), sc[:, 1:]], 1)
+    nll_ref = torch.logsumexp(sc, 1) - sc.gather(1, torch.from_numpy(target)[:, None])[:, 0]
+    (nll_ref * torch.from_numpy(wts).double()).sum().backward()
+    old = ops.CE_CHUNK
+    ops.CE_CHUNK = chunk
+    try:
+        Xg, Wg = t(seq).requires_grad_(), t(W).requires_grad_()
+        nll = ops.score_ce_loss(Xg, Wg, t(target))
+        (nll * t(wts)).sum().backward()
+    finally:
+        ops.CE_CHUNK = old
+    assert np.abs(nll.detach().cpu().numpy() - nll_ref.detach().numpy()).max() < 4e-3 * max(1.0, float(sc[:, 1:].abs().max()))
+    for got, ref, name in ((Xg.grad, X64.grad, "d seq_out"), (Wg.grad, W64.grad, "d table")):
+        err = (got.double().cpu() - ref).abs().max().item()
+        assert err < 2e-3 * ref.abs().max().item(), (name, err, ref.abs().max().item())
+    assert Wg.grad[0].abs().max().item() < 1e-6                      # the padding item gets no gradient
+
+
 @pytest.mark.parametrize("B_e,N,D,k", [(5, 300, 64, 10), (300, 5003, 512, 10), (1024, 20011, 512, 10), (33, 777, 128, 20)])
 @pytest.mark.parametrize("ares", [0, 128], ids=["ring", "resident_seq"])
 def test_score_topk_f16_exact_on_small_integers(B_e, N, D, k, ares):

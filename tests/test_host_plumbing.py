@@ -230,3 +230,33 @@ def test_tcgen05_ptx_forms_match_the_vendored_cutlass_headers():
     assert re.search(r"F16\s*=\s*0,\s*BF16\s*=\s*1,\s*TF32\s*=\s*2", desc)
     assert "c_format_      : 2,  // bit [ 4, 6)" in desc and "a_format_      : 3,  // bit [ 7,10)" in desc
     assert "n_dim_         : 6,  // bit [17,23)" in desc and "m_dim_         : 5,  // bit [24,29)" in desc
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("phase", ["valid", "test"])
+def test_device_eval_loader_equals_dataloader_collate(world, phase):
+    """DeviceSeqEvalLoader (resident CSR, a batch = four slices) yields element for element what the reference's
+    SeqEvalDataset.__getitem__ + seq_eval_collate build per batch (evalset.py:24-37, collate_fn.py:6-32), for every rank's
+    strided share of the users (data/utils.py:134-159) -- histories shorter and longer than L, ragged last batch."""
+    from torch.utils.data import DataLoader
+    from pixelrec_b200.data.dataset import SeqEvalDataset, seq_eval_collate
+    from pixelrec_b200.data.utils import DeviceSeqEvalLoader, NonConsecutiveSequentialDistributedSampler
+
+    class Dl:
+        item_num = 50
+        user_seq = {}
+    g = np.random.default_rng(4)
+    for u in range(23):
+        Dl.user_seq[f"u{u}"] = g.integers(1, 50, size=int(g.integers(3, 14))).astype(np.int64)
+    ds = SeqEvalDataset(dict(MAX_ITEM_LIST_LENGTH=6), Dl, phase=phase)
+    for rank in range(world):
+        ref = DataLoader(ds, batch_size=4, sampler=NonConsecutiveSequentialDistributedSampler(ds, rank=rank, num_replicas=world),
+                         collate_fn=seq_eval_collate)
+        got = DeviceSeqEvalLoader(ds, 4, "cpu", rank, world)
+        assert len(got) == len(ref) and len(got.sampler.dataset) == len(ref.sampler.dataset)
+        n = 0
+        for (s0, (hu0, hi0), pu0, t0), (s1, (hu1, hi1), pu1, t1) in zip(ref, got):
+            assert torch.equal(s0, s1) and torch.equal(hu0, hu1) and torch.equal(hi0, hi1)
+            assert torch.equal(pu0, pu1) and torch.equal(t0, t1)
+            n += 1
+        assert n == len(ref)
