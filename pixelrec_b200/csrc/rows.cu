@@ -652,9 +652,16 @@ extern "C" int pr_scatter_add_rows_f32(const float* dOut, int64_t R, int64_t D, 
     if ((tune() & PR_TUNE_SCATTER_RING) && D >= 64 && D <= 2048) {
         // TMA-staged ring (rows_ring.cuh): VPL float4 per lane cover a row, 8 KiB stages.  Measured (profiles/r02j_scatter_ab.json):
         // 1.1-2.5x the LDG kernel up to D = 2048; at D = 4096 a row is 32 float4 per lane and the LDG kernel's 4 warps per row win.
+        static int variant = -1;            // PR_SCATTER_VARIANT (A/B runs): 1 = 16 KiB stages at D = 512, 2 = + L2 prefetch of rows
+        if (variant < 0) {
+            const char* e = getenv("PR_SCATTER_VARIANT");
+            variant = e ? atoi(e) : 0;
+        }
         int vpl = 1;
         while (32 * vpl < D4) vpl *= 2;
-        const int rps = std::max(1, 16 / vpl);
+        const bool big = (variant & 1) && vpl == 4;
+        const int l2pf = (variant & 2) ? 1 : 0;
+        const int rps = big ? 8 : std::max(1, 16 / vpl);
         const size_t smem = (size_t)SR_STAGES * rps * D * 4 + SR_BAR_BYTES;
         int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
         ctas_per_sm = std::max(1, std::min(16, ctas_per_sm));
@@ -668,12 +675,12 @@ extern "C" int pr_scatter_add_rows_f32(const float* dOut, int64_t R, int64_t D, 
             PR_CUDA_CALL(cudaFuncSetAttribute(scatter_add_rows_ring_kernel<VPL, RPS>,                               \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
         scatter_add_rows_ring_kernel<VPL, RPS><<<grid, 32, smem, stream>>>(dOut, (int)D, gr, perm, uniq_ids, seg_start, \
-                                                                          n_uniq, max_uniq, scale, out_rows, dense_G); \
+                                                                          n_uniq, max_uniq, scale, out_rows, dense_G, l2pf); \
     } while (0)
         switch (vpl) {
             case 1: PR_LAUNCH_RING(1, 16); break;
             case 2: PR_LAUNCH_RING(2, 8); break;
-            case 4: PR_LAUNCH_RING(4, 4); break;
+            case 4: if (big) PR_LAUNCH_RING(4, 8); else PR_LAUNCH_RING(4, 4); break;
             case 8: PR_LAUNCH_RING(8, 2); break;
             default: PR_LAUNCH_RING(16, 1); break;
         }

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(32) scatter_add_rows_ring_kernel(const float* 
                                                                    const int* __restrict__ seg_start,
                                                                    const int* __restrict__ n_uniq, long long max_uniq,
                                                                    float scale, float* __restrict__ out_rows,
-                                                                   float* __restrict__ dense_G) {
+                                                                   float* __restrict__ dense_G, int l2_prefetch) {
     PR_DYN_SMEM_BYTES(smem_raw);
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x;
@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(32) scatter_add_rows_ring_kernel(const float* 
     auto next_chunk = [&](int& n_out, int& perm_out) {
         n_out = p_live ? min(RPS, pe - pk) : 0;
         perm_out = (lane < n_out) ? perm[pk + lane] : 0;
+        // A/B knob (PR_SCATTER_VARIANT=2): pull the row into L2 now, SR_AHEAD + SR_STAGES - 1 chunks before it is staged
+        if (l2_prefetch && lane < n_out) l2_prefetch_bulk(dOut + (long long)perm_out * D, row_bytes);
         if (p_live) {
             pk += n_out;
             if (pk >= pe) {

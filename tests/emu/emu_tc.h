@@ -182,6 +182,9 @@ inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) 
         emu::complete_tx_at(bar, (long long)bytes);
     });
 }
+inline void l2_prefetch_bulk(const void* src, uint32_t bytes) {          // a hint: only its arguments can be wrong
+    if (bytes % 16 || ((uintptr_t)src & 15)) emu::fail("bulk prefetch needs a 16-byte aligned address and size");
+}
 inline void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
     const CUtensorMap m = *tm;
     unsigned char* d = (unsigned char*)dst;

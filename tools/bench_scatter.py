@@ -68,6 +68,17 @@ def main():
         L_.pr_set_tuning(base)
         out[name] = rec
         print(name, json.dumps(rec), flush=True)
+    # reference point: what random 2 KB row reads + sequential writes reach on this part (every id distinct, L2 flushed):
+    # the gather kernel of the forward on 172 032 distinct rows of a 400 K x 512 table
+    if not a.once:
+        Wt = torch.randn(400000, 512, device=dev)
+        ids = torch.randperm(400000, device=dev)[:172032].contiguous()
+        ms = timeit(lambda: ops.gather_rows(Wt, ids), flush)
+        out["gather_distinct_rows"] = {"rows": 172032, "D": 512, "ms": ms, "GBps": 2 * 172032 * 2048 / ms / 1e6}
+        ids_s = torch.arange(172032, device=dev)
+        ms = timeit(lambda: ops.gather_rows(Wt, ids_s), flush)
+        out["gather_sequential_rows"] = {"rows": 172032, "D": 512, "ms": ms, "GBps": 2 * 172032 * 2048 / ms / 1e6}
+        print(json.dumps({k: out[k] for k in ("gather_distinct_rows", "gather_sequential_rows")}), flush=True)
     if a.json:
         with open(a.json, "w") as f:
             json.dump(out, f, indent=1)
