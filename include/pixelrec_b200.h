@@ -63,7 +63,9 @@ PR_API int pr_set_device(int device);
  *   16 = score_topk with the branch-free 8-warp epilogue, 32 = (with 16) table tile TMA-multicast across a cluster,
  *   128 = fp16 scoring keeps the 128 x D seq_out tile resident in shared memory (D <= 512),
  *   64 = long-sequence attention (forward; backward for dh <= 64) on tensor cores (TF32 operands: results differ from the
- *        fp32 kernels within TF32 tolerance).
+ *        fp32 kernels within TF32 tolerance),
+ *   256 = table-gradient segment reduce as a TMA-staged shared-memory ring (rows of 256 B .. 8 KiB) instead of the LDG
+ *         warp-per-run kernel, 512 = LayerNorm forward (register kernel) with two rows in flight per warp.
  * mask < 0 only queries.  Returns the mask in effect.  Results are identical under every mask except where noted. */
 PR_API int pr_set_tuning(int mask);
 /* CUDA-graph replay of a training step (staged): every dropout kernel adds *seed_offset_dev (a uint64 in device memory, bumped

@@ -140,6 +140,64 @@ __global__ void __launch_bounds__(256, (VPL <= 4) ? 4 : 1) add_ln_fwd_kernel(LnA
     }
 }
 
+// Forward, two rows per warp iteration (PR_TUNE_LN_FWD_ROWS2): the loads of both rows are issued before either is reduced, which
+// doubles the bytes a warp keeps in flight (the one-row kernel alternates load / shuffle-reduce / store and leaves the SM short of
+// outstanding requests once the row is a single tensor, i.e. behind pr_gemm_tf32_drop).  Per-row arithmetic is add_ln_fwd_kernel's.
+template <int VPL>
+__global__ void __launch_bounds__(256, (VPL <= 4) ? 3 : 1) add_ln_fwd_rows2_kernel(LnArgs a, float* __restrict__ y,
+                                                                                   float* __restrict__ mean_out,
+                                                                                   float* __restrict__ rstd_out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const Philox ph(PR_SEED(a));
+    const unsigned thr_pre = drop_threshold(a.p_pre), thr_post = drop_threshold(a.p_post);
+    const float ik_pre = 1.0f / (1.0f - a.p_pre), ik_post = 1.0f / (1.0f - a.p_post);
+    const float4* g4 = reinterpret_cast<const float4*>(a.gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(a.beta);
+    for (long long row0 = 2 * warp; row0 < a.rows; row0 += 2 * nwarps) {
+        const bool two = row0 + 1 < a.rows;
+        float4 z[2][VPL];
+        unsigned mk_pre[2][(VPL + 1) / 2], mk_post[2][(VPL + 1) / 2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (r == 0 || two) {
+                if (a.p_pre > 0.f) row_keep_bits<VPL>(ph, a.stream_pre, thr_pre, row0 + r, a.D4, lane, mk_pre[r]);
+                if (a.p_post > 0.f) row_keep_bits<VPL>(ph, a.stream_post, thr_post, row0 + r, a.D4, lane, mk_post[r]);
+            }
+        }
+        load_z<VPL>(a, row0, lane, mk_pre[0], ik_pre, z[0]);
+        if (two) load_z<VPL>(a, row0 + 1, lane, mk_pre[1], ik_pre, z[1]);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (r == 1 && !two) break;
+            const long long row = row0 + r;
+            float mean, var;
+            row_stats<VPL>(z[r], lane, a.D4, mean, var);
+            const float rstd = 1.0f / sqrtf(var + a.eps);
+            float4* y4 = reinterpret_cast<float4*>(y) + row * a.D4;
+#pragma unroll
+            for (int j = 0; j < VPL; ++j) {
+                const int c = lane + 32 * j;
+                if (c < a.D4) {
+                    const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
+                    float4 o;
+                    o.x = (z[r][j].x - mean) * rstd * g.x + b.x;
+                    o.y = (z[r][j].y - mean) * rstd * g.y + b.y;
+                    o.z = (z[r][j].z - mean) * rstd * g.z + b.z;
+                    o.w = (z[r][j].w - mean) * rstd * g.w + b.w;
+                    if (a.p_post > 0.f) o = apply_keep(o, mk_post[r][j >> 1] >> (4 * (j & 1)), ik_post);
+                    y4[c] = o;
+                }
+            }
+            if (lane == 0) {
+                mean_out[row] = mean;
+                rstd_out[row] = rstd;
+            }
+        }
+    }
+}
+
 // Forward as per-warp TMA row pipelines (PR_TUNE_LN_FWD_PIPE; D == 128*VPL): stage = [h | res] rows, same arithmetic
 template <int VPL, int STAGES>
 __global__ void __launch_bounds__(256, (VPL <= 4) ? 2 : 1) add_ln_fwd_pipe_kernel(LnArgs a, float* __restrict__ y,
@@ -708,6 +766,14 @@ extern "C" int pr_add_ln_fwd_f32(const float* h, int64_t h_seq_stride, int64_t r
         else FPIPE(8, 3);
 #undef FPIPE
         PR_CUDA_LAUNCH_CHECK("add_ln_fwd_pipe_kernel");
+        return PR_OK;
+    }
+    if ((tune() & PR_TUNE_LN_FWD_ROWS2) && a.D4 <= 128) {
+        const int grid2 = (int)std::max<long long>(1, std::min<long long>((rows + 15) / 16, (long long)sm_count() * 3));   // persistent: 3 CTAs per SM resident
+#define CALL2(V) add_ln_fwd_rows2_kernel<V><<<grid2, 256, 0, stream>>>(a, y, mean, rstd)
+        if (a.D4 <= 32) { CALL2(1); } else if (a.D4 <= 64) { CALL2(2); } else { CALL2(4); }
+#undef CALL2
+        PR_CUDA_LAUNCH_CHECK("add_ln_fwd_rows2_kernel");
         return PR_OK;
     }
     const int grid = ln_grid(rows);

@@ -10,6 +10,7 @@
 
 #define PR_DYN_SMEM_BYTES(name) extern __shared__ __align__(128) unsigned char name[]
 #include "rows_ring.cuh"
+#include "rows_plan.cuh"
 
 namespace pr {
 
@@ -127,222 +128,6 @@ __global__ void __launch_bounds__(32) gather_rows_bulk_kernel(const float* __res
         }
     }
     if (lane == 0) bulk_wait_all<0>();
-}
-
-// =====================================================================================
-// K2 plan: stable LSD radix sort (8-bit digits) of (key, position), run boundaries, compaction
-// =====================================================================================
-constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 8;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 keys per CTA
-constexpr int SCAN_THREADS = 1024;
-
-__global__ void __launch_bounds__(256) plan_convert_kernel(const long long* __restrict__ idx, int R, long long N,
-                                                           long long pad, uint32_t* __restrict__ keys,
-                                                           int* __restrict__ vals, int* __restrict__ status) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R) return;
-    const long long id = idx[i];
-    const bool oor = (id < 0) || (id >= N);
-    if (oor && status) atomicOr(status, 1);
-    keys[i] = (oor || id == pad) ? (uint32_t)N : (uint32_t)id;  // sentinel N sorts last and is dropped
-    vals[i] = i;
-}
-
-__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32_t* __restrict__ keys, int R, int shift,
-                                                             uint32_t* __restrict__ tile_hist, int T) {
-    __shared__ uint32_t hist[256];
-    hist[threadIdx.x] = 0;
-    __syncthreads();
-    const int base = blockIdx.x * RS_TILE;
-#pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-        const int i = base + j * RS_THREADS + threadIdx.x;
-        if (i < R) atomicAdd(&hist[(keys[i] >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    tile_hist[(size_t)threadIdx.x * T + blockIdx.x] = hist[threadIdx.x];  // digit-major
-}
-
-// single-CTA in-place exclusive scan of a[0..n); optionally writes the grand total
-__global__ void __launch_bounds__(SCAN_THREADS) scan_single_kernel(uint32_t* __restrict__ a, int n,
-                                                                   uint32_t* __restrict__ total_out) {
-    __shared__ uint32_t warp_tot[32];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int chunk = (n + SCAN_THREADS - 1) / SCAN_THREADS;
-    const int lo = min(n, tid * chunk), hi = min(n, lo + chunk);
-    uint32_t s = 0;
-    for (int i = lo; i < hi; ++i) s += a[i];
-    uint32_t inc = s;  // inclusive warp scan
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) warp_tot[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-        const uint32_t w = warp_tot[lane];
-        uint32_t winc = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += t;
-        }
-        warp_tot[lane] = winc - w;  // exclusive offsets of the warps
-        if (lane == 31 && total_out) *total_out = winc;
-    }
-    __syncthreads();
-    uint32_t run = warp_tot[wid] + (inc - s);
-    for (int i = lo; i < hi; ++i) {
-        const uint32_t t = a[i];
-        a[i] = run;
-        run += t;
-    }
-}
-
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* __restrict__ keys_in,
-                                                                const int* __restrict__ vals_in,
-                                                                uint32_t* __restrict__ keys_out,
-                                                                int* __restrict__ vals_out, int R, int shift,
-                                                                const uint32_t* __restrict__ tile_base, int T) {
-    __shared__ uint32_t whist[RS_THREADS / 32][256];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    for (int i = tid; i < (RS_THREADS / 32) * 256; i += RS_THREADS) (&whist[0][0])[i] = 0;
-    __syncthreads();
-    // warp w owns the contiguous sub-tile [base, base + 256): order inside = (round j, lane) -> stable
-    const int base = blockIdx.x * RS_TILE + w * (32 * RS_ITEMS);
-    uint32_t key[RS_ITEMS];
-    uint32_t local[RS_ITEMS];
-#pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-        const int i = base + j * 32 + lane;
-        const bool valid = i < R;
-        key[j] = valid ? keys_in[i] : 0xffffffffu;
-        const uint32_t d = (key[j] >> shift) & 255u;
-        const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 0x100u);
-        const int rank = __popc(peers & ((1u << lane) - 1u));
-        const int leader = __ffs(peers) - 1;
-        uint32_t b = 0;
-        if (valid) b = whist[w][d];
-        __syncwarp();
-        if (valid && lane == leader) whist[w][d] = b + (uint32_t)__popc(peers);
-        __syncwarp();
-        local[j] = b + (uint32_t)rank;
-    }
-    __syncthreads();
-    {  // exclusive prefix over the 8 warps, per digit (thread == digit)
-        uint32_t run = 0;
-#pragma unroll
-        for (int ww = 0; ww < RS_THREADS / 32; ++ww) {
-            const uint32_t t = whist[ww][tid];
-            whist[ww][tid] = run;
-            run += t;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-        const int i = base + j * 32 + lane;
-        if (i < R) {
-            const uint32_t d = (key[j] >> shift) & 255u;
-            const uint32_t pos = tile_base[(size_t)d * T + blockIdx.x] + whist[w][d] + local[j];
-            keys_out[pos] = key[j];
-            vals_out[pos] = vals_in[i];
-        }
-    }
-}
-
-// flags[i] = 1 at the first position of every run of a real key (< N)
-__global__ void __launch_bounds__(256) seg_flag_kernel(const uint32_t* __restrict__ skeys, int R, uint32_t N,
-                                                       uint32_t* __restrict__ flags) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R) return;
-    const uint32_t k = skeys[i];
-    flags[i] = (k < N && (i == 0 || skeys[i - 1] != k)) ? 1u : 0u;
-}
-
-// multi-CTA exclusive scan, phase 1: per-tile totals
-__global__ void __launch_bounds__(RS_THREADS) scan_tile_reduce_kernel(const uint32_t* __restrict__ a, int n,
-                                                                      uint32_t* __restrict__ tile_sum) {
-    __shared__ uint32_t ws[RS_THREADS / 32];
-    const int base = blockIdx.x * RS_TILE;
-    uint32_t s = 0;
-#pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-        const int i = base + j * RS_THREADS + threadIdx.x;
-        if (i < n) s += a[i];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < RS_THREADS / 32; ++w) t += ws[w];
-        tile_sum[blockIdx.x] = t;
-    }
-}
-
-// phase 3: out[i] = tile_off[tile] + exclusive prefix inside the tile (blocked: thread owns 8 consecutive)
-__global__ void __launch_bounds__(RS_THREADS) scan_tile_apply_kernel(const uint32_t* __restrict__ a, int n,
-                                                                     const uint32_t* __restrict__ tile_off,
-                                                                     uint32_t* __restrict__ out) {
-    __shared__ uint32_t ws[RS_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int base = blockIdx.x * RS_TILE + tid * RS_ITEMS;
-    uint32_t v[RS_ITEMS];
-    uint32_t s = 0;
-#pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-        v[j] = (base + j < n) ? a[base + j] : 0u;
-        s += v[j];
-    }
-    uint32_t inc = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) ws[wid] = inc;
-    __syncthreads();
-    uint32_t woff = 0;
-    for (int w = 0; w < wid; ++w) woff += ws[w];
-    uint32_t run = tile_off[blockIdx.x] + woff + (inc - s);
-#pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-        if (base + j < n) out[base + j] = run;
-        run += v[j];
-    }
-}
-
-__global__ void __launch_bounds__(256) seg_emit_kernel(const uint32_t* __restrict__ skeys,
-                                                       const uint32_t* __restrict__ flags,
-                                                       const uint32_t* __restrict__ pos, int R, uint32_t N,
-                                                       int* __restrict__ uniq_ids, int* __restrict__ seg_start,
-                                                       int* __restrict__ n_uniq, int* __restrict__ row2slot) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R) return;
-    const uint32_t k = skeys[i];
-    const uint32_t u = pos[i];
-    if (flags[i]) {
-        uniq_ids[u] = (int)k;
-        seg_start[u] = i;
-        if (row2slot) row2slot[k] = (int)u;
-    }
-    if (k >= N && (i == 0 || skeys[i - 1] < N)) {  // first dropped row closes the last real run
-        seg_start[u] = i;
-        *n_uniq = (int)u;
-    }
-    if (i == R - 1 && k < N) {
-        seg_start[u + flags[i]] = R;
-        *n_uniq = (int)(u + flags[i]);
-    }
-}
-
-__global__ void plan_empty_kernel(int* seg_start, int* n_uniq) {
-    seg_start[0] = 0;
-    *n_uniq = 0;
 }
 
 // =====================================================================================
@@ -504,8 +289,6 @@ __global__ void __launch_bounds__(256) adamw_dense_kernel(float* __restrict__ w,
     }
 }
 
-static inline int ceil_div_ll(long long a, long long b) { return (int)((a + b - 1) / b); }
-
 }  // namespace pr
 
 using namespace pr;
@@ -552,7 +335,7 @@ extern "C" int pr_gather_rows_f32(const float* W, int64_t N, int64_t D, const in
 
 namespace {
 struct PlanLayout {
-    size_t keys0, keys1, tmpv, tile_hist, flags, pos, tile_sum, total;
+    size_t keys0, keys1, tmpv, tile_hist, tile_sum, total;
     int T;
 };
 PlanLayout plan_layout(int64_t R) {
@@ -565,9 +348,7 @@ PlanLayout plan_layout(int64_t R) {
     L.keys0 = take(r);
     L.keys1 = take(r);
     L.tmpv = take(r);
-    L.tile_hist = take((size_t)256 * L.T);
-    L.flags = take(r);
-    L.pos = take(r);
+    L.tile_hist = take((size_t)RS_MAX_BINS * L.T);
     L.tile_sum = take((size_t)L.T + 1);
     L.total = o;
     return L;
@@ -599,37 +380,33 @@ extern "C" int pr_scatter_plan(const int64_t* idx, int64_t R, int64_t N, int64_t
     uint32_t* kbuf[2] = {(uint32_t*)(ws + L.keys0), (uint32_t*)(ws + L.keys1)};
     int* tmpv = (int*)(ws + L.tmpv);
     uint32_t* tile_hist = (uint32_t*)(ws + L.tile_hist);
-    uint32_t* flags = (uint32_t*)(ws + L.flags);
-    uint32_t* pos = (uint32_t*)(ws + L.pos);
     uint32_t* tile_sum = (uint32_t*)(ws + L.tile_sum);
     const int T = L.T;
     int bits = 1;
     while ((1LL << bits) <= N) ++bits;  // keys take values 0..N (N = sentinel)
-    const int passes = (bits + 7) / 8;
+    const int passes = (bits + 9) / 10;                 // digits of up to 10 bits: 2 passes up to N = 2^20 - 1
+    const int rb = (bits + passes - 1) / passes;        // bits per digit, passes * rb >= bits
+    const int bins = 1 << rb;
     // ping-pong so that the final pass lands the positions in `perm`
     int* vbuf[2];
     if (passes % 2 == 0) { vbuf[0] = perm; vbuf[1] = tmpv; } else { vbuf[0] = tmpv; vbuf[1] = perm; }
     const int iR = (int)R;
-    plan_convert_kernel<<<ceil_div_ll(R, 256), 256, 0, stream>>>((const long long*)idx, iR, N, padding_idx, kbuf[0],
-                                                                 vbuf[0], status);
-    PR_CUDA_LAUNCH_CHECK("plan_convert_kernel");
     int cur = 0;
     for (int p = 0; p < passes; ++p) {
-        const int shift = 8 * p;
-        rs_hist_kernel<<<T, RS_THREADS, 0, stream>>>(kbuf[cur], iR, shift, tile_hist, T);
-        scan_single_kernel<<<1, SCAN_THREADS, 0, stream>>>(tile_hist, 256 * T, nullptr);
-        rs_scatter_kernel<<<T, RS_THREADS, 0, stream>>>(kbuf[cur], vbuf[cur], kbuf[cur ^ 1], vbuf[cur ^ 1], iR, shift,
-                                                        tile_hist, T);
+        const int shift = rb * p;
+        // pass 0 makes the keys from the ids on the fly and needs no value array (value of key i = i)
+        rs_hist_kernel<<<T, RS_THREADS, 0, stream>>>(p == 0 ? (const long long*)idx : nullptr, N, padding_idx, status, kbuf[cur],
+                                                     iR, shift, bins, tile_hist, T);
+        scan_single_kernel<<<1, SCAN_THREADS, 0, stream>>>(tile_hist, bins * T, nullptr);
+        rs_scatter_kernel<<<T, RS_THREADS, 0, stream>>>(kbuf[cur], p == 0 ? nullptr : vbuf[cur], kbuf[cur ^ 1], vbuf[cur ^ 1], iR,
+                                                        shift, bins, tile_hist, T);
         cur ^= 1;
     }
     PR_CUDA_LAUNCH_CHECK("radix sort passes");
     const uint32_t* skeys = kbuf[cur];
-    seg_flag_kernel<<<ceil_div_ll(R, 256), 256, 0, stream>>>(skeys, iR, (uint32_t)N, flags);
-    scan_tile_reduce_kernel<<<T, RS_THREADS, 0, stream>>>(flags, iR, tile_sum);
+    seg_reduce_kernel<<<T, RS_THREADS, 0, stream>>>(skeys, iR, (uint32_t)N, tile_sum);
     scan_single_kernel<<<1, SCAN_THREADS, 0, stream>>>(tile_sum, T, nullptr);
-    scan_tile_apply_kernel<<<T, RS_THREADS, 0, stream>>>(flags, iR, tile_sum, pos);
-    seg_emit_kernel<<<ceil_div_ll(R, 256), 256, 0, stream>>>(skeys, flags, pos, iR, (uint32_t)N, uniq_ids, seg_start,
-                                                             n_uniq, row2slot);
+    seg_emit_kernel<<<T, RS_THREADS, 0, stream>>>(skeys, iR, (uint32_t)N, tile_sum, uniq_ids, seg_start, n_uniq, row2slot);
     PR_CUDA_LAUNCH_CHECK("segment kernels");
     return PR_OK;
 }

@@ -124,7 +124,7 @@ class ScatterPlan:
                                             _p(self.seg_start), _p(self.n_uniq), _p(row2slot), _p(self._ws), ws_bytes,
                                             _p(status), _stream(idx)), "pr_scatter_plan")
         bits = max(1, int(self.N).bit_length())
-        _count(1 + 3 * ((bits + 7) // 8) + 5 if self.R else 1)
+        _count(3 * ((bits + 9) // 10) + 3 if self.R else 1)      # digits of up to 10 bits; convert / flag / emit ride in other passes
 
 
 def scatter_add_rows(dOut, plan: ScatterPlan, scale=1.0, dense_G=None, out_rows=True):

@@ -127,6 +127,7 @@ inline T warp_read(T v, int src_lane) {
 #define __restrict__
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
+#define __shared__ static   /* CTAs of a launch run one after the other here, so one static array per kernel is a CTA's shared memory */
 
 static inline void __syncthreads() { pthread_barrier_wait(&emu::cta()->block_bar); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_sync(); }
@@ -134,6 +135,17 @@ template <typename T>
 static inline T __shfl_xor_sync(unsigned, T v, int off) { return emu::warp_read(v, emu::lane_id() ^ off); }
 template <typename T>
 static inline T __shfl_sync(unsigned, T v, int src) { return emu::warp_read(v, src); }
+template <typename T>
+static inline T __shfl_up_sync(unsigned, T v, int delta) {
+    const int src = emu::lane_id() - delta;
+    const T r = emu::warp_read(v, src < 0 ? emu::lane_id() : src);
+    return src < 0 ? v : r;
+}
+static inline unsigned __match_any_sync(unsigned, uint32_t v) {
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) m |= (emu::warp_read<uint32_t>(v, l) == v ? 1u : 0u) << l;
+    return m;
+}
 static inline unsigned __ballot_sync(unsigned, bool p) {
     unsigned m = 0;
     for (int l = 0; l < 32; ++l) m |= (emu::warp_read<uint32_t>(p ? 1u : 0u, l) & 1u) << l;
@@ -143,6 +155,7 @@ static inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) !
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 template <typename T>

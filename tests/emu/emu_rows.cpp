@@ -3,6 +3,7 @@
 #include "emu_tc.h"
 
 #include "../../pixelrec_b200/csrc/rows_ring.cuh"
+#include "../../pixelrec_b200/csrc/rows_plan.cuh"
 
 using namespace pr;
 
@@ -32,4 +33,42 @@ extern "C" int emu_scatter_add_rows_ring(const float* dOut, int D, int gr, const
         default: return -1;
     }
     return vpl;
+}
+
+// the launch sequence of pr_scatter_plan (rows.cu) on the emulated kernels; `bits_per_digit` = 0 picks the production digits
+extern "C" int emu_scatter_plan(const long long* idx, int R, long long N, long long pad, int* perm, int* uniq_ids, int* seg_start,
+                                int* n_uniq, int* row2slot, int* status, int bits_per_digit) {
+    if (R == 0) {
+        emu::launch(1, 1, 0, [&]() { plan_empty_kernel(seg_start, n_uniq); });
+        return 0;
+    }
+    const int T = (R + RS_TILE - 1) / RS_TILE;
+    std::vector<uint32_t> k0(R), k1(R), tile_hist((size_t)RS_MAX_BINS * T), tile_sum(T + 1);
+    std::vector<int> tmpv(R);
+    uint32_t* kbuf[2] = {k0.data(), k1.data()};
+    int bits = 1;
+    while ((1LL << bits) <= N) ++bits;
+    int passes = (bits + 9) / 10;
+    int rb = (bits + passes - 1) / passes;
+    if (bits_per_digit) { rb = bits_per_digit; passes = (bits + rb - 1) / rb; }
+    const int bins = 1 << rb;
+    int* vbuf[2];
+    if (passes % 2 == 0) { vbuf[0] = perm; vbuf[1] = tmpv.data(); } else { vbuf[0] = tmpv.data(); vbuf[1] = perm; }
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+        const int shift = rb * p;
+        emu::launch(T, RS_THREADS, 0, [&]() {
+            rs_hist_kernel(p == 0 ? idx : nullptr, N, pad, status, kbuf[cur], R, shift, bins, tile_hist.data(), T);
+        });
+        emu::launch(1, SCAN_THREADS, 0, [&]() { scan_single_kernel(tile_hist.data(), bins * T, nullptr); });
+        emu::launch(T, RS_THREADS, 0, [&]() {
+            rs_scatter_kernel(kbuf[cur], p == 0 ? nullptr : vbuf[cur], kbuf[cur ^ 1], vbuf[cur ^ 1], R, shift, bins, tile_hist.data(), T);
+        });
+        cur ^= 1;
+    }
+    const uint32_t* skeys = kbuf[cur];
+    emu::launch(T, RS_THREADS, 0, [&]() { seg_reduce_kernel(skeys, R, (uint32_t)N, tile_sum.data()); });
+    emu::launch(1, SCAN_THREADS, 0, [&]() { scan_single_kernel(tile_sum.data(), T, nullptr); });
+    emu::launch(T, RS_THREADS, 0, [&]() { seg_emit_kernel(skeys, R, (uint32_t)N, tile_sum.data(), uniq_ids, seg_start, n_uniq, row2slot); });
+    return passes;
 }

@@ -295,6 +295,7 @@ def emu_rows():
     assert r.returncode == 0, r.stderr
     lib = C.CDLL(out)
     lib.emu_scatter_add_rows_ring.argtypes = [_P, _I, _I, _P, _P, _P, _P, _LL, C.c_float, _P, _P, _I]
+    lib.emu_scatter_plan.argtypes = [_P, _I, _LL, _LL, _P, _P, _P, _P, _P, _P, _I]
     return lib
 
 
@@ -340,3 +341,40 @@ def test_scatter_add_rows_ring_emulated(emu_rows, N, D, R, gr, grid, hot):
     emu_rows.emu_scatter_add_rows_ring(_ptr(dOc), D, gr, _ptr(perm), _ptr(uniq_b), _ptr(seg_b), _ptr(n_uniq), max_uniq, 0.25,
                                        _ptr(rows2), None, grid)
     np.testing.assert_array_equal(rows2[:U], G_ref[uniq] * np.float32(0.25))
+
+
+@pytest.mark.parametrize("N,R,pad,digit", [(50, 300, 0, 0), (97001, 5000, 0, 0), (1000, 4100, 0, 5), (300, 2048, None, 0), (7, 40, 0, 2),
+                                           (5000, 2049, 0, 0), (64, 100, 0, 0), (20, 0, 0, 0), (9, 30, 3, 0)])
+def test_scatter_plan_emulated(emu_rows, N, R, pad, digit):
+    """pr_scatter_plan's kernels (rows_plan.cuh: radix passes with the id conversion folded into the first histogram, run flags
+    folded into the scan, emission folded into its apply pass) == a stable sort of (id, position): perm, the distinct ids, the run
+    boundaries, n_uniq and row2slot -- with padding ids, out-of-range ids (flagged, dropped), several tiles and digit widths."""
+    g = np.random.default_rng(N + R)
+    idx = g.integers(0, N, size=R).astype(np.int64)
+    if R > 10:
+        idx[3] = -5                       # out of range: dropped + status bit 0
+        idx[7] = N + 2
+    padv = -1 if pad is None else pad
+    key = np.where((idx < 0) | (idx >= N) | (idx == padv), N, idx)
+    perm_ref = np.argsort(key, kind="stable").astype(np.int32)
+    sk = key[perm_ref]
+    nreal = int((sk < N).sum())
+    starts = np.flatnonzero(np.r_[True, sk[1:nreal] != sk[:nreal - 1]]) if nreal else np.zeros(0, np.int64)
+    U = len(starts)
+    cap = max(1, min(R, N))
+    perm = np.full(max(R, 1), -1, np.int32)
+    uniq = np.full(cap, -1, np.int32)
+    seg = np.full(cap + 1, -1, np.int32)
+    n_uniq = np.full(1, -1, np.int32)
+    row2slot = np.full(N, -1, np.int32)
+    status = np.zeros(1, np.int32)
+    emu_rows.emu_scatter_plan(_ptr(idx), R, N, padv, _ptr(perm), _ptr(uniq), _ptr(seg), _ptr(n_uniq), _ptr(row2slot), _ptr(status), digit)
+    assert n_uniq[0] == U
+    assert seg[U] == nreal and np.array_equal(seg[:U], starts)
+    if R:
+        assert np.array_equal(perm[:R], perm_ref)
+        assert np.array_equal(uniq[:U], sk[starts])
+        ref_slot = np.full(N, -1, np.int32)
+        ref_slot[sk[starts]] = np.arange(U)
+        assert np.array_equal(row2slot, ref_slot)
+        assert status[0] == (1 if R > 10 else 0)

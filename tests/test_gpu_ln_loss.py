@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 TOL = 2e-5
 
 
-@pytest.fixture(params=[0, 1, 2, 5], ids=["tune0", "tune_pipe", "tune_l2pf", "tune_pipe_fwd_bwd"])
+@pytest.fixture(params=[0, 1, 2, 5, 513], ids=["tune0", "tune_pipe", "tune_l2pf", "tune_pipe_fwd_bwd", "tune_fwd_rows2"])
 def ln_tune(request):
     """runs a test under each LayerNorm kernel variant (pr_set_tuning); results must not depend on it"""
     from pixelrec_b200 import lib
