@@ -33,8 +33,9 @@ const unsigned long long* seed_device();
 #define PR_TUNE_SCATTER_RING 256  /* scatter_add_rows as a TMA-staged ring (rows_ring.cuh) instead of the LDG warp-per-run kernel */
 #define PR_TUNE_LN_FWD_ROWS2 512   /* LayerNorm forward (register kernel) with two rows in flight per warp */
 #ifndef PR_TUNE_DEFAULT
-/* measured: profiles/r01h_rowkernels_ab.md, r01l_attention_pair.md, r02a_bench_score.json, r02a_bench_attn_long.json */
-#define PR_TUNE_DEFAULT (PR_TUNE_LN_BWD_PIPE | PR_TUNE_ATTN_PAIR | PR_TUNE_SCORE_V2 | PR_TUNE_ATTN_LONG_TC | PR_TUNE_SCATTER_RING)
+/* measured: profiles/r01h_rowkernels_ab.md, r01l_attention_pair.md, r02a_bench_score.json, r02a_bench_attn_long.json,
+   r02j_scatter_ab.json, r02k_bench_n1_rows2.json */
+#define PR_TUNE_DEFAULT (PR_TUNE_LN_BWD_PIPE | PR_TUNE_ATTN_PAIR | PR_TUNE_SCORE_V2 | PR_TUNE_ATTN_LONG_TC | PR_TUNE_SCATTER_RING | PR_TUNE_LN_FWD_ROWS2)
 #endif
 
 #define PR_CHECK_ARG(cond, ...)                 \

@@ -426,11 +426,12 @@ extern "C" int pr_scatter_add_rows_f32(const float* dOut, int64_t R, int64_t D, 
     const int D4 = (int)(D / 4);
     const int sms = sm_count();
     const long long work_hint = std::min<long long>(max_uniq, R);
-    if ((tune() & PR_TUNE_SCATTER_RING) && D >= 64 && D <= 2048) {
-        // TMA-staged ring (rows_ring.cuh): VPL float4 per lane cover a row, 8 KiB stages.  Measured (profiles/r02j_scatter_ab.json):
-        // 1.1-2.5x the LDG kernel up to D = 2048; at D = 4096 a row is 32 float4 per lane and the LDG kernel's 4 warps per row win.
-        static int variant = -1;            // PR_SCATTER_VARIANT (A/B runs): 1 = 16 KiB stages at D = 512, 2 = + L2 prefetch of rows
-        if (variant < 0) {
+    if ((tune() & PR_TUNE_SCATTER_RING) && D >= 64 && D <= 1024) {
+        // TMA-staged ring (rows_ring.cuh): VPL float4 per lane cover a row, 4 KiB stages, 6 of them per one-warp CTA, ~9 CTAs per SM.
+        // Measured (profiles/r02j_scatter_ab.json, r02k_scatter_variants.json): 1.4-2.5x the LDG kernel up to D = 1024; from 8 KiB
+        // rows on the LDG kernel's several warps per row are as fast or faster.
+        static int variant = -1;            // PR_SCATTER_VARIANT (A/B runs): 1 = 8 KiB stages (4 rows at D = 512), 2 = + L2 prefetch of
+        if (variant < 0) {                  // rows, 4 = 4-stage ring
             const char* e = getenv("PR_SCATTER_VARIANT");
             variant = e ? atoi(e) : 0;
         }
@@ -438,13 +439,16 @@ extern "C" int pr_scatter_add_rows_f32(const float* dOut, int64_t R, int64_t D, 
         while (32 * vpl < D4) vpl *= 2;
         const bool big = (variant & 1) && vpl == 4;
         const int l2pf = (variant & 2) ? 1 : 0;
-        const int rps = big ? 8 : std::max(1, 16 / vpl);
-        const size_t smem = (size_t)SR_STAGES * rps * D * 4 + SR_BAR_BYTES;
+        const int nst = (variant & 4) ? 4 : SR_STAGES;
+        const int rps = big ? 4 : std::max(1, 8 / vpl);
+        const size_t smem = (size_t)nst * rps * D * 4 + SR_BAR_BYTES;
         int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
         ctas_per_sm = std::max(1, std::min(16, ctas_per_sm));
         const long long max_ctas = (long long)sms * ctas_per_sm;
-        int gr = 32;   // runs per group: fewer when the step is small, so that every CTA still gets work
-        while (gr > 2 && work_hint / gr < 2 * max_ctas) gr >>= 1;
+        // runs per group: every CTA should get several groups, and the number of distinct ids is only known on the device --
+        // assume a third of the rows (long-tail batches: 0.3-0.55), which errs towards more, smaller groups
+        int gr = 32;
+        while (gr > 2 && work_hint / (3 * gr) < 4 * max_ctas) gr >>= 1;
         const int grid = (int)std::max<long long>(1, std::min<long long>((work_hint + gr - 1) / gr, max_ctas));
 #define PR_LAUNCH_RING(VPL, RPS)                                                                                    \
     do {                                                                                                            \
@@ -452,14 +456,13 @@ extern "C" int pr_scatter_add_rows_f32(const float* dOut, int64_t R, int64_t D, 
             PR_CUDA_CALL(cudaFuncSetAttribute(scatter_add_rows_ring_kernel<VPL, RPS>,                               \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
         scatter_add_rows_ring_kernel<VPL, RPS><<<grid, 32, smem, stream>>>(dOut, (int)D, gr, perm, uniq_ids, seg_start, \
-                                                                          n_uniq, max_uniq, scale, out_rows, dense_G, l2pf); \
+                                                                          n_uniq, max_uniq, scale, out_rows, dense_G, l2pf, nst); \
     } while (0)
         switch (vpl) {
-            case 1: PR_LAUNCH_RING(1, 16); break;
-            case 2: PR_LAUNCH_RING(2, 8); break;
-            case 4: if (big) PR_LAUNCH_RING(4, 8); else PR_LAUNCH_RING(4, 4); break;
-            case 8: PR_LAUNCH_RING(8, 2); break;
-            default: PR_LAUNCH_RING(16, 1); break;
+            case 1: PR_LAUNCH_RING(1, 8); break;
+            case 2: PR_LAUNCH_RING(2, 4); break;
+            case 4: if (big) PR_LAUNCH_RING(4, 4); else PR_LAUNCH_RING(4, 2); break;
+            default: PR_LAUNCH_RING(8, 1); break;
         }
 #undef PR_LAUNCH_RING
         PR_CUDA_LAUNCH_CHECK("scatter_add_rows_ring_kernel");

@@ -5,9 +5,12 @@
 //   fill   lane l issues ONE cp.async.bulk global->shared for row perm[k + l] of the chunk (2 KB at D=512); the stage's
 //          mbarrier counts the bytes; the perm entries of the next SR_AHEAD chunks and the boundaries of the next group
 //          are already in registers, so the issue never waits on an index load;
-//   drain  SR_STAGES-1 chunks later the warp adds the staged rows, lane = 4-float column slice, IN ASCENDING SORTED
+//   drain  nst-1 chunks later the warp adds the staged rows, lane = 4-float column slice, IN ASCENDING SORTED
 //          POSITION (the oracle's order: results are bit-identical to oracle.scatter_add_rows), and writes a reduced
 //          row whenever a run ends.
+// The drain side (one warp: shared-memory loads, adds, run bookkeeping, row stores) is what bounds a CTA, so rings are kept SMALL
+// (24 KiB: 6 stages of 2 rows at D=512) and many CTAs share an SM: 16 KiB stages with 2 CTAs per SM measured 0.160 ms, 8 KiB
+// stages with 4 CTAs 0.102 ms at C2 / B=4096 (profiles/r02k_scatter_variants.json).
 // Rows in flight therefore do not depend on the run structure: a run of one row and a run of 500 duplicates of a hot
 // item stream at the same rate (the LDG kernel it replaces walked a run with two loads in flight: 0.40 of HBM peak).
 // Written against the primitives rows.cu defines (mbar_*, bulk_g2s, PR_DYN_SMEM_BYTES); tests/emu compiles this file
@@ -28,16 +31,16 @@ __global__ void __launch_bounds__(32) scatter_add_rows_ring_kernel(const float* 
                                                                    const int* __restrict__ seg_start,
                                                                    const int* __restrict__ n_uniq, long long max_uniq,
                                                                    float scale, float* __restrict__ out_rows,
-                                                                   float* __restrict__ dense_G, int l2_prefetch) {
+                                                                   float* __restrict__ dense_G, int l2_prefetch, int nst) {
     PR_DYN_SMEM_BYTES(smem_raw);
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x;
     const int D4 = D >> 2;
     const uint32_t row_bytes = (uint32_t)D * 4u;
     const uint32_t stage_bytes = row_bytes * (uint32_t)RPS;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)SR_STAGES * stage_bytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nst * stage_bytes);   // nst <= SR_STAGES ring stages
     if (lane == 0) {
-        for (int s = 0; s < SR_STAGES; ++s) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < nst; ++s) mbar_init(&full_bar[s], 1);
         fence_mbar_init();
     }
     __syncwarp();
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(32) scatter_add_rows_ring_kernel(const float* 
     for (int j = 0; j < VPL; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     for (int it = 0;; ++it) {
-        if (it >= SR_STAGES - 1) {
+        if (it >= nst - 1) {
             if (!c_live) break;
             const int n = min(RPS, ce - ck);
             mbar_wait(&full_bar[cs], cphase);
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(32) scatter_add_rows_ring_kernel(const float* 
                 }
             }
             __syncwarp();   // every lane is done reading the stage before it is refilled below
-            if (++cs == SR_STAGES) { cs = 0; cphase ^= 1u; }
+            if (++cs == nst) { cs = 0; cphase ^= 1u; }
             if (ck == ce) {   // group exhausted
                 cg += G;
                 if (cg >= ngroups) {
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(32) scatter_add_rows_ring_kernel(const float* 
             if (lane == 0) mbar_arrive_expect_tx(&full_bar[ps], (uint32_t)qn[0] * row_bytes);
             __syncwarp();
             if (lane < qn[0]) bulk_g2s(st + (size_t)lane * row_bytes, dOut + (long long)qperm[0] * D, row_bytes, &full_bar[ps]);
-            if (++ps == SR_STAGES) ps = 0;
+            if (++ps == nst) ps = 0;
 #pragma unroll
             for (int i = 0; i + 1 < SR_AHEAD; ++i) { qn[i] = qn[i + 1]; qperm[i] = qperm[i + 1]; }
             next_chunk(qn[SR_AHEAD - 1], qperm[SR_AHEAD - 1]);

@@ -9,29 +9,31 @@ using namespace pr;
 
 template <int VPL, int RPS>
 static void run_ring(const float* dOut, int D, int gr, const int* perm, const int* uniq_ids, const int* seg_start, const int* n_uniq,
-                     long long max_uniq, float scale, float* out_rows, float* dense_G, int grid) {
-    const size_t smem = (size_t)SR_STAGES * RPS * D * 4 + SR_BAR_BYTES;
+                     long long max_uniq, float scale, float* out_rows, float* dense_G, int grid, int nst) {
+    const size_t smem = (size_t)nst * RPS * D * 4 + SR_BAR_BYTES;
     emu::after_launch_hook() = emu::join_async;
     emu::launch(grid, 32, smem, [&]() {
-        scatter_add_rows_ring_kernel<VPL, RPS>(dOut, D, gr, perm, uniq_ids, seg_start, n_uniq, max_uniq, scale, out_rows, dense_G, 1);
+        scatter_add_rows_ring_kernel<VPL, RPS>(dOut, D, gr, perm, uniq_ids, seg_start, n_uniq, max_uniq, scale, out_rows, dense_G, 1, nst);
     });
     emu::after_launch_hook() = nullptr;
 }
 
-// same VPL / RPS choice as pr_scatter_add_rows_f32 (rows.cu); gr and grid are explicit so that tests can force group switches
+// same VPL / RPS choice as pr_scatter_add_rows_f32 (rows.cu); gr, grid and the ring depth are explicit so that tests can force
+// group switches and both ring depths; big != 0: the 4-rows-per-stage A/B geometry at VPL = 4
 extern "C" int emu_scatter_add_rows_ring(const float* dOut, int D, int gr, const int* perm, const int* uniq_ids, const int* seg_start,
                                          const int* n_uniq, long long max_uniq, float scale, float* out_rows, float* dense_G,
-                                         int grid) {
+                                         int grid, int nst, int big) {
     int vpl = 1;
     while (32 * vpl < D / 4) vpl *= 2;
+#define RUN(V, R) run_ring<V, R>(dOut, D, gr, perm, uniq_ids, seg_start, n_uniq, max_uniq, scale, out_rows, dense_G, grid, nst)
     switch (vpl) {
-        case 1: run_ring<1, 16>(dOut, D, gr, perm, uniq_ids, seg_start, n_uniq, max_uniq, scale, out_rows, dense_G, grid); break;
-        case 2: run_ring<2, 8>(dOut, D, gr, perm, uniq_ids, seg_start, n_uniq, max_uniq, scale, out_rows, dense_G, grid); break;
-        case 4: run_ring<4, 4>(dOut, D, gr, perm, uniq_ids, seg_start, n_uniq, max_uniq, scale, out_rows, dense_G, grid); break;
-        case 8: run_ring<8, 2>(dOut, D, gr, perm, uniq_ids, seg_start, n_uniq, max_uniq, scale, out_rows, dense_G, grid); break;
-        case 16: run_ring<16, 1>(dOut, D, gr, perm, uniq_ids, seg_start, n_uniq, max_uniq, scale, out_rows, dense_G, grid); break;
+        case 1: RUN(1, 8); break;
+        case 2: RUN(2, 4); break;
+        case 4: if (big) RUN(4, 4); else RUN(4, 2); break;
+        case 8: RUN(8, 1); break;
         default: return -1;
     }
+#undef RUN
     return vpl;
 }
 

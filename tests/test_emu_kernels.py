@@ -294,7 +294,7 @@ def emu_rows():
     r = subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", out, src], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     lib = C.CDLL(out)
-    lib.emu_scatter_add_rows_ring.argtypes = [_P, _I, _I, _P, _P, _P, _P, _LL, C.c_float, _P, _P, _I]
+    lib.emu_scatter_add_rows_ring.argtypes = [_P, _I, _I, _P, _P, _P, _P, _LL, C.c_float, _P, _P, _I, _I, _I]
     lib.emu_scatter_plan.argtypes = [_P, _I, _LL, _LL, _P, _P, _P, _P, _P, _P, _I]
     return lib
 
@@ -311,10 +311,12 @@ def _np_plan(idx, N, pad):
     return perm, uniq, seg
 
 
-@pytest.mark.parametrize("N,D,R,gr,grid,hot", [(50, 64, 300, 4, 3, 0), (200, 512, 260, 32, 2, 0), (40, 384, 200, 8, 1, 0),
-                                               (30, 128, 500, 2, 7, 0.6), (300, 1024, 90, 32, 5, 0), (64, 2048, 70, 16, 2, 0.3),
-                                               (20, 1536, 40, 32, 3, 0), (10, 512, 0, 32, 2, 0), (10, 512, 40, 32, 2, 1.0)])
-def test_scatter_add_rows_ring_emulated(emu_rows, N, D, R, gr, grid, hot):
+@pytest.mark.parametrize("N,D,R,gr,grid,hot,nst,big", [(50, 64, 300, 4, 3, 0, 6, 0), (200, 512, 260, 32, 2, 0, 6, 0), (40, 384, 200, 8, 1, 0, 4, 0),
+                                                       (30, 128, 500, 2, 7, 0.6, 6, 0), (300, 1024, 90, 32, 5, 0, 6, 0),
+                                                       (64, 512, 170, 16, 2, 0.3, 4, 1), (20, 768, 40, 32, 3, 0, 6, 0),
+                                                       (10, 512, 0, 32, 2, 0, 6, 0), (10, 512, 40, 32, 2, 1.0, 6, 0),
+                                                       (100, 256, 333, 8, 4, 0.2, 3, 0)])
+def test_scatter_add_rows_ring_emulated(emu_rows, N, D, R, gr, grid, hot, nst, big):
     """TMA-staged segment reduce (rows_ring.cuh): ring protocol, group / run bookkeeping and the summation order, bit for bit
     against oracle.scatter_add_rows -- including one hot id that owns most rows, all-padding input and R = 0."""
     g = np.random.default_rng(N * 131 + D + R)
@@ -332,14 +334,14 @@ def test_scatter_add_rows_ring_emulated(emu_rows, N, D, R, gr, grid, hot):
     G = np.zeros((N, D), np.float32)
     dOc = np.ascontiguousarray(dO) if R else np.zeros((1, D), np.float32)
     assert emu_rows.emu_scatter_add_rows_ring(_ptr(dOc), D, gr, _ptr(perm), _ptr(uniq_b), _ptr(seg_b), _ptr(n_uniq), max_uniq, 1.0,
-                                              _ptr(rows), _ptr(G), grid) > 0
+                                              _ptr(rows), _ptr(G), grid, nst, big) > 0
     G_ref = O.scatter_add_rows(dO, idx, N, 0) if R else np.zeros((N, D), np.float32)
     np.testing.assert_array_equal(G, G_ref)
     np.testing.assert_array_equal(rows[:U], G_ref[uniq])
     assert np.isnan(rows[U:]).all()                    # rows beyond n_uniq are never written
     rows2 = np.full((max_uniq, D), np.nan, np.float32)
     emu_rows.emu_scatter_add_rows_ring(_ptr(dOc), D, gr, _ptr(perm), _ptr(uniq_b), _ptr(seg_b), _ptr(n_uniq), max_uniq, 0.25,
-                                       _ptr(rows2), None, grid)
+                                       _ptr(rows2), None, grid, nst, big)
     np.testing.assert_array_equal(rows2[:U], G_ref[uniq] * np.float32(0.25))
 
 

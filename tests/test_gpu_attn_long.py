@@ -1,7 +1,6 @@
 """GPU parity: long-sequence attention core (pr_attn_long_*_f32, 64 < L <= 256: the ViT-B/16 item encoder's 197 tokens) vs the
 fp64 oracle (oracle/sasrec_np.py attn_core_fwd/bwd, REC/model/layers.py:590-612).  Tolerance 3e-5 relative-to-max (strict
-fp32).  The kernels' logic is already pinned on CPU (tests/test_emu_kernels.py); they have not run on a GPU yet, so this file
-is opt-in (PR_EXPERIMENTAL=1) until a B200 run has confirmed it."""
+fp32).  The kernels' logic is also pinned on CPU (tests/test_emu_kernels.py)."""
 import os
 
 import numpy as np

@@ -1,14 +1,13 @@
-"""GPU parity of the CUDA-graph replay of the training step (pixelrec_b200/trainer/graph.py, staged): K replays must leave the
-model exactly where K eager steps leave it -- including the dropout masks (device-side seed offset) and AdamW's bias correction
-(device-side step count).  Opt-in (PR_EXPERIMENTAL=1); the dropout case also needs a library built with -DPR_SEED_DEV."""
+"""GPU parity of the CUDA-graph replay of the training step (pixelrec_b200/trainer/graph.py): K replays must leave the
+model exactly where K eager steps leave it -- including the dropout masks (device-side seed offset; the default build's
+-DPR_SEED_DEV) and AdamW's bias correction (device-side step count)."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-]
+pytestmark = pytest.mark.gpu
 
 N, B, L = 503, 32, 10
 

@@ -1,7 +1,7 @@
 """GPU parity of the peer-memory row kernels (csrc/peer.cu) on ONE device: the "peers" are separate allocations of the same
 GPU, so pr_gather_rows_peers_f32 / pr_push_rows_peers_f32 and the SharedBuffer aliasing are exercised without NVLink.
 The multi-process path (CUDA IPC + NCCL barriers) is tests/test_gpu_dist.py[p2p]; its host logic runs on CPU in
-tests/test_dist_gloo.py.  Staged code (written without GPU access): opt-in with PR_EXPERIMENTAL=1 until confirmed."""
+tests/test_dist_gloo.py."""
 import os
 
 import numpy as np
@@ -11,8 +11,7 @@ import torch
 from oracle import sasrec_np as O
 from tests.gpu_util import dev, t
 
-pytestmark = [pytest.mark.gpu,
-]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("G,N,D,R", [(1, 50, 8, 33), (2, 101, 64, 500), (4, 1003, 512, 4097), (8, 97001, 512, 20000), (3, 77, 36, 10)])

@@ -11,9 +11,8 @@ from tests.gpu_util import t
 
 pytestmark = pytest.mark.gpu
 
-# Kernel variants of pr_score_topk_f32 (pr_set_tuning bits 16 / 32, csrc/score.cu "v2").  The default kernel always runs;
-# the staged variants were written without GPU access and stay opt-in (PR_EXPERIMENTAL=1, run under a timeout: see
-# tools/round2_gpu.sh) until a B200 run has confirmed them.
+# Kernel variants of pr_score_topk_f32 (pr_set_tuning bits 16 / 32, csrc/score.cu "v2"): every test runs under all three
+# (v2 is the default since round 2; all of them have run on a B200, profiles/r02a_stage1_staged_kernels.md).
 _VARIANTS = [0, 16, 48]
 
 
