@@ -413,7 +413,7 @@ def run_ours(args, out):
         "gather_rows": R_u * (8 * D + 8),
         "scatter_add_rows": None,                           # depends on U (unique ids); filled below
         "adamw_rows": 6 * n_local * D * 4,
-        "add_ln_fwd": 3 * B * L * D * 4, "add_ln_bwd": 5 * B * L * D * 4,
+        "add_ln_fwd": None, "add_ln_bwd": None,                # depend on the fusion mode; filled below
         "attn_fwd": 16 * B * L * D, "attn_bwd": 32 * B * L * D,
         "bpr_fwd": 3 * B * L * D * 4, "bpr_bwd": 6 * B * L * D * 4,
         "act_fwd": 2 * B * L * 2 * D * 4, "act_bwd": 3 * B * L * 2 * D * 4,
@@ -423,6 +423,21 @@ def run_ours(args, out):
     valid = float(np.mean([int(resident[i % POOL][1].sum().item()) for i in range(n_prof)]))
     alg["bpr_fwd"] = 3 * valid * D * 4
     alg["bpr_bwd"] = 6 * valid * D * 4
+    # LayerNorm launches per step: the embedding LN (forward: rows of E in, x out = 2 passes of B*L*D floats; backward: dy and the
+    # rows in, read-modify-write of the table-gradient rows = 4 passes) + 2 per layer.  With dense / dense_2 writing z themselves
+    # (ops.FUSE_LN_Z, default) a layer LN reads z and writes y (2 passes) and its backward reads dy, z and writes dz, dh (4 passes);
+    # with separate kernels it is 3 (h, residual -> y) and 5 (dy, h, residual -> dh, dres).  Mean over the launches of a step:
+    zmode = bool(ops.FUSE_LN_Z) and ops._use_tc(D, D, c["inner"] * D)
+    n_ln = 2 * c["layers"]
+    alg["add_ln_fwd"] = (2 + n_ln * (2 if zmode else 3)) / (1 + n_ln) * B * L * D * 4
+    alg["add_ln_bwd"] = (4 + n_ln * (4 if zmode else 5)) / (1 + n_ln) * B * L * D * 4
+    if world == 1:                        # segment reduce of the table gradient: 4D(R_valid + U) + 8R, U = distinct non-pad ids
+        uv = []
+        for i in range(n_prof):
+            ids = resident[i % POOL][0].reshape(-1)
+            nz = ids[ids != 0]
+            uv.append((int(nz.numel()), int(torch.unique(nz).numel())))
+        alg["scatter_add_rows"] = 4 * D * float(np.mean([a + b for a, b in uv])) + 8 * B * 2 * (L + 1)
     if world > 1:                         # sharded lookup: three gathers of different sizes per step, no single per-launch figure
         alg["gather_rows"] = None
     gemm_flop = 96.0 * B * L * D * D      # forward + input-gradient + weight-gradient GEMMs of the 2 layers

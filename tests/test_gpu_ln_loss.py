@@ -114,7 +114,7 @@ def test_activation(act, n):
         ops.activation(tx, "mish")
 
 
-@pytest.mark.parametrize("B,L,D", [(4, 10, 128), (64, 20, 512), (3, 7, 64), (2, 20, 2048), (5, 3, 36)])
+@pytest.mark.parametrize("B,L,D", [(4, 10, 128), (64, 20, 512), (3, 7, 64), (2, 20, 2048), (5, 3, 36), (3, 5, 256), (2, 4, 1024), (2, 3, 768)])
 def test_bpr_loss_fwd_bwd(B, L, D):
     from pixelrec_b200 import ops
     g = np.random.default_rng(B * L + D)
