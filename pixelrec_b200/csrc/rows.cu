@@ -430,15 +430,14 @@ extern "C" int pr_scatter_add_rows_f32(const float* dOut, int64_t R, int64_t D, 
         // TMA-staged ring (rows_ring.cuh): VPL float4 per lane cover a row, 4 KiB stages, 6 of them per one-warp CTA, ~9 CTAs per SM.
         // Measured (profiles/r02j_scatter_ab.json, r02k_scatter_variants.json): 1.4-2.5x the LDG kernel up to D = 1024; from 8 KiB
         // rows on the LDG kernel's several warps per row are as fast or faster.
-        static int variant = -1;            // PR_SCATTER_VARIANT (A/B runs): 1 = 8 KiB stages (4 rows at D = 512), 2 = + L2 prefetch of
-        if (variant < 0) {                  // rows, 4 = 4-stage ring
+        static int variant = -1;            // PR_SCATTER_VARIANT (A/B runs): 1 = 8 KiB stages (4 rows at D = 512), 4 = 4-stage ring
+        if (variant < 0) {
             const char* e = getenv("PR_SCATTER_VARIANT");
             variant = e ? atoi(e) : 0;
         }
         int vpl = 1;
         while (32 * vpl < D4) vpl *= 2;
         const bool big = (variant & 1) && vpl == 4;
-        const int l2pf = (variant & 2) ? 1 : 0;
         const int nst = (variant & 4) ? 4 : SR_STAGES;
         const int rps = big ? 4 : std::max(1, 8 / vpl);
         const size_t smem = (size_t)nst * rps * D * 4 + SR_BAR_BYTES;
@@ -456,7 +455,7 @@ extern "C" int pr_scatter_add_rows_f32(const float* dOut, int64_t R, int64_t D, 
             PR_CUDA_CALL(cudaFuncSetAttribute(scatter_add_rows_ring_kernel<VPL, RPS>,                               \
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
         scatter_add_rows_ring_kernel<VPL, RPS><<<grid, 32, smem, stream>>>(dOut, (int)D, gr, perm, uniq_ids, seg_start, \
-                                                                          n_uniq, max_uniq, scale, out_rows, dense_G, l2pf, nst); \
+                                                                          n_uniq, max_uniq, scale, out_rows, dense_G, nst); \
     } while (0)
         switch (vpl) {
             case 1: PR_LAUNCH_RING(1, 8); break;

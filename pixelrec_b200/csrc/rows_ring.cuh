@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(32) scatter_add_rows_ring_kernel(const float* 
                                                                    const int* __restrict__ seg_start,
                                                                    const int* __restrict__ n_uniq, long long max_uniq,
                                                                    float scale, float* __restrict__ out_rows,
-                                                                   float* __restrict__ dense_G, int l2_prefetch, int nst) {
+                                                                   float* __restrict__ dense_G, int nst) {
     PR_DYN_SMEM_BYTES(smem_raw);
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x;
@@ -67,8 +67,6 @@ __global__ void __launch_bounds__(32) scatter_add_rows_ring_kernel(const float* 
     auto next_chunk = [&](int& n_out, int& perm_out) {
         n_out = p_live ? min(RPS, pe - pk) : 0;
         perm_out = (lane < n_out) ? perm[pk + lane] : 0;
-        // A/B knob (PR_SCATTER_VARIANT=2): pull the row into L2 now, SR_AHEAD + SR_STAGES - 1 chunks before it is staged
-        if (l2_prefetch && lane < n_out) l2_prefetch_bulk(dOut + (long long)perm_out * D, row_bytes);
         if (p_live) {
             pk += n_out;
             if (pk >= pe) {
@@ -104,9 +102,14 @@ __global__ void __launch_bounds__(32) scatter_add_rows_ring_kernel(const float* 
 #pragma unroll
     for (int j = 0; j < VPL; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    for (int it = 0;; ++it) {
+    // One iteration = drain the oldest staged chunk, then issue the chunk held in queue slot (qn_s, qperm_s) and refill that slot
+    // with the chunk SR_AHEAD further on.  The slots are used round-robin by the unrolled loop below, so a perm entry is never
+    // touched between its load and its use (a shifting register queue MOVed the pending loads every iteration, and every chunk
+    // then waited a full memory latency: ncu, profiles/r02k_rowkernels_ncu.md).
+    int it = 0;
+    auto iteration = [&](int& qn_s, int& qperm_s) -> bool {
         if (it >= nst - 1) {
-            if (!c_live) break;
+            if (!c_live) return true;
             const int n = min(RPS, ce - ck);
             mbar_wait(&full_bar[cs], cphase);
             const unsigned char* st = smem_raw + (size_t)cs * stage_bytes;
@@ -171,17 +174,24 @@ __global__ void __launch_bounds__(32) scatter_add_rows_ring_kernel(const float* 
                 }
             }
         }
-        if (qn[0] > 0) {
+        if (qn_s > 0) {
             // stage ps held the chunk drained one iteration ago
             unsigned char* st = smem_raw + (size_t)ps * stage_bytes;
-            if (lane == 0) mbar_arrive_expect_tx(&full_bar[ps], (uint32_t)qn[0] * row_bytes);
+            if (lane == 0) mbar_arrive_expect_tx(&full_bar[ps], (uint32_t)qn_s * row_bytes);
             __syncwarp();
-            if (lane < qn[0]) bulk_g2s(st + (size_t)lane * row_bytes, dOut + (long long)qperm[0] * D, row_bytes, &full_bar[ps]);
+            if (lane < qn_s) bulk_g2s(st + (size_t)lane * row_bytes, dOut + (long long)qperm_s * D, row_bytes, &full_bar[ps]);
             if (++ps == nst) ps = 0;
-#pragma unroll
-            for (int i = 0; i + 1 < SR_AHEAD; ++i) { qn[i] = qn[i + 1]; qperm[i] = qperm[i + 1]; }
-            next_chunk(qn[SR_AHEAD - 1], qperm[SR_AHEAD - 1]);
+            next_chunk(qn_s, qperm_s);
         }
+        ++it;
+        return false;
+    };
+    static_assert(SR_AHEAD == 4, "the loop below is unrolled over the queue slots");
+    for (;;) {
+        if (iteration(qn[0], qperm[0])) break;
+        if (iteration(qn[1], qperm[1])) break;
+        if (iteration(qn[2], qperm[2])) break;
+        if (iteration(qn[3], qperm[3])) break;
     }
 }
 

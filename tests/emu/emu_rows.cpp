@@ -13,7 +13,7 @@ static void run_ring(const float* dOut, int D, int gr, const int* perm, const in
     const size_t smem = (size_t)nst * RPS * D * 4 + SR_BAR_BYTES;
     emu::after_launch_hook() = emu::join_async;
     emu::launch(grid, 32, smem, [&]() {
-        scatter_add_rows_ring_kernel<VPL, RPS>(dOut, D, gr, perm, uniq_ids, seg_start, n_uniq, max_uniq, scale, out_rows, dense_G, 1, nst);
+        scatter_add_rows_ring_kernel<VPL, RPS>(dOut, D, gr, perm, uniq_ids, seg_start, n_uniq, max_uniq, scale, out_rows, dense_G, nst);
     });
     emu::after_launch_hook() = nullptr;
 }
