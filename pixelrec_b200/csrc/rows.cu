@@ -430,17 +430,18 @@ extern "C" int pr_scatter_add_rows_f32(const float* dOut, int64_t R, int64_t D, 
         // TMA-staged ring (rows_ring.cuh): VPL float4 per lane cover a row, 4 KiB stages, 6 of them per one-warp CTA, ~9 CTAs per SM.
         // Measured (profiles/r02j_scatter_ab.json, r02k_scatter_variants.json): 1.4-2.5x the LDG kernel up to D = 1024; from 8 KiB
         // rows on the LDG kernel's several warps per row are as fast or faster.
-        static int variant = -1;            // PR_SCATTER_VARIANT (A/B runs): 1 = 8 KiB stages (4 rows at D = 512), 4 = 4-stage ring
-        if (variant < 0) {
+        static int variant = -1;            // PR_SCATTER_VARIANT (A/B runs): 1 = 8 KiB stages (4 rows at D = 512), 4 = 4-stage ring,
+        if (variant < 0) {                  // 8 = look-ahead queue in registers (ring v1) instead of shared memory (ring v2)
             const char* e = getenv("PR_SCATTER_VARIANT");
             variant = e ? atoi(e) : 0;
         }
         int vpl = 1;
         while (32 * vpl < D4) vpl *= 2;
         const bool big = (variant & 1) && vpl == 4;
-        const int nst = (variant & 4) ? 4 : SR_STAGES;
+        const bool v2 = !(variant & 8) && !big;
+        const int nst = v2 ? ((variant & 4) ? 4 : 3) : ((variant & 4) ? 4 : SR_STAGES);
         const int rps = big ? 4 : std::max(1, 8 / vpl);
-        const size_t smem = (size_t)nst * rps * D * 4 + SR_BAR_BYTES;
+        const size_t smem = (size_t)nst * rps * D * 4 + SR_BAR_BYTES + (v2 ? SR_Q_BYTES : 0);
         int ctas_per_sm = (int)((220 * 1024) / (smem + 1024));
         ctas_per_sm = std::max(1, std::min(16, ctas_per_sm));
         const long long max_ctas = (long long)sms * ctas_per_sm;
@@ -457,13 +458,17 @@ extern "C" int pr_scatter_add_rows_f32(const float* dOut, int64_t R, int64_t D, 
         scatter_add_rows_ring_kernel<VPL, RPS><<<grid, 32, smem, stream>>>(dOut, (int)D, gr, perm, uniq_ids, seg_start, \
                                                                           n_uniq, max_uniq, scale, out_rows, dense_G, nst); \
     } while (0)
+#define PR_LAUNCH_RING2(VPL, RPS)                                                                                   \
+    scatter_add_rows_ring2_kernel<VPL, RPS><<<grid, 32, smem, stream>>>(dOut, (int)D, gr, perm, uniq_ids, seg_start, n_uniq,  \
+                                                                       max_uniq, scale, out_rows, dense_G, nst)
         switch (vpl) {
-            case 1: PR_LAUNCH_RING(1, 8); break;
-            case 2: PR_LAUNCH_RING(2, 4); break;
-            case 4: if (big) PR_LAUNCH_RING(4, 4); else PR_LAUNCH_RING(4, 2); break;
-            default: PR_LAUNCH_RING(8, 1); break;
+            case 1: if (v2) PR_LAUNCH_RING2(1, 8); else PR_LAUNCH_RING(1, 8); break;
+            case 2: if (v2) PR_LAUNCH_RING2(2, 4); else PR_LAUNCH_RING(2, 4); break;
+            case 4: if (v2) PR_LAUNCH_RING2(4, 2); else if (big) PR_LAUNCH_RING(4, 4); else PR_LAUNCH_RING(4, 2); break;
+            default: if (v2) PR_LAUNCH_RING2(8, 1); else PR_LAUNCH_RING(8, 1); break;
         }
 #undef PR_LAUNCH_RING
+#undef PR_LAUNCH_RING2
         PR_CUDA_LAUNCH_CHECK("scatter_add_rows_ring_kernel");
         return PR_OK;
     }

@@ -8,6 +8,17 @@
 using namespace pr;
 
 template <int VPL, int RPS>
+static void run_ring2(const float* dOut, int D, int gr, const int* perm, const int* uniq_ids, const int* seg_start, const int* n_uniq,
+                      long long max_uniq, float scale, float* out_rows, float* dense_G, int grid, int nst) {
+    const size_t smem = (size_t)nst * RPS * D * 4 + SR_BAR_BYTES + SR_Q_BYTES;
+    emu::after_launch_hook() = emu::join_async;
+    emu::launch(grid, 32, smem, [&]() {
+        scatter_add_rows_ring2_kernel<VPL, RPS>(dOut, D, gr, perm, uniq_ids, seg_start, n_uniq, max_uniq, scale, out_rows, dense_G, nst);
+    });
+    emu::after_launch_hook() = nullptr;
+}
+
+template <int VPL, int RPS>
 static void run_ring(const float* dOut, int D, int gr, const int* perm, const int* uniq_ids, const int* seg_start, const int* n_uniq,
                      long long max_uniq, float scale, float* out_rows, float* dense_G, int grid, int nst) {
     const size_t smem = (size_t)nst * RPS * D * 4 + SR_BAR_BYTES;
@@ -26,14 +37,17 @@ extern "C" int emu_scatter_add_rows_ring(const float* dOut, int D, int gr, const
     int vpl = 1;
     while (32 * vpl < D / 4) vpl *= 2;
 #define RUN(V, R) run_ring<V, R>(dOut, D, gr, perm, uniq_ids, seg_start, n_uniq, max_uniq, scale, out_rows, dense_G, grid, nst)
+#define RUN2(V, R) run_ring2<V, R>(dOut, D, gr, perm, uniq_ids, seg_start, n_uniq, max_uniq, scale, out_rows, dense_G, grid, nst)
+    const bool v2 = big == 2;       // big: 0 = ring v1, 1 = ring v1 with 4 rows per stage, 2 = ring v2 (look-ahead queue in shared memory)
     switch (vpl) {
-        case 1: RUN(1, 8); break;
-        case 2: RUN(2, 4); break;
-        case 4: if (big) RUN(4, 4); else RUN(4, 2); break;
-        case 8: RUN(8, 1); break;
+        case 1: if (v2) RUN2(1, 8); else RUN(1, 8); break;
+        case 2: if (v2) RUN2(2, 4); else RUN(2, 4); break;
+        case 4: if (v2) RUN2(4, 2); else if (big) RUN(4, 4); else RUN(4, 2); break;
+        case 8: if (v2) RUN2(8, 1); else RUN(8, 1); break;
         default: return -1;
     }
 #undef RUN
+#undef RUN2
     return vpl;
 }
 

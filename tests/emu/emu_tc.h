@@ -182,6 +182,22 @@ inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) 
         emu::complete_tx_at(bar, (long long)bytes);
     });
 }
+// cp.async (LDGSTS) 4-byte copies: performed when the issuing thread waits for the group (the latest moment the hardware allows),
+// so code that reads the destination without waiting sees the 0xAB fill of fresh shared memory
+struct PendingCp { void* dst; const void* src; };
+inline thread_local std::vector<std::vector<PendingCp>> t_cp_groups{std::vector<PendingCp>{}};
+inline void cp_async4(void* dst, const void* src) {
+    if (((uintptr_t)dst & 3) || ((uintptr_t)src & 3)) emu::fail("cp.async 4-byte copy needs 4-byte aligned addresses");
+    t_cp_groups.back().push_back(PendingCp{dst, src});
+}
+inline void cp_async_commit() { t_cp_groups.emplace_back(); }
+template <int N>
+inline void cp_async_wait() {       // all but the N most recently committed groups complete
+    while ((int)t_cp_groups.size() - 1 > N) {
+        for (const PendingCp& c : t_cp_groups.front()) memcpy(c.dst, c.src, 4);
+        t_cp_groups.erase(t_cp_groups.begin());
+    }
+}
 inline void l2_prefetch_bulk(const void* src, uint32_t bytes) {          // a hint: only its arguments can be wrong
     if (bytes % 16 || ((uintptr_t)src & 15)) emu::fail("bulk prefetch needs a 16-byte aligned address and size");
 }

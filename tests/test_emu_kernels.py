@@ -315,7 +315,12 @@ def _np_plan(idx, N, pad):
                                                        (30, 128, 500, 2, 7, 0.6, 6, 0), (300, 1024, 90, 32, 5, 0, 6, 0),
                                                        (64, 512, 170, 16, 2, 0.3, 4, 1), (20, 768, 40, 32, 3, 0, 6, 0),
                                                        (10, 512, 0, 32, 2, 0, 6, 0), (10, 512, 40, 32, 2, 1.0, 6, 0),
-                                                       (100, 256, 333, 8, 4, 0.2, 3, 0)])
+                                                       (100, 256, 333, 8, 4, 0.2, 3, 0),
+                                                       # ring v2: look-ahead queue in shared memory (cp.async), 3- and 4-stage rings
+                                                       (50, 64, 300, 4, 3, 0, 3, 2), (200, 512, 260, 32, 2, 0, 3, 2), (40, 384, 200, 8, 1, 0, 4, 2),
+                                                       (30, 128, 500, 2, 7, 0.6, 3, 2), (300, 1024, 90, 32, 5, 0, 3, 2),
+                                                       (10, 512, 0, 32, 2, 0, 3, 2), (10, 512, 40, 32, 2, 1.0, 3, 2),
+                                                       (64, 512, 170, 16, 2, 0.3, 6, 2)])
 def test_scatter_add_rows_ring_emulated(emu_rows, N, D, R, gr, grid, hot, nst, big):
     """TMA-staged segment reduce (rows_ring.cuh): ring protocol, group / run bookkeeping and the summation order, bit for bit
     against oracle.scatter_add_rows -- including one hot id that owns most rows, all-padding input and R = 0."""

@@ -37,6 +37,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default=None)
     ap.add_argument("--once", action="store_true", help="one launch per case (ncu captures)")
+    ap.add_argument("--quick", action="store_true", help="three C2 / C1 cases only, no gather reference point")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     L_ = _lib.load()
@@ -44,6 +45,8 @@ def main():
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     cases = [("C2_B4096", 97001, 512, 20, 4096), ("C2_B64", 97001, 512, 20, 64), ("C2_B16384", 97001, 512, 20, 16384),
              ("C3_B1024", 408375, 2048, 20, 1024), ("C5_B1024", 100001, 4096, 10, 1024), ("C1_B4096", 10001, 128, 10, 4096)]
+    if a.quick:
+        cases = [c for c in cases if c[0] in ("C2_B4096", "C2_B16384", "C1_B4096")]
     out = {}
     for name, N, D, L, B in cases:
         perm, p = bench.popularity(N)
@@ -70,7 +73,7 @@ def main():
         print(name, json.dumps(rec), flush=True)
     # reference point: what random 2 KB row reads + sequential writes reach on this part (every id distinct, L2 flushed):
     # the gather kernel of the forward on 172 032 distinct rows of a 400 K x 512 table
-    if not a.once:
+    if not a.once and not a.quick:
         Wt = torch.randn(400000, 512, device=dev)
         ids = torch.randperm(400000, device=dev)[:172032].contiguous()
         ms = timeit(lambda: ops.gather_rows(Wt, ids), flush)
