@@ -461,7 +461,7 @@ def bpr_loss(out, E, masked_index, slab=None):
 
 
 # ------------------------------------------------------------------------------------------- table gather w/ sparse grad
-PLAN_AHEAD = os.environ.get("PR_PLAN_AHEAD", "0") == "1"     # staged: build the scatter plan during the forward, on a side stream
+PLAN_AHEAD = os.environ.get("PR_PLAN_AHEAD", "0") == "1"     # build the scatter plan during the forward, on a side stream (r02a: no gain)
 _plan_streams = {}
 
 
@@ -475,7 +475,7 @@ def _plan_stream(device):
 class GatherFn(torch.autograd.Function):
     """E = W[idx].  backward: dense mode returns a zero-filled [N,D] grad (reference semantics);
     sparse mode deposits (plan, reduced rows) on `sink` and leaves W.grad untouched.
-    PR_PLAN_AHEAD=1: the index plan of the backward (14 small sort / scan launches that depend only on idx) is enqueued on a
+    PR_PLAN_AHEAD=1: the index plan of the backward (9 small sort / scan launches that depend only on idx) is enqueued on a
     side stream at forward time, ordered after everything already on the current stream (the previous step's AdamW hands the
     row2slot entries back), and overlaps the encoder; the backward only waits for its event."""
 
