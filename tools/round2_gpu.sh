@@ -92,3 +92,24 @@ elif [ "$stage" = stage8 ]; then
       tools/bench_configs.py --config c3 --exchange p2p
 fi
 exit 0
+
+# ---- stages j / k (second half of round 2): the calls behind profiles/r02j_* and r02k_*, one gpurun call per stage
+if [ "$stage" = rowk ]; then            # segment reduce / plan / LayerNorm / loss kernels: parity, A/B, bench, ncu
+  run 700 k_pytest_all   python -m pytest tests -m gpu -q --maxfail=40
+  run 300 k_bench_n1     python bench.py
+  run 300 k_bench_noz    env PR_FUSE_LN_Z=0 python bench.py --no-cpu              # dropout + residual NOT in the GEMM epilogue
+  run 300 k_bench_ln1row env PR_TUNE=345 python bench.py --no-cpu                  # LayerNorm forward, one row per warp
+  for v in 0 4 8 1; do                                                             # ring v2 (3 / 4 stages), ring v1 (register queue), v1 with 8 KiB stages
+    run 120 k_scatter_v$v env PR_SCATTER_VARIANT=$v python tools/bench_scatter.py --json gpurun_out/k_scatter_v$v.json
+  done
+  run 300 k_ncu_list ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/k_launches.csv \
+      python bench.py --steps 2 --warmup 1 --no-cpu
+  run 300 k_ncu_rowk ncu --set full --clock-control none --import-source on \
+      -k regex:"scatter_add_rows_ring|add_ln_fwd_rows2|bpr_fwd|bpr_bwd" -c 8 -o gpurun_out/k_rowkernels \
+      python bench.py --steps 1 --warmup 1 --no-cpu --no-graph
+fi
+if [ "$stage" = dist2 ]; then           # gpurun --gpus 2: exchanges, graph replay, sharded evaluation; N=2 bench
+  run 500 k_pytest_dist python -m pytest tests/test_gpu_dist.py -m gpu -q
+  run 240 k_bench_n2 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+      bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu
+fi
