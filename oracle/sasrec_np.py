@@ -390,6 +390,22 @@ def full_catalog_ce(scores, target, mask_col0=True):
     return lse, tl, lse - tl
 
 
+def full_catalog_ce_bwd(seq_out, W, target, dnll, mask_col0=True):
+    """Backward of full_catalog_ce(seq_out @ W.T, target) (same extension; what pixelrec_b200.ops.ScoreCEFn.backward computes in
+    column chunks on pr_gemm_tf32 + pr_ce_grad_chunk_f32):  dS = dnll[:, None] * (softmax(S) - onehot(target)) with the padding
+    column excluded from the softmax (its dS is 0);  d seq_out = dS @ W,  d W = dS.T @ seq_out.  Returns (d seq_out, d W)."""
+    X = np.asarray(seq_out, dtype=np.float64)
+    Wd = np.asarray(W, dtype=np.float64)
+    S = X @ Wd.T
+    if mask_col0:
+        S[:, 0] = -np.inf
+    P = np.exp(S - S.max(1, keepdims=True))
+    P /= P.sum(1, keepdims=True)
+    P[np.arange(S.shape[0]), np.asarray(target)] -= 1.0
+    dS = P * np.asarray(dnll, dtype=np.float64)[:, None]
+    return dS @ Wd, dS.T @ X
+
+
 def topk_hits(topk_idx, positive_u, positive_i, n_users):
     """collector.py:134-139: pos_idx[u, r] = 1 iff topk_idx[u, r] is u's positive item; pos_len = #positives."""
     pos = np.zeros(topk_idx.shape, dtype=np.int32)

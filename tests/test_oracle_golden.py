@@ -200,3 +200,24 @@ def test_bench_shape_golden_pins_the_oracle_at_d512_l20():
     assert rel(scores, g["eval_scores_raw"]) < 1e-4
     _, idx = O.full_sort_topk(g["eval_scores_raw"], g["eval_hist_u"], g["eval_hist_i"], 10)
     assert np.array_equal(idx, g["eval_topk_idx"])
+
+
+def test_full_catalog_ce_backward_oracle_restates_autograd():
+    """oracle.full_catalog_ce_bwd (extension) == float64 autograd of logsumexp - target logit with the padding column excluded"""
+    import torch
+    g = np.random.default_rng(11)
+    B, N, D = 9, 40, 6
+    seq, W = g.standard_normal((B, D)), g.standard_normal((N, D))
+    target = g.integers(1, N, size=B)
+    wts = g.random(B) + 0.5
+    X = torch.from_numpy(seq).requires_grad_()
+    Wt = torch.from_numpy(W).requires_grad_()
+    sc = X @ Wt.t()
+    sc = torch.cat([torch.full_like(sc[:, :1], -float("inf")), sc[:, 1:]], 1)
+    nll = torch.logsumexp(sc, 1) - sc.gather(1, torch.from_numpy(target)[:, None])[:, 0]
+    (nll * torch.from_numpy(wts)).sum().backward()
+    dX, dW = O.full_catalog_ce_bwd(seq, W, target, wts)
+    assert np.abs(dX - X.grad.numpy()).max() < 1e-12 and np.abs(dW - Wt.grad.numpy()).max() < 1e-12
+    assert np.abs(dW[0]).max() == 0.0                                   # the padding item gets no gradient
+    lse, tl, nll_o = O.full_catalog_ce(seq @ W.T, target)
+    assert np.abs(nll_o - nll.detach().numpy()).max() < 1e-12
