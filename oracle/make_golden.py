@@ -335,7 +335,52 @@ def make_seqtrain_case(name="seqtrain_ref"):
     print(name, {k: v.shape for k, v in out.items() if k.endswith("items")})
 
 
+def make_seqeval_case(name="seqeval_ref"):
+    """A11 data side pin: the reference's own SeqEvalDataset.__getitem__ (data/dataset/evalset.py:24-37) + seq_eval_collate
+    (data/dataset/collate_fn.py:6-32) through a DataLoader with the reference's strided sampler order (rank r: users r, r+W, ...:
+    data/utils.py:134-159), for both phases, histories shorter and longer than L, ragged last batch.
+    tests/test_host_plumbing.py replays pixelrec_b200's SeqEvalDataset / seq_eval_collate / DeviceSeqEvalLoader against it."""
+    import torch
+    from torch.utils.data import DataLoader
+    from oracle.refload import load_reference
+    load_reference()
+    from REC.data.dataset.collate_fn import seq_eval_collate
+    from REC.data.dataset.evalset import SeqEvalDataset
+    g = np.random.default_rng(7)
+    n_users, item_num, L, bs = 23, 60, 6, 4
+    user_seq = {}
+    for u in range(n_users):
+        user_seq[u] = g.integers(1, item_num, size=int(g.integers(3, 15))).astype(np.int64)
+
+    class Dl:
+        pass
+    dl = Dl()
+    dl.item_num = item_num
+    dl.user_seq = user_seq
+    out = {"meta": np.array([n_users, item_num, L, bs], dtype=np.int64),
+           "flat": np.concatenate([user_seq[u] for u in range(n_users)]),
+           "offs": np.cumsum([0] + [len(user_seq[u]) for u in range(n_users)]).astype(np.int64)}
+    for phase in ("valid", "test"):
+        ds = SeqEvalDataset({"MAX_ITEM_LIST_LENGTH": L}, dl, phase=phase)
+        for world in (1, 2, 3):
+            for rank in range(world):
+                order = list(range(rank, len(ds), world))
+                loader = DataLoader(ds, batch_size=bs, sampler=order, collate_fn=seq_eval_collate)
+                for bi, (item_seq, (hu, hi), pu, tgt) in enumerate(loader):
+                    key = f"{phase}_w{world}_r{rank}_b{bi}"
+                    out[key + "_seq"] = item_seq.numpy()
+                    out[key + "_hu"] = hu.numpy()
+                    out[key + "_hi"] = hi.numpy()
+                    out[key + "_pu"] = pu.numpy()
+                    out[key + "_tgt"] = tgt.numpy()
+                out[f"{phase}_w{world}_r{rank}_nb"] = np.array([bi + 1], dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, len(out), "arrays", os.path.getsize(os.path.join(OUT, name + ".npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__" and (len(sys.argv) == 1 or "sasrec_bench_shape" in sys.argv[1:]):
     make_bench_shape_case()
 if __name__ == "__main__" and (len(sys.argv) == 1 or "seqtrain_ref" in sys.argv[1:]):
     make_seqtrain_case()
+if __name__ == "__main__" and (len(sys.argv) == 1 or "seqeval_ref" in sys.argv[1:]):
+    make_seqeval_case()

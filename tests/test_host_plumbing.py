@@ -260,3 +260,37 @@ def test_device_eval_loader_equals_dataloader_collate(world, phase):
             assert torch.equal(pu0, pu1) and torch.equal(t0, t1)
             n += 1
         assert n == len(ref)
+
+
+@pytest.mark.parametrize("phase", ["valid", "test"])
+def test_eval_batches_equal_the_reference_dataset_and_collate_golden(phase):
+    """tests/golden/seqeval_ref.npz holds what the UNMODIFIED reference builds per eval batch -- SeqEvalDataset.__getitem__
+    (evalset.py:24-37) + seq_eval_collate (collate_fn.py:6-32) in the strided sampler's order (data/utils.py:134-159), generated by
+    oracle/make_golden.py.  Both of our routes must reproduce it element for element: the DataLoader + collate port and the
+    resident-CSR DeviceSeqEvalLoader (device_sampler: True)."""
+    from torch.utils.data import DataLoader
+    from pixelrec_b200.data.dataset import SeqEvalDataset, seq_eval_collate
+    from pixelrec_b200.data.utils import DeviceSeqEvalLoader, NonConsecutiveSequentialDistributedSampler
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "seqeval_ref.npz"))
+    n_users, item_num, L, bs = (int(x) for x in gold["meta"])
+    flat, offs = gold["flat"], gold["offs"]
+
+    class Dl:
+        pass
+    Dl.item_num = item_num
+    Dl.user_seq = {u: flat[offs[u]:offs[u + 1]] for u in range(n_users)}
+    ds = SeqEvalDataset(dict(MAX_ITEM_LIST_LENGTH=L), Dl, phase=phase)
+    for world in (1, 2, 3):
+        for rank in range(world):
+            nb = int(gold[f"{phase}_w{world}_r{rank}_nb"][0])
+            ours_dl = DataLoader(ds, batch_size=bs, collate_fn=seq_eval_collate,
+                                 sampler=NonConsecutiveSequentialDistributedSampler(ds, rank=rank, num_replicas=world))
+            ours_dev = DeviceSeqEvalLoader(ds, bs, "cpu", rank, world)
+            assert len(ours_dl) == nb and len(ours_dev) == nb
+            for route in (ours_dl, ours_dev):
+                for bi, (seq, (hu, hi), pu, tgt) in enumerate(route):
+                    key = f"{phase}_w{world}_r{rank}_b{bi}"
+                    assert np.array_equal(seq.numpy(), gold[key + "_seq"]), key
+                    assert np.array_equal(hu.numpy(), gold[key + "_hu"]) and np.array_equal(hi.numpy(), gold[key + "_hi"]), key
+                    assert np.array_equal(pu.numpy(), gold[key + "_pu"]) and np.array_equal(tgt.numpy(), gold[key + "_tgt"]), key
+                assert bi == nb - 1
