@@ -378,9 +378,46 @@ def make_seqeval_case(name="seqeval_ref"):
     print(name, len(out), "arrays", os.path.getsize(os.path.join(OUT, name + ".npz")) // 1024, "KiB")
 
 
+def make_evalmetrics_case(name="evalmetrics_ref"):
+    """A11 metric side pin: the reference's own Collector.eval_batch_collect (evaluator/collector.py:113-139) + Evaluator /
+    Recall / NDCG (evaluator/metrics.py:115-178, base_metric.py:43-67) on three batches of masked random scores (per-rank SUMS over
+    users, as trainer.py:402-408 divides them afterwards).  tests/test_host_plumbing.py replays pixelrec_b200's evaluator on the
+    same scores, through both of its entry points (scores, and the fused kernel's top-k ids)."""
+    import torch
+    from oracle.refload import load_reference
+    load_reference()
+    from REC.evaluator import Collector, Evaluator
+
+    class Cfg(dict):
+        def __getitem__(self, k):
+            return self.get(k)
+    cfg = Cfg(topk=[5, 10], metrics=["Recall", "NDCG"], device="cpu", metric_decimal_place=7)
+    col, ev = Collector(cfg), Evaluator(cfg)
+    g = torch.Generator().manual_seed(3)
+    out = {"topk": np.array([5, 10], dtype=np.int64)}
+    for bi, n in enumerate((7, 7, 3)):
+        scores = torch.randn(n, 60, generator=g)
+        scores[:, 0] = -float("inf")
+        hu = torch.randint(0, n, (4 * n,), generator=g)
+        hi = torch.randint(1, 60, (4 * n,), generator=g)
+        pi = torch.randint(1, 60, (n,), generator=g)
+        scores[hu, hi] = -float("inf")
+        scores[torch.arange(n), pi] = torch.randn(n, generator=g) + 1.5      # positives are never masked (they are held out)
+        col.eval_batch_collect(scores, torch.arange(n), pi)
+        out[f"b{bi}_scores"] = scores.numpy()
+        out[f"b{bi}_pi"] = pi.numpy()
+    res = ev.evaluate(col.get_data_struct())
+    out["names"] = np.array(list(res.keys()))
+    out["values"] = np.array([float(v) for v in res.values()], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, dict(res))
+
+
 if __name__ == "__main__" and (len(sys.argv) == 1 or "sasrec_bench_shape" in sys.argv[1:]):
     make_bench_shape_case()
 if __name__ == "__main__" and (len(sys.argv) == 1 or "seqtrain_ref" in sys.argv[1:]):
     make_seqtrain_case()
 if __name__ == "__main__" and (len(sys.argv) == 1 or "seqeval_ref" in sys.argv[1:]):
     make_seqeval_case()
+if __name__ == "__main__" and (len(sys.argv) == 1 or "evalmetrics_ref" in sys.argv[1:]):
+    make_evalmetrics_case()

@@ -294,3 +294,27 @@ def test_eval_batches_equal_the_reference_dataset_and_collate_golden(phase):
                     assert np.array_equal(hu.numpy(), gold[key + "_hu"]) and np.array_equal(hi.numpy(), gold[key + "_hi"]), key
                     assert np.array_equal(pu.numpy(), gold[key + "_pu"]) and np.array_equal(tgt.numpy(), gold[key + "_tgt"]), key
                 assert bi == nb - 1
+
+
+def test_evaluator_equals_the_reference_evaluator_golden():
+    """tests/golden/evalmetrics_ref.npz: Recall / NDCG sums produced by the UNMODIFIED reference Collector + Evaluator
+    (evaluator/collector.py:113-139, metrics.py:115-178) on three batches of masked scores.  Our evaluator must give the same
+    numbers through both entry points: full score rows (the reference contract) and top-k ids (what the fused scoring returns)."""
+    from pixelrec_b200.evaluator import Collector, Evaluator
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "evalmetrics_ref.npz"))
+    cfg = {"topk": [int(k) for k in gold["topk"]], "metrics": ["Recall", "NDCG"], "device": "cpu"}
+    want = dict(zip([str(n) for n in gold["names"]], gold["values"]))
+    for route in ("scores", "topk"):
+        col, ev = Collector(cfg), Evaluator(cfg)
+        for bi in range(3):
+            scores = torch.from_numpy(gold[f"b{bi}_scores"])
+            pi = torch.from_numpy(gold[f"b{bi}_pi"])
+            pu = torch.arange(scores.shape[0])
+            if route == "scores":
+                col.eval_batch_collect(scores, pu, pi)
+            else:
+                col.eval_batch_collect_topk(torch.topk(scores, max(cfg["topk"]), dim=-1)[1], pu, pi)
+        res = ev.evaluate(col.get_data_struct())
+        assert set(res) == set(want)
+        for k, v in want.items():
+            assert abs(float(res[k]) - v) < 1e-9, (route, k, float(res[k]), v)
