@@ -413,6 +413,32 @@ def make_evalmetrics_case(name="evalmetrics_ref"):
     print(name, dict(res))
 
 
+def make_config_case(name="config_ref"):
+    """Boundary pin: the final config dict the reference's own Config builds (config/configurator.py) from ITS yaml
+    files for the three hot-path model plugins -- model yaml + overall yaml, MODEL_INPUT_TYPE / eval_type / valid_metric_bigger
+    derived keys included.  tests/test_host_plumbing.py loads this repo's copies of those yaml files with pixelrec_b200.config.Config
+    and compares key by key.  Stored as JSON (enums as their str())."""
+    import json
+    from oracle.refload import load_reference
+    load_reference()
+    from REC.config import Config
+    here = os.getcwd()
+    os.chdir("/tmp")                     # the reference's logger / config may touch relative paths
+    out = {}
+    try:
+        for tag, files in (("sasrec", ["IDNet/sasrec.yaml", "overall/ID.yaml"]), ("gru4rec", ["IDNet/gru4rec.yaml", "overall/ID.yaml"]),
+                           ("mosasrec", ["PixelNet/sasrec.yaml", "overall/ViT.yaml"])):
+            c = Config(config_file_list=["/root/reference/code/" + f for f in files])
+            d = {k: (v if isinstance(v, (int, float, str, list, dict, bool, type(None))) else str(v))
+                 for k, v in dict(c.final_config_dict).items()}
+            out[tag] = {"files": files, "final": d}
+    finally:
+        os.chdir(here)
+    with open(os.path.join(OUT, name + ".json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print(name, {k: len(v["final"]) for k, v in out.items()})
+
+
 if __name__ == "__main__" and (len(sys.argv) == 1 or "sasrec_bench_shape" in sys.argv[1:]):
     make_bench_shape_case()
 if __name__ == "__main__" and (len(sys.argv) == 1 or "seqtrain_ref" in sys.argv[1:]):
@@ -421,3 +447,5 @@ if __name__ == "__main__" and (len(sys.argv) == 1 or "seqeval_ref" in sys.argv[1
     make_seqeval_case()
 if __name__ == "__main__" and (len(sys.argv) == 1 or "evalmetrics_ref" in sys.argv[1:]):
     make_evalmetrics_case()
+if __name__ == "__main__" and (len(sys.argv) == 1 or "config_ref" in sys.argv[1:]):
+    make_config_case()

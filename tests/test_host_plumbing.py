@@ -318,3 +318,21 @@ def test_evaluator_equals_the_reference_evaluator_golden():
         assert set(res) == set(want)
         for k, v in want.items():
             assert abs(float(res[k]) - v) < 1e-9, (route, k, float(res[k]), v)
+
+
+@pytest.mark.parametrize("tag", ["sasrec", "gru4rec", "mosasrec"])
+def test_config_equals_the_reference_config_golden(tag):
+    """tests/golden/config_ref.json: the final config dict the UNMODIFIED reference Config (config/configurator.py) builds from its
+    own yaml files, derived keys (MODEL_INPUT_TYPE, eval_type, valid_metric_bigger) included.  This repo's copies of those yaml
+    files through pixelrec_b200.config.Config must give the same value for every key the reference defines."""
+    import json
+    from pixelrec_b200.config import Config
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config_ref.json")) as f:
+        gold = json.load(f)[tag]
+    c = Config(_yaml(*gold["files"]))
+    assert len(gold["final"]) >= 29
+    for k, want in gold["final"].items():
+        got = c[k]
+        if not isinstance(got, (int, float, str, list, dict, bool, type(None))):
+            got = str(got)
+        assert got == want, (k, got, want)
