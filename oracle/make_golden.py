@@ -413,6 +413,46 @@ def make_evalmetrics_case(name="evalmetrics_ref"):
     print(name, dict(res))
 
 
+def make_dataload_case(name="dataload_ref"):
+    """A1 upstream pin: the reference's own Data (data/dataload.py:16-150) on a toy <dataset>.csv whose rows are NOT in time
+    order: id re-mapping with [PAD] = 0 (:42-57), user_seq in order of first appearance after the timestamp sort (:66-76), training
+    windows of L+1 items with the oldest n mod (L+1) dropped (:103-150).  Timestamps are distinct (the reference's DataFrame sort
+    is unstable for ties).  tests/test_host_plumbing.py rebuilds the CSV from the stored rows and replays pixelrec_b200's Data."""
+    import tempfile
+    from oracle.refload import load_reference
+    load_reference()
+    from REC.data.dataload import Data
+    from REC.utils.enum_type import InputType
+    g = np.random.default_rng(5)
+    n, L = 400, 5
+    ts = g.permutation(n) + 1000
+    item_tok = g.integers(0, 40, size=n)
+    user_tok = g.integers(0, 14, size=n)
+    user_tok[:3] = 99                    # a user with 3 interactions (one training item) ...
+    user_tok[3:5] = 98                   # ... and one with 2 (none)
+    d = tempfile.mkdtemp()
+    with open(os.path.join(d, "toy.csv"), "w") as f:
+        f.write("item_id,user_id,timestamp\n" + "\n".join(f"i{a},u{b},{c}" for a, b, c in zip(item_tok, user_tok, ts)))
+
+    class Cfg(dict):
+        def __getitem__(self, k):
+            return self.get(k)
+    data = Data(Cfg(data_path=d, dataset="toy", MAX_ITEM_LIST_LENGTH=L, MODEL_INPUT_TYPE=InputType.SEQ))
+    data.build()
+    keys = list(data.user_seq.keys())
+    out = {"rows": np.stack([item_tok, user_tok, ts], 1).astype(np.int64), "L": np.array([L]),
+           "item_num": np.array([data.item_num]), "user_num": np.array([data.user_num]),
+           "user_order": np.array(keys, dtype=np.int64),
+           "user_seq_flat": np.concatenate([data.user_seq[k] for k in keys]).astype(np.int64),
+           "user_seq_offs": np.cumsum([0] + [len(data.user_seq[k]) for k in keys]).astype(np.int64),
+           "train_uid": np.asarray(data.train_feat["user_id"], dtype=np.int64),
+           "train_flat": np.concatenate(data.train_feat["item_seq"]).astype(np.int64),
+           "train_offs": np.cumsum([0] + [len(s) for s in data.train_feat["item_seq"]]).astype(np.int64),
+           "item_tokens": np.array(list(data.id2token["item_id"])), "user_tokens": np.array(list(data.id2token["user_id"]))}
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "users", len(keys), "windows", len(data.train_feat["item_seq"]))
+
+
 def make_config_case(name="config_ref"):
     """Boundary pin: the final config dict the reference's own Config builds (config/configurator.py) from ITS yaml
     files for the three hot-path model plugins -- model yaml + overall yaml, MODEL_INPUT_TYPE / eval_type / valid_metric_bigger
@@ -449,3 +489,5 @@ if __name__ == "__main__" and (len(sys.argv) == 1 or "evalmetrics_ref" in sys.ar
     make_evalmetrics_case()
 if __name__ == "__main__" and (len(sys.argv) == 1 or "config_ref" in sys.argv[1:]):
     make_config_case()
+if __name__ == "__main__" and (len(sys.argv) == 1 or "dataload_ref" in sys.argv[1:]):
+    make_dataload_case()

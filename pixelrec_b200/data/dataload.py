@@ -59,16 +59,21 @@ class Data:
         self.inter_num = len(df)
 
     def build(self):
+        # dataload.py:66-76: sort by timestamp, then group by user IN ORDER OF FIRST APPEARANCE (dict insertion order of
+        # _grouped_index) -- the order of user_seq is the order of the eval users and of the training windows, i.e. what a seeded
+        # sampler permutes; tests/golden/dataload_ref.npz pins it to the reference.  (The reference sorts a DataFrame with pandas'
+        # default unstable sort: equal timestamps have no defined order there; here they keep file order.)
         order = np.argsort(self.inter_feat["timestamp"], kind="stable")
         users = self.inter_feat["user_id"][order]
         items = self.inter_feat["item_id"][order]
         uorder = np.argsort(users, kind="stable")          # group by user, keep time order inside a user
-        users, items = users[uorder], items[uorder]
-        bounds = np.flatnonzero(np.r_[True, users[1:] != users[:-1], True])
-        first_seen = {}
+        us, it = users[uorder], items[uorder]
+        bounds = np.flatnonzero(np.r_[True, us[1:] != us[:-1], True])
+        first_pos = uorder[bounds[:-1]]                    # where (in time order) each user appears first
         self.user_seq = {}
-        for s, e in zip(bounds[:-1], bounds[1:]):
-            self.user_seq[int(users[s])] = items[s:e]
+        for gi in np.argsort(first_pos, kind="stable"):
+            s, e = bounds[gi], bounds[gi + 1]
+            self.user_seq[int(us[s])] = it[s:e]
         self._build_train()
 
     def _build_train(self):

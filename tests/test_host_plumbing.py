@@ -336,3 +336,31 @@ def test_config_equals_the_reference_config_golden(tag):
         if not isinstance(got, (int, float, str, list, dict, bool, type(None))):
             got = str(got)
         assert got == want, (k, got, want)
+
+
+def test_dataload_equals_the_reference_data_golden(tmp_path):
+    """tests/golden/dataload_ref.npz: what the UNMODIFIED reference Data (data/dataload.py:16-150) builds from a toy CSV whose rows
+    are not in time order -- token re-mapping, user_seq INCLUDING its order (first appearance after the timestamp sort: the order
+    of the eval users and of the training windows that a seeded sampler permutes), training windows.  Our Data must match it."""
+    from pixelrec_b200.data.dataload import Data
+    from pixelrec_b200.utils.enum_type import InputType
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dataload_ref.npz"))
+    (tmp_path / "toy.csv").write_text("item_id,user_id,timestamp\n" + "\n".join(f"i{a},u{b},{c}" for a, b, c in gold["rows"]))
+
+    class Cfg(dict):
+        def __getitem__(self, k):
+            return self.get(k)
+    data = Data(Cfg(data_path=str(tmp_path), dataset="toy", MAX_ITEM_LIST_LENGTH=int(gold["L"][0]), MODEL_INPUT_TYPE=InputType.SEQ))
+    data.build()
+    assert data.item_num == int(gold["item_num"][0]) and data.user_num == int(gold["user_num"][0])
+    assert list(data.id2token["item_id"]) == list(gold["item_tokens"]) and list(data.id2token["user_id"]) == list(gold["user_tokens"])
+    keys = list(data.user_seq.keys())
+    assert keys == [int(k) for k in gold["user_order"]]
+    offs = gold["user_seq_offs"]
+    for j, k in enumerate(keys):
+        assert np.array_equal(data.user_seq[k], gold["user_seq_flat"][offs[j]:offs[j + 1]]), k
+    assert np.array_equal(data.train_feat["user_id"], gold["train_uid"])
+    toffs = gold["train_offs"]
+    assert len(data.train_feat["item_seq"]) == len(toffs) - 1
+    for j, w in enumerate(data.train_feat["item_seq"]):
+        assert np.array_equal(w, gold["train_flat"][toffs[j]:toffs[j + 1]]), j
