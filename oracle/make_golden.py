@@ -453,6 +453,40 @@ def make_dataload_case(name="dataload_ref"):
     print(name, "users", len(keys), "windows", len(data.train_feat["item_seq"]))
 
 
+def make_init_case(name="init_ref"):
+    """Plugin-construction pin: the state_dict the reference's own SASRec / GRU4Rec hold right after `init_seed(2020, True)` +
+    construction (utils/utils.py init_seed; sasrec.py:49-61 `self.apply(self._init_weights)`; gru4rec.py:38-48) on a small config.
+    The plugins here must draw the SAME initial weights from the same seed (same module order, same initialisers), so that a run of
+    the reference's yaml + seed starts from the reference's model.  tests/test_host_plumbing.py replays it on the CPU."""
+    import torch
+    from oracle.refload import load_reference
+    load_reference()
+    from REC.model.IDNet.gru4rec import GRU4Rec
+    from REC.model.IDNet.sasrec import SASRec
+    from REC.utils import init_seed
+
+    class Dl:
+        item_num = 101
+        user_num = 20
+    out = {}
+    init_seed(2020, True)
+    m = SASRec(dict(SASREC_INIT_CFG), Dl())
+    for k, v in m.state_dict().items():
+        out["sasrec/" + k] = v.numpy()
+    init_seed(2020, True)
+    m = GRU4Rec(dict(GRU4REC_INIT_CFG), Dl())
+    for k, v in m.state_dict().items():
+        out["gru4rec/" + k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, len(out), "tensors")
+
+
+SASREC_INIT_CFG = dict(n_layers=2, n_heads=2, embedding_size=32, inner_size=2, hidden_dropout_prob=0.1, attn_dropout_prob=0.1,
+                       hidden_act="gelu", layer_norm_eps=1e-12, initializer_range=0.02, MAX_ITEM_LIST_LENGTH=10, seed=2020, device="cpu")
+GRU4REC_INIT_CFG = dict(embedding_size=32, hidden_size=2, num_layers=1, dropout_prob=0.0, MAX_ITEM_LIST_LENGTH=10, seed=2020,
+                        device="cpu")
+
+
 def make_config_case(name="config_ref"):
     """Boundary pin: the final config dict the reference's own Config builds (config/configurator.py) from ITS yaml
     files for the three hot-path model plugins -- model yaml + overall yaml, MODEL_INPUT_TYPE / eval_type / valid_metric_bigger
@@ -491,3 +525,5 @@ if __name__ == "__main__" and (len(sys.argv) == 1 or "config_ref" in sys.argv[1:
     make_config_case()
 if __name__ == "__main__" and (len(sys.argv) == 1 or "dataload_ref" in sys.argv[1:]):
     make_dataload_case()
+if __name__ == "__main__" and (len(sys.argv) == 1 or "init_ref" in sys.argv[1:]):
+    make_init_case()

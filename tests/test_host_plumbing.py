@@ -364,3 +364,30 @@ def test_dataload_equals_the_reference_data_golden(tmp_path):
     assert len(data.train_feat["item_seq"]) == len(toffs) - 1
     for j, w in enumerate(data.train_feat["item_seq"]):
         assert np.array_equal(w, gold["train_flat"][toffs[j]:toffs[j + 1]]), j
+
+
+def test_plugins_draw_the_reference_initial_weights_from_the_same_seed():
+    """tests/golden/init_ref.npz: state_dict of the UNMODIFIED reference SASRec / GRU4Rec right after init_seed(2020, True) +
+    construction.  Our plugins (same module order, same initialisers: sasrec.py:49-61, gru4rec.py:38-48) must hold identical tensors,
+    so the reference's yaml + seed starts from the reference's model."""
+    # the configs oracle/make_golden.py (SASREC_INIT_CFG / GRU4REC_INIT_CFG) built the reference models with
+    SASREC_INIT_CFG = dict(n_layers=2, n_heads=2, embedding_size=32, inner_size=2, hidden_dropout_prob=0.1, attn_dropout_prob=0.1,
+                           hidden_act="gelu", layer_norm_eps=1e-12, initializer_range=0.02, MAX_ITEM_LIST_LENGTH=10, seed=2020,
+                           device="cpu")
+    GRU4REC_INIT_CFG = dict(embedding_size=32, hidden_size=2, num_layers=1, dropout_prob=0.0, MAX_ITEM_LIST_LENGTH=10, seed=2020,
+                            device="cpu")
+    from pixelrec_b200.model.IDNet.gru4rec import GRU4Rec
+    from pixelrec_b200.model.IDNet.sasrec import SASRec
+    from pixelrec_b200.utils import init_seed
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "init_ref.npz"))
+
+    class Dl:
+        item_num = 101
+        user_num = 20
+    for tag, cls, cfg in (("sasrec", SASRec, SASREC_INIT_CFG), ("gru4rec", GRU4Rec, GRU4REC_INIT_CFG)):
+        init_seed(2020, True)
+        sd = cls(dict(cfg), Dl()).state_dict()
+        want = {k.split("/", 1)[1]: gold[k] for k in gold.files if k.startswith(tag + "/")}
+        assert list(sd.keys()) == list(want.keys()), tag
+        for k, v in sd.items():
+            assert np.array_equal(v.numpy(), want[k]), (tag, k)
