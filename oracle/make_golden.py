@@ -487,6 +487,30 @@ GRU4REC_INIT_CFG = dict(embedding_size=32, hidden_size=2, num_layers=1, dropout_
                         device="cpu")
 
 
+def make_utils_case(name="utils_ref"):
+    """Trainer-control pin: the reference's own early_stopping / calculate_valid_score / dict2str (utils/utils.py:65-135) on a grid
+    of inputs -- they decide when the reference saves a checkpoint and when it stops (trainer.py:234-262)."""
+    import json
+    from collections import OrderedDict
+    from oracle.refload import load_reference
+    load_reference()
+    from REC.utils import calculate_valid_score, dict2str, early_stopping
+    cases = []
+    for bigger in (True, False):
+        for value, best in ((0.5, 0.4), (0.3, 0.4), (0.4, 0.4), (0.41, 0.4)):
+            for cur_step, max_step in ((0, 5), (3, 5), (4, 5), (5, 5), (29, 30)):
+                out = early_stopping(value, best, cur_step, max_step=max_step, bigger=bigger)
+                cases.append({"in": [value, best, cur_step, max_step, bigger], "out": [float(out[0]), int(out[1]), bool(out[2]), bool(out[3])]})
+    res = OrderedDict([("recall@5", 0.1234567), ("recall@10", 0.2), ("ndcg@5", 0.05), ("ndcg@10", 0.0712345)])
+    out = {"early_stopping": cases,
+           # the trainer passes config['valid_metric'].lower() (trainer.py:55), i.e. the lower-case keys of the result dict
+           "valid_score": [[m, float(calculate_valid_score(res, m))] for m in ("ndcg@10", "recall@5", "ndcg@5")],
+           "dict2str_in": list(res.items()), "dict2str_out": dict2str(res)}
+    with open(os.path.join(OUT, name + ".json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print(name, len(cases), "early_stopping cases")
+
+
 def make_config_case(name="config_ref"):
     """Boundary pin: the final config dict the reference's own Config builds (config/configurator.py) from ITS yaml
     files for the three hot-path model plugins -- model yaml + overall yaml, MODEL_INPUT_TYPE / eval_type / valid_metric_bigger
@@ -527,3 +551,5 @@ if __name__ == "__main__" and (len(sys.argv) == 1 or "dataload_ref" in sys.argv[
     make_dataload_case()
 if __name__ == "__main__" and (len(sys.argv) == 1 or "init_ref" in sys.argv[1:]):
     make_init_case()
+if __name__ == "__main__" and (len(sys.argv) == 1 or "utils_ref" in sys.argv[1:]):
+    make_utils_case()

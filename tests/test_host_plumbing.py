@@ -391,3 +391,22 @@ def test_plugins_draw_the_reference_initial_weights_from_the_same_seed():
         assert list(sd.keys()) == list(want.keys()), tag
         for k, v in sd.items():
             assert np.array_equal(v.numpy(), want[k]), (tag, k)
+
+
+def test_trainer_control_helpers_equal_the_reference_golden():
+    """tests/golden/utils_ref.json: outputs of the UNMODIFIED reference early_stopping / calculate_valid_score / dict2str
+    (utils/utils.py:65-135) on a grid -- they decide when the reference checkpoints and stops (trainer.py:234-262)."""
+    import json
+    from collections import OrderedDict
+    from pixelrec_b200.utils import calculate_valid_score, dict2str, early_stopping
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "utils_ref.json")) as f:
+        gold = json.load(f)
+    assert len(gold["early_stopping"]) == 40
+    for c in gold["early_stopping"]:
+        value, best, cur_step, max_step, bigger = c["in"]
+        got = early_stopping(value, best, cur_step, max_step=max_step, bigger=bigger)
+        assert [float(got[0]), int(got[1]), bool(got[2]), bool(got[3])] == c["out"], c
+    res = OrderedDict((k, v) for k, v in gold["dict2str_in"])
+    for m, want in gold["valid_score"]:
+        assert calculate_valid_score(res, m) == want
+    assert dict2str(res) == gold["dict2str_out"]
